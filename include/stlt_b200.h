@@ -1,0 +1,155 @@
+/*
+ * stlt_b200.h — C ABI of libstlt_b200.so: the B200 (sm_100a) implementation of the STLT
+ * layout-encoding forward path of gorjanradevski/revisiting-spatial-temporal-layouts.
+ *
+ * The reference has no FFI layer: its boundary is the Python nn.Module protocol of `Stlt`
+ * (reference src/modelling/models.py:166-195) as called from src/train.py:125,142 and
+ * src/inference.py:77. This header is what a binding for that path calls; the Python shim in
+ * revisiting-spatial-temporal-layouts_b200/module.py binds it with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative STLT_ERR_* code otherwise; no exceptions
+ *     cross the ABI. stlt_last_error() returns a human-readable message for the last failure.
+ *   - all tensor pointers are DEVICE pointers, contiguous, row-major. The caller owns every byte
+ *     of device memory (inputs, weights, packed weights, workspace, outputs); the library never
+ *     allocates device memory and never synchronises, except stlt_check_errors().
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it and
+ *     is CUDA-graph capturable.
+ *   - a handle is not thread-safe; distinct handles are independent. One handle per device.
+ *   - there is no CPU fallback: a machine without an sm_100 GPU gets STLT_ERR_CUDA.
+ */
+#ifndef STLT_B200_H_
+#define STLT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STLT_OK 0
+#define STLT_ERR_INVALID (-1) /* bad argument / shape / missing weight */
+#define STLT_ERR_CUDA (-2)    /* CUDA runtime or driver error */
+#define STLT_ERR_STATE (-3)   /* call order (weights not bound / packed) */
+#define STLT_ERR_INPUT (-4)   /* out-of-range categories / frame_types / lengths (check_errors) */
+
+/* precision of the projection GEMMs */
+#define STLT_PRECISION_FP32 0 /* 3-term bf16 split on tcgen05; logits within 1e-4 of fp32 */
+#define STLT_PRECISION_BF16 1 /* bf16 operands, fp32 accumulate/residual/LN/softmax */
+
+/* dtype codes for StltTensor */
+#define STLT_DTYPE_F32 0
+#define STLT_DTYPE_I64 1
+
+/* Mirrors the fields of the reference StltModelConfig (src/modelling/configs.py:92-111) that
+ * reach the forward path. hidden_size/num_heads must be 768/12 (kernels are specialised). */
+typedef struct StltDims {
+  int32_t hidden_size;         /* configs.py:96  (768) */
+  int32_t num_heads;           /* configs.py:99  (12) */
+  int32_t num_spatial_layers;  /* configs.py:107 (4) */
+  int32_t num_temporal_layers; /* configs.py:108 (8) */
+  int32_t unique_categories;   /* configs.py:105 */
+  int32_t num_classes;         /* configs.py:94 */
+  int32_t max_positions;       /* configs.py:109 layout_num_frames (256) */
+  int32_t num_frame_types;     /* models.py:91 (5) */
+  float layer_norm_eps;        /* configs.py:98 (1e-12): embeddings, frames, head LayerNorms */
+  float encoder_norm_eps;      /* 1e-5: LayerNorms inside nn.TransformerEncoderLayer */
+} StltDims;
+
+/* One named parameter tensor; `name` is the reference state_dict key. */
+typedef struct StltTensor {
+  const char* name;
+  const void* data; /* device pointer */
+  int32_t dtype;    /* STLT_DTYPE_* */
+  int32_t ndim;
+  int64_t shape[4];
+} StltTensor;
+
+/* Optional device buffers that receive the fp32 activations after each stage (parity tests).
+ * Any pointer may be NULL. Shapes: embed/spatial [B*L*S, 768]; frames/temporal [B*L, 768];
+ * pooled [B, 768]. */
+typedef struct StltTaps {
+  float* embed;    /* CategoryBoxEmbeddings output       (models.py:29-39) */
+  float* spatial;  /* spatial encoder output, all slots  (models.py:68-71) */
+  float* frames;   /* FramesEmbeddings output            (models.py:98-111) */
+  float* temporal; /* temporal encoder output            (models.py:146-150) */
+  float* pooled;   /* gathered extract-frame token       (models.py:189-192) */
+} StltTaps;
+
+/* Replaces Stlt.__init__ (models.py:167-178): validates the dimensions, creates host state. */
+int stlt_create(const StltDims* dims, void** handle);
+int stlt_destroy(void* handle);
+const char* stlt_last_error(void* handle);
+
+/* Replaces module.load_state_dict / .to(device) on the library side (inference.py:58-69): binds
+ * device pointers of the fp32 parameters by their reference state_dict names. Pointers are
+ * borrowed, not copied. Unknown names (the orphan encoder_layer.*, position_ids) are ignored. */
+int stlt_bind_weights(void* handle, const StltTensor* tensors, int32_t count);
+
+/* The tcgen05 GEMMs read bf16 copies of the 4 projection matrices of every encoder layer
+ * (2 planes hi/lo for STLT_PRECISION_FP32, 1 plane for BF16). The caller provides the buffer and
+ * re-runs stlt_pack_weights whenever the fp32 parameters change. */
+int stlt_packed_weights_bytes(void* handle, int32_t precision, size_t* bytes);
+int stlt_pack_weights(void* handle, void* stream, int32_t precision, void* packed, size_t bytes);
+
+int stlt_workspace_bytes(void* handle, int32_t batch, int32_t frames, int32_t slots,
+                         int32_t precision, size_t* bytes);
+
+/* K0 — replaces fix_box (src/utils/data_utils.py:205-231), the division by the video size
+ * (src/modelling/datasets.py:54,82) and the two padding masks of StltCollater
+ * (src/modelling/datasets.py:274-286) for an already padded layout:
+ *   raw_boxes   f64 [B, L, S, 4] pixel boxes (x1, y1, x2, y2) as read from the dataset JSON
+ *   video_sizes i64 [B, 2] (width, height)
+ *   categories  i64 [B, L, S], frame_types i64 [B, L]
+ * Slot 0 of every frame receives the CLS box [0,0,1,1], slots with category 0 receive zeros.
+ *   boxes_out f32 [B, L, S, 4]; mask_boxes_out u8 [B, L, S]; mask_frames_out u8 [B, L]. */
+int stlt_prepare(void* handle, void* stream, const double* raw_boxes, const int64_t* video_sizes,
+                 const int64_t* categories, const int64_t* frame_types, int32_t batch,
+                 int32_t frames, int32_t slots, float* boxes_out, uint8_t* mask_boxes_out,
+                 uint8_t* mask_frames_out);
+
+/* Replaces Stlt.forward (models.py:185-195) in eval mode.
+ *   categories i64 [B, L, S]; boxes f32 [B, L, S, 4]; scores f32 [B, L, S] or NULL (presence
+ *   toggles the score embedding, models.py:33-35); frame_types i64 [B, L]; lengths i64 [B].
+ *   logits_out f32 [B, num_classes]. mask_*_out (u8, optional) receive the padding masks the
+ *   reference collater would have produced (categories == 0, frame_types == 0). */
+int stlt_forward(void* handle, void* stream, int32_t precision, const int64_t* categories,
+                 const float* boxes, const float* scores_or_null, const int64_t* frame_types,
+                 const int64_t* lengths, int32_t batch, int32_t frames, int32_t slots,
+                 void* workspace, size_t workspace_bytes, float* logits_out,
+                 uint8_t* mask_boxes_out_or_null, uint8_t* mask_frames_out_or_null);
+
+/* Synchronises `stream` and reports STLT_ERR_INPUT if the last forward on `workspace` saw an
+ * index outside its table (PyTorch raises IndexError for those on CPU). */
+int stlt_check_errors(void* handle, void* stream, const void* workspace);
+
+/* Number of kernels enqueued by the most recent stlt_forward on this handle. */
+int stlt_last_launch_count(void* handle);
+
+/* Test taps (NULL disables). The struct is copied. */
+int stlt_set_taps(void* handle, const StltTaps* taps);
+
+/* ---- single-operator entry points used by the parity tests -------------------------------- */
+
+/* out = epilogue(sum_terms A_t W_t^T + bias): A bf16 [terms>1 ? 2 : 1][m_rows][k], W bf16
+ * [terms>1 ? 2 : 1][n][k]; out_kind 0 = f32 [m_rows][n], 1 = bf16, 2 = bf16 hi/lo planes. */
+int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w_planes,
+                 const float* bias, void* out, int32_t m_rows, int32_t n, int32_t k, int32_t terms,
+                 int32_t out_kind, int32_t gelu);
+int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w,
+                      const float* bias, float* out, int32_t m, int32_t n, int32_t k, int32_t gelu);
+int stlt_op_attention(void* handle, void* stream, const void* qkv, int32_t qkv_is_bf16,
+                      const int64_t* mask_src, int64_t num_seqs, int32_t seq_len, int32_t causal,
+                      void* out_bf16, int32_t planes, int64_t plane_rows);
+int stlt_op_add_ln(void* handle, void* stream, const float* x, const float* y_or_null,
+                   const float* gamma, const float* beta, float eps, int64_t rows, float* out_f32,
+                   void* out_bf16, int32_t planes, int64_t plane_rows);
+int stlt_op_pack_bf16(void* handle, void* stream, const float* src, void* dst, int64_t n,
+                      int32_t planes);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* STLT_B200_H_ */

@@ -1,0 +1,181 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference from /root/reference on CPU.
+
+TEST INFRASTRUCTURE. Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+The reference ships no tests or golden vectors, so these fixtures — outputs of the
+reference's own ``fix_box``, ``StltDataset`` + ``StltCollater`` and ``Stlt`` module on seeded
+inputs — are what pins the oracle (oracle/stlt_oracle.py) and, through it, the CUDA path.
+Inputs come from the seeded generators in the package (synthetic.py) so tests can rebuild them;
+model weights are regenerated from a seed at test time (a checksum is stored here).
+"""
+from __future__ import annotations
+
+import json
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+REFERENCE_SRC = Path("/root/reference/src")
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def import_reference():
+    if not REFERENCE_SRC.exists():
+        raise SystemExit("/root/reference is not available here")
+    sys.path.insert(0, str(REFERENCE_SRC))
+    for name in ("h5py", "ffmpeg"):  # imported by the reference data modules, unused on this path
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    from modelling import configs, datasets, models  # noqa
+    from utils import data_utils  # noqa
+    return configs, datasets, models, data_utils
+
+
+def weights_checksum(sd) -> float:
+    return float(sum(v.double().abs().sum().item() for v in sd.values() if v.is_floating_point()))
+
+
+def golden_fix_box(data_utils):
+    g = torch.Generator().manual_seed(11)
+    n = 4096
+    sizes = torch.tensor([(427, 240), (320, 240), (240, 427), (1280, 720)])[torch.randint(0, 4, (n,), generator=g)]
+    u = torch.rand((n, 4), generator=g, dtype=torch.float64) * 1.4 - 0.2
+    raw = u * torch.stack([sizes[:, 0], sizes[:, 1], sizes[:, 0], sizes[:, 1]], dim=1).double()
+    kind = torch.randint(0, 8, (n,), generator=g)
+    raw = torch.where((kind == 0).unsqueeze(1), raw.round(), raw)
+    raw[:, 2] = torch.where(kind == 1, raw[:, 0], raw[:, 2])
+    raw[:, 3] = torch.where(kind == 2, raw[:, 1], raw[:, 3])
+    raw = torch.where((kind == 3).unsqueeze(1), torch.zeros_like(raw), raw)
+    raw[0] = torch.tensor([-3.2, 500.9, 10.5, 10.5], dtype=torch.float64)  # SURVEY.md A.2 example
+    sizes[0] = torch.tensor([427, 240])
+    fixed = torch.zeros((n, 4), dtype=torch.int64)
+    norm = torch.zeros((n, 4), dtype=torch.float32)
+    for i in range(n):
+        w, h = int(sizes[i, 0]), int(sizes[i, 1])
+        box = data_utils.fix_box([float(v) for v in raw[i]], (h, w))       # reference call
+        fixed[i] = torch.tensor(box)
+        video_size = torch.tensor([w, h]).repeat(2)                       # datasets.py:54
+        norm[i] = torch.tensor(box) / video_size                          # datasets.py:82
+    assert fixed[0].tolist() == [0, 10, 10, 239]
+    np.savez_compressed(GOLDEN / "fix_box.npz", raw=raw.numpy(), sizes=sizes.numpy(),
+                        fixed=fixed.numpy(), normalized=norm.numpy())
+    print("fix_box.npz", n)
+
+
+def synth_dataset_json(dataset: str, n_videos: int, seed: int):
+    """A small dataset in the on-disk JSON schema the reference reads (datasets.py:35-37)."""
+    from oracle.stlt_oracle import DATASETS
+    g = torch.Generator().manual_seed(seed)
+    names = [n for n in DATASETS[dataset]["category2id"] if n not in ("pad", "cls")]
+    max_obj = 4 if dataset == "something" else 6
+    videos, sizes = [], {}
+    for v in range(n_videos):
+        vid = f"video{v}"
+        w, h = [(427, 240), (320, 240), (240, 427)][int(torch.randint(0, 3, (1,), generator=g))]
+        sizes[vid] = [w, h]
+        n_frames = int(torch.randint(1, 40, (1,), generator=g))
+        frames = []
+        for _ in range(n_frames):
+            objs = []
+            for _ in range(int(torch.randint(0, max_obj + 1, (1,), generator=g))):
+                c = torch.rand(4, generator=g, dtype=torch.float64) * 1.3 - 0.15
+                objs.append({
+                    "category": names[int(torch.randint(0, len(names), (1,), generator=g))],
+                    "x1": float(c[0] * w), "y1": float(c[1] * h), "x2": float(c[2] * w), "y2": float(c[3] * h),
+                    "score": float(torch.rand(1, generator=g, dtype=torch.float64) * 0.7 + 0.3)
+                    if dataset == "action_genome" else 1.0,
+                })
+            frames.append({"frame_objects": objs})
+        video = {"id": vid, "frames": frames}
+        if dataset == "something":
+            video["template"] = "Doing [something]"
+        else:
+            video["actions"] = ["c001", "c017"]
+        videos.append(video)
+    labels = {"Doing something": "7"} if dataset == "something" else {f"c{i:03d}": i for i in range(157)}
+    return videos, labels, sizes
+
+
+def golden_dataset(configs, datasets, dataset: str, seed: int):
+    videos, labels, sizes = synth_dataset_json(dataset, n_videos=6, seed=seed)
+    with tempfile.TemporaryDirectory() as td:
+        paths = {}
+        for name, obj in (("dataset", videos), ("labels", labels), ("sizes", sizes)):
+            paths[name] = str(Path(td) / f"{name}.json")
+            json.dump(obj, open(paths[name], "w"))
+        cfg = configs.DataConfig(dataset_name=dataset, dataset_path=paths["dataset"], labels_path=paths["labels"],
+                                 videoid2size_path=paths["sizes"], videos_path=None, train=False)
+        ds = datasets.StltDataset(cfg)                 # reference, discovers max_num_objects
+        batch = datasets.StltCollater(cfg)([ds[i] for i in range(len(ds))])
+    out = {
+        "json": np.frombuffer(json.dumps({"videos": videos, "sizes": sizes}).encode(), dtype=np.uint8),
+        "max_num_objects": np.int64(cfg.max_num_objects),
+        "categories": batch["categories"].numpy(), "boxes": batch["boxes"].numpy(),
+        "frame_types": batch["frame_types"].numpy(), "lengths": batch["lengths"].numpy(),
+        "src_key_padding_mask_boxes": batch["src_key_padding_mask_boxes"].numpy(),
+        "src_key_padding_mask_frames": batch["src_key_padding_mask_frames"].numpy(),
+    }
+    if "scores" in batch:
+        out["scores"] = batch["scores"].numpy()
+    np.savez_compressed(GOLDEN / f"collate_{dataset}.npz", **out)
+    print(f"collate_{dataset}.npz", tuple(batch["categories"].shape), "max_num_objects", cfg.max_num_objects)
+
+
+def golden_model(configs, models, layout: str, batch_size: int, weight_seed: int, batch_seed: int):
+    import stlt_b200
+    from stlt_b200.synthetic import make_batch, random_state_dict
+    spec = stlt_b200.SOMETHING_ELSE if layout == "something" else stlt_b200.ACTION_GENOME
+    cfg = configs.StltModelConfig(num_classes=spec["num_classes"], unique_categories=spec["unique_categories"])
+    torch.manual_seed(0)
+    ref = models.Stlt(cfg)              # the unmodified reference module
+    ref.train(False)
+    sd = random_state_dict(ref.state_dict(), seed=weight_seed)
+    ref.load_state_dict(sd, strict=True)
+    batch = make_batch(batch_size, layout=layout, ragged=True, seed=batch_seed)
+    B, L, S = batch["categories"].shape
+    taps = {}
+    be = ref.backbone.frames_embeddings
+    hooks = [
+        be.layout_embedding.category_box_embeddings.register_forward_hook(lambda m, i, o: taps.__setitem__("embed", o.detach().clone())),
+        be.layout_embedding.transformer.register_forward_hook(
+            lambda m, i, o: taps.__setitem__("spatial", o.detach().transpose(0, 1).reshape(B, L, S, -1).clone())),
+        be.register_forward_hook(lambda m, i, o: taps.__setitem__("frames", o.detach().clone())),
+        ref.backbone.register_forward_hook(lambda m, i, o: taps.__setitem__("temporal", o.detach().transpose(0, 1).clone())),
+    ]
+    with torch.no_grad():
+        logits = ref({k: v.clone() for k, v in batch.items()})["stlt"]
+    for h in hooks:
+        h.remove()
+    out = {
+        "layout": np.array(layout), "batch_size": np.int64(batch_size), "weight_seed": np.int64(weight_seed),
+        "batch_seed": np.int64(batch_seed), "weights_checksum": np.float64(weights_checksum(sd)),
+        "logits": logits.numpy(),
+        "embed_b0": taps["embed"][0].numpy(), "spatial_b0": taps["spatial"][0].numpy(),
+        "frames": taps["frames"].numpy(), "temporal": taps["temporal"].numpy(),
+    }
+    for k, v in batch.items():
+        out["in_" + k] = v.numpy()
+    np.savez_compressed(GOLDEN / f"stlt_{layout}.npz", **out)
+    print(f"stlt_{layout}.npz logits", tuple(logits.shape), "max|logit|", float(logits.abs().max()))
+
+
+def main():
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    configs, datasets, models, data_utils = import_reference()
+    golden_fix_box(data_utils)
+    golden_dataset(configs, datasets, "something", seed=21)
+    golden_dataset(configs, datasets, "action_genome", seed=22)
+    golden_model(configs, models, "something", batch_size=3, weight_seed=1, batch_seed=3)
+    golden_model(configs, models, "action_genome", batch_size=2, weight_seed=2, batch_seed=4)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,395 @@
+// HBM-bound stages of the STLT forward: box preparation + masks (K0), category/box embedding + LN
+// (K1), residual add + LayerNorm, frame embedding (K7), last-frame gather (K9), weight packing.
+// One warp owns one 768-wide row; lane l holds columns 4*l + 128*k + {0..3}, k = 0..5, so every
+// global access is a coalesced 16-byte vector.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace stlt {
+
+namespace {
+
+constexpr int kVec = kHidden / 128;  // 6 float4 per lane
+
+struct RowRegs {
+  float4 v[kVec];
+};
+
+__device__ __forceinline__ const float4* row4(const float* base, long long row) {
+  return reinterpret_cast<const float4*>(base + row * kHidden);
+}
+
+__device__ __forceinline__ RowRegs load_row(const float* base, long long row, int lane) {
+  RowRegs r;
+  const float4* p = row4(base, row);
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) r.v[k] = __ldg(p + lane + 32 * k);
+  return r;
+}
+
+// LayerNorm over the 768 features held by one warp (biased variance, two-pass in registers).
+__device__ __forceinline__ void layer_norm_row(RowRegs& r, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) s += (r.v[k].x + r.v[k].y) + (r.v[k].z + r.v[k].w);
+  const float mean = warp_sum(s) * (1.0f / kHidden);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    const float a = r.v[k].x - mean, b = r.v[k].y - mean, c = r.v[k].z - mean, d = r.v[k].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) * (1.0f / kHidden);
+  const float rstd = 1.0f / sqrtf(var + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    const float4 g = __ldg(g4 + lane + 32 * k);
+    const float4 b = __ldg(b4 + lane + 32 * k);
+    r.v[k].x = (r.v[k].x - mean) * rstd * g.x + b.x;
+    r.v[k].y = (r.v[k].y - mean) * rstd * g.y + b.y;
+    r.v[k].z = (r.v[k].z - mean) * rstd * g.z + b.z;
+    r.v[k].w = (r.v[k].w - mean) * rstd * g.w + b.w;
+  }
+}
+
+__device__ __forceinline__ void store_act(const ActOut& out, long long row, const RowRegs& r,
+                                          int lane) {
+  if (out.x != nullptr) {
+    float4* p = reinterpret_cast<float4*>(out.x + row * kHidden);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) p[lane + 32 * k] = r.v[k];
+  }
+  if (out.xb != nullptr) {
+    uint2* hi = reinterpret_cast<uint2*>(out.xb + row * kHidden);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      uint2 h;
+      h.x = pack_bf16x2(r.v[k].x, r.v[k].y);
+      h.y = pack_bf16x2(r.v[k].z, r.v[k].w);
+      hi[lane + 32 * k] = h;
+    }
+    if (out.planes == 2) {
+      uint2* lo = reinterpret_cast<uint2*>(out.xb + (out.plane_rows + row) * kHidden);
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) {
+        uint2 l;
+        l.x = pack_bf16x2(bf16_residual(r.v[k].x), bf16_residual(r.v[k].y));
+        l.y = pack_bf16x2(bf16_residual(r.v[k].z), bf16_residual(r.v[k].w));
+        lo[lane + 32 * k] = l;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: fix_box (src/utils/data_utils.py:205-231) + division by the video size
+// (src/modelling/datasets.py:54,82) + the two padding masks (src/modelling/datasets.py:274-286).
+// One thread per (video, frame, slot).
+// ------------------------------------------------------------------------------------------------
+__global__ void prepare_kernel(const double* __restrict__ raw_boxes,
+                               const long long* __restrict__ video_sizes,
+                               const long long* __restrict__ categories,
+                               const long long* __restrict__ frame_types, int L, int S,
+                               long long total, float4* __restrict__ boxes_out,
+                               uint8_t* __restrict__ mask_boxes, uint8_t* __restrict__ mask_frames) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int s = static_cast<int>(idx % S);
+  const long long frame = idx / S;
+  const long long b = frame / L;
+  const long long cat = categories[idx];
+  mask_boxes[idx] = (cat == 0) ? 1 : 0;  // src/modelling/datasets.py:277
+  if (s == 0) mask_frames[frame] = (frame_types[frame] == 0) ? 1 : 0;  // :283-285
+
+  float4 out;
+  if (s == 0) {
+    // CLS object / extract frame / padded frame: box [0, 0, 1, 1] (datasets.py:70,100,263)
+    out = make_float4(0.f, 0.f, 1.f, 1.f);
+  } else if (cat == 0) {
+    out = make_float4(0.f, 0.f, 0.f, 0.f);  // padded object slot (datasets.py:91)
+  } else {
+    const long long W = video_sizes[2 * b + 0];
+    const long long H = video_sizes[2 * b + 1];
+    const double* rb = raw_boxes + idx * 4;
+    long long x1 = static_cast<long long>(rb[0]);  // int(): truncation toward zero
+    long long y1 = static_cast<long long>(rb[1]);
+    long long x2 = static_cast<long long>(rb[2]);
+    long long y2 = static_cast<long long>(rb[3]);
+    x1 = x1 < 0 ? 0 : x1;
+    y1 = y1 < 0 ? 0 : y1;
+    x2 = x2 < 0 ? 0 : x2;
+    y2 = y2 < 0 ? 0 : y2;
+    if (x1 > x2) { const long long t = x1; x1 = x2; x2 = t; }
+    if (y1 > y2) { const long long t = y1; y1 = y2; y2 = t; }
+    if (x1 >= W) x1 = W - 1;
+    if (y1 >= H) y1 = H - 1;
+    if (x2 >= W) x2 = W - 1;
+    if (y2 >= H) y2 = H - 1;
+    if (x1 == x2 && x1 == 0) x2 = 1;
+    if (y1 == y2 && y1 == 0) y2 = 1;
+    if (x1 == x2) x1 -= 1;
+    if (y1 == y2) y1 -= 1;
+    // torch int64 / int64 true-divide: both operands rounded to fp32, IEEE divide.
+    const float fw = __ll2float_rn(W), fh = __ll2float_rn(H);
+    out.x = __fdiv_rn(__ll2float_rn(x1), fw);
+    out.y = __fdiv_rn(__ll2float_rn(y1), fh);
+    out.z = __fdiv_rn(__ll2float_rn(x2), fw);
+    out.w = __fdiv_rn(__ll2float_rn(y2), fh);
+  }
+  boxes_out[idx] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: CategoryBoxEmbeddings.forward (src/modelling/models.py:29-39)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_kernel(const long long* __restrict__ categories, const float4* __restrict__ boxes,
+             const float* __restrict__ scores, const float* __restrict__ cat_table,
+             int unique_categories, const float* __restrict__ box_w,
+             const float* __restrict__ box_b, const float* __restrict__ score_w,
+             const float* __restrict__ score_b, const float* __restrict__ ln_g,
+             const float* __restrict__ ln_b, float eps, long long tokens, ActOut out,
+             int* __restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  const float4* bw4 = reinterpret_cast<const float4*>(box_w);  // [768][4]: one float4 per feature
+  for (long long t = warp0; t < tokens; t += nwarps) {
+    long long cat = categories[t];
+    if (cat < 0 || cat >= unique_categories) {
+      if (lane == 0) atomicExch(err_flag, 1);
+      cat = 0;
+    }
+    const float4 box = __ldg(boxes + t);
+    const float score = scores != nullptr ? __ldg(scores + t) : 0.f;
+    RowRegs r = load_row(cat_table, cat, lane);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(box_b + c));
+      float e[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = __ldg(bw4 + c + q);
+        e[q] += box.x * w.x + box.y * w.y + box.z * w.z + box.w * w.w;
+      }
+      if (scores != nullptr) {
+        const float4 sw = __ldg(reinterpret_cast<const float4*>(score_w + c));  // [768][1]
+        const float4 sb = __ldg(reinterpret_cast<const float4*>(score_b + c));
+        e[0] += score * sw.x + sb.x;
+        e[1] += score * sw.y + sb.y;
+        e[2] += score * sw.z + sb.z;
+        e[3] += score * sw.w + sb.w;
+      }
+      r.v[k].x += e[0];
+      r.v[k].y += e[1];
+      r.v[k].z += e[2];
+      r.v[k].w += e[3];
+    }
+    layer_norm_row(r, ln_g, ln_b, eps, lane);
+    store_act(out, t, r, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x <- LN(x + y): the two post-norm residual sites of every encoder layer.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y,
+              const float* __restrict__ g, const float* __restrict__ b, float eps, long long rows,
+              ActOut out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    RowRegs r = load_row(x_in, row, lane);
+    if (y != nullptr) {
+      const RowRegs a = load_row(y, row, lane);
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) {
+        r.v[k].x += a.v[k].x;
+        r.v[k].y += a.v[k].y;
+        r.v[k].z += a.v[k].z;
+        r.v[k].w += a.v[k].w;
+      }
+    }
+    layer_norm_row(r, g, b, eps, lane);
+    store_act(out, row, r, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: FramesEmbeddings.forward (src/modelling/models.py:98-111); position_ids[:, :L] = 0..L-1.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+frame_embed_kernel(const float* __restrict__ spatial_x, int S,
+                   const long long* __restrict__ frame_types, const float* __restrict__ pos_table,
+                   const float* __restrict__ ft_table, int n_frame_types,
+                   const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps, int L,
+                   long long frames, ActOut out, int* __restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  for (long long f = warp0; f < frames; f += nwarps) {
+    const int l = static_cast<int>(f % L);
+    long long ft = frame_types[f];
+    if (ft < 0 || ft >= n_frame_types) {
+      if (lane == 0) atomicExch(err_flag, 2);
+      ft = 0;
+    }
+    RowRegs r = load_row(spatial_x, f * S, lane);  // slot 0 = CLS object (models.py:79)
+    const RowRegs p = load_row(pos_table, l, lane);
+    const RowRegs t = load_row(ft_table, ft, lane);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      r.v[k].x = (r.v[k].x + p.v[k].x) + t.v[k].x;
+      r.v[k].y = (r.v[k].y + p.v[k].y) + t.v[k].y;
+      r.v[k].z = (r.v[k].z + p.v[k].z) + t.v[k].z;
+      r.v[k].w = (r.v[k].w + p.v[k].w) + t.v[k].w;
+    }
+    layer_norm_row(r, ln_g, ln_b, eps, lane);
+    store_act(out, f, r, lane);
+  }
+}
+
+// K9: stlt_output[lengths - 1, arange(B)] (src/modelling/models.py:189-192)
+__global__ void __launch_bounds__(256)
+gather_last_kernel(const float* __restrict__ x, const long long* __restrict__ lengths, int B, int L,
+                   float* __restrict__ out, int* __restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  for (long long b = warp0; b < B; b += nwarps) {
+    long long len = lengths[b];
+    if (len < 1 || len > L) {
+      if (lane == 0) atomicExch(err_flag, 3);
+      len = 1;
+    }
+    const RowRegs r = load_row(x, b * L + (len - 1), lane);
+    float4* p = reinterpret_cast<float4*>(out + b * kHidden);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) p[lane + 32 * k] = r.v[k];
+  }
+}
+
+__global__ void pack_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ hi,
+                                 uint2* __restrict__ lo, long long n4) {
+  const long long stride = gridDim.x * static_cast<long long>(blockDim.x);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += stride) {
+    const float4 v = __ldg(src + i);
+    uint2 h;
+    h.x = pack_bf16x2(v.x, v.y);
+    h.y = pack_bf16x2(v.z, v.w);
+    hi[i] = h;
+    if (lo != nullptr) {
+      uint2 l;
+      l.x = pack_bf16x2(bf16_residual(v.x), bf16_residual(v.y));
+      l.y = pack_bf16x2(bf16_residual(v.z), bf16_residual(v.w));
+      lo[i] = l;
+    }
+  }
+}
+
+// Padding masks of StltCollater (src/modelling/datasets.py:274-286) from the already padded ids.
+__global__ void masks_kernel(const long long* __restrict__ categories,
+                             const long long* __restrict__ frame_types, long long n_slots,
+                             long long n_frames, uint8_t* __restrict__ mask_boxes,
+                             uint8_t* __restrict__ mask_frames) {
+  const long long stride = gridDim.x * static_cast<long long>(blockDim.x);
+  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (mask_boxes != nullptr)
+    for (long long i = i0; i < n_slots; i += stride) mask_boxes[i] = categories[i] == 0 ? 1 : 0;
+  if (mask_frames != nullptr)
+    for (long long i = i0; i < n_frames; i += stride) mask_frames[i] = frame_types[i] == 0 ? 1 : 0;
+}
+
+inline int row_grid(long long rows, int warps_per_block) {
+  long long blocks = (rows + warps_per_block - 1) / warps_per_block;
+  const long long cap = 148LL * 16;  // 16 resident 256-thread... capped; kernels are grid-stride
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+cudaError_t launch_prepare(const double* raw_boxes, const long long* video_sizes,
+                           const long long* categories, const long long* frame_types, int B, int L,
+                           int S, float* boxes_out, uint8_t* mask_boxes, uint8_t* mask_frames,
+                           cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * L * S;
+  if (total == 0) return cudaSuccess;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  prepare_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      raw_boxes, video_sizes, categories, frame_types, L, S, total,
+      reinterpret_cast<float4*>(boxes_out), mask_boxes, mask_frames);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_masks(const long long* categories, const long long* frame_types,
+                         long long n_slots, long long n_frames, uint8_t* mask_boxes,
+                         uint8_t* mask_frames, cudaStream_t stream) {
+  if (n_slots == 0) return cudaSuccess;
+  long long blocks = (n_slots + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  masks_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(categories, frame_types, n_slots,
+                                                                  n_frames, mask_boxes, mask_frames);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_embed(const long long* categories, const float* boxes, const float* scores,
+                         const float* cat_table, int unique_categories, const float* box_w,
+                         const float* box_b, const float* score_w, const float* score_b,
+                         const float* ln_g, const float* ln_b, float eps, long long tokens,
+                         ActOut out, int* err_flag, cudaStream_t stream) {
+  if (tokens == 0) return cudaSuccess;
+  embed_kernel<<<row_grid(tokens, 8), 256, 0, stream>>>(
+      categories, reinterpret_cast<const float4*>(boxes), scores, cat_table, unique_categories,
+      box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, const float* b,
+                          float eps, long long rows, ActOut out, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  add_ln_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* frame_types,
+                               const float* pos_table, const float* ft_table, int n_frame_types,
+                               const float* ln_g, const float* ln_b, float eps, int B, int L,
+                               ActOut out, int* err_flag, cudaStream_t stream) {
+  const long long frames = static_cast<long long>(B) * L;
+  if (frames == 0) return cudaSuccess;
+  frame_embed_kernel<<<row_grid(frames, 8), 256, 0, stream>>>(spatial_x, S, frame_types, pos_table,
+                                                              ft_table, n_frame_types, ln_g, ln_b,
+                                                              eps, L, frames, out, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, int L, float* out,
+                               int* err_flag, cudaStream_t stream) {
+  if (B == 0) return cudaSuccess;
+  gather_last_kernel<<<row_grid(B, 8), 256, 0, stream>>>(x, lengths, B, L, out, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,
+                             cudaStream_t stream) {
+  if (n % 4 != 0) return cudaErrorInvalidValue;
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst),
+      planes == 2 ? reinterpret_cast<uint2*>(dst + n) : nullptr, n4);
+  return cudaGetLastError();
+}
+
+}  // namespace stlt

@@ -1,0 +1,321 @@
+// tcgen05 projection GEMM for the STLT encoder layers (QKV / out-proj / FFN1 / FFN2).
+//
+//   out[M, N] = epilogue( sum_terms A_t[M, K] * W_t[N, K]^T + bias[N] )
+//
+// Replaces the F.linear calls inside nn.TransformerEncoderLayer / nn.MultiheadAttention that the
+// reference instantiates at src/modelling/models.py:46-55 and :118-128.
+//
+// Operands are bf16, K-major, staged by TMA into 128B-swizzled shared memory; accumulators are fp32
+// in TMEM (2 x 256 columns, double buffered); one thread issues tcgen05.mma (M=128, N=256, K=16).
+//
+// Precision modes:
+//   kTerms == 1 : plain bf16 operands.
+//   kTerms == 3 : fp32-parity mode. Activations and weights are each stored as two bf16 planes
+//                 (hi = bf16(x), lo = bf16(x - hi)); the kernel accumulates hi*hi + lo*hi + hi*lo
+//                 into the same fp32 TMEM accumulator (the dropped lo*lo term is ~2^-16 relative).
+//                 Planes are stacked along the row axis of the same tensor map: plane p of A starts
+//                 at row p * a_plane_rows, plane p of W at row p * b_plane_rows.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warp 3 = idle, warps 4..11 = epilogue (warp w reads TMEM lane quarter w % 4, column half (w-4)/4).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace stlt {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
+constexpr int kABytes = BM * BK * 2;  // 16 KiB
+constexpr int kBBytes = BN * BK * 2;  // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiBufBytes = 32 * 128;  // 32 rows x 128 B staging tile for one TMA store
+constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int kTmemCols = 512;
+constexpr int kMaxStages = 4;
+
+// The split epilogue needs two staging tiles per warp (hi and lo plane), paid for with one stage.
+template <int kOut>
+struct Cfg {
+  static constexpr int kStages = (kOut == GEMM_OUT_BF16_SPLIT) ? 3 : 4;
+  static constexpr int kBufsPerWarp = (kOut == GEMM_OUT_BF16_SPLIT) ? 2 : 1;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kEpiWarps * kBufsPerWarp * kEpiBufBytes + 256 /*barriers*/;
+};
+static_assert(Cfg<GEMM_OUT_F32>::kSmemBytes <= 232448, "smem budget");
+static_assert(Cfg<GEMM_OUT_BF16_SPLIT>::kSmemBytes <= 232448, "smem budget");
+
+struct __align__(8) Barriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+}  // namespace
+
+template <int kTerms, int kOut, bool kGelu>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias,
+                    int m_tiles, int n_tiles, int k_blocks, int a_plane_rows, int b_plane_rows,
+                    int out_plane_rows) {
+  constexpr int kStages = Cfg<kOut>::kStages;
+  constexpr int kBufsPerWarp = Cfg<kOut>::kBufsPerWarp;
+
+  // SWIZZLE_128B tiles need 1024 B alignment; the dynamic smem window starts 1024-aligned when
+  // the kernel has no static shared memory (checked below).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* smem_ab = smem;
+  uint8_t* smem_epi = smem + kStages * kStageBytes;
+  Barriers* bars =
+      reinterpret_cast<Barriers*>(smem_epi + kEpiWarps * kBufsPerWarp * kEpiBufBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = m_tiles * n_tiles;
+  const int total_kb = kTerms * k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles;
+        const int n_blk = tile - m_blk * n_tiles;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int term = kb / k_blocks;
+          const int kk = kb - term * k_blocks;
+          // term 0: A_hi * W_hi, term 1: A_lo * W_hi, term 2: A_hi * W_lo
+          const int a_row = (term == 1 ? a_plane_rows : 0) + m_blk * BM;
+          const int b_row = (term == 2 ? b_plane_rows : 0) + n_blk * BN;
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          mbar_expect_tx(&bars->full[stage], kStageBytes);
+          uint8_t* sa = smem_ab + stage * kStageBytes;
+          tma_load_2d(&tm_a, &bars->full[stage], sa, kk * BK, a_row);
+          tma_load_2d(&tm_b, &bars->full[stage], sa + kABytes, kk * BK, b_row);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);  // epilogue has drained this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);  // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
+            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);  // frees this smem stage once the MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // which 128 columns of the 256-wide tile
+    uint8_t* ebuf = smem_epi + ew * kBufsPerWarp * kEpiBufBytes;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const uint32_t row_smem = smem_u32(ebuf) + lane * 128;  // this thread's 128 B staging row
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int col0 = n_blk * BN + half * 128;
+      const int row0 = m_blk * BM + quarter * 32;
+      const float4* bias4 = reinterpret_cast<const float4*>(bias + col0);  // warp-uniform reads
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + acc * BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {  // 4 chunks of 32 accumulator columns
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(bias4 + c * 8 + (j >> 2));
+          f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+          f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+          f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+          f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        }
+        if (kGelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+
+        if (kOut == GEMM_OUT_F32) {
+          // 32 fp32 columns = 128 B per row -> one TMA store per chunk
+          if (lane == 0) tma_store_wait_read0();  // previous store has finished reading ebuf
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = row_smem + ((static_cast<uint32_t>(j) ^ sw) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f[4 * j]),
+                         "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, ebuf, col0 + c * 32, row0);
+            tma_store_commit();
+          }
+        } else {
+          // bf16 output: two 32-column chunks fill one 128 B row (64 bf16) -> store every 2nd chunk
+          const int hc = c & 1;
+          if (hc == 0) {
+            if (lane == 0) tma_store_wait_read0();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = row_smem + ((static_cast<uint32_t>(hc * 4 + j) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                         "r"(pack_bf16x2(f[8 * j + 0], f[8 * j + 1])),
+                         "r"(pack_bf16x2(f[8 * j + 2], f[8 * j + 3])),
+                         "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])),
+                         "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
+                         : "memory");
+            if (kOut == GEMM_OUT_BF16_SPLIT) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kEpiBufBytes),
+                           "r"(pack_bf16x2(bf16_residual(f[8 * j + 0]), bf16_residual(f[8 * j + 1]))),
+                           "r"(pack_bf16x2(bf16_residual(f[8 * j + 2]), bf16_residual(f[8 * j + 3]))),
+                           "r"(pack_bf16x2(bf16_residual(f[8 * j + 4]), bf16_residual(f[8 * j + 5]))),
+                           "r"(pack_bf16x2(bf16_residual(f[8 * j + 6]), bf16_residual(f[8 * j + 7])))
+                           : "memory");
+            }
+          }
+          if (hc == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tm_out, ebuf, col0 + (c - 1) * 32, row0);
+              if (kOut == GEMM_OUT_BF16_SPLIT)
+                tma_store_2d(&tm_out, ebuf + kEpiBufBytes, col0 + (c - 1) * 32,
+                             out_plane_rows + row0);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator have completed (tmem_ld_wait above) -> release it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+int gemm_smem_bytes() { return Cfg<GEMM_OUT_F32>::kSmemBytes; }
+
+template <int kTerms, int kOut, bool kGelu>
+static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sms) {
+  auto kern = gemm_tcgen05_kernel<kTerms, kOut, kGelu>;
+  constexpr int smem = Cfg<kOut>::kSmemBytes;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int m_tiles = g.m_rows / BM;
+  const int n_tiles = g.n / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, kThreads, smem, stream>>>(g.tm_a, g.tm_b, g.tm_out, g.bias, m_tiles, n_tiles,
+                                         g.k / BK, g.a_plane_rows, g.b_plane_rows,
+                                         g.out_plane_rows);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_sms) {
+  if (g.m_rows <= 0 || g.m_rows % BM != 0 || g.n % BN != 0 || g.k % BK != 0)
+    return cudaErrorInvalidValue;
+#define STLT_GEMM_CASE(T, O, G) \
+  if (g.terms == T && g.out_kind == O && g.gelu == G) return launch_one<T, O, G>(g, stream, num_sms);
+  STLT_GEMM_CASE(1, GEMM_OUT_F32, false)
+  STLT_GEMM_CASE(1, GEMM_OUT_BF16, false)
+  STLT_GEMM_CASE(1, GEMM_OUT_BF16, true)
+  STLT_GEMM_CASE(3, GEMM_OUT_F32, false)
+  STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, true)
+  STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, false)
+#undef STLT_GEMM_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace stlt

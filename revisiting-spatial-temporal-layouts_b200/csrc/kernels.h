@@ -1,0 +1,92 @@
+// Internal launcher declarations shared by the translation units of libstlt_b200.so.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stlt {
+
+enum GemmOutKind : int {
+  GEMM_OUT_F32 = 0,         // fp32 [M, N]
+  GEMM_OUT_BF16 = 1,        // bf16 [M, N]
+  GEMM_OUT_BF16_SPLIT = 2,  // bf16 hi plane [M, N] followed by lo plane [M, N]
+};
+
+struct GemmArgs {
+  CUtensorMap tm_a;    // bf16 [planes * a_plane_rows, K], box {64, 128}, SWIZZLE_128B
+  CUtensorMap tm_b;    // bf16 [planes * b_plane_rows, K], box {64, 256}, SWIZZLE_128B
+  CUtensorMap tm_out;  // fp32 box {32, 32} or bf16 box {64, 32}, SWIZZLE_128B
+  const float* bias;   // [N]
+  int m_rows;          // multiple of 128
+  int n;               // multiple of 256
+  int k;               // multiple of 64
+  int terms;           // 1 (bf16) or 3 (fp32-parity split)
+  int out_kind;        // GemmOutKind
+  bool gelu;
+  int a_plane_rows;    // row offset of the lo plane of A
+  int b_plane_rows;    // row offset of the lo plane of W
+  int out_plane_rows;  // row offset of the lo plane of the output (split only)
+};
+
+int gemm_smem_bytes();
+cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_sms);
+
+// fp32 SIMT GEMM: out[M, N] = act(A[M, K] * W[N, K]^T + bias). Used by the classifier head
+// (src/modelling/models.py:155-163) and as an independent cross-check of the tcgen05 path in tests.
+cudaError_t launch_gemm_simt(const float* a, const float* w, const float* bias, float* out, int m,
+                             int n, int k, bool gelu, cudaStream_t stream);
+
+// Activation outputs: fp32 stream + bf16 plane(s) used as the next GEMM's A operand.
+struct ActOut {
+  float* x;               // fp32 [rows, 768] (may be null)
+  __nv_bfloat16* xb;      // bf16 [planes, plane_rows, 768]
+  int planes;             // 1 or 2
+  long long plane_rows;   // rows per plane (M padded to 128)
+};
+
+// K0: box repair + normalisation + padding masks (src/utils/data_utils.py:205-231,
+// src/modelling/datasets.py:78-83,247-286).
+cudaError_t launch_prepare(const double* raw_boxes, const long long* video_sizes,
+                           const long long* categories, const long long* frame_types, int B, int L,
+                           int S, float* boxes_out, uint8_t* mask_boxes, uint8_t* mask_frames,
+                           cudaStream_t stream);
+
+cudaError_t launch_masks(const long long* categories, const long long* frame_types,
+                         long long n_slots, long long n_frames, uint8_t* mask_boxes,
+                         uint8_t* mask_frames, cudaStream_t stream);
+
+// K1: category + box (+score) embedding and LayerNorm (src/modelling/models.py:29-39).
+cudaError_t launch_embed(const long long* categories, const float* boxes, const float* scores,
+                         const float* cat_table, int unique_categories, const float* box_w,
+                         const float* box_b, const float* score_w, const float* score_b,
+                         const float* ln_g, const float* ln_b, float eps, long long tokens,
+                         ActOut out, int* err_flag, cudaStream_t stream);
+
+// x <- LayerNorm(x + y) (post-norm residual of nn.TransformerEncoderLayer); y may be null.
+cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, const float* b,
+                          float eps, long long rows, ActOut out, cudaStream_t stream);
+
+// K7: frame tokens = LN(spatial CLS slot + position + frame type) (src/modelling/models.py:98-111).
+cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* frame_types,
+                               const float* pos_table, const float* ft_table, int n_frame_types,
+                               const float* ln_g, const float* ln_b, float eps, int B, int L,
+                               ActOut out, int* err_flag, cudaStream_t stream);
+
+// K9: h[b] = x[b * L + lengths[b] - 1] (src/modelling/models.py:189-192).
+cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, int L, float* out,
+                               int* err_flag, cudaStream_t stream);
+
+// K3: masked multi-head attention over short sequences held in shared memory.
+//   qkv: [tokens, 2304] fp32 or bf16; key j of a sequence is masked when mask_src[token_j] == 0,
+//   and (causal) when j > i. Output: bf16 plane(s) [tokens, 768].
+cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long* mask_src,
+                             long long num_seqs, int T, bool causal, ActOut out,
+                             cudaStream_t stream);
+
+// fp32 -> bf16 plane(s) for weights.
+cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,
+                             cudaStream_t stream);
+
+}  // namespace stlt

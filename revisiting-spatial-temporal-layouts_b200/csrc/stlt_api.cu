@@ -1,0 +1,610 @@
+// C ABI of libstlt_b200.so (declared in include/stlt_b200.h): handle management, weight binding
+// and packing, workspace planning and the orchestration of the forward pass
+// (reference: Stlt.forward, src/modelling/models.py:185-195 and everything it calls).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/stlt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+using namespace stlt;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct LayerWeights {
+  const float *in_w = nullptr, *in_b = nullptr, *out_w = nullptr, *out_b = nullptr;
+  const float *l1_w = nullptr, *l1_b = nullptr, *l2_w = nullptr, *l2_b = nullptr;
+  const float *n1_g = nullptr, *n1_b = nullptr, *n2_g = nullptr, *n2_b = nullptr;
+  // packed bf16 planes (inside the caller-provided packed buffer)
+  const __nv_bfloat16 *in_p = nullptr, *out_p = nullptr, *l1_p = nullptr, *l2_p = nullptr;
+};
+
+struct Weights {
+  const float *cat_table = nullptr, *box_w = nullptr, *box_b = nullptr, *score_w = nullptr,
+              *score_b = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  const float *pos_table = nullptr, *ft_table = nullptr, *fr_g = nullptr, *fr_b = nullptr;
+  const float *fc1_w = nullptr, *fc1_b = nullptr, *head_g = nullptr, *head_b = nullptr,
+              *fc2_w = nullptr, *fc2_b = nullptr;
+  std::vector<LayerWeights> spatial, temporal;
+};
+
+struct Handle {
+  StltDims dims{};
+  Weights w;
+  bool bound = false;
+  int packed_precision = -1;
+  const void* packed_ptr = nullptr;
+  int num_sms = 0;
+  int launches = 0;
+  EncodeTiledFn encode = nullptr;
+  StltTaps taps{};
+  std::map<std::tuple<const void*, int, long long, long long, int, int>, CUtensorMap> tm_cache;
+  char err[512] = {0};
+};
+
+thread_local char g_err[512] = "invalid handle";
+
+int fail(Handle* h, int code, const char* fmt, ...) {
+  char* dst = h ? h->err : g_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define STLT_CUDA(h, expr)                                                                  \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(h, STLT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+inline long long pad128(long long v) { return (v + 127) / 128 * 128; }
+inline size_t align1k(size_t v) { return (v + 1023) / 1024 * 1024; }
+
+// 2-D row-major tensor map with 128-byte swizzle. dtype: 0 = f32, 1 = bf16.
+int make_tm(Handle* h, CUtensorMap* tm, const void* ptr, int dtype, long long rows, long long cols,
+            int box_cols, int box_rows) {
+  auto key = std::make_tuple(ptr, dtype, rows, cols, box_cols, box_rows);
+  auto it = h->tm_cache.find(key);
+  if (it != h->tm_cache.end()) {
+    *tm = it->second;
+    return STLT_OK;
+  }
+  const size_t es = dtype == 0 ? 4 : 2;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(tm, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, STLT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box=%dx%d",
+                static_cast<int>(r), rows, cols, box_cols, box_rows);
+  if (h->tm_cache.size() > 4096) h->tm_cache.clear();
+  h->tm_cache[key] = *tm;
+  return STLT_OK;
+}
+
+// out = epilogue(A W^T + bias) on tcgen05. a/w point at plane 0; planes are a_plane_rows / n rows apart.
+int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_rows, long long a_plane_rows,
+             const void* w, int n, int k, const float* bias, void* out, int terms, int out_kind,
+             bool gelu) {
+  GemmArgs g{};
+  const int planes = terms == 3 ? 2 : 1;
+  int rc = make_tm(h, &g.tm_a, a, 1, a_plane_rows * (planes - 1) + m_rows, k, 64, 128);
+  if (rc) return rc;
+  rc = make_tm(h, &g.tm_b, w, 1, static_cast<long long>(n) * planes, k, 64, 256);
+  if (rc) return rc;
+  if (out_kind == GEMM_OUT_F32)
+    rc = make_tm(h, &g.tm_out, out, 0, m_rows, n, 32, 32);
+  else if (out_kind == GEMM_OUT_BF16)
+    rc = make_tm(h, &g.tm_out, out, 1, m_rows, n, 64, 32);
+  else
+    rc = make_tm(h, &g.tm_out, out, 1, a_plane_rows + m_rows, n, 64, 32);
+  if (rc) return rc;
+  g.bias = bias;
+  g.m_rows = static_cast<int>(m_rows);
+  g.n = n;
+  g.k = k;
+  g.terms = terms;
+  g.out_kind = out_kind;
+  g.gelu = gelu;
+  g.a_plane_rows = static_cast<int>(a_plane_rows);
+  g.b_plane_rows = n;
+  g.out_plane_rows = static_cast<int>(a_plane_rows);
+  STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
+  h->launches++;
+  return STLT_OK;
+}
+
+struct WorkspacePlan {
+  long long m_sp, m_tm;  // padded token counts
+  size_t off_err, off_x, off_y, off_xb, off_att, off_qkv, off_h, off_head, total;
+};
+
+WorkspacePlan plan_workspace(int B, int L, int S, int precision) {
+  WorkspacePlan p{};
+  const int planes = precision == STLT_PRECISION_FP32 ? 2 : 1;
+  p.m_sp = pad128(static_cast<long long>(B) * L * S);
+  p.m_tm = pad128(static_cast<long long>(B) * L);
+  const size_t m = static_cast<size_t>(p.m_sp);
+  size_t off = 0;
+  p.off_err = off;  off += 1024;
+  p.off_x = off;    off += align1k(m * kHidden * 4);
+  p.off_y = off;    off += align1k(m * kHidden * 4);
+  p.off_xb = off;   off += align1k(m * kHidden * 2 * planes);
+  p.off_att = off;  off += align1k(m * kHidden * 2 * planes);
+  p.off_qkv = off;  off += align1k(m * kQkv * (precision == STLT_PRECISION_FP32 ? 4 : 2));
+  p.off_h = off;    off += align1k(m * kFfn * 2 * planes);
+  p.off_head = off; off += align1k(static_cast<size_t>(B) * kHidden * 4 * 3);
+  p.total = off;
+  return p;
+}
+
+struct Phase {
+  float* x;              // fp32 residual stream [m, 768]
+  float* y;              // fp32 GEMM output [m, 768]
+  __nv_bfloat16* xb;     // bf16 plane(s) of x
+  __nv_bfloat16* att;    // bf16 plane(s) of the attention context
+  void* qkv;             // [m, 2304] f32 or bf16
+  __nv_bfloat16* hid;    // bf16 plane(s) of the FFN hidden [m, 3072]
+  long long m_pad;       // rows per plane
+  long long m_valid;     // real tokens
+};
+
+// One post-norm nn.TransformerEncoderLayer (eval mode): MHA -> +res -> LN -> FFN -> +res -> LN.
+int run_layer(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw, const Phase& ph,
+              const long long* mask_src, long long num_seqs, int T, bool causal) {
+  const bool fp32 = precision == STLT_PRECISION_FP32;
+  const int terms = fp32 ? 3 : 1;
+  const int planes = fp32 ? 2 : 1;
+  const float eps = h->dims.encoder_norm_eps;
+  int rc;
+  // QKV projection
+  rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv, terms,
+                fp32 ? GEMM_OUT_F32 : GEMM_OUT_BF16, false);
+  if (rc) return rc;
+  // attention
+  ActOut att{nullptr, ph.att, planes, ph.m_pad};
+  STLT_CUDA(h, launch_attention(ph.qkv, !fp32, mask_src, num_seqs, T, causal, att, stream));
+  h->launches++;
+  // output projection, residual, LayerNorm
+  rc = run_gemm(h, stream, ph.att, ph.m_pad, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.y,
+                terms, GEMM_OUT_F32, false);
+  if (rc) return rc;
+  ActOut xo{ph.x, ph.xb, planes, ph.m_pad};
+  STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
+  h->launches++;
+  // feed-forward
+  rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.l1_p, kFfn, kHidden, lw.l1_b, ph.hid, terms,
+                fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, true);
+  if (rc) return rc;
+  rc = run_gemm(h, stream, ph.hid, ph.m_pad, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.y, terms,
+                GEMM_OUT_F32, false);
+  if (rc) return rc;
+  STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n2_g, lw.n2_b, eps, ph.m_valid, xo, stream));
+  h->launches++;
+  return STLT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int stlt_create(const StltDims* dims, void** handle) {
+  if (!dims || !handle) return fail(nullptr, STLT_ERR_INVALID, "null argument");
+  if (dims->hidden_size != kHidden || dims->num_heads != kHeads)
+    return fail(nullptr, STLT_ERR_INVALID,
+                "kernels are specialised for hidden_size=768, num_heads=12 (got %d, %d)",
+                dims->hidden_size, dims->num_heads);
+  if (dims->num_spatial_layers < 0 || dims->num_temporal_layers < 0 || dims->unique_categories < 1 ||
+      dims->num_classes < 1 || dims->max_positions < 1 || dims->num_frame_types < 1)
+    return fail(nullptr, STLT_ERR_INVALID, "invalid model dimensions");
+  Handle* h = new Handle();
+  h->dims = *dims;
+  h->w.spatial.resize(dims->num_spatial_layers);
+  h->w.temporal.resize(dims->num_temporal_layers);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  cudaDeviceProp prop{};
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    fail(nullptr, STLT_ERR_CUDA, "no usable CUDA device: %s", cudaGetErrorString(e));
+    delete h;
+    return STLT_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    fail(nullptr, STLT_ERR_CUDA, "libstlt_b200 requires an sm_100 GPU (found sm_%d%d); no fallback",
+         prop.major, prop.minor);
+    delete h;
+    return STLT_ERR_CUDA;
+  }
+  h->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    fail(nullptr, STLT_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    delete h;
+    return STLT_ERR_CUDA;
+  }
+  h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  *handle = h;
+  return STLT_OK;
+}
+
+int stlt_destroy(void* handle) {
+  delete static_cast<Handle*>(handle);
+  return STLT_OK;
+}
+
+const char* stlt_last_error(void* handle) {
+  return handle ? static_cast<Handle*>(handle)->err : g_err;
+}
+
+int stlt_bind_weights(void* handle, const StltTensor* tensors, int32_t count) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !tensors) return fail(h, STLT_ERR_INVALID, "null argument");
+  const StltDims& d = h->dims;
+  Weights w;
+  w.spatial.resize(d.num_spatial_layers);
+  w.temporal.resize(d.num_temporal_layers);
+  const std::string bfe = "backbone.frames_embeddings.";
+  const std::string cbe = bfe + "layout_embedding.category_box_embeddings.";
+  const std::string sp = bfe + "layout_embedding.transformer.layers.";
+  const std::string tp = "backbone.transformer.layers.";
+  const std::string hd = "prediction_head.";
+
+  struct Slot {
+    const float** dst;
+    std::vector<long long> shape;
+  };
+  std::map<std::string, Slot> slots;
+  auto add = [&](const std::string& name, const float** dst, std::vector<long long> shape) {
+    slots[name] = Slot{dst, std::move(shape)};
+  };
+  const long long H = kHidden, F = kFfn;
+  add(cbe + "category_embeddings.weight", &w.cat_table, {d.unique_categories, H});
+  add(cbe + "box_embedding.weight", &w.box_w, {H, 4});
+  add(cbe + "box_embedding.bias", &w.box_b, {H});
+  add(cbe + "score_embeddings.weight", &w.score_w, {H, 1});
+  add(cbe + "score_embeddings.bias", &w.score_b, {H});
+  add(cbe + "layer_norm.weight", &w.emb_g, {H});
+  add(cbe + "layer_norm.bias", &w.emb_b, {H});
+  add(bfe + "position_embeddings.weight", &w.pos_table, {d.max_positions, H});
+  add(bfe + "frame_type_embedding.weight", &w.ft_table, {d.num_frame_types, H});
+  add(bfe + "layer_norm.weight", &w.fr_g, {H});
+  add(bfe + "layer_norm.bias", &w.fr_b, {H});
+  add(hd + "fc1.weight", &w.fc1_w, {H, H});
+  add(hd + "fc1.bias", &w.fc1_b, {H});
+  add(hd + "layer_norm.weight", &w.head_g, {H});
+  add(hd + "layer_norm.bias", &w.head_b, {H});
+  add(hd + "fc2.weight", &w.fc2_w, {d.num_classes, H});
+  add(hd + "fc2.bias", &w.fc2_b, {d.num_classes});
+  auto add_layer = [&](const std::string& p, LayerWeights& lw) {
+    add(p + "self_attn.in_proj_weight", &lw.in_w, {3 * H, H});
+    add(p + "self_attn.in_proj_bias", &lw.in_b, {3 * H});
+    add(p + "self_attn.out_proj.weight", &lw.out_w, {H, H});
+    add(p + "self_attn.out_proj.bias", &lw.out_b, {H});
+    add(p + "linear1.weight", &lw.l1_w, {F, H});
+    add(p + "linear1.bias", &lw.l1_b, {F});
+    add(p + "linear2.weight", &lw.l2_w, {H, F});
+    add(p + "linear2.bias", &lw.l2_b, {H});
+    add(p + "norm1.weight", &lw.n1_g, {H});
+    add(p + "norm1.bias", &lw.n1_b, {H});
+    add(p + "norm2.weight", &lw.n2_g, {H});
+    add(p + "norm2.bias", &lw.n2_b, {H});
+  };
+  for (int i = 0; i < d.num_spatial_layers; ++i) add_layer(sp + std::to_string(i) + ".", w.spatial[i]);
+  for (int i = 0; i < d.num_temporal_layers; ++i) add_layer(tp + std::to_string(i) + ".", w.temporal[i]);
+
+  for (int i = 0; i < count; ++i) {
+    const StltTensor& t = tensors[i];
+    if (!t.name) return fail(h, STLT_ERR_INVALID, "tensor %d has no name", i);
+    auto it = slots.find(t.name);
+    if (it == slots.end()) continue;  // orphan encoder_layer.*, position_ids, ...
+    if (t.dtype != STLT_DTYPE_F32) return fail(h, STLT_ERR_INVALID, "%s: expected float32", t.name);
+    if (!t.data) return fail(h, STLT_ERR_INVALID, "%s: null data pointer", t.name);
+    if ((reinterpret_cast<uintptr_t>(t.data) & 15) != 0)
+      return fail(h, STLT_ERR_INVALID, "%s: data pointer must be 16-byte aligned", t.name);
+    const auto& want = it->second.shape;
+    bool ok = t.ndim == static_cast<int>(want.size());
+    for (size_t k = 0; ok && k < want.size(); ++k) ok = t.shape[k] == want[k];
+    if (!ok) return fail(h, STLT_ERR_INVALID, "%s: unexpected shape", t.name);
+    *it->second.dst = static_cast<const float*>(t.data);
+  }
+  for (auto& kv : slots)
+    if (*kv.second.dst == nullptr) return fail(h, STLT_ERR_INVALID, "missing weight: %s", kv.first.c_str());
+  h->w = w;
+  h->bound = true;
+  h->packed_precision = -1;
+  h->packed_ptr = nullptr;
+  return STLT_OK;
+}
+
+int stlt_packed_weights_bytes(void* handle, int32_t precision, size_t* bytes) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !bytes) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (precision != STLT_PRECISION_FP32 && precision != STLT_PRECISION_BF16)
+    return fail(h, STLT_ERR_INVALID, "unknown precision %d", precision);
+  const size_t planes = precision == STLT_PRECISION_FP32 ? 2 : 1;
+  const size_t per_layer = static_cast<size_t>(kHidden) * (kQkv + kHidden + 2 * kFfn);
+  const size_t layers = h->dims.num_spatial_layers + h->dims.num_temporal_layers;
+  *bytes = layers * per_layer * planes * 2;
+  return STLT_OK;
+}
+
+int stlt_pack_weights(void* handle, void* stream_, int32_t precision, void* packed, size_t bytes) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !packed) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (!h->bound) return fail(h, STLT_ERR_STATE, "stlt_bind_weights has not been called");
+  size_t need = 0;
+  int rc = stlt_packed_weights_bytes(handle, precision, &need);
+  if (rc) return rc;
+  if (bytes < need) return fail(h, STLT_ERR_INVALID, "packed buffer too small: %zu < %zu", bytes, need);
+  if ((reinterpret_cast<uintptr_t>(packed) & 127) != 0)
+    return fail(h, STLT_ERR_INVALID, "packed buffer must be 128-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int planes = precision == STLT_PRECISION_FP32 ? 2 : 1;
+  __nv_bfloat16* cur = static_cast<__nv_bfloat16*>(packed);
+  auto pack = [&](const float* src, long long n, const __nv_bfloat16** dst) -> cudaError_t {
+    *dst = cur;
+    cudaError_t e = launch_pack_bf16(src, cur, n, planes, stream);
+    cur += n * planes;
+    return e;
+  };
+  auto pack_layer = [&](LayerWeights& lw) -> cudaError_t {
+    cudaError_t e;
+    if ((e = pack(lw.in_w, static_cast<long long>(kQkv) * kHidden, &lw.in_p)) != cudaSuccess) return e;
+    if ((e = pack(lw.out_w, static_cast<long long>(kHidden) * kHidden, &lw.out_p)) != cudaSuccess) return e;
+    if ((e = pack(lw.l1_w, static_cast<long long>(kFfn) * kHidden, &lw.l1_p)) != cudaSuccess) return e;
+    if ((e = pack(lw.l2_w, static_cast<long long>(kHidden) * kFfn, &lw.l2_p)) != cudaSuccess) return e;
+    return cudaSuccess;
+  };
+  for (auto& lw : h->w.spatial) STLT_CUDA(h, pack_layer(lw));
+  for (auto& lw : h->w.temporal) STLT_CUDA(h, pack_layer(lw));
+  h->packed_precision = precision;
+  h->packed_ptr = packed;
+  return STLT_OK;
+}
+
+int stlt_workspace_bytes(void* handle, int32_t B, int32_t L, int32_t S, int32_t precision,
+                         size_t* bytes) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !bytes) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (B < 0 || L < 1 || S < 1) return fail(h, STLT_ERR_INVALID, "invalid batch shape");
+  *bytes = plan_workspace(B, L, S, precision).total;
+  return STLT_OK;
+}
+
+int stlt_prepare(void* handle, void* stream, const double* raw_boxes, const int64_t* video_sizes,
+                 const int64_t* categories, const int64_t* frame_types, int32_t B, int32_t L,
+                 int32_t S, float* boxes_out, uint8_t* mask_boxes_out, uint8_t* mask_frames_out) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  if (B < 0 || L < 1 || S < 1) return fail(h, STLT_ERR_INVALID, "invalid batch shape");
+  if (B == 0) return STLT_OK;
+  if (!raw_boxes || !video_sizes || !categories || !frame_types || !boxes_out || !mask_boxes_out ||
+      !mask_frames_out)
+    return fail(h, STLT_ERR_INVALID, "null tensor pointer");
+  STLT_CUDA(h, launch_prepare(raw_boxes, reinterpret_cast<const long long*>(video_sizes),
+                              reinterpret_cast<const long long*>(categories),
+                              reinterpret_cast<const long long*>(frame_types), B, L, S, boxes_out,
+                              mask_boxes_out, mask_frames_out, static_cast<cudaStream_t>(stream)));
+  return STLT_OK;
+}
+
+int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* categories_,
+                 const float* boxes, const float* scores, const int64_t* frame_types_,
+                 const int64_t* lengths_, int32_t B, int32_t L, int32_t S, void* workspace,
+                 size_t workspace_bytes, float* logits, uint8_t* mask_boxes, uint8_t* mask_frames) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  const StltDims& d = h->dims;
+  if (!h->bound) return fail(h, STLT_ERR_STATE, "stlt_bind_weights has not been called");
+  if (precision != STLT_PRECISION_FP32 && precision != STLT_PRECISION_BF16)
+    return fail(h, STLT_ERR_INVALID, "unknown precision %d", precision);
+  if (h->packed_precision != precision)
+    return fail(h, STLT_ERR_STATE, "weights are not packed for precision %d (call stlt_pack_weights)",
+                precision);
+  if (B < 0) return fail(h, STLT_ERR_INVALID, "negative batch size");
+  if (L < 1 || L > d.max_positions)
+    return fail(h, STLT_ERR_INVALID, "frames=%d outside [1, %d] (position table)", L, d.max_positions);
+  if (L > 32) return fail(h, STLT_ERR_INVALID, "frames=%d > 32 is not supported by the attention kernel", L);
+  if (S < 1 || S > 32) return fail(h, STLT_ERR_INVALID, "slots=%d outside [1, 32]", S);
+  h->launches = 0;
+  if (B == 0) return STLT_OK;
+  if (!categories_ || !boxes || !frame_types_ || !lengths_ || !workspace || !logits)
+    return fail(h, STLT_ERR_INVALID, "null tensor pointer");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
+    return fail(h, STLT_ERR_INVALID, "workspace must be 1024-byte aligned");
+  const WorkspacePlan p = plan_workspace(B, L, S, precision);
+  if (workspace_bytes < p.total)
+    return fail(h, STLT_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, p.total);
+  if (p.m_sp > 0x7fffffffLL / 2) return fail(h, STLT_ERR_INVALID, "batch too large for one call");
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long* categories = reinterpret_cast<const long long*>(categories_);
+  const long long* frame_types = reinterpret_cast<const long long*>(frame_types_);
+  const long long* lengths = reinterpret_cast<const long long*>(lengths_);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const bool fp32 = precision == STLT_PRECISION_FP32;
+  const int planes = fp32 ? 2 : 1;
+  int* err_flag = reinterpret_cast<int*>(ws + p.off_err);
+  const long long n_sp = static_cast<long long>(B) * L * S;
+  const long long n_tm = static_cast<long long>(B) * L;
+
+  STLT_CUDA(h, cudaMemsetAsync(err_flag, 0, sizeof(int), stream));
+  if (mask_boxes || mask_frames) {
+    STLT_CUDA(h, launch_masks(categories, frame_types, n_sp, n_tm, mask_boxes, mask_frames, stream));
+    h->launches++;
+  }
+
+  // ---- spatial phase: B*L sequences of S object tokens (models.py:57-81) ----
+  Phase sp{};
+  sp.x = reinterpret_cast<float*>(ws + p.off_x);
+  sp.y = reinterpret_cast<float*>(ws + p.off_y);
+  sp.xb = reinterpret_cast<__nv_bfloat16*>(ws + p.off_xb);
+  sp.att = reinterpret_cast<__nv_bfloat16*>(ws + p.off_att);
+  sp.qkv = ws + p.off_qkv;
+  sp.hid = reinterpret_cast<__nv_bfloat16*>(ws + p.off_h);
+  sp.m_pad = p.m_sp;
+  sp.m_valid = n_sp;
+
+  ActOut emb{sp.x, sp.xb, planes, sp.m_pad};
+  STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories,
+                            h->w.box_w, h->w.box_b, h->w.score_w, h->w.score_b, h->w.emb_g,
+                            h->w.emb_b, d.layer_norm_eps, n_sp, emb, err_flag, stream));
+  h->launches++;
+  if (h->taps.embed)
+    STLT_CUDA(h, cudaMemcpyAsync(h->taps.embed, sp.x, n_sp * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
+
+  for (int i = 0; i < d.num_spatial_layers; ++i) {
+    int rc = run_layer(h, stream, precision, h->w.spatial[i], sp, categories, n_tm, S, false);
+    if (rc) return rc;
+  }
+  if (h->taps.spatial)
+    STLT_CUDA(h, cudaMemcpyAsync(h->taps.spatial, sp.x, n_sp * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
+
+  // ---- temporal phase: B sequences of L frame tokens (models.py:98-111,136-152) ----
+  // The frame tokens are written into the (now free) y / att buffers; the roles of the two
+  // buffer pairs swap so nothing is copied.
+  Phase tp{};
+  tp.x = sp.y;
+  tp.y = sp.x;
+  tp.xb = sp.att;
+  tp.att = sp.xb;
+  tp.qkv = sp.qkv;
+  tp.hid = sp.hid;
+  tp.m_pad = p.m_tm;
+  tp.m_valid = n_tm;
+  ActOut fr{tp.x, tp.xb, planes, tp.m_pad};
+  STLT_CUDA(h, launch_frame_embed(sp.x, S, frame_types, h->w.pos_table, h->w.ft_table,
+                                  d.num_frame_types, h->w.fr_g, h->w.fr_b, d.layer_norm_eps, B, L, fr,
+                                  err_flag, stream));
+  h->launches++;
+  if (h->taps.frames)
+    STLT_CUDA(h, cudaMemcpyAsync(h->taps.frames, tp.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
+
+  for (int i = 0; i < d.num_temporal_layers; ++i) {
+    int rc = run_layer(h, stream, precision, h->w.temporal[i], tp, frame_types, B, L, true);
+    if (rc) return rc;
+  }
+  if (h->taps.temporal)
+    STLT_CUDA(h, cudaMemcpyAsync(h->taps.temporal, tp.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
+
+  // ---- head (models.py:155-163,189-193) ----
+  float* pooled = reinterpret_cast<float*>(ws + p.off_head);
+  float* h1 = pooled + static_cast<size_t>(B) * kHidden;
+  float* h2 = h1 + static_cast<size_t>(B) * kHidden;
+  STLT_CUDA(h, launch_gather_last(tp.x, lengths, B, L, pooled, err_flag, stream));
+  h->launches++;
+  if (h->taps.pooled)
+    STLT_CUDA(h, cudaMemcpyAsync(h->taps.pooled, pooled, static_cast<size_t>(B) * kHidden * 4,
+                                 cudaMemcpyDeviceToDevice, stream));
+  STLT_CUDA(h, launch_gemm_simt(pooled, h->w.fc1_w, h->w.fc1_b, h1, B, kHidden, kHidden, true, stream));
+  h->launches++;
+  ActOut ho{h2, nullptr, 1, 0};
+  STLT_CUDA(h, launch_add_ln(h1, nullptr, h->w.head_g, h->w.head_b, d.layer_norm_eps, B, ho, stream));
+  h->launches++;
+  STLT_CUDA(h, launch_gemm_simt(h2, h->w.fc2_w, h->w.fc2_b, logits, B, d.num_classes, kHidden, false, stream));
+  h->launches++;
+  return STLT_OK;
+}
+
+int stlt_check_errors(void* handle, void* stream, const void* workspace) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !workspace) return fail(h, STLT_ERR_INVALID, "null argument");
+  int flag = 0;
+  STLT_CUDA(h, cudaMemcpyAsync(&flag, workspace, sizeof(int), cudaMemcpyDeviceToHost,
+                               static_cast<cudaStream_t>(stream)));
+  STLT_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  if (flag == 1) return fail(h, STLT_ERR_INPUT, "categories index out of range");
+  if (flag == 2) return fail(h, STLT_ERR_INPUT, "frame_types index out of range");
+  if (flag == 3) return fail(h, STLT_ERR_INPUT, "lengths outside [1, frames]");
+  return STLT_OK;
+}
+
+int stlt_last_launch_count(void* handle) {
+  Handle* h = static_cast<Handle*>(handle);
+  return h ? h->launches : -1;
+}
+
+int stlt_set_taps(void* handle, const StltTaps* taps) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  if (taps)
+    h->taps = *taps;
+  else
+    h->taps = StltTaps{};
+  return STLT_OK;
+}
+
+// ---- single-operator entry points -------------------------------------------------------------
+
+int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w_planes,
+                 const float* bias, void* out, int32_t m_rows, int32_t n, int32_t k, int32_t terms,
+                 int32_t out_kind, int32_t gelu) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !a_planes || !w_planes || !bias || !out) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (terms != 1 && terms != 3) return fail(h, STLT_ERR_INVALID, "terms must be 1 or 3");
+  if (m_rows % 128 || n % 256 || k % 64) return fail(h, STLT_ERR_INVALID, "shape not tile aligned");
+  return run_gemm(h, static_cast<cudaStream_t>(stream), a_planes, m_rows, m_rows, w_planes, n, k, bias,
+                  out, terms, out_kind, gelu != 0);
+}
+
+int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w, const float* bias,
+                      float* out, int32_t m, int32_t n, int32_t k, int32_t gelu) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  STLT_CUDA(h, launch_gemm_simt(a, w, bias, out, m, n, k, gelu != 0, static_cast<cudaStream_t>(stream)));
+  return STLT_OK;
+}
+
+int stlt_op_attention(void* handle, void* stream, const void* qkv, int32_t qkv_is_bf16,
+                      const int64_t* mask_src, int64_t num_seqs, int32_t seq_len, int32_t causal,
+                      void* out_bf16, int32_t planes, int64_t plane_rows) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  ActOut o{nullptr, static_cast<__nv_bfloat16*>(out_bf16), planes, plane_rows};
+  STLT_CUDA(h, launch_attention(qkv, qkv_is_bf16 != 0, reinterpret_cast<const long long*>(mask_src),
+                                num_seqs, seq_len, causal != 0, o, static_cast<cudaStream_t>(stream)));
+  return STLT_OK;
+}
+
+int stlt_op_add_ln(void* handle, void* stream, const float* x, const float* y, const float* gamma,
+                   const float* beta, float eps, int64_t rows, float* out_f32, void* out_bf16,
+                   int32_t planes, int64_t plane_rows) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  ActOut o{out_f32, static_cast<__nv_bfloat16*>(out_bf16), planes, plane_rows};
+  STLT_CUDA(h, launch_add_ln(x, y, gamma, beta, eps, rows, o, static_cast<cudaStream_t>(stream)));
+  return STLT_OK;
+}
+
+int stlt_op_pack_bf16(void* handle, void* stream, const float* src, void* dst, int64_t n,
+                      int32_t planes) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  STLT_CUDA(h, launch_pack_bf16(src, static_cast<__nv_bfloat16*>(dst), n, planes,
+                                static_cast<cudaStream_t>(stream)));
+  return STLT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+"""Drop-in replacement for the reference ``Stlt`` nn.Module (reference
+src/modelling/models.py:166-195): same constructor argument (an ``StltModelConfig``), same batch
+dict, same ``state_dict`` keys / shapes / dtypes (174 entries for the Something-Else config,
+SURVEY.md Appendix A.3), same ``{"stlt": logits}`` output — but ``forward`` is one call into
+libstlt_b200.so (hand-written sm_100a CUDA behind the C ABI of include/stlt_b200.h).
+
+The sub-modules below are *parameter holders*: they exist so that parameter names, shapes and
+default initialisation match the reference; none of them has a PyTorch compute path. There is no
+CPU fallback — a non-CUDA batch raises.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import lib as _lib
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders (names follow the reference module tree)
+# ------------------------------------------------------------------------------------------------
+class _Affine(nn.Module):
+    """weight [out, in] + bias [out] with nn.Linear's default initialisation."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(in_features)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class _Norm(nn.Module):
+    def __init__(self, size: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(size))
+        self.bias = nn.Parameter(torch.zeros(size))
+
+
+class _Table(nn.Module):
+    """Embedding table; ``padding_idx`` only affects initialisation (row zeroed), as in nn.Embedding."""
+
+    def __init__(self, rows: int, size: int, padding_idx: Optional[int] = None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(rows, size))
+        nn.init.normal_(self.weight)
+        if padding_idx is not None:
+            with torch.no_grad():
+                self.weight[padding_idx].fill_(0)
+
+
+class _SelfAttention(nn.Module):
+    """Packed in-projection [3H, H] (rows Q; K; V) + out_proj, initialised like nn.MultiheadAttention."""
+
+    def __init__(self, hidden: int):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * hidden, hidden))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * hidden))
+        self.out_proj = _Affine(hidden, hidden)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.out_proj.bias, 0.0)
+
+
+class _EncoderLayer(nn.Module):
+    """Parameters of one post-norm nn.TransformerEncoderLayer (reference models.py:46-52,118-124)."""
+
+    def __init__(self, hidden: int):
+        super().__init__()
+        self.self_attn = _SelfAttention(hidden)
+        self.linear1 = _Affine(hidden, 4 * hidden)
+        self.linear2 = _Affine(4 * hidden, hidden)
+        self.norm1 = _Norm(hidden)
+        self.norm2 = _Norm(hidden)
+
+
+class _Encoder(nn.Module):
+    """nn.TransformerEncoder deep-copies ONE layer num_layers times (identical clones at init)."""
+
+    def __init__(self, layer: _EncoderLayer, num_layers: int):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(layer) for _ in range(num_layers)])
+
+
+class _CategoryBoxEmbeddings(nn.Module):  # reference models.py:16-27
+    def __init__(self, config):
+        super().__init__()
+        h = config.hidden_size
+        self.category_embeddings = _Table(config.unique_categories, h, padding_idx=0)
+        self.box_embedding = _Affine(4, h)
+        self.score_embeddings = _Affine(1, h)
+        self.layer_norm = _Norm(h)
+
+
+class _SpatialTransformer(nn.Module):  # reference models.py:42-55
+    def __init__(self, config):
+        super().__init__()
+        self.category_box_embeddings = _CategoryBoxEmbeddings(config)
+        # The reference registers the prototype layer as a sub-module too; it is never used in
+        # forward but its 12 tensors are part of every checkpoint.
+        self.encoder_layer = _EncoderLayer(config.hidden_size)
+        self.transformer = _Encoder(self.encoder_layer, config.num_spatial_layers)
+
+
+class _FramesEmbeddings(nn.Module):  # reference models.py:84-96
+    def __init__(self, config):
+        super().__init__()
+        h = config.hidden_size
+        self.layout_embedding = _SpatialTransformer(config)
+        self.position_embeddings = _Table(config.layout_num_frames, h)
+        self.frame_type_embedding = _Table(5, h, padding_idx=0)
+        self.layer_norm = _Norm(h)
+        self.register_buffer("position_ids", torch.arange(config.layout_num_frames).expand((1, -1)))
+
+
+class StltBackbone(nn.Module):
+    """Parameter tree of the reference StltBackbone (models.py:114-152)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.frames_embeddings = _FramesEmbeddings(config)
+        self.transformer = _Encoder(_EncoderLayer(config.hidden_size), config.num_temporal_layers)
+
+    @classmethod
+    def from_pretrained(cls, config):  # models.py:130-134
+        model = cls(config)
+        model.load_state_dict(torch.load(config.load_backbone_path, map_location="cpu"))
+        return model
+
+    def forward(self, batch):
+        raise NotImplementedError(
+            "StltBackbone is a parameter holder; call Stlt.forward (the backbone-only output is "
+            "available through Stlt.forward_with_taps()['temporal']).")
+
+
+class _ClassificationHead(nn.Module):  # reference models.py:155-160
+    def __init__(self, config):
+        super().__init__()
+        self.fc1 = _Affine(config.hidden_size, config.hidden_size)
+        self.layer_norm = _Norm(config.hidden_size)
+        self.fc2 = _Affine(config.hidden_size, config.num_classes)
+
+
+# ------------------------------------------------------------------------------------------------
+# the drop-in module
+# ------------------------------------------------------------------------------------------------
+class Stlt(nn.Module):
+    """B200 implementation of the reference ``Stlt`` (models.py:166-195).
+
+    ``precision``: "fp32" (default; 3-term bf16 split on tcgen05, logits within 1e-4 of the fp32
+    reference) or "bf16" (bf16 GEMM operands, fp32 accumulate / residual / LayerNorm / softmax).
+    """
+
+    def __init__(self, config, precision: str = "fp32"):
+        super().__init__()
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        if config.hidden_size != 768 or config.num_attention_heads != 12:
+            raise ValueError("the sm_100a kernels are specialised for hidden_size=768, 12 heads")
+        self.config = config
+        self.precision = precision
+        if getattr(config, "load_backbone_path", None) is not None:
+            self.backbone = StltBackbone.from_pretrained(config)
+            if config.freeze_backbone:
+                for param in self.backbone.parameters():
+                    param.requires_grad = False
+        else:
+            self.backbone = StltBackbone(config)
+        self.prediction_head = _ClassificationHead(config)
+        self.logit_names = ("stlt",)
+        # library state (not part of the state_dict)
+        self._handle = None
+        self._handle_device = None
+        self._weights_key = None
+        self._packed = {}       # precision -> packed bf16 weight buffer
+        self._packed_key = {}   # precision -> weights key the buffer was packed from
+        self._workspace = None
+        self._keepalive = None
+
+    # -- nn.Module protocol ------------------------------------------------------------------
+    def train(self, mode: bool = True):  # reference models.py:180-183
+        super().train(mode)
+        if getattr(self.config, "load_backbone_path", None) and self.config.freeze_backbone:
+            self.backbone.train(False)
+        return self
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.load_library().stlt_destroy(self._handle)
+        except Exception:
+            pass
+
+    # -- library plumbing ----------------------------------------------------------------------
+    def _dims(self) -> _lib.StltDims:
+        c = self.config
+        return _lib.StltDims(
+            hidden_size=c.hidden_size, num_heads=c.num_attention_heads,
+            num_spatial_layers=c.num_spatial_layers, num_temporal_layers=c.num_temporal_layers,
+            unique_categories=c.unique_categories, num_classes=c.num_classes,
+            max_positions=c.layout_num_frames, num_frame_types=5,
+            layer_norm_eps=c.layer_norm_eps, encoder_norm_eps=1e-5)
+
+    def _ensure_handle(self, device: torch.device):
+        if self._handle is not None and self._handle_device == device:
+            return
+        lib = _lib.load_library()
+        if self._handle is not None:
+            lib.stlt_destroy(self._handle)
+            self._handle = None
+        handle = ctypes.c_void_p()
+        dims = self._dims()
+        rc = lib.stlt_create(ctypes.byref(dims), ctypes.byref(handle))
+        _lib.check(None, rc)
+        self._handle = handle
+        self._handle_device = device
+        self._weights_key = None
+        self._packed.clear()
+        self._packed_key.clear()
+
+    def _sync_weights(self, device: torch.device, stream: int):
+        lib = _lib.load_library()
+        named = [(n, p) for n, p in self.named_parameters()]
+        key = tuple((p.data_ptr(), p._version) for _, p in named)
+        if key != self._weights_key:
+            arr = (_lib.StltTensor * len(named))()
+            keep = []
+            for i, (name, p) in enumerate(named):
+                if p.device != device:
+                    raise RuntimeError(f"parameter {name} is on {p.device}, batch is on {device}")
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError(f"parameter {name} must be contiguous float32")
+                bname = name.encode()
+                keep.append(bname)
+                arr[i].name = bname
+                arr[i].data = p.data_ptr()
+                arr[i].dtype = _lib.DTYPE_F32
+                arr[i].ndim = p.dim()
+                for d, s in enumerate(p.shape):
+                    arr[i].shape[d] = s
+            _lib.check(self._handle, lib.stlt_bind_weights(self._handle, arr, len(named)))
+            self._weights_key = key
+            self._packed_key.clear()
+        prec = _lib.PRECISIONS[self.precision]
+        if self._packed_key.get(prec) != key or self._last_packed != prec:
+            nbytes = ctypes.c_size_t()
+            _lib.check(self._handle, lib.stlt_packed_weights_bytes(self._handle, prec, ctypes.byref(nbytes)))
+            buf = self._packed.get(prec)
+            if buf is None or buf.numel() < nbytes.value or buf.device != device:
+                buf = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+                self._packed[prec] = buf
+            _lib.check(self._handle, lib.stlt_pack_weights(self._handle, stream, prec, buf.data_ptr(), buf.numel()))
+            self._packed_key[prec] = key
+            self._last_packed = prec
+
+    _last_packed = None
+
+    def _get_workspace(self, B: int, L: int, S: int, device: torch.device) -> torch.Tensor:
+        lib = _lib.load_library()
+        nbytes = ctypes.c_size_t()
+        prec = _lib.PRECISIONS[self.precision]
+        _lib.check(self._handle, lib.stlt_workspace_bytes(self._handle, B, L, S, prec, ctypes.byref(nbytes)))
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes.value or ws.device != device:
+            ws = torch.empty(max(nbytes.value, 1024), dtype=torch.uint8, device=device)
+            self._workspace = ws
+        return ws
+
+    @staticmethod
+    def _as_input(batch, key, dtype, shape, device):
+        t = batch[key]
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"batch['{key}'] must be a tensor")
+        if t.device != device:
+            raise RuntimeError(f"batch['{key}'] is on {t.device}, expected {device}")
+        if t.dtype != dtype:
+            raise TypeError(f"batch['{key}'] must be {dtype}, got {t.dtype}")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"batch['{key}'] has shape {tuple(t.shape)}, expected {tuple(shape)}")
+        return t.contiguous()
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return self._run(batch, want_taps=False)
+
+    def forward_with_taps(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Forward that also returns the fp32 activations after every stage (parity tests)."""
+        return self._run(batch, want_taps=True)
+
+    def _run(self, batch, want_taps: bool):
+        if self.training:
+            raise NotImplementedError(
+                "the training step (backward + AdamW + NCCL all-reduce) is not part of this build "
+                "yet (SURVEY.md §8(f) rank 1); call model.train(False) for the inference path")
+        cats = batch["categories"]
+        if not isinstance(cats, torch.Tensor) or cats.dim() != 3:
+            raise ValueError("batch['categories'] must be an int64 tensor [B, L, S]")
+        device = cats.device
+        if device.type != "cuda":
+            raise RuntimeError(
+                "stlt_b200.Stlt has no CPU path: move the batch to a CUDA device (the CPU "
+                "implementation of this path is the reference module itself)")
+        B, L, S = cats.shape
+        cats = self._as_input(batch, "categories", torch.int64, (B, L, S), device)
+        boxes = self._as_input(batch, "boxes", torch.float32, (B, L, S, 4), device)
+        ftypes = self._as_input(batch, "frame_types", torch.int64, (B, L), device)
+        lengths = self._as_input(batch, "lengths", torch.int64, (B,), device)
+        scores = None
+        if "scores" in batch:  # presence toggles the score embedding (models.py:33-35)
+            scores = self._as_input(batch, "scores", torch.float32, (B, L, S), device)
+
+        lib = _lib.load_library()
+        with torch.cuda.device(device):
+            self._ensure_handle(device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            self._sync_weights(device, stream)
+            ws = self._get_workspace(B, L, S, device)
+            logits = torch.empty((B, self.config.num_classes), dtype=torch.float32, device=device)
+            out = {}
+            if want_taps:
+                H = self.config.hidden_size
+                taps_t = {
+                    "embed": torch.empty((B, L, S, H), dtype=torch.float32, device=device),
+                    "spatial": torch.empty((B, L, S, H), dtype=torch.float32, device=device),
+                    "frames": torch.empty((B, L, H), dtype=torch.float32, device=device),
+                    "temporal": torch.empty((B, L, H), dtype=torch.float32, device=device),
+                    "pooled": torch.empty((B, H), dtype=torch.float32, device=device),
+                    "src_key_padding_mask_boxes": torch.empty((B, L, S), dtype=torch.bool, device=device),
+                    "src_key_padding_mask_frames": torch.empty((B, L), dtype=torch.bool, device=device),
+                }
+                taps = _lib.StltTaps(*(taps_t[k].data_ptr() for k in ("embed", "spatial", "frames", "temporal", "pooled")))
+                _lib.check(self._handle, lib.stlt_set_taps(self._handle, ctypes.byref(taps)))
+                out.update(taps_t)
+                mb = taps_t["src_key_padding_mask_boxes"].data_ptr()
+                mf = taps_t["src_key_padding_mask_frames"].data_ptr()
+            else:
+                mb = mf = None
+            try:
+                rc = lib.stlt_forward(
+                    self._handle, stream, _lib.PRECISIONS[self.precision], cats.data_ptr(),
+                    boxes.data_ptr(), scores.data_ptr() if scores is not None else None,
+                    ftypes.data_ptr(), lengths.data_ptr(), B, L, S, ws.data_ptr(), ws.numel(),
+                    logits.data_ptr(), mb, mf)
+                _lib.check(self._handle, rc)
+            finally:
+                if want_taps:
+                    lib.stlt_set_taps(self._handle, None)
+            # keep the inputs alive until the (asynchronous) kernels that read them are enqueued
+            # behind the next call; contiguous() may have created temporaries
+            self._keepalive = (cats, boxes, ftypes, lengths, scores)
+        out["stlt"] = logits
+        if want_taps:
+            return out
+        return {k: v for k, v in zip(self.logit_names, (logits,))}
+
+    def check_inputs(self) -> None:
+        """Synchronises and raises if the last forward saw an out-of-range index (debug aid)."""
+        if self._handle is None or self._workspace is None:
+            return
+        lib = _lib.load_library()
+        stream = torch.cuda.current_stream(self._workspace.device).cuda_stream
+        _lib.check(self._handle, lib.stlt_check_errors(self._handle, stream, self._workspace.data_ptr()))
+
+    def last_launch_count(self) -> int:
+        if self._handle is None:
+            return 0
+        return int(_lib.load_library().stlt_last_launch_count(self._handle))
+
+
+models_factory = {"stlt": Stlt}
