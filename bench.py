@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Headline benchmark: STLT inference throughput (videos/sec) on N B200s, batch-sharded.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # CPU port of the reference path
+
+One "step" is one forward of the hot path over one batch of synthetic layouts of the
+Something-Else shape (BASELINE.json configs[1]: 16+1 frames x 5 slots, 174 classes, batch 4096 per
+GPU, dense: every frame carries 4 boxes). Rank 0 prints ONE JSON line:
+  value   : videos/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e     : videos/s through the public module call with pinned-host inputs (H2D + forward + D2H
+            of the logits + a sync per step, as the reference's inference loop does)
+  roofline: the tcgen05 projection GEMMs (99.8 % of the FLOPs): executed FLOPs per step / their
+            summed CUDA-event time inside the same timed steps, vs the measured bf16 peak
+  cpu_baseline: the CPU oracle (a PyTorch-CPU restatement of the reference forward) on this box's
+            host cores, bounded sample.
+For N > 1 launch with torchrun (one process per GPU); inference needs no collective — every rank
+runs its own batch (weak scaling) and only the timing is reduced (MAX) over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+FLOPS_PER_VIDEO = {"something": 6_752_443_392, "action_genome": 12_548_941_824}
+FALLBACK_PEAKS = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=4096, help="videos per GPU per step")
+    p.add_argument("--layout", default="something", choices=["something", "action_genome"])
+    p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"],
+                   help="headline precision; the other one is reported under 'secondary'")
+    p.add_argument("--no-secondary", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+def load_peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            d = json.loads(path.read_text())
+            return d, "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, sm_max, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                sm_max.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(sm_max) if sm_max else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_throughput(layout: str, batch: int, seconds: float, warmup: int = 1, steps: int | None = None):
+    """videos/s of the CPU oracle (PyTorch-CPU restatement of the reference forward)."""
+    import torch
+    import stlt_b200
+    from oracle import stlt_oracle
+    from stlt_b200.synthetic import make_batch, random_state_dict
+    spec = stlt_b200.SOMETHING_ELSE if layout == "something" else stlt_b200.ACTION_GENOME
+    cfg = stlt_b200.StltModelConfig(num_classes=spec["num_classes"], unique_categories=spec["unique_categories"])
+    torch.manual_seed(0)
+    sd = random_state_dict(stlt_b200.Stlt(cfg).state_dict(), seed=0)
+    data = make_batch(batch, layout, ragged=False, seed=0)
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            stlt_oracle.stlt_forward(sd, data)
+        t_end = time.perf_counter() + seconds
+        n = 0
+        while (steps is not None and n < steps) or (steps is None and (time.perf_counter() < t_end or n < 2)):
+            t0 = time.perf_counter()
+            stlt_oracle.stlt_forward(sd, data)
+            times.append(time.perf_counter() - t0)
+            n += 1
+    total = sum(times)
+    return {"value": batch * len(times) / total, "ms_per_step": 1e3 * total / len(times),
+            "steps": len(times), "cores": torch.get_num_threads(), "host_cpus": os.cpu_count()}
+
+
+def run_reference(args, rank: int):
+    """Reference arm: the reference's CPU implementation of the path, timed on the host cores.
+    The reference is a Python/PyTorch repo that is not present on the GPU box, so this runs the
+    oracle port (oracle/stlt_oracle.py, pinned to the reference's outputs by tests/golden)."""
+    if rank != 0:
+        return
+    sample = 64
+    r = cpu_oracle_throughput(args.layout, sample, seconds=0, warmup=max(args.warmup, 1), steps=args.steps)
+    line = {
+        "impl": "reference", "metric": "stlt_inference_videos_per_sec", "value": r["value"], "unit": "videos/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"STLT inference, {args.layout} shape (17 frames x {5 if args.layout == 'something' else 11} slots), "
+                               f"CPU fp32, {sample}-video sample per step"},
+        "cpu_baseline": {"value": r["value"], "unit": "videos/s", "cores": r["cores"], "kind": "port",
+                         "sample": f"{r['steps']} forwards of {sample} videos (dense layouts), host cpus {r['host_cpus']}"},
+        "e2e": {"value": r["value"], "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_resident(model, batch_dev, steps, warmup, world, torch, dist):
+    """Device-resident timing: K forwards bracketed by barrier + synchronize, CUDA events."""
+    with torch.no_grad():
+        for _ in range(warmup):
+            model(batch_dev)
+        torch.cuda.synchronize()
+        model.set_profiling(True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            model(batch_dev)
+        end.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = start.elapsed_time(end)
+        prof = model.get_profile()
+        model.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, prof
+
+
+def time_e2e(model, batch_host, batch_dev, logits_host, steps, warmup, world, torch, dist):
+    """Public-API timing with HOST inputs: H2D of the step's inputs from pinned memory, forward,
+    D2H of the logits, and a sync per step (the reference loop reads logits.cpu() every batch)."""
+    def step():
+        for k, v in batch_host.items():
+            batch_dev[k].copy_(v, non_blocking=True)
+        out = model(batch_dev)["stlt"]
+        logits_host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            step()
+        end.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = start.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def roofline_from_profile(prof, steps, precision, peaks, peak_src):
+    gemm = prof["gemm"]
+    executed = gemm["flops"] / max(steps, 1)                      # MMA FLOPs issued (3x in fp32 mode)
+    algorithmic = executed / (3.0 if precision == "fp32" else 1.0)
+    ms = gemm["ms"] / max(steps, 1)
+    achieved = algorithmic / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    peak = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
+    traffic = None
+    tpath = ROOT / "profiles" / "roofline_traffic.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get(precision)
+        except Exception:
+            traffic = None
+    return {
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "traffic": traffic, "kernel": "gemm_tcgen05_kernel (all projection GEMMs of a step)",
+        "launches_per_step": gemm["launches"] / max(steps, 1), "kernel_ms_per_step": ms,
+        "algorithmic_flops_per_step": algorithmic,
+        "mma_flops_executed_per_step": executed,
+        "peak_source": f"bf16 dense sustained, {peak_src}"
+                       + ("; fp32 mode issues 3 bf16 MMAs per algorithmic MMA" if precision == "fp32" else ""),
+    }
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    import stlt_b200
+    from stlt_b200.synthetic import make_batch, random_state_dict
+
+    spec = stlt_b200.SOMETHING_ELSE if args.layout == "something" else stlt_b200.ACTION_GENOME
+    cfg = stlt_b200.StltModelConfig(num_classes=spec["num_classes"], unique_categories=spec["unique_categories"])
+    torch.manual_seed(0)
+    model = stlt_b200.Stlt(cfg, precision=args.dtype)
+    model.load_state_dict(random_state_dict(model.state_dict(), seed=0))
+    model = model.to("cuda")
+    model.train(False)
+
+    keys = ["categories", "boxes", "frame_types", "lengths"] + (["scores"] if spec["scores"] else [])
+    full = make_batch(args.batch, args.layout, ragged=False, seed=100 + rank)
+    batch_host = {k: full[k].pin_memory() for k in keys}
+    batch_dev = {k: v.cuda() for k, v in batch_host.items()}
+    logits_host = torch.empty((args.batch, spec["num_classes"]), dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in batch_host.values())
+    d2h = logits_host.numel() * logits_host.element_size()
+    peaks, peak_src = load_peaks()
+    B, L, S = full["categories"].shape
+
+    def measure(precision, with_clocks):
+        model.precision = precision
+        with torch.no_grad():
+            model(batch_dev)  # packs weights, sizes the workspace
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank) if with_clocks else None
+        if sampler:
+            sampler.start()
+        ms, prof = time_resident(model, batch_dev, args.steps, args.warmup, world, torch, dist)
+        clocks = sampler.stop() if sampler else None
+        launches = model.last_launch_count() * args.steps
+        e2e_ms = time_e2e(model, batch_host, batch_dev, logits_host, args.steps, max(args.warmup, 1), world, torch, dist)
+        videos = args.batch * world * args.steps
+        res = {
+            "value": videos / (ms * 1e-3), "ms_per_step": ms / args.steps,
+            "e2e": {"value": videos / (e2e_ms * 1e-3), "unit": "videos/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "roofline": roofline_from_profile(prof, args.steps, precision, peaks, peak_src),
+            "gpu_launches": launches,
+            "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+        }
+        flops = FLOPS_PER_VIDEO[args.layout] * args.batch
+        res["model_tflops"] = flops / (ms / args.steps * 1e-3) / 1e12
+        return res, clocks
+
+    main_res, clocks = measure(args.dtype, with_clocks=True)
+    secondary = None
+    if not args.no_secondary:
+        other = "fp32" if args.dtype == "bf16" else "bf16"
+        sec, _ = measure(other, with_clocks=False)
+        secondary = {"dtype": other, "value": sec["value"], "unit": "videos/s", "ms_per_step": sec["ms_per_step"],
+                     "e2e": sec["e2e"], "roofline": sec["roofline"], "model_tflops": sec["model_tflops"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_oracle_throughput(args.layout, 8, seconds=args.cpu_seconds)
+        cpu = {"value": r["value"], "unit": "videos/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} forwards of batch 8 (BASELINE configs[0]) in {args.cpu_seconds:.0f} s, "
+                         f"oracle/stlt_oracle.py on {r['cores']} torch threads (host cpus {r['host_cpus']})"}
+
+    if rank == 0:
+        line = {
+            "metric": "stlt_inference_videos_per_sec", "value": main_res["value"], "unit": "videos/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "f32 (3xbf16 split MMA)", "data": "synthetic",
+            "config": {
+                "workload": f"STLT inference, {args.layout} shape (L={L} frames x S={S} slots, "
+                            f"{spec['num_classes']} classes), batch {args.batch} per GPU, dense layouts, random-init weights",
+                "global_batch": args.batch * world, "parallelism": f"batch-sharded x{world}, no collective",
+                "l2_policy": "activations (GBs per step) far exceed the 126 MB L2; no explicit flush",
+            },
+            "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
+            "cpu_baseline": cpu, "clocks": clocks, "model_tflops": main_res["model_tflops"],
+            "breakdown_ms_per_step": main_res["breakdown_ms_per_step"], "secondary": secondary,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,22 @@ int stlt_check_errors(void* handle, void* stream, const void* workspace);
 /* Number of kernels enqueued by the most recent stlt_forward on this handle. */
 int stlt_last_launch_count(void* handle);
 
+/* Per-category device timing of the launches issued by stlt_forward, measured with CUDA events on
+ * the launching stream. stlt_set_profiling(1) starts collecting (and clears previous spans);
+ * stlt_get_profile() synchronises on the recorded events, sums them per category and clears. */
+#define STLT_PROF_GEMM 0      /* tcgen05 projection GEMMs */
+#define STLT_PROF_ATTENTION 1 /* shared-memory attention */
+#define STLT_PROF_ADD_LN 2    /* residual + LayerNorm */
+#define STLT_PROF_OTHER 3     /* embeddings, gather, classifier head */
+#define STLT_PROF_CATEGORIES 4
+typedef struct StltProfile {
+  double ms[STLT_PROF_CATEGORIES];
+  double flops[STLT_PROF_CATEGORIES]; /* executed multiply-add FLOPs (2*M*N*K), GEMM only */
+  int64_t launches[STLT_PROF_CATEGORIES];
+} StltProfile;
+int stlt_set_profiling(void* handle, int32_t enable);
+int stlt_get_profile(void* handle, StltProfile* out);
+
 /* Test taps (NULL disables). The struct is copied. */
 int stlt_set_taps(void* handle, const StltTaps* taps);
 

@@ -56,7 +56,7 @@ attention_kernel(const TIn* __restrict__ qkv, const long long* __restrict__ mask
   const int lane = threadIdx.x & 31;
   const int R = G * T;       // token rows per group (<= 32)
   const int PT = T + 1;      // pitch of the probability rows
-  const int per_warp = R * kQPitch + R * kVPitch + R * PT;
+  const int per_warp = (R * kQPitch + R * kVPitch + R * PT + 3) & ~3;  // keep float4 alignment
   float* Qs = smem_f + warp * per_warp;
   float* Vs = Qs + R * kQPitch;
   float* Ps = Vs + R * kVPitch;
@@ -157,7 +157,7 @@ cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long*
   const int R = G * T;
   const long long groups = (num_seqs + G - 1) / G;
   const long long items = groups * kHeads;
-  const int per_warp = R * kQPitch + R * kVPitch + R * (T + 1);
+  const int per_warp = (R * kQPitch + R * kVPitch + R * (T + 1) + 3) & ~3;
   const int smem = per_warp * kWarpsPerBlock * static_cast<int>(sizeof(float));
   long long blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const long long cap = 148LL * 32;

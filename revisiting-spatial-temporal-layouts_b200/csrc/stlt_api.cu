@@ -49,6 +49,12 @@ struct Handle {
   int launches = 0;
   EncodeTiledFn encode = nullptr;
   StltTaps taps{};
+  // optional per-category timing (CUDA events on the launching stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int cat; cudaEvent_t a, b; double flops; };
+  std::vector<Span> spans;
   std::map<std::tuple<const void*, int, long long, long long, int, int>, CUtensorMap> tm_cache;
   char err[512] = {0};
 };
@@ -63,6 +69,36 @@ int fail(Handle* h, int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+cudaEvent_t next_event(Handle* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+
+// RAII span: records an event before and after the launches issued in its scope.
+struct ProfileScope {
+  Handle* h;
+  cudaStream_t s;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int cat;
+  double flops;
+  ProfileScope(Handle* h_, cudaStream_t s_, int cat_, double flops_ = 0.0)
+      : h(h_), s(s_), cat(cat_), flops(flops_) {
+    if (!h->profiling) return;
+    a = next_event(h);
+    b = next_event(h);
+    if (a && b) cudaEventRecord(a, s);
+  }
+  ~ProfileScope() {
+    if (!h->profiling || !a || !b) return;
+    cudaEventRecord(b, s);
+    h->spans.push_back({cat, a, b, flops});
+  }
+};
 
 #define STLT_CUDA(h, expr)                                                                  \
   do {                                                                                      \
@@ -128,6 +164,7 @@ int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_rows, lo
   g.a_plane_rows = static_cast<int>(a_plane_rows);
   g.b_plane_rows = n;
   g.out_plane_rows = static_cast<int>(a_plane_rows);
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
   return STLT_OK;
@@ -182,14 +219,20 @@ int run_layer(Handle* h, cudaStream_t stream, int precision, const LayerWeights&
   if (rc) return rc;
   // attention
   ActOut att{nullptr, ph.att, planes, ph.m_pad};
-  STLT_CUDA(h, launch_attention(ph.qkv, !fp32, mask_src, num_seqs, T, causal, att, stream));
+  {
+    ProfileScope prof(h, stream, STLT_PROF_ATTENTION);
+    STLT_CUDA(h, launch_attention(ph.qkv, !fp32, mask_src, num_seqs, T, causal, att, stream));
+  }
   h->launches++;
   // output projection, residual, LayerNorm
   rc = run_gemm(h, stream, ph.att, ph.m_pad, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.y,
                 terms, GEMM_OUT_F32, false);
   if (rc) return rc;
   ActOut xo{ph.x, ph.xb, planes, ph.m_pad};
-  STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
+  {
+    ProfileScope prof(h, stream, STLT_PROF_ADD_LN);
+    STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
+  }
   h->launches++;
   // feed-forward
   rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.l1_p, kFfn, kHidden, lw.l1_b, ph.hid, terms,
@@ -198,7 +241,10 @@ int run_layer(Handle* h, cudaStream_t stream, int precision, const LayerWeights&
   rc = run_gemm(h, stream, ph.hid, ph.m_pad, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.y, terms,
                 GEMM_OUT_F32, false);
   if (rc) return rc;
-  STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n2_g, lw.n2_b, eps, ph.m_valid, xo, stream));
+  {
+    ProfileScope prof(h, stream, STLT_PROF_ADD_LN);
+    STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n2_g, lw.n2_b, eps, ph.m_valid, xo, stream));
+  }
   h->launches++;
   return STLT_OK;
 }
@@ -250,7 +296,10 @@ int stlt_create(const StltDims* dims, void** handle) {
 }
 
 int stlt_destroy(void* handle) {
-  delete static_cast<Handle*>(handle);
+  Handle* h = static_cast<Handle*>(handle);
+  if (h)
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  delete h;
   return STLT_OK;
 }
 
@@ -468,9 +517,12 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   sp.m_valid = n_sp;
 
   ActOut emb{sp.x, sp.xb, planes, sp.m_pad};
-  STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories,
-                            h->w.box_w, h->w.box_b, h->w.score_w, h->w.score_b, h->w.emb_g,
-                            h->w.emb_b, d.layer_norm_eps, n_sp, emb, err_flag, stream));
+  {
+    ProfileScope prof(h, stream, STLT_PROF_OTHER);
+    STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories,
+                              h->w.box_w, h->w.box_b, h->w.score_w, h->w.score_b, h->w.emb_g,
+                              h->w.emb_b, d.layer_norm_eps, n_sp, emb, err_flag, stream));
+  }
   h->launches++;
   if (h->taps.embed)
     STLT_CUDA(h, cudaMemcpyAsync(h->taps.embed, sp.x, n_sp * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
@@ -495,9 +547,12 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   tp.m_pad = p.m_tm;
   tp.m_valid = n_tm;
   ActOut fr{tp.x, tp.xb, planes, tp.m_pad};
-  STLT_CUDA(h, launch_frame_embed(sp.x, S, frame_types, h->w.pos_table, h->w.ft_table,
-                                  d.num_frame_types, h->w.fr_g, h->w.fr_b, d.layer_norm_eps, B, L, fr,
-                                  err_flag, stream));
+  {
+    ProfileScope prof(h, stream, STLT_PROF_OTHER);
+    STLT_CUDA(h, launch_frame_embed(sp.x, S, frame_types, h->w.pos_table, h->w.ft_table,
+                                    d.num_frame_types, h->w.fr_g, h->w.fr_b, d.layer_norm_eps, B, L,
+                                    fr, err_flag, stream));
+  }
   h->launches++;
   if (h->taps.frames)
     STLT_CUDA(h, cudaMemcpyAsync(h->taps.frames, tp.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
@@ -513,18 +568,21 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   float* pooled = reinterpret_cast<float*>(ws + p.off_head);
   float* h1 = pooled + static_cast<size_t>(B) * kHidden;
   float* h2 = h1 + static_cast<size_t>(B) * kHidden;
-  STLT_CUDA(h, launch_gather_last(tp.x, lengths, B, L, pooled, err_flag, stream));
-  h->launches++;
-  if (h->taps.pooled)
-    STLT_CUDA(h, cudaMemcpyAsync(h->taps.pooled, pooled, static_cast<size_t>(B) * kHidden * 4,
-                                 cudaMemcpyDeviceToDevice, stream));
-  STLT_CUDA(h, launch_gemm_simt(pooled, h->w.fc1_w, h->w.fc1_b, h1, B, kHidden, kHidden, true, stream));
-  h->launches++;
-  ActOut ho{h2, nullptr, 1, 0};
-  STLT_CUDA(h, launch_add_ln(h1, nullptr, h->w.head_g, h->w.head_b, d.layer_norm_eps, B, ho, stream));
-  h->launches++;
-  STLT_CUDA(h, launch_gemm_simt(h2, h->w.fc2_w, h->w.fc2_b, logits, B, d.num_classes, kHidden, false, stream));
-  h->launches++;
+  {
+    ProfileScope prof(h, stream, STLT_PROF_OTHER);
+    STLT_CUDA(h, launch_gather_last(tp.x, lengths, B, L, pooled, err_flag, stream));
+    h->launches++;
+    if (h->taps.pooled)
+      STLT_CUDA(h, cudaMemcpyAsync(h->taps.pooled, pooled, static_cast<size_t>(B) * kHidden * 4,
+                                   cudaMemcpyDeviceToDevice, stream));
+    STLT_CUDA(h, launch_gemm_simt(pooled, h->w.fc1_w, h->w.fc1_b, h1, B, kHidden, kHidden, true, stream));
+    h->launches++;
+    ActOut ho{h2, nullptr, 1, 0};
+    STLT_CUDA(h, launch_add_ln(h1, nullptr, h->w.head_g, h->w.head_b, d.layer_norm_eps, B, ho, stream));
+    h->launches++;
+    STLT_CUDA(h, launch_gemm_simt(h2, h->w.fc2_w, h->w.fc2_b, logits, B, d.num_classes, kHidden, false, stream));
+    h->launches++;
+  }
   return STLT_OK;
 }
 
@@ -553,6 +611,33 @@ int stlt_set_taps(void* handle, const StltTaps* taps) {
     h->taps = *taps;
   else
     h->taps = StltTaps{};
+  return STLT_OK;
+}
+
+int stlt_set_profiling(void* handle, int32_t enable) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  h->profiling = enable != 0;
+  h->spans.clear();
+  h->ev_used = 0;
+  return STLT_OK;
+}
+
+int stlt_get_profile(void* handle, StltProfile* out) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !out) return fail(h, STLT_ERR_INVALID, "null argument");
+  std::memset(out, 0, sizeof(*out));
+  for (const auto& sp : h->spans) {
+    STLT_CUDA(h, cudaEventSynchronize(sp.b));
+    float ms = 0.f;
+    STLT_CUDA(h, cudaEventElapsedTime(&ms, sp.a, sp.b));
+    if (sp.cat < 0 || sp.cat >= STLT_PROF_CATEGORIES) continue;
+    out->ms[sp.cat] += ms;
+    out->launches[sp.cat] += 1;
+    out->flops[sp.cat] += sp.flops;
+  }
+  h->spans.clear();
+  h->ev_used = 0;
   return STLT_OK;
 }
 

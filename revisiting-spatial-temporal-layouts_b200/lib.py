@@ -66,6 +66,17 @@ class StltTaps(Structure):
     ]
 
 
+PROF_CATEGORIES = ("gemm", "attention", "add_ln", "other")
+
+
+class StltProfile(Structure):
+    _fields_ = [
+        ("ms", c_double * 4),
+        ("flops", c_double * 4),
+        ("launches", c_int64 * 4),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/stlt_b200.h one to one.
 SIGNATURES = {
     "stlt_create": (c_int32, [POINTER(StltDims), POINTER(c_void_p)]),
@@ -83,6 +94,8 @@ SIGNATURES = {
     "stlt_check_errors": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "stlt_last_launch_count": (c_int32, [c_void_p]),
     "stlt_set_taps": (c_int32, [c_void_p, POINTER(StltTaps)]),
+    "stlt_set_profiling": (c_int32, [c_void_p, c_int32]),
+    "stlt_get_profile": (c_int32, [c_void_p, POINTER(StltProfile)]),
     "stlt_op_gemm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                c_int32, c_int32, c_int32, c_int32, c_int32]),
     "stlt_op_gemm_simt": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

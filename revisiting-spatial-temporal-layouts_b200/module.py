@@ -366,6 +366,18 @@ class Stlt(nn.Module):
         stream = torch.cuda.current_stream(self._workspace.device).cuda_stream
         _lib.check(self._handle, lib.stlt_check_errors(self._handle, stream, self._workspace.data_ptr()))
 
+    def set_profiling(self, enable: bool) -> None:
+        """Per-category CUDA-event timing of the kernels launched by forward (bench / profiles)."""
+        if self._handle is None:
+            raise RuntimeError("run one forward before enabling profiling")
+        _lib.check(self._handle, _lib.load_library().stlt_set_profiling(self._handle, int(enable)))
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        prof = _lib.StltProfile()
+        _lib.check(self._handle, _lib.load_library().stlt_get_profile(self._handle, ctypes.byref(prof)))
+        return {name: {"ms": prof.ms[i], "flops": prof.flops[i], "launches": int(prof.launches[i])}
+                for i, name in enumerate(_lib.PROF_CATEGORIES)}
+
     def last_launch_count(self) -> int:
         if self._handle is None:
             return 0

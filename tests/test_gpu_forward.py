@@ -1,0 +1,237 @@
+"""GPU parity tests of the whole path through the drop-in module / C ABI: CUDA vs the CPU oracle
+and vs the golden fixtures produced by the reference. Tolerances are BASELINE.json's: fp32 logits
+max|d|/max|ref| <= 1e-4, bf16 <= 2e-2 with identical top-1; masks and boxes bit-exact."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import stlt_b200
+from oracle import stlt_oracle as O
+from stlt_b200 import Stlt, StltModelConfig, prepare_layout_batch
+from stlt_b200.synthetic import make_batch, make_raw_boxes, random_state_dict
+from tests.util import golden_model_case, load_golden, nerr, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+def _model(cfg, sd, precision):
+    torch.manual_seed(0)
+    m = Stlt(cfg, precision=precision)
+    m.load_state_dict(sd, strict=True)
+    m = m.to("cuda")
+    m.train(False)
+    return m
+
+
+# ---------------------------------------------------------------- K0: boxes + masks (bit exact)
+def test_prepare_matches_reference_fix_box_golden():
+    g = load_golden("fix_box.npz")
+    n = g["raw"].shape[0]
+    raw = torch.from_numpy(g["raw"]).view(n, 1, 1, 4).expand(n, 1, 2, 4).contiguous().cuda()
+    cats = torch.tensor([[[3, 2]]]).expand(n, 1, 2).contiguous().cuda()
+    out = prepare_layout_batch(raw, torch.from_numpy(g["sizes"]).cuda(), cats, torch.full((n, 1), 2).cuda())
+    got = out["boxes"][:, 0, 1, :].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), g["normalized"].view(np.uint32))
+    assert torch.equal(out["boxes"][:, 0, 0, :].cpu(), torch.tensor([0.0, 0.0, 1.0, 1.0]).expand(n, 4))
+
+
+@pytest.mark.parametrize("dataset", ["something", "action_genome"])
+def test_prepare_matches_reference_collater_golden(dataset):
+    """Raw JSON boxes scattered into the padded layout -> K0 -> must equal the reference
+    StltDataset + StltCollater output bit for bit (boxes and both masks)."""
+    g = load_golden(f"collate_{dataset}.npz")
+    meta = json.loads(bytes(g["json"]).decode())
+    cats = torch.from_numpy(g["categories"])
+    B, L, S = cats.shape
+    raw = torch.zeros(B, L, S, 4, dtype=torch.float64)
+    sizes = torch.zeros(B, 2, dtype=torch.int64)
+    for b, video in enumerate(meta["videos"]):
+        sizes[b] = torch.tensor(meta["sizes"][video["id"]])
+        idx = O.get_test_layout_indices(16, len(video["frames"]))
+        for l, fi in enumerate(idx):
+            objs = [e for e in video["frames"][fi]["frame_objects"] if e["score"] >= 0.5]
+            for s, e in enumerate(objs, start=1):
+                raw[b, l, s] = torch.tensor([e["x1"], e["y1"], e["x2"], e["y2"]], dtype=torch.float64)
+    out = prepare_layout_batch(raw.cuda(), sizes.cuda(), cats.cuda(), torch.from_numpy(g["frame_types"]).cuda())
+    assert np.array_equal(out["boxes"].cpu().numpy().view(np.uint32), g["boxes"].view(np.uint32))
+    assert np.array_equal(out["src_key_padding_mask_boxes"].cpu().numpy(), g["src_key_padding_mask_boxes"])
+    assert np.array_equal(out["src_key_padding_mask_frames"].cpu().numpy(), g["src_key_padding_mask_frames"])
+
+
+def test_prepare_large_batch_matches_oracle_bit_exact():
+    b = make_batch(4096, "something", ragged=True, seed=12)
+    raw, sizes = make_raw_boxes(b["categories"], seed=13)
+    want = O.prepare_padded(raw, sizes, b["categories"], b["frame_types"])
+    got = prepare_layout_batch(raw.cuda(), sizes.cuda(), b["categories"].cuda(), b["frame_types"].cuda())
+    for k in want:
+        w, g_ = want[k].numpy(), got[k].cpu().numpy()
+        assert np.array_equal(w.view(np.uint32) if w.dtype == np.float32 else w,
+                              g_.view(np.uint32) if g_.dtype == np.float32 else g_), k
+    empty = prepare_layout_batch(raw[:0].cuda(), sizes[:0].cuda(), b["categories"][:0].cuda(), b["frame_types"][:0].cuda())
+    assert empty["boxes"].shape == (0, 17, 5, 4)
+
+
+# ---------------------------------------------------------------- forward vs golden / oracle
+@pytest.mark.parametrize("layout", ["something", "action_genome"])
+def test_forward_fp32_matches_reference_golden_per_stage(layout):
+    cfg, sd, batch, g = golden_model_case(layout)
+    m = _model(cfg, sd, "fp32")
+    with torch.no_grad():
+        out = m.forward_with_taps(to_cuda(batch))
+    assert torch.equal(out["src_key_padding_mask_boxes"].cpu(), batch["src_key_padding_mask_boxes"])
+    assert torch.equal(out["src_key_padding_mask_frames"].cpu(), batch["src_key_padding_mask_frames"])
+    assert nerr(out["embed"][0], torch.from_numpy(g["embed_b0"])) < 1e-5
+    valid = ~batch["src_key_padding_mask_boxes"][0]
+    assert nerr(out["spatial"][0].cpu()[valid], torch.from_numpy(g["spatial_b0"])[valid]) < FP32_TOL
+    assert nerr(out["frames"], torch.from_numpy(g["frames"])) < FP32_TOL
+    for b in range(batch["lengths"].shape[0]):
+        n = int(batch["lengths"][b])
+        assert nerr(out["temporal"][b, :n], torch.from_numpy(g["temporal"][b, :n])) < FP32_TOL
+    err = nerr(out["stlt"], torch.from_numpy(g["logits"]))
+    print(f"{layout} fp32 logits nerr {err:.3e}")
+    assert err < FP32_TOL
+    m.check_inputs()
+    assert m.last_launch_count() > 80
+
+
+@pytest.mark.parametrize("layout", ["something", "action_genome"])
+def test_forward_bf16_matches_reference_golden(layout):
+    cfg, sd, batch, g = golden_model_case(layout)
+    m = _model(cfg, sd, "bf16")
+    with torch.no_grad():
+        got = m(to_cuda(batch))["stlt"].cpu()
+    want = torch.from_numpy(g["logits"])
+    err = nerr(got, want)
+    print(f"{layout} bf16 logits nerr {err:.3e}")
+    assert err < BF16_TOL
+
+
+def test_forward_batch8_config1_fp32_and_bf16_top1():
+    """BASELINE config 1 shape (batch 8) on independently drawn weights, both precisions."""
+    cfg = StltModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=31)
+    batch = make_batch(8, "something", ragged=True, seed=32)
+    with torch.no_grad():
+        want = O.stlt_forward(sd, batch)
+        want64 = O.stlt_forward(sd, batch, dtype=torch.float64)
+    m = _model(cfg, sd, "fp32")
+    with torch.no_grad():
+        got = m(to_cuda(batch))["stlt"].cpu()
+    assert nerr(got, want) < FP32_TOL and nerr(got, want64) < FP32_TOL
+    assert torch.equal(got.argmax(-1), want.argmax(-1))
+    m.precision = "bf16"
+    with torch.no_grad():
+        got16 = m(to_cuda(batch))["stlt"].cpu()
+    assert nerr(got16, want) < BF16_TOL
+    margin = want.topk(2, -1).values
+    safe = (margin[:, 0] - margin[:, 1]) > 4 * (got16 - want).abs().max()
+    assert torch.equal(got16.argmax(-1)[safe], want.argmax(-1)[safe])
+    assert torch.equal(got16.argmax(-1), want.argmax(-1)), "bf16 top-1 differs on the fixed batch"
+    m.precision = "fp32"  # switching back re-packs the weights
+    with torch.no_grad():
+        again = m(to_cuda(batch))["stlt"].cpu()
+    assert torch.equal(again, got)
+
+
+def test_forward_default_init_clone_layers():
+    """Default init (all encoder layers identical clones, zero padding rows), non-128-multiple M."""
+    cfg = StltModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(3)
+    m = Stlt(cfg).to("cuda")
+    m.train(False)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    batch = make_batch(5, "something", ragged=True, seed=33)
+    with torch.no_grad():
+        want = O.stlt_forward(sd, batch)
+        got = m(to_cuda(batch))["stlt"].cpu()
+    assert nerr(got, want) < FP32_TOL
+
+
+def test_weight_update_is_picked_up():
+    cfg = StltModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=41)
+    m = _model(cfg, sd, "fp32")
+    batch = to_cuda(make_batch(2, "something", seed=1))
+    with torch.no_grad():
+        a = m(batch)["stlt"].clone()
+        m.backbone.transformer.layers[7].linear2.weight.mul_(0.5)     # in-place: version bump
+        m.prediction_head.fc2.bias.add_(1.0)
+        b = m(batch)["stlt"]
+    sd2 = {k: v.cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        want = O.stlt_forward(sd2, {k: v.cpu() for k, v in batch.items()})
+    assert not torch.allclose(a, b) and nerr(b, want) < FP32_TOL
+
+
+def test_edge_cases_empty_single_and_bad_inputs():
+    cfg = StltModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=42)
+    m = _model(cfg, sd, "fp32")
+    empty = to_cuda(make_batch(0, "something"))
+    with torch.no_grad():
+        assert m(empty)["stlt"].shape == (0, 174)
+    # a single video with the minimum length (1 real frame + extract), L = 2, S = 2
+    one = make_batch(1, "something", ragged=False, seed=2, num_frames=1, max_objects=1)
+    with torch.no_grad():
+        want = O.stlt_forward(sd, one)
+        got = m(to_cuda(one))["stlt"].cpu()
+    assert nerr(got, want) < FP32_TOL
+    # extra keys are tolerated (move_batch_to_device leaves non-tensors in place)
+    b = to_cuda(make_batch(2, "something", seed=3))
+    b["video_id"] = ["a", "b"]
+    b["labels"] = torch.zeros(2, dtype=torch.int64, device="cuda")
+    with torch.no_grad():
+        m(b)
+    # out-of-range category is reported (PyTorch raises IndexError on CPU)
+    bad = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in b.items()}
+    bad["categories"][0, 0, 1] = 99
+    with torch.no_grad():
+        m(bad)
+    with pytest.raises(stlt_b200.lib.StltError, match="categories"):
+        m.check_inputs()
+    with pytest.raises(TypeError):
+        m({**b, "categories": b["categories"].int()})
+    with pytest.raises(ValueError):
+        m({**b, "boxes": b["boxes"][:, :, :, :3]})
+
+
+# ---------------------------------------------------------------- full-size properties (B = 4096)
+def test_full_size_batch_properties():
+    """BASELINE config 2 size. The oracle cannot run 4096 videos in seconds, so check
+    size-independent properties: (1) a 64-video sub-batch run alone gives the same logits as inside
+    the big batch; (2) scrambling padded slots / padded frames changes nothing;
+    (3) a sample of videos matches the oracle within the fp32 tolerance."""
+    cfg = StltModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=51)
+    m = _model(cfg, sd, "fp32")
+    batch = make_batch(4096, "something", ragged=True, seed=52)
+    gb = to_cuda(batch)
+    with torch.no_grad():
+        full = m(gb)["stlt"].clone()
+        assert torch.isfinite(full).all()
+        sub = {k: v[1000:1064].contiguous() for k, v in gb.items()}
+        part = m(sub)["stlt"]
+        assert torch.equal(part, full[1000:1064]), "logits depend on batch composition"
+        scr = {k: v.clone() for k, v in gb.items()}
+        scr["boxes"][scr["categories"] == 0] = 0.77
+        pad_frames = scr["frame_types"] == 0
+        scr["boxes"][pad_frames] = 0.123
+        assert torch.equal(m(scr)["stlt"], full), "padded payload leaked into the logits"
+    idx = torch.tensor([0, 1, 777, 2048, 4095])
+    small = {k: v[idx] for k, v in batch.items()}
+    with torch.no_grad():
+        want = O.stlt_forward(sd, small)
+    assert nerr(full[idx.cuda()].cpu(), want) < FP32_TOL
+    m.precision = "bf16"
+    with torch.no_grad():
+        b16 = m(gb)["stlt"]
+    assert nerr(b16[idx.cuda()].cpu(), want) < BF16_TOL
