@@ -33,20 +33,6 @@ __device__ __forceinline__ void load_slice(const float* p, float (&dst)[64]) {
   }
 }
 
-__device__ __forceinline__ void load_slice(const __nv_bfloat16* p, float (&dst)[64]) {
-  const uint4* p4 = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint4 v = __ldg(p4 + i);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      dst[8 * i + 2 * q + 0] = __uint_as_float(w[q] << 16);
-      dst[8 * i + 2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
-    }
-  }
-}
-
 template <typename TIn>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 attention_kernel(const TIn* __restrict__ qkv, const long long* __restrict__ mask_src,
@@ -164,12 +150,9 @@ cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long*
   if (blocks > cap) blocks = cap;
   cudaError_t e;
   if (qkv_is_bf16) {
-    auto kern = attention_kernel<__nv_bfloat16>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    kern<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, smem, stream>>>(
-        static_cast<const __nv_bfloat16*>(qkv), mask_src, num_seqs, T, G, causal ? 1 : 0, out,
-        items);
+    if (out.planes != 1) return cudaErrorInvalidValue;
+    return launch_attention_mma(static_cast<const __nv_bfloat16*>(qkv), mask_src, num_seqs, T, causal,
+                                out.xb, stream);
   } else {
     auto kern = attention_kernel<float>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

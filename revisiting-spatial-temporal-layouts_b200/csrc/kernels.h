@@ -79,11 +79,16 @@ cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, 
                                int* err_flag, cudaStream_t stream);
 
 // K3: masked multi-head attention over short sequences held in shared memory.
-//   qkv: [tokens, 2304] fp32 or bf16; key j of a sequence is masked when mask_src[token_j] == 0,
+//   qkv: [tokens, 2304] fp32 (fp32-parity mode; bf16 input is handled by launch_attention_mma); key j of a sequence is masked when mask_src[token_j] == 0,
 //   and (causal) when j > i. Output: bf16 plane(s) [tokens, 768].
 cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long* mask_src,
                              long long num_seqs, int T, bool causal, ActOut out,
                              cudaStream_t stream);
+
+// K3, bf16 mode: the same attention on warp-level tensor-core tiles (attention_mma.cu).
+cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, const long long* mask_src,
+                                 long long num_seqs, int T, bool causal, __nv_bfloat16* out,
+                                 cudaStream_t stream);
 
 // fp32 -> bf16 plane(s) for weights.
 cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,
