@@ -143,6 +143,12 @@ typedef struct StltProfile {
 int stlt_set_profiling(void* handle, int32_t enable);
 int stlt_get_profile(void* handle, StltProfile* out);
 
+/* Last-layer pruning (default on): only slot 0 of the spatial stack's output (models.py:79) and
+ * only frame lengths-1 of the temporal stack's output (models.py:192) are read, so the row-wise
+ * half of the last layer of each stack (out-proj, FFN, LayerNorms) runs on those rows only. The
+ * logits are bit-identical with pruning off; taps of the full stack outputs disable it. */
+int stlt_set_pruning(void* handle, int32_t enable);
+
 /* Test taps (NULL disables). The struct is copied. */
 int stlt_set_taps(void* handle, const StltTaps* taps);
 
@@ -152,7 +158,7 @@ int stlt_set_taps(void* handle, const StltTaps* taps);
  * [terms>1 ? 2 : 1][n][k]; out_kind 0 = f32 [m_rows][n], 1 = bf16, 2 = bf16 hi/lo planes. */
 int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w_planes,
                  const float* bias, void* out, int32_t m_rows, int32_t n, int32_t k, int32_t terms,
-                 int32_t out_kind, int32_t gelu);
+                 int32_t out_kind, int32_t gelu /* 0 none, 1 erf GELU (erff), 2 fast erf GELU */);
 int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w,
                       const float* bias, float* out, int32_t m, int32_t n, int32_t k, int32_t gelu);
 int stlt_op_attention(void* handle, void* stream, const void* qkv, int32_t qkv_is_bf16,

@@ -275,6 +275,44 @@ gather_last_kernel(const float* __restrict__ x, const long long* __restrict__ le
   }
 }
 
+// Row compaction for the pruned last layer of each stack: copies the fp32 residual row and the
+// bf16 attention-context row(s) of the tokens whose output is actually consumed.
+//   stride > 0 : source row = r * stride            (spatial CLS slot, models.py:79)
+//   stride == 0: source row = r * L + lengths[r] - 1 (extract frame, models.py:189-192)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __restrict__ src_att,
+                   int planes, long long src_plane_rows, int stride,
+                   const long long* __restrict__ lengths, int L, long long rows,
+                   float* __restrict__ dst_x, __nv_bfloat16* __restrict__ dst_att,
+                   long long dst_plane_rows, int* __restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    long long src;
+    if (stride > 0) {
+      src = r * stride;
+    } else {
+      long long len = lengths[r];
+      if (len < 1 || len > L) {
+        if (lane == 0) atomicExch(err_flag, 3);
+        len = 1;
+      }
+      src = r * L + (len - 1);
+    }
+    const RowRegs x = load_row(src_x, src, lane);
+    float4* px = reinterpret_cast<float4*>(dst_x + r * kHidden);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) px[lane + 32 * k] = x.v[k];
+    for (int pl = 0; pl < planes; ++pl) {
+      const uint4* sa = reinterpret_cast<const uint4*>(src_att + (pl * src_plane_rows + src) * kHidden);
+      uint4* da = reinterpret_cast<uint4*>(dst_att + (pl * dst_plane_rows + r) * kHidden);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) da[lane + 32 * k] = __ldg(sa + lane + 32 * k);  // 96 x 16 B
+    }
+  }
+}
+
 __global__ void pack_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ hi,
                                  uint2* __restrict__ lo, long long n4) {
   const long long stride = gridDim.x * static_cast<long long>(blockDim.x);
@@ -377,6 +415,17 @@ cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, 
                                int* err_flag, cudaStream_t stream) {
   if (B == 0) return cudaSuccess;
   gather_last_kernel<<<row_grid(B, 8), 256, 0, stream>>>(x, lengths, B, L, out, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const float* src_x, const __nv_bfloat16* src_att, int planes,
+                               long long src_plane_rows, int stride, const long long* lengths, int L,
+                               long long rows, float* dst_x, __nv_bfloat16* dst_att,
+                               long long dst_plane_rows, int* err_flag, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  gather_rows_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(src_x, src_att, planes, src_plane_rows,
+                                                            stride, lengths, L, rows, dst_x, dst_att,
+                                                            dst_plane_rows, err_flag);
   return cudaGetLastError();
 }
 

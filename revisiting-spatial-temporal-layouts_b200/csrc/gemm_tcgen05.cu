@@ -16,6 +16,11 @@
 //                 Planes are stacked along the row axis of the same tensor map: plane p of A starts
 //                 at row p * a_plane_rows, plane p of W at row p * b_plane_rows.
 //
+// CTAs run in clusters of 2 that work on two vertically adjacent 128-row tiles of the same 256-wide
+// column block: each CTA loads its own A tile and HALF of the shared W tile, multicasting that half
+// into both CTAs' shared memory, which cuts the L2 -> SM traffic per k-block from 48 KB to 32 KB per
+// CTA (the 1-CTA version of this kernel measured L2-bandwidth-bound, profiles/).
+//
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warp 3 = idle, warps 4..11 = epilogue (warp w reads TMEM lane quarter w % 4, column half (w-4)/4).
 #include "common.cuh"
@@ -36,6 +41,8 @@ constexpr int kEpiBufBytes = 32 * 128;  // 32 rows x 128 B staging tile for one 
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 4;
+constexpr int kCluster = 2;
+constexpr uint16_t kClusterMask = (1u << kCluster) - 1;
 
 // The split epilogue needs two staging tiles per warp (hi and lo plane), paid for with one stage.
 template <int kOut>
@@ -59,7 +66,7 @@ struct __align__(8) Barriers {
 
 }  // namespace
 
-template <int kTerms, int kOut, bool kGelu>
+template <int kTerms, int kOut, int kGelu>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias,
@@ -79,7 +86,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = m_tiles * n_tiles;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = blockIdx.x / kCluster;
+  const int num_clusters = gridDim.x / kCluster;
+  // A "pair tile" is two vertically adjacent 128-row tiles (one per CTA of the cluster).
+  const int num_tiles = ((m_tiles + kCluster - 1) / kCluster) * n_tiles;
   const int total_kb = kTerms * k_blocks;
 
   if (warp == 0 && lane == 0) {
@@ -90,7 +101,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bars->full[i], 1);
-      mbar_init(&bars->empty[i], 1);
+      mbar_init(&bars->empty[i], kCluster);  // freed by the MMA warps of BOTH CTAs (multicast)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
@@ -104,6 +115,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -112,9 +124,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles;
-        const int n_blk = tile - m_blk * n_tiles;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = (tile / n_tiles) * kCluster + cta_rank;
+        const int n_blk = tile % n_tiles;
         for (int kb = 0; kb < total_kb; ++kb) {
           const int term = kb / k_blocks;
           const int kk = kb - term * k_blocks;
@@ -125,7 +137,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           mbar_expect_tx(&bars->full[stage], kStageBytes);
           uint8_t* sa = smem_ab + stage * kStageBytes;
           tma_load_2d(&tm_a, &bars->full[stage], sa, kk * BK, a_row);
-          tma_load_2d(&tm_b, &bars->full[stage], sa + kABytes, kk * BK, b_row);
+          // this CTA's half of the W tile goes to both CTAs of the cluster
+          tma_load_2d_multicast(&tm_b, &bars->full[stage],
+                                sa + kABytes + cta_rank * (kBBytes / kCluster), kk * BK,
+                                b_row + cta_rank * (BN / kCluster), kClusterMask);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -140,7 +155,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);  // epilogue has drained this buffer
@@ -157,7 +172,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
             umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bars->empty[stage]);  // frees this smem stage once the MMAs have read it
+          // frees this smem stage in BOTH CTAs once these MMAs have read it (the peer multicasts
+          // its W half into our copy of the stage, so it must see our release too)
+          umma_commit_multicast(&bars->empty[stage], kClusterMask);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -175,9 +192,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     const uint32_t row_smem = smem_u32(ebuf) + lane * 128;  // this thread's 128 B staging row
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / n_tiles;
-      const int n_blk = tile - m_blk * n_tiles;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m_blk = (tile / n_tiles) * kCluster + cta_rank;
+      const int n_blk = tile % n_tiles;
+      const bool store_ok = m_blk < m_tiles;  // odd tile counts: the last pair has a dummy half
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int col0 = n_blk * BN + half * 128;
@@ -202,9 +220,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
           f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
-        if (kGelu) {
+        if (kGelu == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        } else if (kGelu == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
         }
 
         if (kOut == GEMM_OUT_F32) {
@@ -220,7 +241,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && store_ok) {
             tma_store_2d(&tm_out, ebuf, col0 + c * 32, row0);
             tma_store_commit();
           }
@@ -252,7 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           if (hc == 1) {
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && store_ok) {
               tma_store_2d(&tm_out, ebuf, col0 + (c - 1) * 32, row0);
               if (kOut == GEMM_OUT_BF16_SPLIT)
                 tma_store_2d(&tm_out, ebuf + kEpiBufBytes, col0 + (c - 1) * 32,
@@ -272,6 +293,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // no CTA exits while its peer may still signal its barriers / write its smem
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -283,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 // -------------------------------------------------------------------------------------------------
 int gemm_smem_bytes() { return Cfg<GEMM_OUT_F32>::kSmemBytes; }
 
-template <int kTerms, int kOut, bool kGelu>
+template <int kTerms, int kOut, int kGelu>
 static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   auto kern = gemm_tcgen05_kernel<kTerms, kOut, kGelu>;
   constexpr int smem = Cfg<kOut>::kSmemBytes;
@@ -295,12 +317,23 @@ static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sm
   }
   const int m_tiles = g.m_rows / BM;
   const int n_tiles = g.n / BN;
-  const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, kThreads, smem, stream>>>(g.tm_a, g.tm_b, g.tm_out, g.bias, m_tiles, n_tiles,
-                                         g.k / BK, g.a_plane_rows, g.b_plane_rows,
-                                         g.out_plane_rows);
-  return cudaGetLastError();
+  const int pair_tiles = ((m_tiles + kCluster - 1) / kCluster) * n_tiles;
+  const int max_clusters = num_sms / kCluster;
+  const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * kCluster);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, g.tm_a, g.tm_b, g.tm_out, g.bias, m_tiles, n_tiles,
+                            g.k / BK, g.a_plane_rows, g.b_plane_rows, g.out_plane_rows);
 }
 
 cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_sms) {
@@ -308,12 +341,13 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
     return cudaErrorInvalidValue;
 #define STLT_GEMM_CASE(T, O, G) \
   if (g.terms == T && g.out_kind == O && g.gelu == G) return launch_one<T, O, G>(g, stream, num_sms);
-  STLT_GEMM_CASE(1, GEMM_OUT_F32, false)
-  STLT_GEMM_CASE(1, GEMM_OUT_BF16, false)
-  STLT_GEMM_CASE(1, GEMM_OUT_BF16, true)
-  STLT_GEMM_CASE(3, GEMM_OUT_F32, false)
-  STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, true)
-  STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, false)
+  STLT_GEMM_CASE(1, GEMM_OUT_F32, 0)
+  STLT_GEMM_CASE(1, GEMM_OUT_BF16, 0)
+  STLT_GEMM_CASE(1, GEMM_OUT_BF16, 1)
+  STLT_GEMM_CASE(1, GEMM_OUT_BF16, 2)
+  STLT_GEMM_CASE(3, GEMM_OUT_F32, 0)
+  STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 1)
+  STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 0)
 #undef STLT_GEMM_CASE
   return cudaErrorInvalidValue;
 }

@@ -16,7 +16,7 @@ enum GemmOutKind : int {
 
 struct GemmArgs {
   CUtensorMap tm_a;    // bf16 [planes * a_plane_rows, K], box {64, 128}, SWIZZLE_128B
-  CUtensorMap tm_b;    // bf16 [planes * b_plane_rows, K], box {64, 256}, SWIZZLE_128B
+  CUtensorMap tm_b;    // bf16 [planes * b_plane_rows, K], box {64, 128} (half a W tile), SWIZZLE_128B
   CUtensorMap tm_out;  // fp32 box {32, 32} or bf16 box {64, 32}, SWIZZLE_128B
   const float* bias;   // [N]
   int m_rows;          // multiple of 128
@@ -24,7 +24,7 @@ struct GemmArgs {
   int k;               // multiple of 64
   int terms;           // 1 (bf16) or 3 (fp32-parity split)
   int out_kind;        // GemmOutKind
-  bool gelu;
+  int gelu;            // 0 none, 1 exact erf GELU (erff), 2 fast erf GELU (|erf err| < 7e-7)
   int a_plane_rows;    // row offset of the lo plane of A
   int b_plane_rows;    // row offset of the lo plane of W
   int out_plane_rows;  // row offset of the lo plane of the output (split only)
@@ -77,6 +77,12 @@ cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* f
 // K9: h[b] = x[b * L + lengths[b] - 1] (src/modelling/models.py:189-192).
 cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, int L, float* out,
                                int* err_flag, cudaStream_t stream);
+
+// Row compaction for the pruned last layer of each stack (see elementwise.cu).
+cudaError_t launch_gather_rows(const float* src_x, const __nv_bfloat16* src_att, int planes,
+                               long long src_plane_rows, int stride, const long long* lengths, int L,
+                               long long rows, float* dst_x, __nv_bfloat16* dst_att,
+                               long long dst_plane_rows, int* err_flag, cudaStream_t stream);
 
 // K3: masked multi-head attention over short sequences held in shared memory.
 //   qkv: [tokens, 2304] fp32 (fp32-parity mode; bf16 input is handled by launch_attention_mma); key j of a sequence is masked when mask_src[token_j] == 0,

@@ -50,6 +50,7 @@ struct Handle {
   EncodeTiledFn encode = nullptr;
   StltTaps taps{};
   // optional per-category timing (CUDA events on the launching stream)
+  bool pruning = true;  // run the row-wise tail of the last layer of each stack on the rows that are read
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -140,12 +141,12 @@ int make_tm(Handle* h, CUtensorMap* tm, const void* ptr, int dtype, long long ro
 // out = epilogue(A W^T + bias) on tcgen05. a/w point at plane 0; planes are a_plane_rows / n rows apart.
 int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_rows, long long a_plane_rows,
              const void* w, int n, int k, const float* bias, void* out, int terms, int out_kind,
-             bool gelu) {
+             int gelu) {
   GemmArgs g{};
   const int planes = terms == 3 ? 2 : 1;
   int rc = make_tm(h, &g.tm_a, a, 1, a_plane_rows * (planes - 1) + m_rows, k, 64, 128);
   if (rc) return rc;
-  rc = make_tm(h, &g.tm_b, w, 1, static_cast<long long>(n) * planes, k, 64, 256);
+  rc = make_tm(h, &g.tm_b, w, 1, static_cast<long long>(n) * planes, k, 64, 128);  // half tile per CTA
   if (rc) return rc;
   if (out_kind == GEMM_OUT_F32)
     rc = make_tm(h, &g.tm_out, out, 0, m_rows, n, 32, 32);
@@ -170,26 +171,43 @@ int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_rows, lo
   return STLT_OK;
 }
 
-struct WorkspacePlan {
-  long long m_sp, m_tm;  // padded token counts
-  size_t off_err, off_x, off_y, off_xb, off_att, off_qkv, off_h, off_head, total;
+// Activation buffers of one phase of the forward (rows padded to the 128-row GEMM tile).
+struct BufSet {
+  size_t x, y, xb, att, qkv, hid;  // byte offsets into the workspace
+  long long m_pad;
 };
+
+struct WorkspacePlan {
+  BufSet sp;  // spatial phase : B*L*S object tokens
+  BufSet tm;  // temporal phase: B*L frame tokens (also the CLS-only tail of the last spatial layer)
+  BufSet hd;  // B extract-frame tokens (tail of the last temporal layer)
+  size_t off_err, off_head, total;
+};
+
+size_t plan_bufset(BufSet* b, size_t off, long long rows, int precision, bool with_qkv) {
+  const size_t planes = precision == STLT_PRECISION_FP32 ? 2 : 1;
+  const size_t m = static_cast<size_t>(pad128(rows));
+  b->m_pad = static_cast<long long>(m);
+  b->x = off;    off += align1k(m * kHidden * 4);
+  b->y = off;    off += align1k(m * kHidden * 4);
+  b->xb = off;   off += align1k(m * kHidden * 2 * planes);
+  b->att = off;  off += align1k(m * kHidden * 2 * planes);
+  b->qkv = off;
+  if (with_qkv) off += align1k(m * kQkv * (precision == STLT_PRECISION_FP32 ? 4 : 2));
+  b->hid = off;  off += align1k(m * kFfn * 2 * planes);
+  return off;
+}
 
 WorkspacePlan plan_workspace(int B, int L, int S, int precision) {
   WorkspacePlan p{};
-  const int planes = precision == STLT_PRECISION_FP32 ? 2 : 1;
-  p.m_sp = pad128(static_cast<long long>(B) * L * S);
-  p.m_tm = pad128(static_cast<long long>(B) * L);
-  const size_t m = static_cast<size_t>(p.m_sp);
   size_t off = 0;
-  p.off_err = off;  off += 1024;
-  p.off_x = off;    off += align1k(m * kHidden * 4);
-  p.off_y = off;    off += align1k(m * kHidden * 4);
-  p.off_xb = off;   off += align1k(m * kHidden * 2 * planes);
-  p.off_att = off;  off += align1k(m * kHidden * 2 * planes);
-  p.off_qkv = off;  off += align1k(m * kQkv * (precision == STLT_PRECISION_FP32 ? 4 : 2));
-  p.off_h = off;    off += align1k(m * kFfn * 2 * planes);
-  p.off_head = off; off += align1k(static_cast<size_t>(B) * kHidden * 4 * 3);
+  p.off_err = off;
+  off += 1024;
+  off = plan_bufset(&p.sp, off, static_cast<long long>(B) * L * S, precision, true);
+  off = plan_bufset(&p.tm, off, static_cast<long long>(B) * L, precision, true);
+  off = plan_bufset(&p.hd, off, B, precision, false);
+  p.off_head = off;
+  off += align1k(static_cast<size_t>(B) * kHidden * 4 * 3);
   p.total = off;
   return p;
 }
@@ -205,28 +223,47 @@ struct Phase {
   long long m_valid;     // real tokens
 };
 
-// One post-norm nn.TransformerEncoderLayer (eval mode): MHA -> +res -> LN -> FFN -> +res -> LN.
-int run_layer(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw, const Phase& ph,
-              const long long* mask_src, long long num_seqs, int T, bool causal) {
+Phase make_phase(uint8_t* ws, const BufSet& b, long long m_valid) {
+  Phase ph{};
+  ph.x = reinterpret_cast<float*>(ws + b.x);
+  ph.y = reinterpret_cast<float*>(ws + b.y);
+  ph.xb = reinterpret_cast<__nv_bfloat16*>(ws + b.xb);
+  ph.att = reinterpret_cast<__nv_bfloat16*>(ws + b.att);
+  ph.qkv = ws + b.qkv;
+  ph.hid = reinterpret_cast<__nv_bfloat16*>(ws + b.hid);
+  ph.m_pad = b.m_pad;
+  ph.m_valid = m_valid;
+  return ph;
+}
+
+// First half of a post-norm nn.TransformerEncoderLayer (eval mode): in-projection + attention.
+// Needs every token of the sequences (keys / values), so it always runs on the full phase.
+int run_attention_part(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw,
+                       const Phase& ph, const long long* mask_src, long long num_seqs, int T,
+                       bool causal) {
   const bool fp32 = precision == STLT_PRECISION_FP32;
-  const int terms = fp32 ? 3 : 1;
-  const int planes = fp32 ? 2 : 1;
-  const float eps = h->dims.encoder_norm_eps;
-  int rc;
-  // QKV projection
-  rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv, terms,
-                fp32 ? GEMM_OUT_F32 : GEMM_OUT_BF16, false);
+  int rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv,
+                    fp32 ? 3 : 1, fp32 ? GEMM_OUT_F32 : GEMM_OUT_BF16, 0);
   if (rc) return rc;
-  // attention
-  ActOut att{nullptr, ph.att, planes, ph.m_pad};
+  ActOut att{nullptr, ph.att, fp32 ? 2 : 1, ph.m_pad};
   {
     ProfileScope prof(h, stream, STLT_PROF_ATTENTION);
     STLT_CUDA(h, launch_attention(ph.qkv, !fp32, mask_src, num_seqs, T, causal, att, stream));
   }
   h->launches++;
-  // output projection, residual, LayerNorm
-  rc = run_gemm(h, stream, ph.att, ph.m_pad, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.y,
-                terms, GEMM_OUT_F32, false);
+  return STLT_OK;
+}
+
+// Second half: out-projection -> +residual -> LN -> FFN -> +residual -> LN. Row-wise, so it may
+// run on a compacted subset of the rows (the pruned last layer of each stack).
+int run_tail_part(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw,
+                  const Phase& ph) {
+  const bool fp32 = precision == STLT_PRECISION_FP32;
+  const int terms = fp32 ? 3 : 1;
+  const int planes = fp32 ? 2 : 1;
+  const float eps = h->dims.encoder_norm_eps;
+  int rc = run_gemm(h, stream, ph.att, ph.m_pad, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.y,
+                    terms, GEMM_OUT_F32, 0);
   if (rc) return rc;
   ActOut xo{ph.x, ph.xb, planes, ph.m_pad};
   {
@@ -234,12 +271,11 @@ int run_layer(Handle* h, cudaStream_t stream, int precision, const LayerWeights&
     STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
   }
   h->launches++;
-  // feed-forward
   rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.l1_p, kFfn, kHidden, lw.l1_b, ph.hid, terms,
-                fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, true);
+                fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, fp32 ? 1 : 2);
   if (rc) return rc;
   rc = run_gemm(h, stream, ph.hid, ph.m_pad, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.y, terms,
-                GEMM_OUT_F32, false);
+                GEMM_OUT_F32, 0);
   if (rc) return rc;
   {
     ProfileScope prof(h, stream, STLT_PROF_ADD_LN);
@@ -486,7 +522,7 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   const WorkspacePlan p = plan_workspace(B, L, S, precision);
   if (workspace_bytes < p.total)
     return fail(h, STLT_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, p.total);
-  if (p.m_sp > 0x7fffffffLL / 2) return fail(h, STLT_ERR_INVALID, "batch too large for one call");
+  if (p.sp.m_pad > 0x7fffffffLL / 2) return fail(h, STLT_ERR_INVALID, "batch too large for one call");
 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long* categories = reinterpret_cast<const long long*>(categories_);
@@ -506,15 +542,14 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   }
 
   // ---- spatial phase: B*L sequences of S object tokens (models.py:57-81) ----
-  Phase sp{};
-  sp.x = reinterpret_cast<float*>(ws + p.off_x);
-  sp.y = reinterpret_cast<float*>(ws + p.off_y);
-  sp.xb = reinterpret_cast<__nv_bfloat16*>(ws + p.off_xb);
-  sp.att = reinterpret_cast<__nv_bfloat16*>(ws + p.off_att);
-  sp.qkv = ws + p.off_qkv;
-  sp.hid = reinterpret_cast<__nv_bfloat16*>(ws + p.off_h);
-  sp.m_pad = p.m_sp;
-  sp.m_valid = n_sp;
+  const Phase sp = make_phase(ws, p.sp, n_sp);
+  const Phase tm = make_phase(ws, p.tm, n_tm);
+  const Phase hd = make_phase(ws, p.hd, B);
+  // Only slot 0 of the spatial output (models.py:79) and only frame lengths-1 of the temporal output
+  // (models.py:192) are ever read, so the row-wise tail of the LAST layer of each stack runs on
+  // those rows only. Taps that expose the full stack output switch the pruning off.
+  const bool prune_sp = h->pruning && h->taps.spatial == nullptr && d.num_spatial_layers > 0;
+  const bool prune_tm = h->pruning && h->taps.temporal == nullptr && d.num_temporal_layers > 0;
 
   ActOut emb{sp.x, sp.xb, planes, sp.m_pad};
   {
@@ -527,51 +562,74 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   if (h->taps.embed)
     STLT_CUDA(h, cudaMemcpyAsync(h->taps.embed, sp.x, n_sp * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
 
+  bool cls_compact = false;  // spatial CLS rows already compacted into tm.x
   for (int i = 0; i < d.num_spatial_layers; ++i) {
-    int rc = run_layer(h, stream, precision, h->w.spatial[i], sp, categories, n_tm, S, false);
+    const LayerWeights& lw = h->w.spatial[i];
+    int rc = run_attention_part(h, stream, precision, lw, sp, categories, n_tm, S, false);
+    if (rc) return rc;
+    if (prune_sp && i == d.num_spatial_layers - 1) {
+      {
+        ProfileScope prof(h, stream, STLT_PROF_OTHER);
+        STLT_CUDA(h, launch_gather_rows(sp.x, sp.att, planes, sp.m_pad, S, nullptr, 0, n_tm, tm.x, tm.att,
+                                        tm.m_pad, err_flag, stream));
+      }
+      h->launches++;
+      rc = run_tail_part(h, stream, precision, lw, tm);
+      cls_compact = true;
+    } else {
+      rc = run_tail_part(h, stream, precision, lw, sp);
+    }
     if (rc) return rc;
   }
   if (h->taps.spatial)
     STLT_CUDA(h, cudaMemcpyAsync(h->taps.spatial, sp.x, n_sp * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
 
   // ---- temporal phase: B sequences of L frame tokens (models.py:98-111,136-152) ----
-  // The frame tokens are written into the (now free) y / att buffers; the roles of the two
-  // buffer pairs swap so nothing is copied.
-  Phase tp{};
-  tp.x = sp.y;
-  tp.y = sp.x;
-  tp.xb = sp.att;
-  tp.att = sp.xb;
-  tp.qkv = sp.qkv;
-  tp.hid = sp.hid;
-  tp.m_pad = p.m_tm;
-  tp.m_valid = n_tm;
-  ActOut fr{tp.x, tp.xb, planes, tp.m_pad};
+  ActOut fr{tm.x, tm.xb, planes, tm.m_pad};
   {
     ProfileScope prof(h, stream, STLT_PROF_OTHER);
-    STLT_CUDA(h, launch_frame_embed(sp.x, S, frame_types, h->w.pos_table, h->w.ft_table,
-                                    d.num_frame_types, h->w.fr_g, h->w.fr_b, d.layer_norm_eps, B, L,
-                                    fr, err_flag, stream));
+    // in-place when the CLS rows were compacted (row f -> row f, one warp per row)
+    STLT_CUDA(h, launch_frame_embed(cls_compact ? tm.x : sp.x, cls_compact ? 1 : S, frame_types,
+                                    h->w.pos_table, h->w.ft_table, d.num_frame_types, h->w.fr_g,
+                                    h->w.fr_b, d.layer_norm_eps, B, L, fr, err_flag, stream));
   }
   h->launches++;
   if (h->taps.frames)
-    STLT_CUDA(h, cudaMemcpyAsync(h->taps.frames, tp.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
+    STLT_CUDA(h, cudaMemcpyAsync(h->taps.frames, tm.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
 
-  for (int i = 0; i < d.num_temporal_layers; ++i) {
-    int rc = run_layer(h, stream, precision, h->w.temporal[i], tp, frame_types, B, L, true);
-    if (rc) return rc;
-  }
-  if (h->taps.temporal)
-    STLT_CUDA(h, cudaMemcpyAsync(h->taps.temporal, tp.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
-
-  // ---- head (models.py:155-163,189-193) ----
   float* pooled = reinterpret_cast<float*>(ws + p.off_head);
   float* h1 = pooled + static_cast<size_t>(B) * kHidden;
   float* h2 = h1 + static_cast<size_t>(B) * kHidden;
+  bool pooled_done = false;
+  for (int i = 0; i < d.num_temporal_layers; ++i) {
+    const LayerWeights& lw = h->w.temporal[i];
+    int rc = run_attention_part(h, stream, precision, lw, tm, frame_types, B, L, true);
+    if (rc) return rc;
+    if (prune_tm && i == d.num_temporal_layers - 1) {
+      {
+        ProfileScope prof(h, stream, STLT_PROF_OTHER);
+        STLT_CUDA(h, launch_gather_rows(tm.x, tm.att, planes, tm.m_pad, 0, lengths, L, B, hd.x, hd.att,
+                                        hd.m_pad, err_flag, stream));
+      }
+      h->launches++;
+      rc = run_tail_part(h, stream, precision, lw, hd);
+      pooled = hd.x;
+      pooled_done = true;
+    } else {
+      rc = run_tail_part(h, stream, precision, lw, tm);
+    }
+    if (rc) return rc;
+  }
+  if (h->taps.temporal)
+    STLT_CUDA(h, cudaMemcpyAsync(h->taps.temporal, tm.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
+
+  // ---- head (models.py:155-163,189-193) ----
   {
     ProfileScope prof(h, stream, STLT_PROF_OTHER);
-    STLT_CUDA(h, launch_gather_last(tp.x, lengths, B, L, pooled, err_flag, stream));
-    h->launches++;
+    if (!pooled_done) {
+      STLT_CUDA(h, launch_gather_last(tm.x, lengths, B, L, pooled, err_flag, stream));
+      h->launches++;
+    }
     if (h->taps.pooled)
       STLT_CUDA(h, cudaMemcpyAsync(h->taps.pooled, pooled, static_cast<size_t>(B) * kHidden * 4,
                                    cudaMemcpyDeviceToDevice, stream));
@@ -583,6 +641,13 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     STLT_CUDA(h, launch_gemm_simt(h2, h->w.fc2_w, h->w.fc2_b, logits, B, d.num_classes, kHidden, false, stream));
     h->launches++;
   }
+  return STLT_OK;
+}
+
+int stlt_set_pruning(void* handle, int32_t enable) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  h->pruning = enable != 0;
   return STLT_OK;
 }
 
@@ -651,7 +716,7 @@ int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w
   if (terms != 1 && terms != 3) return fail(h, STLT_ERR_INVALID, "terms must be 1 or 3");
   if (m_rows % 128 || n % 256 || k % 64) return fail(h, STLT_ERR_INVALID, "shape not tile aligned");
   return run_gemm(h, static_cast<cudaStream_t>(stream), a_planes, m_rows, m_rows, w_planes, n, k, bias,
-                  out, terms, out_kind, gelu != 0);
+                  out, terms, out_kind, gelu);
 }
 
 int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w, const float* bias,

@@ -181,6 +181,7 @@ class Stlt(nn.Module):
         self._packed_key = {}   # precision -> weights key the buffer was packed from
         self._workspace = None
         self._keepalive = None
+        self._pruning = True
 
     # -- nn.Module protocol ------------------------------------------------------------------
     def train(self, mode: bool = True):  # reference models.py:180-183
@@ -219,6 +220,7 @@ class Stlt(nn.Module):
         _lib.check(None, rc)
         self._handle = handle
         self._handle_device = device
+        _lib.check(handle, lib.stlt_set_pruning(handle, int(self._pruning)))
         self._weights_key = None
         self._packed.clear()
         self._packed_key.clear()
@@ -365,6 +367,12 @@ class Stlt(nn.Module):
         lib = _lib.load_library()
         stream = torch.cuda.current_stream(self._workspace.device).cuda_stream
         _lib.check(self._handle, lib.stlt_check_errors(self._handle, stream, self._workspace.data_ptr()))
+
+    def set_pruning(self, enable: bool) -> None:
+        """Last-layer row pruning (default on; logits are bit-identical either way)."""
+        self._pruning = bool(enable)
+        if self._handle is not None:
+            _lib.check(self._handle, _lib.load_library().stlt_set_pruning(self._handle, int(self._pruning)))
 
     def set_profiling(self, enable: bool) -> None:
         """Per-category CUDA-event timing of the kernels launched by forward (bench / profiles)."""

@@ -153,6 +153,26 @@ def test_forward_default_init_clone_layers():
     assert nerr(got, want) < FP32_TOL
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_last_layer_pruning_is_bit_identical(precision):
+    """Only slot 0 / frame lengths-1 of the stack outputs are read; running the
+    row-wise tail of the last layers on those rows only must not change a single bit."""
+    cfg = StltModelConfig(num_classes=157, unique_categories=38)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=61)
+    m = _model(cfg, sd, precision)
+    batch = to_cuda(make_batch(37, "action_genome", ragged=True, seed=62))
+    with torch.no_grad():
+        pruned = m(batch)["stlt"].clone()
+        n_pruned = m.last_launch_count()
+        m.set_pruning(False)
+        full = m(batch)["stlt"].clone()
+        n_full = m.last_launch_count()
+        m.set_pruning(True)
+    assert torch.equal(pruned, full)
+    assert n_pruned == n_full + 1  # two gathers replace the final gather_last
+
+
 def test_weight_update_is_picked_up():
     cfg = StltModelConfig(num_classes=174, unique_categories=4)
     torch.manual_seed(0)

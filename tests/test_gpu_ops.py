@@ -45,6 +45,7 @@ GEMM_CASES = [
     (256, 2304, 768, 1, L.GEMM_OUT_BF16, 0),
     (384, 768, 768, 1, L.GEMM_OUT_F32, 0),
     (256, 3072, 768, 1, L.GEMM_OUT_BF16, 1),
+    (256, 3072, 768, 1, L.GEMM_OUT_BF16, 2),   # fast single-branch erf GELU (bf16 mode)
     (256, 768, 3072, 1, L.GEMM_OUT_F32, 0),
     (256, 2304, 768, 3, L.GEMM_OUT_F32, 0),
     (256, 3072, 768, 3, L.GEMM_OUT_BF16_SPLIT, 1),
