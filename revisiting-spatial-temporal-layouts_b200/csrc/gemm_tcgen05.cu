@@ -16,13 +16,20 @@
 //                 Planes are stacked along the row axis of the same tensor map: plane p of A starts
 //                 at row p * a_plane_rows, plane p of W at row p * b_plane_rows.
 //
-// CTAs run in clusters of 2 that work on two vertically adjacent 128-row tiles of the same 256-wide
-// column block: each CTA loads its own A tile and HALF of the shared W tile, multicasting that half
-// into both CTAs' shared memory, which cuts the L2 -> SM traffic per k-block from 48 KB to 32 KB per
-// CTA (the 1-CTA version of this kernel measured L2-bandwidth-bound, profiles/).
+// CTAs run as pairs (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x 256 output tile
+// with ONE M=256 MMA stream issued by the leader CTA. Each CTA stages its own 128 A rows and HALF
+// (128 rows) of the W tile, so a k-block costs 32 KB of L2->SM traffic and shared-memory fill per CTA
+// instead of 48 KB, the tensor core reads each W half from shared memory once for both SMs, and the
+// smaller stage buys a 6-deep pipeline. (The 1-CTA version measured 71 % tensor-pipe utilisation,
+// paced by shared-memory bandwidth: 96 B/clk of operand reads + 96 B/clk of TMA fill per SM.)
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warp 3 = idle, warps 4..11 = epilogue (warp w reads TMEM lane quarter w % 4, column half (w-4)/4).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only), warp 2 =
+// TMEM allocator, warp 3 = idle, warps 4..11 = epilogue (warp w reads TMEM lane quarter w % 4, column
+// half (w-4)/4 of this CTA's 128 x 256 accumulator).
+//
+// Barriers: full[s] lives in the leader (both CTAs' TMA loads signal it); empty[s] and tmem_full[a]
+// exist in both CTAs and are signalled by the leader's multicast tcgen05.commit; tmem_empty[a] lives
+// in the leader and collects the epilogue warps of both CTAs.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -34,20 +41,20 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int kABytes = BM * BK * 2;  // 16 KiB
-constexpr int kBBytes = BN * BK * 2;  // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kBHalfBytes = (BN / 2) * BK * 2;  // 16 KiB: this CTA's half of the W tile
+constexpr int kStageBytes = kABytes + kBHalfBytes;  // per CTA
 constexpr int kEpiWarps = 8;
 constexpr int kEpiBufBytes = 32 * 128;  // 32 rows x 128 B staging tile for one TMA store
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kCluster = 2;
 constexpr uint16_t kClusterMask = (1u << kCluster) - 1;
 
 // The split epilogue needs two staging tiles per warp (hi and lo plane), paid for with one stage.
 template <int kOut>
 struct Cfg {
-  static constexpr int kStages = (kOut == GEMM_OUT_BF16_SPLIT) ? 3 : 4;
+  static constexpr int kStages = (kOut == GEMM_OUT_BF16_SPLIT) ? 5 : 6;
   static constexpr int kBufsPerWarp = (kOut == GEMM_OUT_BF16_SPLIT) ? 2 : 1;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kEpiWarps * kBufsPerWarp * kEpiBufBytes + 256 /*barriers*/;
@@ -100,18 +107,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&bars->full[i], 1);
-      mbar_init(&bars->empty[i], kCluster);  // freed by the MMA warps of BOTH CTAs (multicast)
+      mbar_init(&bars->full[i], 1);   // used in the leader: its producer arms the bytes of both CTAs
+      mbar_init(&bars->empty[i], 1);  // leader's tcgen05.commit, multicast to both CTAs
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], kEpiWarps);
+      mbar_init(&bars->tmem_full[i], 1);                     // leader's commit, multicast
+      mbar_init(&bars->tmem_empty[i], kCluster * kEpiWarps);  // used in the leader: both epilogues
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&bars->tmem_base, kTmemCols);
-    tmem_relinquish();
+    tmem_alloc_pair(&bars->tmem_base, kTmemCols);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
   __syncthreads();
@@ -134,13 +141,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           const int a_row = (term == 1 ? a_plane_rows : 0) + m_blk * BM;
           const int b_row = (term == 2 ? b_plane_rows : 0) + n_blk * BN;
           mbar_wait(&bars->empty[stage], phase ^ 1u);
-          mbar_expect_tx(&bars->full[stage], kStageBytes);
+          if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], kCluster * kStageBytes);
           uint8_t* sa = smem_ab + stage * kStageBytes;
-          tma_load_2d(&tm_a, &bars->full[stage], sa, kk * BK, a_row);
-          // this CTA's half of the W tile goes to both CTAs of the cluster
-          tma_load_2d_multicast(&tm_b, &bars->full[stage],
-                                sa + kABytes + cta_rank * (kBBytes / kCluster), kk * BK,
-                                b_row + cta_rank * (BN / kCluster), kClusterMask);
+          const uint32_t full_leader = mapa_u32(&bars->full[stage], 0);
+          tma_load_2d_pair(&tm_a, full_leader, sa, kk * BK, a_row);
+          // this CTA's half (128 rows) of the 256-row W tile
+          tma_load_2d_pair(&tm_b, full_leader, sa + kABytes, kk * BK, b_row + cta_rank * (BN / kCluster));
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -150,8 +156,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kCluster * BM, BN);  // M = 256 across the pair
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -170,17 +176,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
-            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          // frees this smem stage in BOTH CTAs once these MMAs have read it (the peer multicasts
-          // its W half into our copy of the stage, so it must see our release too)
-          umma_commit_multicast(&bars->empty[stage], kClusterMask);
+          // frees this smem stage in BOTH CTAs once these MMAs have read it
+          umma_commit_pair(&bars->empty[stage], kClusterMask);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+        umma_commit_pair(&bars->tmem_full[acc], kClusterMask);  // accumulators complete -> epilogues
       }
     }
   } else if (warp >= 4) {
@@ -286,7 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       // all TMEM reads of this accumulator have completed (tmem_ld_wait above) -> release it
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&bars->tmem_empty[acc], 0));
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -296,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   cluster_sync_all();  // no CTA exits while its peer may still signal its barriers / write its smem
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 
