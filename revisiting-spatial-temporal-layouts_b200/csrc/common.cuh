@@ -34,7 +34,8 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   q = fmaf(q, a, 5.256125276e-02f);
   q = fmaf(q, a, 4.592546886e-01f);
   q = fmaf(q, a, 1.151091390e+00f);
-  const float e = exp2f(-q * a);          // erfc(|x|/sqrt(2))
+  float e;                                // erfc(|x|/sqrt(2)) = 2^(-q*a)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q * a));
   const float h = fmaf(-ax, e, ax);       // |x| * erf(|x|/sqrt(2))
   return 0.5f * (x + h);                  // 0.5*x*(1 + erf(x/sqrt(2)))
 }
@@ -270,8 +271,9 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr)
-               : "memory");
+  // default (.release at CTA scope): the only ordering needed is against this warp's tcgen05.ld,
+  // which tcgen05.fence::before_thread_sync provides. A cluster-scope release costs a MEMBAR.ALL.GPU.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
