@@ -109,6 +109,45 @@ int stlt_prepare(void* handle, void* stream, const double* raw_boxes, const int6
                  int32_t frames, int32_t slots, float* boxes_out, uint8_t* mask_boxes_out,
                  uint8_t* mask_frames_out);
 
+/* A dataset's layouts in CSR form on the device (the reference keeps them as nested JSON lists,
+ * src/modelling/datasets.py:35-37; schema written by src/create_something_datasets.py:18-34). */
+typedef struct StltLayoutStore {
+  const int64_t* video_frame_offsets;  /* [V + 1] frame range of every video */
+  const int64_t* frame_object_offsets; /* [F + 1] object range of every frame */
+  const double* obj_boxes;             /* [O, 4] raw pixel (x1, y1, x2, y2) */
+  const int64_t* obj_categories;       /* [O] category ids (category2id applied, configs.py:30-78) */
+  const double* obj_scores;            /* [O] detector scores */
+  const int64_t* video_sizes;          /* [V, 2] (width, height) */
+} StltLayoutStore;
+
+/* Category / frame-type ids of the dataset (configs.py:30-88). */
+typedef struct StltLayoutIds {
+  int64_t cls, ft_pad, ft_regular, ft_empty, ft_extract;
+} StltLayoutIds;
+
+/* §8(f) rank 3 — replaces StltDataset.__getitem__ (datasets.py:52-125) + StltCollater.__call__
+ * (datasets.py:243-288) for a batch of `batch` videos `video_index[b]` of the store: frame sampling
+ * (test-time get_test_layout_indices, data_utils.py:47-56, unless explicit `frame_indices` i64
+ * [batch, layout_num_frames] + `num_sampled` i64 [batch] are given), score filter, CLS slot, fix_box +
+ * normalisation, extract frame, object / frame padding and both masks, in one kernel.
+ * `frames` must be max_b(min(n_frames_b, layout_num_frames)) + 1 (what pad_sequence produces),
+ * `slots` = max_num_objects + 1. Outputs as the reference collater: categories i64 [B,L,S], boxes f32
+ * [B,L,S,4], scores f32 [B,L,S] (or NULL), frame_types i64 [B,L], lengths i64 [B], masks u8.
+ * `status_out` (device int32) receives 0, or 4/5/6 for inconsistent frames / indices / slots. */
+int stlt_build_batch(void* handle, void* stream, const StltLayoutStore* store, const StltLayoutIds* ids,
+                     const int64_t* video_index, const int64_t* frame_indices_or_null,
+                     const int64_t* num_sampled_or_null, int32_t batch, int32_t layout_num_frames,
+                     int32_t frames, int32_t slots, double score_threshold, int64_t* categories_out,
+                     float* boxes_out, float* scores_out_or_null, int64_t* frame_types_out,
+                     int64_t* lengths_out, uint8_t* mask_boxes_out, uint8_t* mask_frames_out,
+                     int32_t* status_out);
+
+/* §8(f) rank 4 — replaces the per-batch `.cpu()` bookkeeping of EvaluatorSomething.process
+ * (src/utils/evaluation.py:21-34): adds the number of top-1 and top-5 hits of logits f32 [rows,
+ * classes] against labels i64 [rows] to counters[0] / counters[1] (device uint64[2]), no sync. */
+int stlt_topk_count(void* handle, void* stream, const float* logits, const int64_t* labels, int32_t rows,
+                    int32_t classes, uint64_t* counters);
+
 /* Replaces Stlt.forward (models.py:185-195) in eval mode.
  *   categories i64 [B, L, S]; boxes f32 [B, L, S, 4]; scores f32 [B, L, S] or NULL (presence
  *   toggles the score embedding, models.py:33-35); frame_types i64 [B, L]; lengths i64 [B].

@@ -84,6 +84,8 @@ __device__ __forceinline__ void store_act(const ActOut& out, long long row, cons
   }
 }
 
+__device__ __forceinline__ float4 fix_and_normalize_box(const double* rb, long long W, long long H);
+
 // ------------------------------------------------------------------------------------------------
 // K0: fix_box (src/utils/data_utils.py:205-231) + division by the video size
 // (src/modelling/datasets.py:54,82) + the two padding masks (src/modelling/datasets.py:274-286).
@@ -111,35 +113,164 @@ __global__ void prepare_kernel(const double* __restrict__ raw_boxes,
   } else if (cat == 0) {
     out = make_float4(0.f, 0.f, 0.f, 0.f);  // padded object slot (datasets.py:91)
   } else {
-    const long long W = video_sizes[2 * b + 0];
-    const long long H = video_sizes[2 * b + 1];
-    const double* rb = raw_boxes + idx * 4;
-    long long x1 = static_cast<long long>(rb[0]);  // int(): truncation toward zero
-    long long y1 = static_cast<long long>(rb[1]);
-    long long x2 = static_cast<long long>(rb[2]);
-    long long y2 = static_cast<long long>(rb[3]);
-    x1 = x1 < 0 ? 0 : x1;
-    y1 = y1 < 0 ? 0 : y1;
-    x2 = x2 < 0 ? 0 : x2;
-    y2 = y2 < 0 ? 0 : y2;
-    if (x1 > x2) { const long long t = x1; x1 = x2; x2 = t; }
-    if (y1 > y2) { const long long t = y1; y1 = y2; y2 = t; }
-    if (x1 >= W) x1 = W - 1;
-    if (y1 >= H) y1 = H - 1;
-    if (x2 >= W) x2 = W - 1;
-    if (y2 >= H) y2 = H - 1;
-    if (x1 == x2 && x1 == 0) x2 = 1;
-    if (y1 == y2 && y1 == 0) y2 = 1;
-    if (x1 == x2) x1 -= 1;
-    if (y1 == y2) y1 -= 1;
-    // torch int64 / int64 true-divide: both operands rounded to fp32, IEEE divide.
-    const float fw = __ll2float_rn(W), fh = __ll2float_rn(H);
-    out.x = __fdiv_rn(__ll2float_rn(x1), fw);
-    out.y = __fdiv_rn(__ll2float_rn(y1), fh);
-    out.z = __fdiv_rn(__ll2float_rn(x2), fw);
-    out.w = __fdiv_rn(__ll2float_rn(y2), fh);
+    out = fix_and_normalize_box(raw_boxes + idx * 4, video_sizes[2 * b + 0], video_sizes[2 * b + 1]);
   }
   boxes_out[idx] = out;
+}
+
+__device__ __forceinline__ float4 fix_and_normalize_box(const double* rb, long long W, long long H) {
+  // fix_box (src/utils/data_utils.py:205-231) then int64 / int64 true-divide (datasets.py:82)
+  long long x1 = static_cast<long long>(rb[0]);  // int(): truncation toward zero
+  long long y1 = static_cast<long long>(rb[1]);
+  long long x2 = static_cast<long long>(rb[2]);
+  long long y2 = static_cast<long long>(rb[3]);
+  x1 = x1 < 0 ? 0 : x1;
+  y1 = y1 < 0 ? 0 : y1;
+  x2 = x2 < 0 ? 0 : x2;
+  y2 = y2 < 0 ? 0 : y2;
+  if (x1 > x2) { const long long t = x1; x1 = x2; x2 = t; }
+  if (y1 > y2) { const long long t = y1; y1 = y2; y2 = t; }
+  if (x1 >= W) x1 = W - 1;
+  if (y1 >= H) y1 = H - 1;
+  if (x2 >= W) x2 = W - 1;
+  if (y2 >= H) y2 = H - 1;
+  if (x1 == x2 && x1 == 0) x2 = 1;
+  if (y1 == y2 && y1 == 0) y2 = 1;
+  if (x1 == x2) x1 -= 1;
+  if (y1 == y2) y1 -= 1;
+  const float fw = __ll2float_rn(W), fh = __ll2float_rn(H);
+  float4 out;
+  out.x = __fdiv_rn(__ll2float_rn(x1), fw);
+  out.y = __fdiv_rn(__ll2float_rn(y1), fh);
+  out.z = __fdiv_rn(__ll2float_rn(x2), fw);
+  out.w = __fdiv_rn(__ll2float_rn(y2), fh);
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batch builder: StltDataset.__getitem__ (src/modelling/datasets.py:52-125) + StltCollater.__call__
+// (:243-288) for B videos of a CSR layout store, one thread per output slot (b, l, s):
+//   frames [0, n_b)   : sampled frames; slot 0 = CLS object, slot s >= 1 = the (s-1)-th object with
+//                       score >= threshold (order preserved), fix_box + normalisation; rest padding
+//   frame n_b         : the "extract" frame (CLS only)
+//   frames (n_b, L)   : collater padding (categories [cls, 0..], slot-0 box [0,0,1,1], type 0)
+// Test-time frame sampling (get_test_layout_indices, src/utils/data_utils.py:47-56) is evaluated
+// here when no explicit indices are given: int(tick / 2 + tick * x), tick = n / T, in fp64.
+// ------------------------------------------------------------------------------------------------
+__global__ void build_batch_kernel(BatchStore st, const long long* __restrict__ video_index,
+                                   const long long* __restrict__ frame_indices,
+                                   const long long* __restrict__ num_sampled, int T, int L, int S,
+                                   double score_threshold, BatchIds ids, long long total,
+                                   long long* __restrict__ categories, float4* __restrict__ boxes,
+                                   float* __restrict__ scores, long long* __restrict__ frame_types,
+                                   long long* __restrict__ lengths, uint8_t* __restrict__ mask_boxes,
+                                   uint8_t* __restrict__ mask_frames, int* __restrict__ err_flag) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int s = static_cast<int>(idx % S);
+  const long long frame_slot = idx / S;
+  const int l = static_cast<int>(frame_slot % L);
+  const long long b = frame_slot / L;
+  const long long vid = video_index[b];
+  const long long f0 = st.video_frame_offsets[vid];
+  const long long n_frames = st.video_frame_offsets[vid + 1] - f0;
+  long long n_s;  // sampled frames of this video
+  if (num_sampled != nullptr) n_s = num_sampled[b];
+  else n_s = n_frames > T ? T : n_frames;
+  if (n_s > L - 1) {
+    if (s == 0 && l == 0) atomicExch(err_flag, 4);
+    n_s = L - 1;
+  }
+
+  long long cat = 0, ftype = 0;
+  float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+  float score = 0.f;
+  if (s == 0) {  // CLS object / extract / collater padding all carry the same slot-0 payload
+    cat = ids.cls;
+    box = make_float4(0.f, 0.f, 1.f, 1.f);
+    score = 1.f;
+  }
+  if (l < n_s) {
+    long long fi;
+    if (frame_indices != nullptr) {
+      fi = frame_indices[b * T + l];
+    } else if (n_frames > T) {
+      const double tick = static_cast<double>(n_frames) * 1.0 / static_cast<double>(T);
+      fi = static_cast<long long>(tick / 2.0 + tick * static_cast<double>(l));
+    } else {
+      fi = l;
+    }
+    if (fi < 0 || fi >= n_frames) {
+      if (s == 0) atomicExch(err_flag, 5);
+      fi = 0;
+    }
+    const long long o0 = st.frame_object_offsets[f0 + fi];
+    const long long o1 = st.frame_object_offsets[f0 + fi + 1];
+    ftype = (o1 == o0) ? ids.ft_empty : ids.ft_regular;  // decided before the score filter (:65-69)
+    if (s > 0) {
+      int seen = 0;
+      for (long long o = o0; o < o1; ++o) {
+        if (st.obj_scores[o] < score_threshold) continue;  // :75
+        if (++seen == s) {
+          const long long W = st.video_sizes[2 * vid], H = st.video_sizes[2 * vid + 1];
+          box = fix_and_normalize_box(st.obj_boxes + o * 4, W, H);
+          cat = st.obj_categories[o];
+          score = __double2float_rn(st.obj_scores[o]);
+          break;
+        }
+      }
+    } else {
+      // more kept objects than slots cannot happen when S-1 is the dataset maximum (:38-47)
+      int kept = 0;
+      for (long long o = o0; o < o1; ++o) kept += st.obj_scores[o] >= score_threshold ? 1 : 0;
+      if (kept > S - 1) atomicExch(err_flag, 6);
+    }
+  } else if (l == n_s) {
+    ftype = ids.ft_extract;
+  } else {
+    ftype = ids.ft_pad;
+  }
+  categories[idx] = cat;
+  boxes[idx] = box;
+  if (scores != nullptr) scores[idx] = score;
+  mask_boxes[idx] = cat == 0 ? 1 : 0;
+  if (s == 0) {
+    frame_types[frame_slot] = ftype;
+    mask_frames[frame_slot] = ftype == ids.ft_pad ? 1 : 0;
+    if (l == 0) lengths[b] = n_s + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Evaluators (src/utils/evaluation.py:21-34): top-1 / top-5 hit counters, one warp per row.
+// argmax / topk semantics: the label is a top-k hit when fewer than k logits rank before it
+// (greater, or equal with a smaller index).
+// ------------------------------------------------------------------------------------------------
+__global__ void topk_count_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                  int rows, int classes, unsigned long long* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long top1 = 0, top5 = 0;
+  for (int r = warp0; r < rows; r += nwarps) {
+    const long long lab = labels[r];
+    if (lab < 0 || lab >= classes) continue;
+    const float* row = logits + static_cast<long long>(r) * classes;
+    const float ref = row[lab];
+    int before = 0;
+    for (int c = lane; c < classes; c += 32) {
+      const float v = row[c];
+      before += (v > ref || (v == ref && c < lab)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    top1 += before == 0 ? 1 : 0;
+    top5 += before < 5 ? 1 : 0;
+  }
+  if (lane == 0 && (top1 | top5)) {
+    atomicAdd(counters + 0, top1);
+    atomicAdd(counters + 1, top5);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -426,6 +557,30 @@ cudaError_t launch_gather_rows(const float* src_x, const __nv_bfloat16* src_att,
   gather_rows_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(src_x, src_att, planes, src_plane_rows,
                                                             stride, lengths, L, rows, dst_x, dst_att,
                                                             dst_plane_rows, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_batch(const BatchStore& st, const long long* video_index,
+                               const long long* frame_indices, const long long* num_sampled, int B,
+                               int T, int L, int S, double score_threshold, const BatchIds& ids,
+                               long long* categories, float* boxes, float* scores,
+                               long long* frame_types, long long* lengths, uint8_t* mask_boxes,
+                               uint8_t* mask_frames, int* err_flag, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * L * S;
+  if (total == 0) return cudaSuccess;
+  const long long blocks = (total + 255) / 256;
+  build_batch_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      st, video_index, frame_indices, num_sampled, T, L, S, score_threshold, ids, total, categories,
+      reinterpret_cast<float4*>(boxes), scores, frame_types, lengths, mask_boxes, mask_frames, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_topk_count(const float* logits, const long long* labels, int rows, int classes,
+                              unsigned long long* counters, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  topk_count_kernel<<<blocks, 256, 0, stream>>>(logits, labels, rows, classes, counters);
   return cudaGetLastError();
 }
 

@@ -57,6 +57,27 @@ cudaError_t launch_masks(const long long* categories, const long long* frame_typ
                          long long n_slots, long long n_frames, uint8_t* mask_boxes,
                          uint8_t* mask_frames, cudaStream_t stream);
 
+// CSR layout store of a dataset on the device (see include/stlt_b200.h: StltLayoutStore).
+struct BatchStore {
+  const long long* video_frame_offsets;   // [V + 1]
+  const long long* frame_object_offsets;  // [F + 1]
+  const double* obj_boxes;                // [O, 4] raw pixel boxes
+  const long long* obj_categories;        // [O] ids (category2id already applied)
+  const double* obj_scores;               // [O]
+  const long long* video_sizes;           // [V, 2] (width, height)
+};
+struct BatchIds {
+  long long cls, ft_pad, ft_regular, ft_empty, ft_extract;
+};
+cudaError_t launch_build_batch(const BatchStore& st, const long long* video_index,
+                               const long long* frame_indices, const long long* num_sampled, int B,
+                               int T, int L, int S, double score_threshold, const BatchIds& ids,
+                               long long* categories, float* boxes, float* scores,
+                               long long* frame_types, long long* lengths, uint8_t* mask_boxes,
+                               uint8_t* mask_frames, int* err_flag, cudaStream_t stream);
+cudaError_t launch_topk_count(const float* logits, const long long* labels, int rows, int classes,
+                              unsigned long long* counters, cudaStream_t stream);
+
 // K1: category + box (+score) embedding and LayerNorm (src/modelling/models.py:29-39).
 cudaError_t launch_embed(const long long* categories, const float* boxes, const float* scores,
                          const float* cat_table, int unique_categories, const float* box_w,

@@ -495,6 +495,53 @@ int stlt_prepare(void* handle, void* stream, const double* raw_boxes, const int6
   return STLT_OK;
 }
 
+int stlt_build_batch(void* handle, void* stream_, const StltLayoutStore* store, const StltLayoutIds* ids,
+                     const int64_t* video_index, const int64_t* frame_indices, const int64_t* num_sampled,
+                     int32_t B, int32_t T, int32_t L, int32_t S, double score_threshold,
+                     int64_t* categories, float* boxes, float* scores, int64_t* frame_types,
+                     int64_t* lengths, uint8_t* mask_boxes, uint8_t* mask_frames, int32_t* status) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  if (B < 0 || T < 1 || L < 1 || S < 1) return fail(h, STLT_ERR_INVALID, "invalid batch shape");
+  if (B == 0) return STLT_OK;
+  if (!store || !ids || !video_index || !categories || !boxes || !frame_types || !lengths ||
+      !mask_boxes || !mask_frames || !status)
+    return fail(h, STLT_ERR_INVALID, "null pointer");
+  if ((frame_indices == nullptr) != (num_sampled == nullptr))
+    return fail(h, STLT_ERR_INVALID, "frame_indices and num_sampled must be given together");
+  if (!store->video_frame_offsets || !store->frame_object_offsets || !store->obj_boxes ||
+      !store->obj_categories || !store->obj_scores || !store->video_sizes)
+    return fail(h, STLT_ERR_INVALID, "incomplete layout store");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BatchStore st{reinterpret_cast<const long long*>(store->video_frame_offsets),
+                reinterpret_cast<const long long*>(store->frame_object_offsets), store->obj_boxes,
+                reinterpret_cast<const long long*>(store->obj_categories), store->obj_scores,
+                reinterpret_cast<const long long*>(store->video_sizes)};
+  BatchIds bi{ids->cls, ids->ft_pad, ids->ft_regular, ids->ft_empty, ids->ft_extract};
+  STLT_CUDA(h, cudaMemsetAsync(status, 0, sizeof(int32_t), stream));
+  STLT_CUDA(h, launch_build_batch(st, reinterpret_cast<const long long*>(video_index),
+                                  reinterpret_cast<const long long*>(frame_indices),
+                                  reinterpret_cast<const long long*>(num_sampled), B, T, L, S,
+                                  score_threshold, bi, reinterpret_cast<long long*>(categories), boxes,
+                                  scores, reinterpret_cast<long long*>(frame_types),
+                                  reinterpret_cast<long long*>(lengths), mask_boxes, mask_frames, status,
+                                  stream));
+  return STLT_OK;
+}
+
+int stlt_topk_count(void* handle, void* stream, const float* logits, const int64_t* labels, int32_t rows,
+                    int32_t classes, uint64_t* counters) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  if (rows < 0 || classes < 1) return fail(h, STLT_ERR_INVALID, "invalid shape");
+  if (rows == 0) return STLT_OK;
+  if (!logits || !labels || !counters) return fail(h, STLT_ERR_INVALID, "null pointer");
+  STLT_CUDA(h, launch_topk_count(logits, reinterpret_cast<const long long*>(labels), rows, classes,
+                                 reinterpret_cast<unsigned long long*>(counters),
+                                 static_cast<cudaStream_t>(stream)));
+  return STLT_OK;
+}
+
 int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* categories_,
                  const float* boxes, const float* scores, const int64_t* frame_types_,
                  const int64_t* lengths_, int32_t B, int32_t L, int32_t S, void* workspace,

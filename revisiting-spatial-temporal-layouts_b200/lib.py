@@ -66,6 +66,22 @@ class StltTaps(Structure):
     ]
 
 
+class StltLayoutStore(Structure):
+    _fields_ = [
+        ("video_frame_offsets", c_void_p),
+        ("frame_object_offsets", c_void_p),
+        ("obj_boxes", c_void_p),
+        ("obj_categories", c_void_p),
+        ("obj_scores", c_void_p),
+        ("video_sizes", c_void_p),
+    ]
+
+
+class StltLayoutIds(Structure):
+    _fields_ = [("cls", c_int64), ("ft_pad", c_int64), ("ft_regular", c_int64), ("ft_empty", c_int64),
+                ("ft_extract", c_int64)]
+
+
 PROF_CATEGORIES = ("gemm", "attention", "add_ln", "other")
 
 
@@ -88,6 +104,11 @@ SIGNATURES = {
     "stlt_workspace_bytes": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_size_t)]),
     "stlt_prepare": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "stlt_build_batch": (c_int32, [c_void_p, c_void_p, POINTER(StltLayoutStore), POINTER(StltLayoutIds),
+                                   c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_double,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
+    "stlt_topk_count": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "stlt_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p,
                                c_void_p, c_void_p]),

@@ -8,6 +8,7 @@ __path__.append(str(_PKG_DIR))
 from .configs import ACTION_GENOME, SOMETHING_ELSE, StltModelConfig  # noqa: E402
 from .module import Stlt, StltBackbone, models_factory  # noqa: E402
 from .prepare import prepare_layout_batch  # noqa: E402
+from .data import LayoutStore, TopKCounter  # noqa: E402
 
-__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "models_factory", "prepare_layout_batch",
+__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter",
            "SOMETHING_ELSE", "ACTION_GENOME"]
