@@ -150,9 +150,9 @@ cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long*
   if (blocks > cap) blocks = cap;
   cudaError_t e;
   if (qkv_is_bf16) {
-    if (out.planes != 1) return cudaErrorInvalidValue;
-    return launch_attention_mma(static_cast<const __nv_bfloat16*>(qkv), mask_src, num_seqs, T, causal,
-                                out.xb, stream);
+    // bf16 QKV (1 plane) or hi/lo bf16 planes (2 planes, rows out.plane_rows apart): tensor-core tiles
+    return launch_attention_mma(static_cast<const __nv_bfloat16*>(qkv), out.planes, out.plane_rows,
+                                mask_src, num_seqs, T, causal, out.xb, out.plane_rows, stream);
   } else {
     auto kern = attention_kernel<float>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -1,4 +1,4 @@
-// K3 (bf16 mode): masked multi-head self-attention over the short STLT sequences, evaluated on
+// K3: masked multi-head self-attention over the short STLT sequences, evaluated on
 // warp-level tensor-core tiles. Same semantics as attention.cu (reference: the SDPA inside
 // nn.MultiheadAttention configured at src/modelling/models.py:46-55,118-128, key-padding masks from
 // src/modelling/datasets.py:274-286, causal mask src/utils/model_utils.py:4-7).
@@ -12,6 +12,11 @@
 //   O = P V        P re-used from registers as the A operand (bf16), V via ldmatrix.trans
 // The normalised context rows are staged through the (dead) Q tile and written as 16-byte vectors.
 //
+// kSplit = true is the fp32-parity flavour: Q, K, V arrive as bf16 hi/lo planes (the split output
+// of the in-projection GEMM) and every product is evaluated as hi*hi + lo*hi + hi*lo on the tensor
+// cores (P is split in registers), which keeps ~2^-16 relative accuracy; the context is written as
+// hi/lo planes again.
+//
 // The scores of sequences sharing a tile are computed and then masked away; at T = 5 that is
 // 30x30 computed for 6x(5x5) used, which is still ~4x fewer issued instructions per token than a
 // CUDA-core formulation, and the kernel is HBM-bound (reads 4.6 KB, writes 1.5 KB per token).
@@ -22,7 +27,6 @@ namespace stlt {
 
 namespace {
 
-constexpr int kWarps = 8;
 constexpr int kTileBytes = 32 * 128;  // 32 rows x 64 bf16
 
 __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
@@ -56,19 +60,24 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 2)
-attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const long long* __restrict__ mask_src,
-                     long long num_seqs, int T, int G, int causal, __nv_bfloat16* __restrict__ out,
+template <bool kSplit>
+__global__ void __launch_bounds__(kSplit ? 128 : 256, 2)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_plane_elems,
+                     const long long* __restrict__ mask_src, long long num_seqs, int T, int G,
+                     int causal, __nv_bfloat16* __restrict__ out, long long out_plane_elems,
                      long long num_items) {
+  constexpr int kWarps = kSplit ? 4 : 8;
+  constexpr int kTiles = kSplit ? 6 : 3;  // Q, K, V (+ their lo planes)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2;  // fragment row within an 8-row group
   const int t = lane & 3;   // fragment column pair
   const int R = G * T;
-  const uint32_t q_base = smem_u32(smem_raw) + warp * 3 * kTileBytes;
+  const uint32_t q_base = smem_u32(smem_raw) + warp * kTiles * kTileBytes;
   const uint32_t k_base = q_base + kTileBytes;
   const uint32_t v_base = k_base + kTileBytes;
+  constexpr uint32_t kLo = 3 * kTileBytes;  // lo-plane tiles follow the three hi tiles
 
   // Static part of the mask for this thread's fragment positions: query rows mt*16 + g + 8h,
   // key columns nt*8 + 2t + e. Bit (nt*2 + e) of allow[mt][h] = same sequence (and causal order).
@@ -116,11 +125,20 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const long long* __r
           cp_async16(tile_addr(q_base, row, chunk), src);
           cp_async16(tile_addr(k_base, row, chunk), src + kHidden);
           cp_async16(tile_addr(v_base, row, chunk), src + 2 * kHidden);
+          if (kSplit) {
+            const __nv_bfloat16* lo = src + qkv_plane_elems;
+            cp_async16(tile_addr(q_base + kLo, row, chunk), lo);
+            cp_async16(tile_addr(k_base + kLo, row, chunk), lo + kHidden);
+            cp_async16(tile_addr(v_base + kLo, row, chunk), lo + 2 * kHidden);
+          }
         } else {
           const uint32_t z = 0;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile_addr(q_base, row, chunk)), "r"(z) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile_addr(k_base, row, chunk)), "r"(z) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile_addr(v_base, row, chunk)), "r"(z) : "memory");
+#pragma unroll
+          for (int tl = 0; tl < kTiles; ++tl)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(
+                             tile_addr(q_base + tl * kTileBytes, row, chunk)),
+                         "r"(z)
+                         : "memory");
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -146,24 +164,36 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const long long* __r
         for (int i = 0; i < 4; ++i) s[mt][nt][i] = 0.f;
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
-      uint32_t a[2][4];
+      uint32_t a[2][4], al[2][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-        ldmatrix_x4(tile_addr(q_base, mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kt * 2 + (lane >> 4)), a[mt]);
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chunk = kt * 2 + (lane >> 4);
+        ldmatrix_x4(tile_addr(q_base, row, chunk), a[mt]);
+        if (kSplit) ldmatrix_x4(tile_addr(q_base + kLo, row, chunk), al[mt]);
+      }
 #pragma unroll
       for (int np = 0; np < 2; ++np) {  // pairs of key tiles
-        uint32_t b[4];
-        ldmatrix_x4(tile_addr(k_base, (np * 2 + (lane >> 4)) * 8 + (lane & 7), kt * 2 + ((lane >> 3) & 1)), b);
+        uint32_t b[4], bl[4];
+        const int row = (np * 2 + (lane >> 4)) * 8 + (lane & 7), chunk = kt * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4(tile_addr(k_base, row, chunk), b);
+        if (kSplit) ldmatrix_x4(tile_addr(k_base + kLo, row, chunk), bl);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           mma_bf16(s[mt][np * 2 + 0], a[mt], b[0], b[1]);
           mma_bf16(s[mt][np * 2 + 1], a[mt], b[2], b[3]);
+          if (kSplit) {
+            mma_bf16(s[mt][np * 2 + 0], al[mt], b[0], b[1]);
+            mma_bf16(s[mt][np * 2 + 1], al[mt], b[2], b[3]);
+            mma_bf16(s[mt][np * 2 + 0], a[mt], bl[0], bl[1]);
+            mma_bf16(s[mt][np * 2 + 1], a[mt], bl[2], bl[3]);
+          }
         }
       }
     }
 
     // ---- masked softmax on the accumulator fragments (fp32) ----
-    uint32_t p[2][2][4];  // P as bf16 A fragments: [m tile][key k-step][4 regs]
+    uint32_t p[2][2][4];   // P as bf16 A fragments: [m tile][key k-step][4 regs]
+    uint32_t pl[2][2][4];  // lo plane of P (kSplit)
     float inv_sum[2][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -204,6 +234,12 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const long long* __r
         p[mt][j][1] = pack_bf16x2(s[mt][2 * j][2], s[mt][2 * j][3]);
         p[mt][j][2] = pack_bf16x2(s[mt][2 * j + 1][0], s[mt][2 * j + 1][1]);
         p[mt][j][3] = pack_bf16x2(s[mt][2 * j + 1][2], s[mt][2 * j + 1][3]);
+        if (kSplit) {
+          pl[mt][j][0] = pack_bf16x2(bf16_residual(s[mt][2 * j][0]), bf16_residual(s[mt][2 * j][1]));
+          pl[mt][j][1] = pack_bf16x2(bf16_residual(s[mt][2 * j][2]), bf16_residual(s[mt][2 * j][3]));
+          pl[mt][j][2] = pack_bf16x2(bf16_residual(s[mt][2 * j + 1][0]), bf16_residual(s[mt][2 * j + 1][1]));
+          pl[mt][j][3] = pack_bf16x2(bf16_residual(s[mt][2 * j + 1][2]), bf16_residual(s[mt][2 * j + 1][3]));
+        }
       }
 
     // ---- O = P V ----
@@ -218,12 +254,20 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const long long* __r
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int dp = 0; dp < 4; ++dp) {  // pairs of 8-wide feature tiles
-        uint32_t b[4];
-        ldmatrix_x4_trans(tile_addr(v_base, j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), dp * 2 + (lane >> 4)), b);
+        uint32_t b[4], bl[4];
+        const int row = j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), chunk = dp * 2 + (lane >> 4);
+        ldmatrix_x4_trans(tile_addr(v_base, row, chunk), b);
+        if (kSplit) ldmatrix_x4_trans(tile_addr(v_base + kLo, row, chunk), bl);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           mma_bf16(o[mt][dp * 2 + 0], p[mt][j], b[0], b[1]);
           mma_bf16(o[mt][dp * 2 + 1], p[mt][j], b[2], b[3]);
+          if (kSplit) {
+            mma_bf16(o[mt][dp * 2 + 0], pl[mt][j], b[0], b[1]);
+            mma_bf16(o[mt][dp * 2 + 1], pl[mt][j], b[2], b[3]);
+            mma_bf16(o[mt][dp * 2 + 0], p[mt][j], bl[0], bl[1]);
+            mma_bf16(o[mt][dp * 2 + 1], p[mt][j], bl[2], bl[3]);
+          }
         }
       }
 
@@ -237,8 +281,13 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const long long* __r
         const float is = inv_sum[mt][h];
 #pragma unroll
         for (int dt = 0; dt < 8; ++dt) {
-          const uint32_t v = pack_bf16x2(o[mt][dt][2 * h] * is, o[mt][dt][2 * h + 1] * is);
+          const float x0 = o[mt][dt][2 * h] * is, x1 = o[mt][dt][2 * h + 1] * is;
+          const uint32_t v = pack_bf16x2(x0, x1);
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_addr(q_base, row, dt) + 4 * t), "r"(v) : "memory");
+          if (kSplit) {
+            const uint32_t vl = pack_bf16x2(bf16_residual(x0), bf16_residual(x1));
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_addr(q_base + kLo, row, dt) + 4 * t), "r"(vl) : "memory");
+          }
         }
       }
     __syncwarp();
@@ -254,7 +303,15 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const long long* __r
                        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                        : "r"(tile_addr(q_base, row, chunk))
                        : "memory");
-          *reinterpret_cast<uint4*>(out + (base + row) * kHidden + head * kHeadDim + chunk * 8) = v;
+          __nv_bfloat16* dst = out + (base + row) * kHidden + head * kHeadDim + chunk * 8;
+          *reinterpret_cast<uint4*>(dst) = v;
+          if (kSplit) {
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(tile_addr(q_base + kLo, row, chunk))
+                         : "memory");
+            *reinterpret_cast<uint4*>(dst + out_plane_elems) = v;
+          }
         }
       }
     }
@@ -262,20 +319,19 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const long long* __r
   }
 }
 
-}  // namespace
-
-cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, const long long* mask_src,
-                                 long long num_seqs, int T, bool causal, __nv_bfloat16* out,
-                                 cudaStream_t stream) {
-  if (T < 1 || T > 32) return cudaErrorInvalidValue;
-  if (num_seqs == 0) return cudaSuccess;
+template <bool kSplit>
+static cudaError_t launch_mma(const __nv_bfloat16* qkv, long long qkv_plane_rows,
+                              const long long* mask_src, long long num_seqs, int T, bool causal,
+                              __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream) {
+  constexpr int kWarps = kSplit ? 4 : 8;
+  constexpr int kTiles = kSplit ? 6 : 3;
   const int G = 32 / T;
   const long long groups = (num_seqs + G - 1) / G;
   const long long items = groups * kHeads;
-  const int smem = kWarps * 3 * kTileBytes;
+  const int smem = kWarps * kTiles * kTileBytes;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel,
+    cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<kSplit>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -283,9 +339,22 @@ cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, const long long* mask
   long long blocks = (items + kWarps - 1) / kWarps;
   const long long cap = 148LL * 2 * 8;  // 2 CTAs resident per SM, several waves; grid-stride inside
   if (blocks > cap) blocks = cap;
-  attention_mma_kernel<<<static_cast<unsigned>(blocks), kWarps * 32, smem, stream>>>(
-      qkv, mask_src, num_seqs, T, G, causal ? 1 : 0, out, items);
+  attention_mma_kernel<kSplit><<<static_cast<unsigned>(blocks), kWarps * 32, smem, stream>>>(
+      qkv, qkv_plane_rows * kQkv, mask_src, num_seqs, T, G, causal ? 1 : 0, out,
+      out_plane_rows * kHidden, items);
   return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long qkv_plane_rows,
+                                 const long long* mask_src, long long num_seqs, int T, bool causal,
+                                 __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream) {
+  if (T < 1 || T > 32) return cudaErrorInvalidValue;
+  if (num_seqs == 0) return cudaSuccess;
+  if (planes == 2)
+    return launch_mma<true>(qkv, qkv_plane_rows, mask_src, num_seqs, T, causal, out, out_plane_rows, stream);
+  return launch_mma<false>(qkv, 0, mask_src, num_seqs, T, causal, out, 0, stream);
 }
 
 }  // namespace stlt

@@ -112,10 +112,11 @@ cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long*
                              long long num_seqs, int T, bool causal, ActOut out,
                              cudaStream_t stream);
 
-// K3, bf16 mode: the same attention on warp-level tensor-core tiles (attention_mma.cu).
-cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, const long long* mask_src,
-                                 long long num_seqs, int T, bool causal, __nv_bfloat16* out,
-                                 cudaStream_t stream);
+// K3 on warp-level tensor-core tiles (attention_mma.cu). planes = 1: bf16 QKV [tokens, 2304] ->
+// bf16 context; planes = 2: hi/lo bf16 planes in and out (fp32-parity mode, 3-term split products).
+cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long qkv_plane_rows,
+                                 const long long* mask_src, long long num_seqs, int T, bool causal,
+                                 __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream);
 
 // fp32 -> bf16 plane(s) for weights.
 cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,

@@ -217,7 +217,7 @@ struct Phase {
   float* y;              // fp32 GEMM output [m, 768]
   __nv_bfloat16* xb;     // bf16 plane(s) of x
   __nv_bfloat16* att;    // bf16 plane(s) of the attention context
-  void* qkv;             // [m, 2304] f32 or bf16
+  void* qkv;             // bf16 [P, m, 2304]
   __nv_bfloat16* hid;    // bf16 plane(s) of the FFN hidden [m, 3072]
   long long m_pad;       // rows per plane
   long long m_valid;     // real tokens
@@ -243,12 +243,13 @@ int run_attention_part(Handle* h, cudaStream_t stream, int precision, const Laye
                        bool causal) {
   const bool fp32 = precision == STLT_PRECISION_FP32;
   int rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv,
-                    fp32 ? 3 : 1, fp32 ? GEMM_OUT_F32 : GEMM_OUT_BF16, 0);
+                    fp32 ? 3 : 1, fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, 0);
   if (rc) return rc;
+  // fp32 mode: q/k/v and the context travel as bf16 hi/lo planes; products are 3-term splits
   ActOut att{nullptr, ph.att, fp32 ? 2 : 1, ph.m_pad};
   {
     ProfileScope prof(h, stream, STLT_PROF_ATTENTION);
-    STLT_CUDA(h, launch_attention(ph.qkv, !fp32, mask_src, num_seqs, T, causal, att, stream));
+    STLT_CUDA(h, launch_attention(ph.qkv, true, mask_src, num_seqs, T, causal, att, stream));
   }
   h->launches++;
   return STLT_OK;

@@ -128,31 +128,40 @@ def _attention_ref(qkv, masked_keys, T, causal):
 
 @pytest.mark.parametrize("T,causal,n_seqs", [(5, False, 1000), (11, False, 333), (17, True, 257), (1, False, 64),
                                              (32, True, 31), (7, True, 50)])
-@pytest.mark.parametrize("bf16_in", [False, True])
-def test_attention(handle, T, causal, n_seqs, bf16_in):
+@pytest.mark.parametrize("flavour", ["simt_f32", "mma_bf16", "mma_split"])
+def test_attention(handle, T, causal, n_seqs, flavour):
+    """simt_f32: fp32 QKV on CUDA cores (cross-check); mma_bf16: bf16 mode; mma_split: fp32-parity mode
+    (hi/lo bf16 planes in and out, 3-term split products on the tensor cores)."""
     lib = L.load_library()
     g = torch.Generator(device="cuda").manual_seed(T * 7 + n_seqs)
     tokens = n_seqs * T
+    rows = tokens + 5
     qkv = torch.randn(tokens, 2304, device="cuda", generator=g)
-    if bf16_in:
+    if flavour == "mma_bf16":
         qkv_in = qkv.to(torch.bfloat16)
         qkv = qkv_in.float()
+        planes, is_bf16, tol = 1, 1, 4e-3
+    elif flavour == "mma_split":
+        hi, lo = _split(qkv)
+        qkv_in = torch.zeros(2 * rows, 2304, dtype=torch.bfloat16, device="cuda")
+        qkv_in[:tokens] = hi
+        qkv_in[rows: rows + tokens] = lo
+        planes, is_bf16, tol = 2, 1, 3e-5
     else:
         qkv_in = qkv
+        planes, is_bf16, tol = 2, 0, 2e-5
     mask_src = torch.randint(0, 3, (n_seqs, T), device="cuda", generator=g)
     mask_src[:, 0] = 2  # first key always valid (CLS slot / first frame)
     mask_src = mask_src.view(-1).contiguous()
-    planes = 1 if bf16_in else 2
-    rows = tokens + 5
     out = torch.zeros(planes * rows, 768, dtype=torch.bfloat16, device="cuda")
-    L.check(handle, lib.stlt_op_attention(handle, _stream(), qkv_in.data_ptr(), int(bf16_in), mask_src.data_ptr(),
+    L.check(handle, lib.stlt_op_attention(handle, _stream(), qkv_in.data_ptr(), is_bf16, mask_src.data_ptr(),
                                           n_seqs, T, int(causal), out.data_ptr(), planes, rows))
     torch.cuda.synchronize()
     got = out[:tokens].float()
     if planes == 2:
         got = got + out[rows: rows + tokens].float()
     ref = _attention_ref(qkv, mask_src == 0, T, causal)
-    assert nerr(got, ref) < (4e-3 if bf16_in else 2e-5)
+    assert nerr(got, ref) < tol
 
 
 @pytest.mark.parametrize("rows,with_y,planes", [(1000, True, 2), (77, False, 1), (3, True, 1)])
