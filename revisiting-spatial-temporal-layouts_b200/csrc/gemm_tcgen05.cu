@@ -211,11 +211,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const uint32_t taddr =
           tmem_base + acc * BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
 
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {  // 4 chunks of 32 accumulator columns
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
+      // 4 chunks of 32 accumulator columns; the TMEM load of chunk c+1 is in flight while chunk c is
+      // converted and stored (register double buffer).
+      uint32_t vbuf[2][32];
+      tmem_ld_32x32(taddr, vbuf[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t(&v)[32] = vbuf[c & 1];
+        tmem_ld_wait_regs(v);
+        if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -288,7 +292,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           }
         }
       }
-      // all TMEM reads of this accumulator have completed (tmem_ld_wait above) -> release it
+      // all TMEM reads of this accumulator have completed (last tmem_ld_wait_regs) -> release it
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&bars->tmem_empty[acc], 0));
