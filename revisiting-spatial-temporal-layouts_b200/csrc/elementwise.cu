@@ -276,6 +276,8 @@ __global__ void topk_count_kernel(const float* __restrict__ logits, const long l
 // ------------------------------------------------------------------------------------------------
 // K1: CategoryBoxEmbeddings.forward (src/modelling/models.py:29-39)
 // ------------------------------------------------------------------------------------------------
+constexpr int kEmbedTok = 4;  // tokens per warp iteration: parameter loads are amortised over them
+
 __global__ void __launch_bounds__(256)
 embed_kernel(const long long* __restrict__ categories, const float4* __restrict__ boxes,
              const float* __restrict__ scores, const float* __restrict__ cat_table,
@@ -288,40 +290,62 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
   const float4* bw4 = reinterpret_cast<const float4*>(box_w);  // [768][4]: one float4 per feature
-  for (long long t = warp0; t < tokens; t += nwarps) {
-    long long cat = categories[t];
-    if (cat < 0 || cat >= unique_categories) {
-      if (lane == 0) atomicExch(err_flag, 1);
-      cat = 0;
+  const long long groups = (tokens + kEmbedTok - 1) / kEmbedTok;
+  for (long long grp = warp0; grp < groups; grp += nwarps) {
+    const long long t0 = grp * kEmbedTok;
+    long long cat[kEmbedTok];
+    float4 box[kEmbedTok];
+    float score[kEmbedTok];
+    RowRegs r[kEmbedTok];
+#pragma unroll
+    for (int i = 0; i < kEmbedTok; ++i) {
+      const long long t = t0 + i < tokens ? t0 + i : tokens - 1;  // tail: recompute the last token
+      cat[i] = categories[t];
+      if (cat[i] < 0 || cat[i] >= unique_categories) {
+        if (lane == 0) atomicExch(err_flag, 1);
+        cat[i] = 0;
+      }
+      box[i] = __ldg(boxes + t);
+      score[i] = scores != nullptr ? __ldg(scores + t) : 0.f;
+      r[i] = load_row(cat_table, cat[i], lane);
     }
-    const float4 box = __ldg(boxes + t);
-    const float score = scores != nullptr ? __ldg(scores + t) : 0.f;
-    RowRegs r = load_row(cat_table, cat, lane);
 #pragma unroll
     for (int k = 0; k < kVec; ++k) {
       const int c = 4 * (lane + 32 * k);
       const float4 bb = __ldg(reinterpret_cast<const float4*>(box_b + c));
-      float e[4] = {bb.x, bb.y, bb.z, bb.w};
+      float4 w[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 w = __ldg(bw4 + c + q);
-        e[q] += box.x * w.x + box.y * w.y + box.z * w.z + box.w * w.w;
-      }
+      for (int q = 0; q < 4; ++q) w[q] = __ldg(bw4 + c + q);
+      float4 sw = make_float4(0.f, 0.f, 0.f, 0.f), sb = sw;
       if (scores != nullptr) {
-        const float4 sw = __ldg(reinterpret_cast<const float4*>(score_w + c));  // [768][1]
-        const float4 sb = __ldg(reinterpret_cast<const float4*>(score_b + c));
-        e[0] += score * sw.x + sb.x;
-        e[1] += score * sw.y + sb.y;
-        e[2] += score * sw.z + sb.z;
-        e[3] += score * sw.w + sb.w;
+        sw = __ldg(reinterpret_cast<const float4*>(score_w + c));  // [768][1]
+        sb = __ldg(reinterpret_cast<const float4*>(score_b + c));
       }
-      r.v[k].x += e[0];
-      r.v[k].y += e[1];
-      r.v[k].z += e[2];
-      r.v[k].w += e[3];
+#pragma unroll
+      for (int i = 0; i < kEmbedTok; ++i) {
+        float e[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          e[q] += box[i].x * w[q].x + box[i].y * w[q].y + box[i].z * w[q].z + box[i].w * w[q].w;
+        if (scores != nullptr) {
+          e[0] += score[i] * sw.x + sb.x;
+          e[1] += score[i] * sw.y + sb.y;
+          e[2] += score[i] * sw.z + sb.z;
+          e[3] += score[i] * sw.w + sb.w;
+        }
+        r[i].v[k].x += e[0];
+        r[i].v[k].y += e[1];
+        r[i].v[k].z += e[2];
+        r[i].v[k].w += e[3];
+      }
     }
-    layer_norm_row(r, ln_g, ln_b, eps, lane);
-    store_act(out, t, r, lane);
+#pragma unroll
+    for (int i = 0; i < kEmbedTok; ++i) {
+      if (t0 + i < tokens) {
+        layer_norm_row(r[i], ln_g, ln_b, eps, lane);
+        store_act(out, t0 + i, r[i], lane);
+      }
+    }
   }
 }
 
@@ -517,7 +541,7 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
                          const float* ln_g, const float* ln_b, float eps, long long tokens,
                          ActOut out, int* err_flag, cudaStream_t stream) {
   if (tokens == 0) return cudaSuccess;
-  embed_kernel<<<row_grid(tokens, 8), 256, 0, stream>>>(
+  embed_kernel<<<row_grid((tokens + kEmbedTok - 1) / kEmbedTok, 8), 256, 0, stream>>>(
       categories, reinterpret_cast<const float4*>(boxes), scores, cat_table, unique_categories,
       box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag);
   return cudaGetLastError();
