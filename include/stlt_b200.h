@@ -198,6 +198,12 @@ int stlt_set_taps(void* handle, const StltTaps* taps);
 int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w_planes,
                  const float* bias, void* out, int32_t m_rows, int32_t n, int32_t k, int32_t terms,
                  int32_t out_kind, int32_t gelu /* 0 none, 1 erf GELU (erff), 2 fast erf GELU */);
+/* Gradient GEMMs of the training step on the same tcgen05 kernel (bf16 operands, no bias):
+ *   layout 1: out[m_rows][n]  = A[m_rows][k] * B[k][n]     (data gradient; out_kind 0 f32 / 1 bf16)
+ *   layout 2: out[m_rows][n] += A[k][m_rows]^T * B[k][n]   (weight gradient; out f32, accumulated with
+ *             TMA reduce-add stores, work split stream-K over the token axis k; any k >= 1). */
+int stlt_op_gemm_grad(void* handle, void* stream, int32_t layout, const void* a, const void* b,
+                      void* out, int32_t m_rows, int32_t n, int64_t k, int32_t out_kind);
 int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w,
                       const float* bias, float* out, int32_t m, int32_t n, int32_t k, int32_t gelu);
 int stlt_op_attention(void* handle, void* stream, const void* qkv, int32_t qkv_is_bf16,

@@ -164,6 +164,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* d, const void* s
       : "memory");
 }
 
+// TMA reduce-add store: global[tile] += smem tile (fp32 adds performed by the memory system).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* d, const void* smem_src,
+                                                  int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(d)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -327,6 +337,19 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;              // SBO (16 B units) [32,46)
   d |= static_cast<uint64_t>(1) << 46;                      // version         [46,48)
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B    [61,64)
+  return d;
+}
+
+// Same for an MN-major operand (the MN index is the contiguous one): the tile is a row of 64-element
+// (128 B) wide, 128-byte-swizzled chunks; `chunk_bytes` apart along MN (LBO), 8-row groups of the
+// reduction axis 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t chunk_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(chunk_bytes >> 4) << 16;  // LBO
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;         // SBO
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
 

@@ -27,6 +27,16 @@
 // TMEM allocator, warp 3 = idle, warps 4..11 = epilogue (warp w reads TMEM lane quarter w % 4, column
 // half (w-4)/4 of this CTA's 128 x 256 accumulator).
 //
+// Operand layouts (kLayout), used by the training step:
+//   GEMM_NT    (forward)        out[M,N]  = A[M,K] * B[N,K]^T + bias      A, B K-major
+//   GEMM_NN    (data gradient)  out[M,N]  = A[M,K] * B[K,N]                B MN-major (no transposed copy of W)
+//   GEMM_TN_RED(weight gradient) out[M,N] += A[K,M]^T * B[K,N]             A, B MN-major; the reduction runs
+//              over the token axis, the work is split stream-K style over all CTA pairs (each pair owns a
+//              contiguous range of (tile, k-block) steps) and every partial tile is added to the fp32
+//              output with a TMA reduce-add store, so no fix-up pass exists.
+// MN-major tiles are staged as 64-element (128 B) wide TMA boxes of 64 reduction rows: a 128-wide
+// operand is two boxes 8 KiB apart (descriptor LBO), 8-row groups are 1 KiB apart (SBO).
+//
 // Barriers: full[s] lives in the leader (both CTAs' TMA loads signal it); empty[s] and tmem_full[a]
 // exist in both CTAs and are signalled by the leader's multicast tcgen05.commit; tmem_empty[a] lives
 // in the leader and collects the epilogue warps of both CTAs.
@@ -54,13 +64,56 @@ constexpr uint16_t kClusterMask = (1u << kCluster) - 1;
 // The split epilogue needs two staging tiles per warp (hi and lo plane), paid for with one stage.
 template <int kOut>
 struct Cfg {
-  static constexpr int kStages = (kOut == GEMM_OUT_BF16_SPLIT) ? 5 : 6;
-  static constexpr int kBufsPerWarp = (kOut == GEMM_OUT_BF16_SPLIT) ? 2 : 1;
+  static constexpr bool kTwoPlanes = kOut == GEMM_OUT_BF16_SPLIT || kOut == GEMM_OUT_BF16_DUAL;
+  static constexpr int kStages = kTwoPlanes ? 5 : 6;
+  static constexpr int kBufsPerWarp = kTwoPlanes ? 2 : 1;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kEpiWarps * kBufsPerWarp * kEpiBufBytes + 256 /*barriers*/;
 };
 static_assert(Cfg<GEMM_OUT_F32>::kSmemBytes <= 232448, "smem budget");
 static_assert(Cfg<GEMM_OUT_BF16_SPLIT>::kSmemBytes <= 232448, "smem budget");
+static_assert(Cfg<GEMM_OUT_BF16_DUAL>::kSmemBytes <= 232448, "smem budget");
+
+constexpr int kMnChunkBytes = 64 * BK * 2;  // one MN-major TMA box: 64 reduction rows x 128 B
+
+struct Work {
+  int tile, kb0, kb1;
+};
+
+// Work distribution of one CTA pair. Tile mode: whole tiles, round-robin. Stream-K mode: the
+// contiguous range [cur, end) of the linearised (tile, k-block) steps.
+template <bool kStreamK>
+struct Sched {
+  int cur, end, total_kb, stride;
+  __device__ Sched(int cluster_id, int num_clusters, int num_tiles, int total_kb_) : total_kb(total_kb_) {
+    if (kStreamK) {
+      const long long total = static_cast<long long>(num_tiles) * total_kb_;
+      cur = static_cast<int>(total * cluster_id / num_clusters);
+      end = static_cast<int>(total * (cluster_id + 1) / num_clusters);
+      stride = 0;
+    } else {
+      cur = cluster_id;
+      end = num_tiles;
+      stride = num_clusters;
+    }
+  }
+  __device__ bool next(Work& w) {
+    if (cur >= end) return false;
+    if (kStreamK) {
+      w.tile = cur / total_kb;
+      w.kb0 = cur - w.tile * total_kb;
+      const int n = min(total_kb - w.kb0, end - cur);
+      w.kb1 = w.kb0 + n;
+      cur += n;
+    } else {
+      w.tile = cur;
+      w.kb0 = 0;
+      w.kb1 = total_kb;
+      cur += stride;
+    }
+    return true;
+  }
+};
 
 struct __align__(8) Barriers {
   uint64_t full[kMaxStages];
@@ -73,7 +126,7 @@ struct __align__(8) Barriers {
 
 }  // namespace
 
-template <int kTerms, int kOut, int kGelu>
+template <int kTerms, int kOut, int kGelu, int kLayout>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias,
@@ -81,6 +134,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     int out_plane_rows) {
   constexpr int kStages = Cfg<kOut>::kStages;
   constexpr int kBufsPerWarp = Cfg<kOut>::kBufsPerWarp;
+  constexpr bool kAMn = kLayout == GEMM_TN_RED;
+  constexpr bool kBMn = kLayout != GEMM_NT;
+  constexpr bool kStreamK = kLayout == GEMM_TN_RED;
+  constexpr bool kBias = kLayout == GEMM_NT;
+  static_assert(kLayout == GEMM_NT || kTerms == 1, "gradient GEMMs are single-term");
+  static_assert(!kStreamK || kOut == GEMM_OUT_F32, "stream-K partials are reduce-added in fp32");
 
   // SWIZZLE_128B tiles need 1024 B alignment; the dynamic smem window starts 1024-aligned when
   // the kernel has no static shared memory (checked below).
@@ -131,10 +190,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = (tile / n_tiles) * kCluster + cta_rank;
-        const int n_blk = tile % n_tiles;
-        for (int kb = 0; kb < total_kb; ++kb) {
+      Sched<kStreamK> sched(cluster_id, num_clusters, num_tiles, total_kb);
+      Work w;
+      while (sched.next(w)) {
+        const int m_blk = (w.tile / n_tiles) * kCluster + cta_rank;
+        const int n_blk = w.tile % n_tiles;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           const int term = kb / k_blocks;
           const int kk = kb - term * k_blocks;
           // term 0: A_hi * W_hi, term 1: A_lo * W_hi, term 2: A_hi * W_lo
@@ -144,9 +205,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], kCluster * kStageBytes);
           uint8_t* sa = smem_ab + stage * kStageBytes;
           const uint32_t full_leader = mapa_u32(&bars->full[stage], 0);
-          tma_load_2d_pair(&tm_a, full_leader, sa, kk * BK, a_row);
+          if (!kAMn) {
+            tma_load_2d_pair(&tm_a, full_leader, sa, kk * BK, a_row);
+          } else {  // A^T operand: tensor [reduction, M], two 64-wide boxes
+            tma_load_2d_pair(&tm_a, full_leader, sa, m_blk * BM, kk * BK);
+            tma_load_2d_pair(&tm_a, full_leader, sa + kMnChunkBytes, m_blk * BM + 64, kk * BK);
+          }
           // this CTA's half (128 rows) of the 256-row W tile
-          tma_load_2d_pair(&tm_b, full_leader, sa + kABytes, kk * BK, b_row + cta_rank * (BN / kCluster));
+          if (!kBMn) {
+            tma_load_2d_pair(&tm_b, full_leader, sa + kABytes, kk * BK, b_row + cta_rank * (BN / kCluster));
+          } else {  // B operand: tensor [reduction, N]
+            const int col = n_blk * BN + cta_rank * (BN / kCluster);
+            tma_load_2d_pair(&tm_b, full_leader, sa + kABytes, col, kk * BK);
+            tma_load_2d_pair(&tm_b, full_leader, sa + kABytes + kMnChunkBytes, col + 64, kk * BK);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -157,26 +229,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kCluster * BM, BN);  // M = 256 across the pair
+      // M = 256 across the pair
+      constexpr uint32_t idesc = umma_idesc_bf16(kCluster * BM, BN) | (kAMn ? (1u << 15) : 0u) |
+                                 (kBMn ? (1u << 16) : 0u);
+      // K advance of 16 elements inside a stage, in 16-byte descriptor units: 32 B along a K-major
+      // row, 16 rows x 128 B for MN-major
+      constexpr uint32_t kStepA = kAMn ? 128 : 2;
+      constexpr uint32_t kStepB = kBMn ? 128 : 2;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      Sched<kStreamK> sched(cluster_id, num_clusters, num_tiles, total_kb);
+      Work w;
+      for (; sched.next(w); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < total_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&bars->full[stage], phase);  // TMA bytes have landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
-          const uint64_t da = umma_desc_k_sw128(sa);
-          const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+          const uint64_t da = kAMn ? umma_desc_mn_sw128(sa, kMnChunkBytes) : umma_desc_k_sw128(sa);
+          const uint64_t db = kBMn ? umma_desc_mn_sw128(sa + kABytes, kMnChunkBytes)
+                                   : umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
-            umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_pair(tmem_d, da + kStepA * k, db + kStepB * k, idesc,
+                              (kb != w.kb0 || k != 0) ? 1u : 0u);
           }
           // frees this smem stage in BOTH CTAs once these MMAs have read it
           umma_commit_pair(&bars->empty[stage], kClusterMask);
@@ -197,9 +278,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     const uint32_t row_smem = smem_u32(ebuf) + lane * 128;  // this thread's 128 B staging row
     int it = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-      const int m_blk = (tile / n_tiles) * kCluster + cta_rank;
-      const int n_blk = tile % n_tiles;
+    Sched<kStreamK> sched(cluster_id, num_clusters, num_tiles, total_kb);
+    Work w;
+    for (; sched.next(w); ++it) {
+      const int m_blk = (w.tile / n_tiles) * kCluster + cta_rank;
+      const int n_blk = w.tile % n_tiles;
       const bool store_ok = m_blk < m_tiles;  // odd tile counts: the last pair has a dummy half
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -223,11 +306,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(bias4 + c * 8 + (j >> 2));
+          const float4 b4 = kBias ? __ldg(bias4 + c * 8 + (j >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
           f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
           f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
           f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
           f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        }
+        uint32_t pre[kOut == GEMM_OUT_BF16_DUAL ? 16 : 1];  // pre-activation values (training)
+        if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pre[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
         }
         if (kGelu == 1) {
 #pragma unroll
@@ -251,7 +339,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && store_ok) {
-            tma_store_2d(&tm_out, ebuf, col0 + c * 32, row0);
+            if (kStreamK) tma_reduce_add_2d(&tm_out, ebuf, col0 + c * 32, row0);
+            else tma_store_2d(&tm_out, ebuf, col0 + c * 32, row0);
             tma_store_commit();
           }
         } else {
@@ -270,6 +359,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                          "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])),
                          "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
                          : "memory");
+            if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kEpiBufBytes),
+                           "r"(pre[4 * j + 0]), "r"(pre[4 * j + 1]), "r"(pre[4 * j + 2]),
+                           "r"(pre[4 * j + 3])
+                           : "memory");
+            }
             if (kOut == GEMM_OUT_BF16_SPLIT) {
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kEpiBufBytes),
                            "r"(pack_bf16x2(bf16_residual(f[8 * j + 0]), bf16_residual(f[8 * j + 1]))),
@@ -284,7 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             __syncwarp();
             if (lane == 0 && store_ok) {
               tma_store_2d(&tm_out, ebuf, col0 + (c - 1) * 32, row0);
-              if (kOut == GEMM_OUT_BF16_SPLIT)
+              if (kOut == GEMM_OUT_BF16_SPLIT || kOut == GEMM_OUT_BF16_DUAL)
                 tma_store_2d(&tm_out, ebuf + kEpiBufBytes, col0 + (c - 1) * 32,
                              out_plane_rows + row0);
               tma_store_commit();
@@ -314,9 +409,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 // -------------------------------------------------------------------------------------------------
 int gemm_smem_bytes() { return Cfg<GEMM_OUT_F32>::kSmemBytes; }
 
-template <int kTerms, int kOut, int kGelu>
+template <int kTerms, int kOut, int kGelu, int kLayout = GEMM_NT>
 static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sms) {
-  auto kern = gemm_tcgen05_kernel<kTerms, kOut, kGelu>;
+  auto kern = gemm_tcgen05_kernel<kTerms, kOut, kGelu, kLayout>;
   constexpr int smem = Cfg<kOut>::kSmemBytes;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -328,7 +423,12 @@ static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sm
   const int n_tiles = g.n / BN;
   const int pair_tiles = ((m_tiles + kCluster - 1) / kCluster) * n_tiles;
   const int max_clusters = num_sms / kCluster;
-  const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
+  const int k_blocks = (g.k + BK - 1) / BK;
+  int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
+  if (kLayout == GEMM_TN_RED) {  // stream-K: every pair gets an equal share of the (tile, k-block) steps
+    const long long steps = static_cast<long long>(pair_tiles) * k_blocks;
+    clusters = steps < max_clusters ? static_cast<int>(steps) : max_clusters;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * kCluster);
   cfg.blockDim = dim3(kThreads);
@@ -342,12 +442,26 @@ static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sm
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, g.tm_a, g.tm_b, g.tm_out, g.bias, m_tiles, n_tiles,
-                            g.k / BK, g.a_plane_rows, g.b_plane_rows, g.out_plane_rows);
+                            k_blocks, g.a_plane_rows, g.b_plane_rows, g.out_plane_rows);
 }
 
 cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_sms) {
-  if (g.m_rows <= 0 || g.m_rows % BM != 0 || g.n % BN != 0 || g.k % BK != 0)
+  if (g.m_rows <= 0 || g.m_rows % BM != 0 || g.n % BN != 0 || g.k <= 0) return cudaErrorInvalidValue;
+  // the reduction of the weight-gradient layout may be ragged (TMA zero-fills rows past the end)
+  if (g.layout != GEMM_TN_RED && g.k % BK != 0) return cudaErrorInvalidValue;
+  if (g.layout == GEMM_NN) {
+    if (g.terms == 1 && g.gelu == 0 && g.out_kind == GEMM_OUT_F32)
+      return launch_one<1, GEMM_OUT_F32, 0, GEMM_NN>(g, stream, num_sms);
+    if (g.terms == 1 && g.gelu == 0 && g.out_kind == GEMM_OUT_BF16)
+      return launch_one<1, GEMM_OUT_BF16, 0, GEMM_NN>(g, stream, num_sms);
     return cudaErrorInvalidValue;
+  }
+  if (g.layout == GEMM_TN_RED) {
+    if (g.terms == 1 && g.gelu == 0 && g.out_kind == GEMM_OUT_F32)
+      return launch_one<1, GEMM_OUT_F32, 0, GEMM_TN_RED>(g, stream, num_sms);
+    return cudaErrorInvalidValue;
+  }
+  if (g.layout != GEMM_NT) return cudaErrorInvalidValue;
 #define STLT_GEMM_CASE(T, O, G) \
   if (g.terms == T && g.out_kind == O && g.gelu == G) return launch_one<T, O, G>(g, stream, num_sms);
   STLT_GEMM_CASE(1, GEMM_OUT_F32, 0)
@@ -357,6 +471,7 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
   STLT_GEMM_CASE(3, GEMM_OUT_F32, 0)
   STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 1)
   STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 0)
+  STLT_GEMM_CASE(1, GEMM_OUT_BF16_DUAL, 2)
 #undef STLT_GEMM_CASE
   return cudaErrorInvalidValue;
 }

@@ -12,6 +12,13 @@ enum GemmOutKind : int {
   GEMM_OUT_F32 = 0,         // fp32 [M, N]
   GEMM_OUT_BF16 = 1,        // bf16 [M, N]
   GEMM_OUT_BF16_SPLIT = 2,  // bf16 hi plane [M, N] followed by lo plane [M, N]
+  GEMM_OUT_BF16_DUAL = 3,   // bf16 act(z) [M, N] followed by bf16 z [M, N] (training: GELU input kept)
+};
+
+enum GemmLayout : int {
+  GEMM_NT = 0,      // out[M,N]  = A[M,K] * B[N,K]^T + bias   (forward projections)
+  GEMM_NN = 1,      // out[M,N]  = A[M,K] * B[K,N]            (data gradients)
+  GEMM_TN_RED = 2,  // out[M,N] += A[K,M]^T * B[K,N]          (weight gradients, stream-K + reduce-add)
 };
 
 struct GemmArgs {
@@ -28,6 +35,7 @@ struct GemmArgs {
   int a_plane_rows;    // row offset of the lo plane of A
   int b_plane_rows;    // row offset of the lo plane of W
   int out_plane_rows;  // row offset of the lo plane of the output (split only)
+  int layout;          // GemmLayout; MN-major operands use box {64, 64} tensor maps
 };
 
 int gemm_smem_bytes();

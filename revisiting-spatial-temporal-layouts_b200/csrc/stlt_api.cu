@@ -165,7 +165,45 @@ int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_rows, lo
   g.a_plane_rows = static_cast<int>(a_plane_rows);
   g.b_plane_rows = n;
   g.out_plane_rows = static_cast<int>(a_plane_rows);
+  g.layout = GEMM_NT;
   ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
+  STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
+  h->launches++;
+  return STLT_OK;
+}
+
+// Gradient GEMMs of the training step (bf16 operands, fp32 accumulation):
+//   GEMM_NN     out[m_rows, n]  = A[m_rows, k] * B[k, n]       (out fp32 or bf16; rows padded to 128)
+//   GEMM_TN_RED out[m_rows, n] += A[k, m_rows]^T * B[k, n]      (out fp32; k = token count, any value)
+int run_gemm_grad(Handle* h, cudaStream_t stream, int layout, const void* a, const void* b, void* out,
+                  long long m_rows, int n, long long k, int out_kind) {
+  GemmArgs g{};
+  int rc;
+  if (layout == GEMM_NN) {
+    rc = make_tm(h, &g.tm_a, a, 1, m_rows, k, 64, 128);
+    if (rc) return rc;
+    rc = make_tm(h, &g.tm_b, b, 1, k, n, 64, 64);
+  } else if (layout == GEMM_TN_RED) {
+    rc = make_tm(h, &g.tm_a, a, 1, k, m_rows, 64, 64);
+    if (rc) return rc;
+    rc = make_tm(h, &g.tm_b, b, 1, k, n, 64, 64);
+  } else {
+    return fail(h, STLT_ERR_INVALID, "run_gemm_grad: bad layout %d", layout);
+  }
+  if (rc) return rc;
+  if (out_kind == GEMM_OUT_F32) rc = make_tm(h, &g.tm_out, out, 0, m_rows, n, 32, 32);
+  else if (out_kind == GEMM_OUT_BF16) rc = make_tm(h, &g.tm_out, out, 1, m_rows, n, 64, 32);
+  else return fail(h, STLT_ERR_INVALID, "run_gemm_grad: bad output kind %d", out_kind);
+  if (rc) return rc;
+  g.bias = nullptr;
+  g.m_rows = static_cast<int>(m_rows);
+  g.n = n;
+  g.k = static_cast<int>(k);
+  g.terms = 1;
+  g.out_kind = out_kind;
+  g.gelu = 0;
+  g.layout = layout;
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * static_cast<double>(k));
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
   return STLT_OK;
@@ -765,6 +803,15 @@ int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w
   if (m_rows % 128 || n % 256 || k % 64) return fail(h, STLT_ERR_INVALID, "shape not tile aligned");
   return run_gemm(h, static_cast<cudaStream_t>(stream), a_planes, m_rows, m_rows, w_planes, n, k, bias,
                   out, terms, out_kind, gelu);
+}
+
+int stlt_op_gemm_grad(void* handle, void* stream, int32_t layout, const void* a, const void* b, void* out,
+                      int32_t m_rows, int32_t n, int64_t k, int32_t out_kind) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !a || !b || !out) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (m_rows % 128 || n % 256 || k < 1) return fail(h, STLT_ERR_INVALID, "shape not tile aligned");
+  if (layout == GEMM_NN && k % 64) return fail(h, STLT_ERR_INVALID, "k must be a multiple of 64");
+  return run_gemm_grad(h, static_cast<cudaStream_t>(stream), layout, a, b, out, m_rows, n, k, out_kind);
 }
 
 int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w, const float* bias,

@@ -120,6 +120,8 @@ SIGNATURES = {
     "stlt_get_profile": (c_int32, [c_void_p, POINTER(StltProfile)]),
     "stlt_op_gemm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "stlt_op_gemm_grad": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                    c_int32, c_int64, c_int32]),
     "stlt_op_gemm_simt": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int32, c_int32, c_int32, c_int32]),
     "stlt_op_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int32,

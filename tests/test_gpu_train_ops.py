@@ -1,0 +1,65 @@
+"""GPU parity tests of the training-step operators, through the C ABI."""
+import ctypes
+import math
+
+import pytest
+import torch
+
+from stlt_b200 import lib as L
+from tests.util import nerr
+
+pytestmark = pytest.mark.gpu
+
+GEMM_NN, GEMM_TN_RED = 1, 2
+
+
+@pytest.fixture(scope="module")
+def handle():
+    lib = L.load_library()
+    dims = L.StltDims(768, 12, 0, 0, 4, 174, 256, 5, 1e-12, 1e-5)
+    h = ctypes.c_void_p()
+    L.check(None, lib.stlt_create(ctypes.byref(dims), ctypes.byref(h)))
+    yield h
+    lib.stlt_destroy(h)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# data gradient dX[M, N] = dY[M, K] * W[K, N]: the four projection shapes + a multi-wave case
+NN_CASES = [(256, 768, 2304, 0), (384, 768, 768, 1), (256, 3072, 768, 1), (256, 768, 3072, 0),
+            (148 * 128 * 2 + 128, 768, 768, 0)]
+
+
+@pytest.mark.parametrize("m,n,k,out_kind", NN_CASES)
+def test_gemm_data_gradient(handle, m, n, k, out_kind):
+    lib = L.load_library()
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(k, n, device="cuda", generator=g) / math.sqrt(k)).to(torch.bfloat16)
+    out = torch.full((m, n), float("nan"), device="cuda",
+                     dtype=torch.float32 if out_kind == 0 else torch.bfloat16)
+    L.check(handle, lib.stlt_op_gemm_grad(handle, _stream(), GEMM_NN, a.data_ptr(), w.data_ptr(),
+                                          out.data_ptr(), m, n, k, out_kind))
+    ref = a.double() @ w.double()
+    assert nerr(out, ref) < (5e-6 if out_kind == 0 else 6e-3)
+
+
+# weight gradient dW[M, N] += dY[K, M]^T * X[K, N], K = token count (ragged allowed)
+TN_CASES = [(2304, 768, 640), (768, 768, 1000), (3072, 768, 4096 + 17), (768, 3072, 85 * 64),
+            (768, 768, 1), (256, 256, 148 * 64 * 3 + 5)]
+
+
+@pytest.mark.parametrize("m,n,k", TN_CASES)
+def test_gemm_weight_gradient(handle, m, n, k):
+    lib = L.load_library()
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(k, m, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(k, n, device="cuda", generator=g).to(torch.bfloat16)
+    init = torch.randn(m, n, device="cuda", generator=g)
+    out = init.clone()
+    L.check(handle, lib.stlt_op_gemm_grad(handle, _stream(), GEMM_TN_RED, a.data_ptr(), b.data_ptr(),
+                                          out.data_ptr(), m, n, k, 0))
+    ref = init.double() + a.double().T @ b.double()
+    assert nerr(out, ref) < 1e-5
