@@ -191,6 +191,57 @@ int stlt_set_pruning(void* handle, int32_t enable);
 /* Test taps (NULL disables). The struct is copied. */
 int stlt_set_taps(void* handle, const StltTaps* taps);
 
+/* ---- training step (BASELINE.json configs[3]) -------------------------
+ * Device side of the reference loop src/train.py:117-135: forward with saved activations,
+ * criterion (src/utils/train_inference_utils.py:64-76), backward, clip_grad_norm_ (train.py:129)
+ * and torch.optim.AdamW (train.py:102-104,130). bf16 GEMM operands, everything else fp32; the
+ * weights must be packed for STLT_PRECISION_BF16. Gradients are ACCUMULATED into the buffers bound
+ * with stlt_bind_grads (zero them first, like optimizer.zero_grad()); the weight-gradient GEMMs and
+ * the column reductions add with atomics, so results are not bit-reproducible run to run. */
+
+/* Binds fp32 gradient buffers by reference state_dict name (same shapes as the parameters). A
+ * parameter without an entry gets no gradient (frozen backbone, models.py:172-176). */
+int stlt_bind_grads(void* handle, const StltTensor* tensors, int32_t count);
+
+int stlt_train_workspace_bytes(void* handle, int32_t batch, int32_t frames, int32_t slots, size_t* bytes);
+
+/* Stlt.forward in train mode. The workspace keeps the activations stlt_backward needs and must not
+ * be touched in between. dropout_p: the reference's hidden_dropout_prob (configs.py:97). */
+int stlt_forward_train(void* handle, void* stream, const int64_t* categories, const float* boxes,
+                       const float* scores_or_null, const int64_t* frame_types, const int64_t* lengths,
+                       int32_t batch, int32_t frames, int32_t slots, void* workspace,
+                       size_t workspace_bytes, float dropout_p, uint64_t seed, float* logits_out);
+
+/* loss.backward() from d loss / d logits (f32 [batch, num_classes]). `phases` selects which half
+ * runs, so a data-parallel caller can start the all-reduce of the first half's gradients while the
+ * second half computes: STLT_BWD_TEMPORAL = classifier head + temporal stack + frame embedding,
+ * STLT_BWD_SPATIAL = spatial stack + category/box embedding (must follow the first half). */
+#define STLT_BWD_TEMPORAL 1
+#define STLT_BWD_SPATIAL 2
+#define STLT_BWD_ALL 3
+int stlt_backward(void* handle, void* stream, const int64_t* categories, const float* boxes,
+                  const float* scores_or_null, const int64_t* frame_types, const int64_t* lengths,
+                  int32_t batch, int32_t frames, int32_t slots, void* workspace, size_t workspace_bytes,
+                  const float* d_logits, int32_t phases);
+
+/* Criterion: mean cross-entropy (labels i64 [rows], Something-Else) or mean BCE-with-logits (targets
+ * f32 [rows, classes], Action Genome). loss_out (device float, may be NULL) receives the loss,
+ * d_logits_out (may be NULL) its gradient times grad_scale. */
+#define STLT_LOSS_CROSS_ENTROPY 0
+#define STLT_LOSS_BCE_LOGITS 1
+int stlt_loss(void* handle, void* stream, int32_t kind, const float* logits, const void* labels,
+              int32_t rows, int32_t classes, float grad_scale, float* loss_out, float* d_logits_out);
+
+/* sumsq_inout[0] += sum(grads^2) over a flat fp32 buffer (the squared total norm of clip_grad_norm_). */
+int stlt_grad_sumsq(void* handle, void* stream, const float* grads, int64_t n, float* sumsq_inout);
+
+/* One AdamW step on flat fp32 buffers (torch.optim.AdamW semantics, decoupled weight decay, bias
+ * correction for `step` >= 1). If sumsq is given, gradients are first scaled by
+ * min(1, max_norm / (sqrt(sumsq) + 1e-6)) as clip_grad_norm_ does — read on the device, no sync. */
+int stlt_adamw_step(void* handle, void* stream, float* params, const float* grads, float* exp_avg,
+                    float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int32_t step, const float* sumsq_or_null, float max_norm);
+
 /* ---- single-operator entry points used by the parity tests -------------------------------- */
 
 /* out = epilogue(sum_terms A_t W_t^T + bias): A bf16 [terms>1 ? 2 : 1][m_rows][k], W bf16

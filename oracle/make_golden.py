@@ -167,6 +167,76 @@ def golden_model(configs, models, layout: str, batch_size: int, weight_seed: int
     print(f"stlt_{layout}.npz logits", tuple(logits.shape), "max|logit|", float(logits.abs().max()))
 
 
+def golden_training(configs, models, train_utils, layout: str, batch_size: int, weight_seed: int, batch_seed: int,
+                    steps: int = 3):
+    """Reference training loop body (src/train.py:117-135) with dropout p = 0 on a fixed batch:
+    loss, per-tensor gradient norms + a few full gradient tensors of the first step, and the loss /
+    per-tensor parameter norms after each AdamW step (clip 5.0, lr 5e-5, wd 1e-3, warm-up schedule)."""
+    import stlt_b200
+    from stlt_b200.synthetic import make_batch, random_state_dict
+    spec = stlt_b200.SOMETHING_ELSE if layout == "something" else stlt_b200.ACTION_GENOME
+    cfg = configs.StltModelConfig(num_classes=spec["num_classes"], unique_categories=spec["unique_categories"],
+                                  hidden_dropout_prob=0.0)
+    torch.manual_seed(0)
+    ref = models.Stlt(cfg)
+    sd = random_state_dict(ref.state_dict(), seed=weight_seed)
+    ref.load_state_dict(sd, strict=True)
+    ref.train(True)
+    batch = make_batch(batch_size, layout=layout, ragged=True, seed=batch_seed)
+    g = torch.Generator().manual_seed(batch_seed + 100)
+    if layout == "something":
+        labels = torch.randint(0, spec["num_classes"], (batch_size,), generator=g)
+    else:
+        labels = (torch.rand((batch_size, spec["num_classes"]), generator=g) < 0.05).float()
+    crit = train_utils.Criterion(layout)
+    optimizer = torch.optim.AdamW(train_utils.add_weight_decay(ref, 1e-3), lr=5e-5)
+    scheduler = train_utils.get_linear_schedule_with_warmup(optimizer, num_warmup_steps=2, num_training_steps=10)
+    out = {"layout": np.array(layout), "batch_size": np.int64(batch_size), "weight_seed": np.int64(weight_seed),
+           "batch_seed": np.int64(batch_seed), "weights_checksum": np.float64(weights_checksum(sd)),
+           "labels": labels.numpy(), "steps": np.int64(steps)}
+    names = [n for n, _ in ref.named_parameters()]
+    out["param_names"] = np.array(names)
+    losses, norms = [], []
+    for step in range(steps):
+        optimizer.zero_grad()
+        logits = ref({k: v.clone() for k, v in batch.items()})
+        loss = crit(logits, labels)
+        loss.backward()
+        if step == 0:
+            out["logits0"] = logits["stlt"].detach().numpy()
+            out["grad_norms"] = np.array([float(p.grad.norm()) if p.grad is not None else -1.0
+                                          for _, p in ref.named_parameters()], dtype=np.float64)
+            keep = ["prediction_head.fc2.bias", "prediction_head.fc1.bias", "prediction_head.layer_norm.weight",
+                    "backbone.frames_embeddings.layout_embedding.category_box_embeddings.category_embeddings.weight",
+                    "backbone.frames_embeddings.layout_embedding.category_box_embeddings.box_embedding.weight",
+                    "backbone.frames_embeddings.layout_embedding.category_box_embeddings.layer_norm.bias",
+                    "backbone.frames_embeddings.frame_type_embedding.weight",
+                    "backbone.frames_embeddings.layer_norm.weight",
+                    "backbone.frames_embeddings.layout_embedding.transformer.layers.0.self_attn.in_proj_bias",
+                    "backbone.frames_embeddings.layout_embedding.transformer.layers.3.norm1.weight",
+                    "backbone.transformer.layers.7.linear1.bias", "backbone.transformer.layers.0.norm2.bias"]
+            if layout == "action_genome":
+                keep.append("backbone.frames_embeddings.layout_embedding.category_box_embeddings.score_embeddings.weight")
+            params = dict(ref.named_parameters())
+            for k in keep:
+                out["grad/" + k] = params[k].grad.detach().numpy().copy()
+            out["grad/position_rows"] = params["backbone.frames_embeddings.position_embeddings.weight"].grad[:17].numpy().copy()
+            out["grad/sp0_in_proj_rows"] = params[
+                "backbone.frames_embeddings.layout_embedding.transformer.layers.0.self_attn.in_proj_weight"].grad[::96, ::8].numpy().copy()
+            out["grad/tm7_linear2_rows"] = params["backbone.transformer.layers.7.linear2.weight"].grad[::32, ::64].numpy().copy()
+        total = torch.nn.utils.clip_grad_norm_(ref.parameters(), 5.0)
+        optimizer.step()
+        scheduler.step()
+        losses.append(float(loss))
+        norms.append(float(total))
+        out[f"param_norms_step{step + 1}"] = np.array([float(p.detach().double().norm()) for _, p in ref.named_parameters()])
+        out[f"param_sums_step{step + 1}"] = np.array([float(p.detach().double().sum()) for _, p in ref.named_parameters()])
+    out["losses"] = np.array(losses)
+    out["total_grad_norms"] = np.array(norms)
+    np.savez_compressed(GOLDEN / f"train_{layout}.npz", **out)
+    print(f"train_{layout}.npz losses", losses, "grad norms", norms)
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     configs, datasets, models, data_utils = import_reference()
@@ -175,6 +245,9 @@ def main():
     golden_dataset(configs, datasets, "action_genome", seed=22)
     golden_model(configs, models, "something", batch_size=3, weight_seed=1, batch_seed=3)
     golden_model(configs, models, "action_genome", batch_size=2, weight_seed=2, batch_seed=4)
+    from utils import train_inference_utils as train_utils
+    golden_training(configs, models, train_utils, "something", batch_size=4, weight_seed=5, batch_seed=6)
+    golden_training(configs, models, train_utils, "action_genome", batch_size=2, weight_seed=6, batch_seed=7)
 
 
 if __name__ == "__main__":

@@ -287,3 +287,65 @@ def stlt_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], nu
     logits = F.linear(h, sd[ph + "fc2.weight"], sd[ph + "fc2.bias"])
     taps["stlt"] = logits
     return taps if return_taps else logits
+
+
+# ---------------------------------------------------------------------------------------------------
+# training step: src/train.py:102-135, src/utils/train_inference_utils.py
+# ---------------------------------------------------------------------------------------------------
+def criterion(logits: torch.Tensor, labels: torch.Tensor, loss: str) -> torch.Tensor:
+    """Criterion.forward for the single "stlt" logit (train_inference_utils.py:64-76): mean
+    cross-entropy (Something-Else) or mean BCE-with-logits (Action Genome)."""
+    if loss == "cross_entropy":
+        lse = torch.logsumexp(logits, dim=-1)
+        return (lse - logits.gather(1, labels.view(-1, 1)).squeeze(1)).mean()
+    x, y = logits, labels.to(logits.dtype)
+    return (x.clamp_min(0) - x * y + torch.log1p(torch.exp(-x.abs()))).mean()
+
+
+def loss_and_grads(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], labels: torch.Tensor,
+                   loss: str = "cross_entropy", dtype: torch.dtype = torch.float32):
+    """loss.backward() of the reference loop (train.py:125-128) with dropout p = 0: returns
+    (loss, logits, {name: grad}) by differentiating the restated forward. Tensors that do not reach
+    the logits (orphan encoder_layer.*, score embedding without scores) have no entry, like
+    ``param.grad is None`` in the reference."""
+    leaves = {k: (v.detach().clone().to(dtype).requires_grad_(True) if v.is_floating_point() else v)
+              for k, v in sd.items()}
+    logits = stlt_forward(leaves, batch, dtype=dtype)
+    value = criterion(logits, labels, loss)
+    names = [k for k, v in leaves.items() if v.is_floating_point()]
+    grads = torch.autograd.grad(value, [leaves[k] for k in names], allow_unused=True)
+    return value.detach(), logits.detach(), {k: g for k, g in zip(names, grads) if g is not None}
+
+
+def is_no_decay(name: str, tensor: torch.Tensor) -> bool:
+    """add_weight_decay (train_inference_utils.py:37-54): 1-D tensors and *.bias are not decayed."""
+    return tensor.dim() == 1 or name.endswith(".bias")
+
+
+def linear_schedule(step: int, num_warmup_steps: int, num_training_steps: int) -> float:
+    """lr_lambda of get_linear_schedule_with_warmup (train_inference_utils.py:21-34)."""
+    if step < num_warmup_steps:
+        return float(step) / float(max(1, num_warmup_steps))
+    return max(0.0, float(num_training_steps - step) / float(max(1, num_training_steps - num_warmup_steps)))
+
+
+def adamw_update(sd: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], state: Dict[str, dict], step: int,
+                 lr: float, weight_decay: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 clip_val: float = 5.0) -> float:
+    """clip_grad_norm_(parameters, clip_val) (train.py:129) followed by one torch.optim.AdamW step
+    (train.py:102-104,130), in place on ``sd``; tensors without a gradient are skipped. ``step`` is
+    1-based. Returns the total gradient norm before clipping."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()
+    coef = min(1.0, clip_val / (total + 1e-6))
+    b1, b2 = betas
+    for name, g in grads.items():
+        g = g * coef
+        st = state.setdefault(name, {"m": torch.zeros_like(g), "v": torch.zeros_like(g)})
+        p = sd[name]
+        wd = 0.0 if is_no_decay(name, p) else weight_decay
+        p.mul_(1.0 - lr * wd)
+        st["m"].mul_(b1).add_(g, alpha=1.0 - b1)
+        st["v"].mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        denom = st["v"].sqrt() / math.sqrt(1.0 - b2 ** step) + eps
+        p.addcdiv_(st["m"], denom, value=-(lr / (1.0 - b1 ** step)))
+    return total

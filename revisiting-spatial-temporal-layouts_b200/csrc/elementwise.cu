@@ -2,87 +2,11 @@
 // (K1), residual add + LayerNorm, frame embedding (K7), last-frame gather (K9), weight packing.
 // One warp owns one 768-wide row; lane l holds columns 4*l + 128*k + {0..3}, k = 0..5, so every
 // global access is a coalesced 16-byte vector.
-#include "common.cuh"
-#include "kernels.h"
+#include "rowops.cuh"
 
 namespace stlt {
 
 namespace {
-
-constexpr int kVec = kHidden / 128;  // 6 float4 per lane
-
-struct RowRegs {
-  float4 v[kVec];
-};
-
-__device__ __forceinline__ const float4* row4(const float* base, long long row) {
-  return reinterpret_cast<const float4*>(base + row * kHidden);
-}
-
-__device__ __forceinline__ RowRegs load_row(const float* base, long long row, int lane) {
-  RowRegs r;
-  const float4* p = row4(base, row);
-#pragma unroll
-  for (int k = 0; k < kVec; ++k) r.v[k] = __ldg(p + lane + 32 * k);
-  return r;
-}
-
-// LayerNorm over the 768 features held by one warp (biased variance, two-pass in registers).
-__device__ __forceinline__ void layer_norm_row(RowRegs& r, const float* __restrict__ gamma,
-                                               const float* __restrict__ beta, float eps, int lane) {
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < kVec; ++k) s += (r.v[k].x + r.v[k].y) + (r.v[k].z + r.v[k].w);
-  const float mean = warp_sum(s) * (1.0f / kHidden);
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < kVec; ++k) {
-    const float a = r.v[k].x - mean, b = r.v[k].y - mean, c = r.v[k].z - mean, d = r.v[k].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-  const float var = warp_sum(q) * (1.0f / kHidden);
-  const float rstd = 1.0f / sqrtf(var + eps);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-#pragma unroll
-  for (int k = 0; k < kVec; ++k) {
-    const float4 g = __ldg(g4 + lane + 32 * k);
-    const float4 b = __ldg(b4 + lane + 32 * k);
-    r.v[k].x = (r.v[k].x - mean) * rstd * g.x + b.x;
-    r.v[k].y = (r.v[k].y - mean) * rstd * g.y + b.y;
-    r.v[k].z = (r.v[k].z - mean) * rstd * g.z + b.z;
-    r.v[k].w = (r.v[k].w - mean) * rstd * g.w + b.w;
-  }
-}
-
-__device__ __forceinline__ void store_act(const ActOut& out, long long row, const RowRegs& r,
-                                          int lane) {
-  if (out.x != nullptr) {
-    float4* p = reinterpret_cast<float4*>(out.x + row * kHidden);
-#pragma unroll
-    for (int k = 0; k < kVec; ++k) p[lane + 32 * k] = r.v[k];
-  }
-  if (out.xb != nullptr) {
-    uint2* hi = reinterpret_cast<uint2*>(out.xb + row * kHidden);
-#pragma unroll
-    for (int k = 0; k < kVec; ++k) {
-      uint2 h;
-      h.x = pack_bf16x2(r.v[k].x, r.v[k].y);
-      h.y = pack_bf16x2(r.v[k].z, r.v[k].w);
-      hi[lane + 32 * k] = h;
-    }
-    if (out.planes == 2) {
-      uint2* lo = reinterpret_cast<uint2*>(out.xb + (out.plane_rows + row) * kHidden);
-#pragma unroll
-      for (int k = 0; k < kVec; ++k) {
-        uint2 l;
-        l.x = pack_bf16x2(bf16_residual(r.v[k].x), bf16_residual(r.v[k].y));
-        l.y = pack_bf16x2(bf16_residual(r.v[k].z), bf16_residual(r.v[k].w));
-        lo[lane + 32 * k] = l;
-      }
-    }
-  }
-}
 
 __device__ __forceinline__ float4 fix_and_normalize_box(const double* rb, long long W, long long H);
 
@@ -355,7 +279,7 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
 __global__ void __launch_bounds__(256)
 add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y,
               const float* __restrict__ g, const float* __restrict__ b, float eps, long long rows,
-              ActOut out) {
+              ActOut out, float* __restrict__ z_out) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -370,6 +294,11 @@ add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y,
         r.v[k].z += a.v[k].z;
         r.v[k].w += a.v[k].w;
       }
+    }
+    if (z_out != nullptr) {  // training: the pre-LayerNorm sum is what the backward pass re-normalises
+      float4* pz = reinterpret_cast<float4*>(z_out + row * kHidden);
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) pz[lane + 32 * k] = r.v[k];
     }
     layer_norm_row(r, g, b, eps, lane);
     store_act(out, row, r, lane);
@@ -500,14 +429,6 @@ __global__ void masks_kernel(const long long* __restrict__ categories,
     for (long long i = i0; i < n_frames; i += stride) mask_frames[i] = frame_types[i] == 0 ? 1 : 0;
 }
 
-inline int row_grid(long long rows, int warps_per_block) {
-  long long blocks = (rows + warps_per_block - 1) / warps_per_block;
-  const long long cap = 148LL * 16;  // 16 resident 256-thread... capped; kernels are grid-stride
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return static_cast<int>(blocks);
-}
-
 }  // namespace
 
 cudaError_t launch_prepare(const double* raw_boxes, const long long* video_sizes,
@@ -548,9 +469,9 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
 }
 
 cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, const float* b,
-                          float eps, long long rows, ActOut out, cudaStream_t stream) {
+                          float eps, long long rows, ActOut out, cudaStream_t stream, float* z_out) {
   if (rows == 0) return cudaSuccess;
-  add_ln_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out);
+  add_ln_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,218 @@
+// Host-side state of a libstlt_b200 handle and the helpers shared by the inference (stlt_api.cu)
+// and training (stlt_train.cu) translation units.
+#pragma once
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/stlt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace stlt {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp32 parameter tensors of one encoder layer (device pointers borrowed from the caller). The same
+// struct describes the matching gradient buffers (written through const_cast by the backward pass).
+struct LayerWeights {
+  const float *in_w = nullptr, *in_b = nullptr, *out_w = nullptr, *out_b = nullptr;
+  const float *l1_w = nullptr, *l1_b = nullptr, *l2_w = nullptr, *l2_b = nullptr;
+  const float *n1_g = nullptr, *n1_b = nullptr, *n2_g = nullptr, *n2_b = nullptr;
+  // packed bf16 planes (inside the caller-provided packed buffer)
+  const __nv_bfloat16 *in_p = nullptr, *out_p = nullptr, *l1_p = nullptr, *l2_p = nullptr;
+};
+
+struct Weights {
+  const float *cat_table = nullptr, *box_w = nullptr, *box_b = nullptr, *score_w = nullptr,
+              *score_b = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  const float *pos_table = nullptr, *ft_table = nullptr, *fr_g = nullptr, *fr_b = nullptr;
+  const float *fc1_w = nullptr, *fc1_b = nullptr, *head_g = nullptr, *head_b = nullptr,
+              *fc2_w = nullptr, *fc2_b = nullptr;
+  std::vector<LayerWeights> spatial, temporal;
+};
+
+struct Handle {
+  StltDims dims{};
+  Weights w;
+  Weights g;  // fp32 gradient buffers bound by stlt_bind_grads (same names; null = not wanted)
+  bool bound = false;
+  bool grads_bound = false;
+  int packed_precision = -1;
+  const void* packed_ptr = nullptr;
+  int num_sms = 0;
+  int launches = 0;
+  EncodeTiledFn encode = nullptr;
+  StltTaps taps{};
+  // optional per-category timing (CUDA events on the launching stream)
+  bool pruning = true;  // run the row-wise tail of the last layer of each stack on the rows that are read
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int cat; cudaEvent_t a, b; double flops; };
+  std::vector<Span> spans;
+  std::map<std::tuple<const void*, int, long long, long long, int, int>, CUtensorMap> tm_cache;
+  char err[512] = {0};
+};
+
+extern thread_local char g_err[512];
+
+inline int fail(Handle* h, int code, const char* fmt, ...) {
+  char* dst = h ? h->err : g_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+inline cudaEvent_t next_event(Handle* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+
+// RAII span: records an event before and after the launches issued in its scope.
+struct ProfileScope {
+  Handle* h;
+  cudaStream_t s;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int cat;
+  double flops;
+  ProfileScope(Handle* h_, cudaStream_t s_, int cat_, double flops_ = 0.0)
+      : h(h_), s(s_), cat(cat_), flops(flops_) {
+    if (!h->profiling) return;
+    a = next_event(h);
+    b = next_event(h);
+    if (a && b) cudaEventRecord(a, s);
+  }
+  ~ProfileScope() {
+    if (!h->profiling || !a || !b) return;
+    cudaEventRecord(b, s);
+    h->spans.push_back({cat, a, b, flops});
+  }
+};
+
+#define STLT_CUDA(h, expr)                                                                  \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(h, STLT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+inline long long pad128(long long v) { return (v + 127) / 128 * 128; }
+inline size_t align1k(size_t v) { return (v + 1023) / 1024 * 1024; }
+
+// 2-D row-major tensor map with 128-byte swizzle. dtype: 0 = f32, 1 = bf16.
+inline int make_tm(Handle* h, CUtensorMap* tm, const void* ptr, int dtype, long long rows, long long cols,
+            int box_cols, int box_rows) {
+  auto key = std::make_tuple(ptr, dtype, rows, cols, box_cols, box_rows);
+  auto it = h->tm_cache.find(key);
+  if (it != h->tm_cache.end()) {
+    *tm = it->second;
+    return STLT_OK;
+  }
+  const size_t es = dtype == 0 ? 4 : 2;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(tm, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, STLT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box=%dx%d",
+                static_cast<int>(r), rows, cols, box_cols, box_rows);
+  if (h->tm_cache.size() > 4096) h->tm_cache.clear();
+  h->tm_cache[key] = *tm;
+  return STLT_OK;
+}
+
+// out = epilogue(A W^T + bias) on tcgen05. a/w point at plane 0; planes are a_plane_rows / n rows apart.
+inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_rows, long long a_plane_rows,
+             const void* w, int n, int k, const float* bias, void* out, int terms, int out_kind,
+             int gelu) {
+  GemmArgs g{};
+  const int planes = terms == 3 ? 2 : 1;
+  int rc = make_tm(h, &g.tm_a, a, 1, a_plane_rows * (planes - 1) + m_rows, k, 64, 128);
+  if (rc) return rc;
+  rc = make_tm(h, &g.tm_b, w, 1, static_cast<long long>(n) * planes, k, 64, 128);  // half tile per CTA
+  if (rc) return rc;
+  if (out_kind == GEMM_OUT_F32)
+    rc = make_tm(h, &g.tm_out, out, 0, m_rows, n, 32, 32);
+  else if (out_kind == GEMM_OUT_BF16)
+    rc = make_tm(h, &g.tm_out, out, 1, m_rows, n, 64, 32);
+  else
+    rc = make_tm(h, &g.tm_out, out, 1, a_plane_rows + m_rows, n, 64, 32);
+  if (rc) return rc;
+  g.bias = bias;
+  g.m_rows = static_cast<int>(m_rows);
+  g.n = n;
+  g.k = k;
+  g.terms = terms;
+  g.out_kind = out_kind;
+  g.gelu = gelu;
+  g.a_plane_rows = static_cast<int>(a_plane_rows);
+  g.b_plane_rows = n;
+  g.out_plane_rows = static_cast<int>(a_plane_rows);
+  g.layout = GEMM_NT;
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
+  STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
+  h->launches++;
+  return STLT_OK;
+}
+
+// Gradient GEMMs of the training step (bf16 operands, fp32 accumulation):
+//   GEMM_NN     out[m_rows, n]  = A[m_rows, k] * B[k, n]       (out fp32 or bf16; rows padded to 128)
+//   GEMM_TN_RED out[m_rows, n] += A[k, m_rows]^T * B[k, n]      (out fp32; k = token count, any value)
+inline int run_gemm_grad(Handle* h, cudaStream_t stream, int layout, const void* a, const void* b, void* out,
+                  long long m_rows, int n, long long k, int out_kind) {
+  GemmArgs g{};
+  int rc;
+  if (layout == GEMM_NN) {
+    rc = make_tm(h, &g.tm_a, a, 1, m_rows, k, 64, 128);
+    if (rc) return rc;
+    rc = make_tm(h, &g.tm_b, b, 1, k, n, 64, 64);
+  } else if (layout == GEMM_TN_RED) {
+    rc = make_tm(h, &g.tm_a, a, 1, k, m_rows, 64, 64);
+    if (rc) return rc;
+    rc = make_tm(h, &g.tm_b, b, 1, k, n, 64, 64);
+  } else {
+    return fail(h, STLT_ERR_INVALID, "run_gemm_grad: bad layout %d", layout);
+  }
+  if (rc) return rc;
+  if (out_kind == GEMM_OUT_F32) rc = make_tm(h, &g.tm_out, out, 0, m_rows, n, 32, 32);
+  else if (out_kind == GEMM_OUT_BF16) rc = make_tm(h, &g.tm_out, out, 1, m_rows, n, 64, 32);
+  else return fail(h, STLT_ERR_INVALID, "run_gemm_grad: bad output kind %d", out_kind);
+  if (rc) return rc;
+  g.bias = nullptr;
+  g.m_rows = static_cast<int>(m_rows);
+  g.n = n;
+  g.k = static_cast<int>(k);
+  g.terms = 1;
+  g.out_kind = out_kind;
+  g.gelu = 0;
+  g.layout = layout;
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * static_cast<double>(k));
+  STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
+  h->launches++;
+  return STLT_OK;
+}
+
+
+int bind_table(Handle* h, const StltTensor* tensors, int32_t count, Weights* dst, bool require_all);
+
+}  // namespace stlt

@@ -94,8 +94,10 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
                          ActOut out, int* err_flag, cudaStream_t stream);
 
 // x <- LayerNorm(x + y) (post-norm residual of nn.TransformerEncoderLayer); y may be null.
+// z_out (optional, training): receives the pre-LayerNorm sum x + y.
 cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, const float* b,
-                          float eps, long long rows, ActOut out, cudaStream_t stream);
+                          float eps, long long rows, ActOut out, cudaStream_t stream,
+                          float* z_out = nullptr);
 
 // K7: frame tokens = LN(spatial CLS slot + position + frame type) (src/modelling/models.py:98-111).
 cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* frame_types,
@@ -129,5 +131,54 @@ cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long
 // fp32 -> bf16 plane(s) for weights.
 cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,
                              cudaStream_t stream);
+
+// ---- training step; see train_kernels.cu / attention_bwd.cu -------------
+
+// Backward of x_out = LN(z): dz (fp32 and/or bf16), d gamma, d beta and colsum(dz) (bias gradient of
+// the linear that produced the residual branch). d_b (second addend of the incoming gradient) and
+// every output may be null.
+cudaError_t launch_ln_bwd(const float* d_a, const float* d_b, const float* z, const float* gamma,
+                          float eps, long long rows, float* dz_out, __nv_bfloat16* dzb_out,
+                          float* d_gamma, float* d_beta, float* d_bias, cudaStream_t stream);
+// In place d <- d * gelu'(u) on bf16 [rows, n] (u == null: no activation) + column sums into d_bias.
+cudaError_t launch_act_bwd_colsum(__nv_bfloat16* d, const __nv_bfloat16* u, long long rows, int n,
+                                  float* d_bias, cudaStream_t stream);
+cudaError_t launch_colsum_f32(const float* x, int rows, int n, float* out, cudaStream_t stream);
+// Adjoint of launch_gather_rows: dst_f[map(r)] += src_f[r]; dst_b[map(r)] = src_b[r].
+cudaError_t launch_scatter_rows(const float* src_f, float* dst_f, const __nv_bfloat16* src_b,
+                                __nv_bfloat16* dst_b, int stride, const long long* lengths, int L,
+                                long long rows, cudaStream_t stream);
+cudaError_t launch_frame_embed_bwd(const float* d_a, const float* d_b, const float* cls_x,
+                                   const long long* frame_types, const float* pos_table,
+                                   const float* ft_table, int n_frame_types, const float* gamma,
+                                   float eps, int B, int L, float* d_cls, float* d_pos, float* d_ft,
+                                   float* d_gamma, float* d_beta, cudaStream_t stream);
+cudaError_t launch_embed_bwd(const float* d_a, const float* d_b, const long long* categories,
+                             const float* boxes, const float* scores, const float* cat_table,
+                             int unique_categories, const float* box_w, const float* box_b,
+                             const float* score_w, const float* score_b, const float* gamma, float eps,
+                             long long tokens, float* d_pre, float* d_cat, float* d_box_w,
+                             float* d_box_b, float* d_score_w, float* d_score_b, float* d_gamma,
+                             float* d_beta, cudaStream_t stream);
+cudaError_t launch_gelu_ln(const float* h1, const float* g, const float* b, float eps, long long rows,
+                           float* out, cudaStream_t stream);
+cudaError_t launch_gelu_ln_bwd(const float* d_h2, const float* h1, const float* gamma, float eps,
+                               long long rows, float* d_h1, float* d_gamma, float* d_beta,
+                               cudaStream_t stream);
+// out[i, j] (+)= sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj], fp32 CUDA cores (classifier-head gradients).
+cudaError_t launch_gemm_strided(const float* a, long long sai, long long sak, const float* b,
+                                long long sbk, long long sbj, float* out, int m, int n, int k,
+                                bool accumulate, cudaStream_t stream);
+cudaError_t launch_cross_entropy(const float* logits, const long long* labels, int rows, int classes,
+                                 float grad_scale, float* loss, float* d_logits, cudaStream_t stream);
+cudaError_t launch_bce_logits(const float* logits, const float* targets, long long n, float grad_scale,
+                              float* loss, float* d_logits, cudaStream_t stream);
+cudaError_t launch_sumsq(const float* g, long long n, float* out, cudaStream_t stream);
+cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float bias_c1,
+                         float bias_c2_sqrt, const float* sumsq, float max_norm, cudaStream_t stream);
+cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* d_ctx,
+                                 const long long* mask_src, long long num_seqs, int T, bool causal,
+                                 __nv_bfloat16* d_qkv, cudaStream_t stream);
 
 }  // namespace stlt

@@ -1,0 +1,93 @@
+// Row-wise helpers shared by the HBM-bound kernels: one warp owns one 768-wide row; lane l holds
+// columns 4*l + 128*k + {0..3}, k = 0..5, so every global access is a coalesced 16-byte vector.
+#pragma once
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace stlt {
+
+constexpr int kVec = kHidden / 128;  // 6 float4 per lane
+
+struct RowRegs {
+  float4 v[kVec];
+};
+
+__device__ __forceinline__ const float4* row4(const float* base, long long row) {
+  return reinterpret_cast<const float4*>(base + row * kHidden);
+}
+
+__device__ __forceinline__ RowRegs load_row(const float* base, long long row, int lane) {
+  RowRegs r;
+  const float4* p = row4(base, row);
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) r.v[k] = __ldg(p + lane + 32 * k);
+  return r;
+}
+
+// LayerNorm over the 768 features held by one warp (biased variance, two-pass in registers).
+__device__ __forceinline__ void layer_norm_row(RowRegs& r, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) s += (r.v[k].x + r.v[k].y) + (r.v[k].z + r.v[k].w);
+  const float mean = warp_sum(s) * (1.0f / kHidden);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    const float a = r.v[k].x - mean, b = r.v[k].y - mean, c = r.v[k].z - mean, d = r.v[k].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) * (1.0f / kHidden);
+  const float rstd = 1.0f / sqrtf(var + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    const float4 g = __ldg(g4 + lane + 32 * k);
+    const float4 b = __ldg(b4 + lane + 32 * k);
+    r.v[k].x = (r.v[k].x - mean) * rstd * g.x + b.x;
+    r.v[k].y = (r.v[k].y - mean) * rstd * g.y + b.y;
+    r.v[k].z = (r.v[k].z - mean) * rstd * g.z + b.z;
+    r.v[k].w = (r.v[k].w - mean) * rstd * g.w + b.w;
+  }
+}
+
+__device__ __forceinline__ void store_act(const ActOut& out, long long row, const RowRegs& r,
+                                          int lane) {
+  if (out.x != nullptr) {
+    float4* p = reinterpret_cast<float4*>(out.x + row * kHidden);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) p[lane + 32 * k] = r.v[k];
+  }
+  if (out.xb != nullptr) {
+    uint2* hi = reinterpret_cast<uint2*>(out.xb + row * kHidden);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      uint2 h;
+      h.x = pack_bf16x2(r.v[k].x, r.v[k].y);
+      h.y = pack_bf16x2(r.v[k].z, r.v[k].w);
+      hi[lane + 32 * k] = h;
+    }
+    if (out.planes == 2) {
+      uint2* lo = reinterpret_cast<uint2*>(out.xb + (out.plane_rows + row) * kHidden);
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) {
+        uint2 l;
+        l.x = pack_bf16x2(bf16_residual(r.v[k].x), bf16_residual(r.v[k].y));
+        l.y = pack_bf16x2(bf16_residual(r.v[k].z), bf16_residual(r.v[k].w));
+        lo[lane + 32 * k] = l;
+      }
+    }
+  }
+}
+
+inline int row_grid(long long rows, int warps_per_block, int blocks_per_sm = 16) {
+  long long blocks = (rows + warps_per_block - 1) / warps_per_block;
+  const long long cap = 148LL * blocks_per_sm;  // kernels are grid-stride
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace stlt

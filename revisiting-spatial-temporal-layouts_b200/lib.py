@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t,
-                    c_uint8, c_void_p)
+                    c_uint8, c_uint64, c_void_p)
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -29,6 +29,11 @@ DTYPE_I64 = 1
 GEMM_OUT_F32 = 0
 GEMM_OUT_BF16 = 1
 GEMM_OUT_BF16_SPLIT = 2
+GEMM_OUT_BF16_DUAL = 3
+GEMM_NT, GEMM_NN, GEMM_TN_RED = 0, 1, 2
+
+BWD_TEMPORAL, BWD_SPATIAL, BWD_ALL = 1, 2, 3
+LOSS_CROSS_ENTROPY, LOSS_BCE_LOGITS = 0, 1
 
 
 class StltDims(Structure):
@@ -118,6 +123,18 @@ SIGNATURES = {
     "stlt_set_pruning": (c_int32, [c_void_p, c_int32]),
     "stlt_set_profiling": (c_int32, [c_void_p, c_int32]),
     "stlt_get_profile": (c_int32, [c_void_p, POINTER(StltProfile)]),
+    "stlt_bind_grads": (c_int32, [c_void_p, POINTER(StltTensor), c_int32]),
+    "stlt_train_workspace_bytes": (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(c_size_t)]),
+    "stlt_forward_train": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int32, c_int32, c_int32, c_void_p, c_size_t, c_float, c_uint64,
+                                     c_void_p]),
+    "stlt_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_int32]),
+    "stlt_loss": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_float,
+                            c_void_p, c_void_p]),
+    "stlt_grad_sumsq": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "stlt_adamw_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_float, c_float, c_float, c_float, c_float, c_int32, c_void_p, c_float]),
     "stlt_op_gemm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                c_int32, c_int32, c_int32, c_int32, c_int32]),
     "stlt_op_gemm_grad": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32,

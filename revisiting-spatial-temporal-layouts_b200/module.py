@@ -225,7 +225,7 @@ class Stlt(nn.Module):
         self._packed.clear()
         self._packed_key.clear()
 
-    def _sync_weights(self, device: torch.device, stream: int):
+    def _sync_weights(self, device: torch.device, stream: int, precision: Optional[str] = None):
         lib = _lib.load_library()
         named = [(n, p) for n, p in self.named_parameters()]
         key = tuple((p.data_ptr(), p._version) for _, p in named)
@@ -248,7 +248,7 @@ class Stlt(nn.Module):
             _lib.check(self._handle, lib.stlt_bind_weights(self._handle, arr, len(named)))
             self._weights_key = key
             self._packed_key.clear()
-        prec = _lib.PRECISIONS[self.precision]
+        prec = _lib.PRECISIONS[precision or self.precision]
         if self._packed_key.get(prec) != key or self._last_packed != prec:
             nbytes = ctypes.c_size_t()
             _lib.check(self._handle, lib.stlt_packed_weights_bytes(self._handle, prec, ctypes.byref(nbytes)))
@@ -295,10 +295,6 @@ class Stlt(nn.Module):
         return self._run(batch, want_taps=True)
 
     def _run(self, batch, want_taps: bool):
-        if self.training:
-            raise NotImplementedError(
-                "the training step (backward + AdamW + NCCL all-reduce) is not part of this build "
-                "yet (SURVEY.md §8(f) rank 1); call model.train(False) for the inference path")
         cats = batch["categories"]
         if not isinstance(cats, torch.Tensor) or cats.dim() != 3:
             raise ValueError("batch['categories'] must be an int64 tensor [B, L, S]")
@@ -315,6 +311,18 @@ class Stlt(nn.Module):
         scores = None
         if "scores" in batch:  # presence toggles the score embedding (models.py:33-35)
             scores = self._as_input(batch, "scores", torch.float32, (B, L, S), device)
+
+        dropout_p = float(getattr(self.config, "hidden_dropout_prob", 0.0)) if self.training else 0.0
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad or dropout_p > 0.0:
+            # training step (src/train.py:125-127): logits carry a grad_fn whose backward is
+            # stlt_backward; the reference's own criterion / clip_grad_norm_ / AdamW then work as is
+            if want_taps:
+                raise RuntimeError("forward_with_taps is an inference-only debugging aid")
+            names, params = zip(*self.named_parameters())
+            logits = _StltTrainFunction.apply(self, names, dropout_p, cats, boxes, scores, ftypes, lengths,
+                                              *params)
+            return {k: v for k, v in zip(self.logit_names, (logits,))}
 
         lib = _lib.load_library()
         with torch.cuda.device(device):
@@ -360,6 +368,53 @@ class Stlt(nn.Module):
             return out
         return {k: v for k, v in zip(self.logit_names, (logits,))}
 
+    # -- training plumbing (used by _StltTrainFunction and training.FusedTrainStep) ----------------
+    def _bind_grads(self, grads: Dict[str, torch.Tensor]) -> None:
+        lib = _lib.load_library()
+        arr = (_lib.StltTensor * max(len(grads), 1))()
+        keep = []
+        for i, (name, g) in enumerate(grads.items()):
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                raise RuntimeError(f"gradient buffer of {name} must be contiguous float32")
+            bname = name.encode()
+            keep.append(bname)
+            arr[i].name = bname
+            arr[i].data = g.data_ptr()
+            arr[i].dtype = _lib.DTYPE_F32
+            arr[i].ndim = g.dim()
+            for d, sz in enumerate(g.shape):
+                arr[i].shape[d] = sz
+        _lib.check(self._handle, lib.stlt_bind_grads(self._handle, arr, len(grads)))
+
+    def _train_workspace(self, B: int, L: int, S: int, device: torch.device) -> torch.Tensor:
+        lib = _lib.load_library()
+        nbytes = ctypes.c_size_t()
+        _lib.check(self._handle, lib.stlt_train_workspace_bytes(self._handle, B, L, S, ctypes.byref(nbytes)))
+        return torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+
+    def _forward_train(self, inputs, ws: torch.Tensor, dropout_p: float, seed: int) -> torch.Tensor:
+        cats, boxes, scores, ftypes, lengths = inputs
+        B, L, S = cats.shape
+        lib = _lib.load_library()
+        logits = torch.empty((B, self.config.num_classes), dtype=torch.float32, device=cats.device)
+        stream = torch.cuda.current_stream(cats.device).cuda_stream
+        _lib.check(self._handle, lib.stlt_forward_train(
+            self._handle, stream, cats.data_ptr(), boxes.data_ptr(),
+            scores.data_ptr() if scores is not None else None, ftypes.data_ptr(), lengths.data_ptr(),
+            B, L, S, ws.data_ptr(), ws.numel(), dropout_p, seed, logits.data_ptr()))
+        return logits
+
+    def _backward(self, inputs, ws: torch.Tensor, d_logits: Optional[torch.Tensor], phases: int) -> None:
+        cats, boxes, scores, ftypes, lengths = inputs
+        B, L, S = cats.shape
+        lib = _lib.load_library()
+        stream = torch.cuda.current_stream(cats.device).cuda_stream
+        _lib.check(self._handle, lib.stlt_backward(
+            self._handle, stream, cats.data_ptr(), boxes.data_ptr(),
+            scores.data_ptr() if scores is not None else None, ftypes.data_ptr(), lengths.data_ptr(),
+            B, L, S, ws.data_ptr(), ws.numel(), d_logits.data_ptr() if d_logits is not None else None,
+            phases))
+
     def check_inputs(self) -> None:
         """Synchronises and raises if the last forward saw an out-of-range index (debug aid)."""
         if self._handle is None or self._workspace is None:
@@ -390,6 +445,59 @@ class Stlt(nn.Module):
         if self._handle is None:
             return 0
         return int(_lib.load_library().stlt_last_launch_count(self._handle))
+
+
+class _StltTrainFunction(torch.autograd.Function):
+    """Stlt.forward with a grad_fn: forward = stlt_forward_train (activations kept in a workspace
+    owned by the autograd context), backward = stlt_backward. Parameters are passed as inputs so
+    autograd accumulates into ``param.grad`` and DDP-style hooks fire as usual."""
+
+    @staticmethod
+    def forward(ctx, module, names, dropout_p, cats, boxes, scores, ftypes, lengths, *params):
+        device = cats.device
+        with torch.cuda.device(device):
+            module._ensure_handle(device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            module._sync_weights(device, stream, "bf16")  # mixed precision: bf16 operands, fp32 master
+            B, L, S = cats.shape
+            ws = module._train_workspace(B, L, S, device)
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if dropout_p > 0 else 0
+            inputs = (cats, boxes, scores, ftypes, lengths)
+            logits = module._forward_train(inputs, ws, dropout_p, seed)
+        ctx.module, ctx.names, ctx.ws, ctx.inputs = module, names, ws, inputs
+        ctx.param_shapes = [p.shape for p in params]
+        return logits
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        module, names = ctx.module, ctx.names
+        device = d_logits.device
+        # ctx.needs_input_grad[8:] lines up with *params
+        want = [ctx.needs_input_grad[8 + i] for i in range(len(names))]
+        has_scores = ctx.inputs[2] is not None
+        sizes, total = [], 0
+        for name, shape, w in zip(names, ctx.param_shapes, want):
+            # the orphan prototype layer (models.py:46-52) and, without scores, the score embedding
+            # never reach the logits: their gradient is None in the reference too
+            used = w and ".encoder_layer." not in name and (has_scores or "score_embeddings" not in name)
+            n = int(torch.Size(shape).numel()) if used else 0
+            sizes.append(n)
+            total += (n + 3) // 4 * 4
+        flat = torch.zeros(max(total, 4), dtype=torch.float32, device=device)
+        grads, out, off = {}, [], 0
+        for name, shape, n in zip(names, ctx.param_shapes, sizes):
+            if n == 0:
+                out.append(None)
+                continue
+            g = flat[off:off + n].view(shape)
+            off += (n + 3) // 4 * 4
+            grads[name] = g
+            out.append(g)
+        with torch.cuda.device(device):
+            module._bind_grads(grads)
+            module._backward(ctx.inputs, ctx.ws, d_logits.contiguous().float(), _lib.BWD_ALL)
+        ctx.ws = None
+        return (None,) * 8 + tuple(out)
 
 
 models_factory = {"stlt": Stlt}

@@ -1,0 +1,133 @@
+"""GPU parity of the training step against the CPU oracle, which is itself
+pinned to the reference loop by tests/test_oracle_train.py. bf16 mixed precision: tolerances are
+relative to each tensor's gradient norm."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import stlt_oracle
+from stlt_b200 import lib as L
+from tests.test_oracle_train import _case
+from tests.util import to_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cfg, sd):
+    import stlt_b200
+    torch.manual_seed(0)
+    m = stlt_b200.Stlt(cfg, precision="bf16")
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("layout", ["something", "action_genome"])
+def test_autograd_backward_matches_oracle(layout):
+    cfg, sd, batch, labels, loss, g = _case(layout)
+    want_loss, want_logits, want = stlt_oracle.loss_and_grads(sd, batch, labels, loss)
+    model = _model(cfg, sd)
+    model.train(True)
+    out = model(to_cuda(batch))["stlt"]
+    assert out.requires_grad
+    if loss == "cross_entropy":
+        value = torch.nn.functional.cross_entropy(out, labels.cuda())
+    else:
+        value = torch.nn.functional.binary_cross_entropy_with_logits(out, labels.cuda())
+    value.backward()
+    assert abs(float(value) - float(want_loss)) < 2e-2 * abs(float(want_loss))
+    worst = []
+    dot = nn_a = nn_b = 0.0
+    for name, p in model.named_parameters():
+        if name not in want:
+            assert p.grad is None, f"{name}: the reference leaves this gradient None"
+            continue
+        assert p.grad is not None, name
+        assert torch.isfinite(p.grad).all(), name
+        ga, gb = p.grad.double().cpu(), want[name].double()
+        dot += float((ga * gb).sum()); nn_a += float((ga * ga).sum()); nn_b += float((gb * gb).sum())
+        worst.append((_rel(p.grad, want[name]), name))
+    worst.sort(reverse=True)
+    print("worst tensors:", worst[:6])
+    cos = dot / (nn_a ** 0.5 * nn_b ** 0.5)
+    print("global cosine", cos, "norm ratio", (nn_a / nn_b) ** 0.5)
+    assert cos > 0.9995
+    assert abs((nn_a / nn_b) ** 0.5 - 1.0) < 1e-2
+    assert worst[0][0] < 2e-2, worst[:6]
+
+
+def test_loss_kernels_match_torch():
+    lib = L.load_library()
+    dims = L.StltDims(768, 12, 1, 1, 4, 174, 256, 5, 1e-12, 1e-5)
+    h = ctypes.c_void_p()
+    L.check(None, lib.stlt_create(ctypes.byref(dims), ctypes.byref(h)))
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(1)
+    logits = torch.randn(37, 174, device="cuda", generator=g) * 3
+    labels = torch.randint(0, 174, (37,), device="cuda", generator=g)
+    loss = torch.zeros(1, device="cuda")
+    d = torch.empty_like(logits)
+    L.check(h, lib.stlt_loss(h, s, L.LOSS_CROSS_ENTROPY, logits.data_ptr(), labels.data_ptr(), 37, 174, 0.5,
+                             loss.data_ptr(), d.data_ptr()))
+    ref_in = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, labels)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * float(ref)
+    assert torch.allclose(d, 0.5 * ref_in.grad, atol=1e-7, rtol=1e-4)
+    targets = (torch.rand(37, 174, device="cuda", generator=g) < 0.1).float()
+    L.check(h, lib.stlt_loss(h, s, L.LOSS_BCE_LOGITS, logits.data_ptr(), targets.data_ptr(), 37, 174, 1.0,
+                             loss.data_ptr(), d.data_ptr()))
+    ref_in = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(ref_in, targets)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * float(ref)
+    assert torch.allclose(d, ref_in.grad, atol=1e-8, rtol=1e-4)
+    lib.stlt_destroy(h)
+
+
+@pytest.mark.parametrize("layout", ["something", "action_genome"])
+def test_fused_train_step_matches_oracle(layout):
+    from stlt_b200.training import FusedTrainStep, linear_schedule_with_warmup
+    cfg, sd, batch, labels, loss, g = _case(layout)
+    model = _model(cfg, sd)
+    model.train(True)
+    before = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+    stepper = FusedTrainStep(model, lr=5e-5, weight_decay=1e-3, clip_val=5.0, loss=loss,
+                             lr_lambda=linear_schedule_with_warmup(2, 10))
+    assert list(model.state_dict().keys()) == list(before.keys())  # flattening keeps the checkpoint format
+    gbatch = dict(to_cuda(batch), labels=labels.cuda())
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    state = {}
+    for step in range(1, 4):
+        got_loss = stepper.step(gbatch)
+        value, _, grads = stlt_oracle.loss_and_grads(ref_sd, batch, labels, loss)
+        total = stlt_oracle.adamw_update(ref_sd, grads, state, step, 5e-5 * stlt_oracle.linear_schedule(step - 1, 2, 10))
+        assert abs(float(got_loss) - float(value)) < 3e-2 * abs(float(value)), (step, float(got_loss), float(value))
+        assert abs(stepper.grad_norm() - total) < 2e-2 * total, (step, stepper.grad_norm(), total)
+    after = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    # tensors the reference never updates stay bit-identical
+    for k in after:
+        if ".encoder_layer." in k or (layout == "something" and "score_embeddings" in k) or not after[k].is_floating_point():
+            assert torch.equal(after[k], before[k]), k
+    # the accumulated update of the big matrices points the same way as the reference's
+    dot = na = nb = 0.0
+    for k in after:
+        if not after[k].is_floating_point() or after[k].dim() < 2 or ".encoder_layer." in k:
+            continue
+        da = (after[k] - before[k]).double()
+        db = (ref_sd[k] - sd[k]).double()
+        dot += float((da * db).sum()); na += float((da * da).sum()); nb += float((db * db).sum())
+    cos = dot / (na ** 0.5 * nb ** 0.5)
+    print("update cosine", cos, "norm ratio", (na / nb) ** 0.5)
+    assert cos > 0.97 and abs((na / nb) ** 0.5 - 1.0) < 5e-2
+    # and inference with the updated weights follows the updated oracle
+    model.train(False)
+    with torch.no_grad():
+        logits = model(to_cuda(batch))["stlt"].float().cpu()
+        want = stlt_oracle.stlt_forward(ref_sd, batch)
+    assert float((logits - want).abs().max() / want.abs().max()) < 3e-2
