@@ -222,7 +222,19 @@ int stlt_forward_train(void* handle, void* stream, const int64_t* categories, co
 int stlt_backward(void* handle, void* stream, const int64_t* categories, const float* boxes,
                   const float* scores_or_null, const int64_t* frame_types, const int64_t* lengths,
                   int32_t batch, int32_t frames, int32_t slots, void* workspace, size_t workspace_bytes,
-                  const float* d_logits, int32_t phases);
+                  float dropout_p, uint64_t seed, const float* d_logits, int32_t phases);
+
+/* Dropout masks are not stored: every site regenerates its mask from (seed, site, element index)
+ * with a counter-based hash, in the forward and again in the backward pass (same dropout_p / seed).
+ * This host-side helper returns the multipliers (0 or 1/(1-p_eff), p_eff = round(p * 65536) / 65536)
+ * of elements [first, first + n) of a site so a test can replay the exact masks in the oracle. Sites:
+ * 0 category/box embedding output [token][768]; 1 frame embedding output [frame][768];
+ * 16 + 4*layer + {0: attention probabilities [(query token * 12 + head) * 32 + key position],
+ * 1: attention branch before the residual [row][768], 2: FFN inner [row][3072], 3: FFN branch
+ * [row][768]}, spatial layers numbered first; rows of the last layer of each stack are the compacted
+ * rows (frame index b*L + l for the spatial stack, video index b for the temporal stack). */
+int stlt_op_dropout_mask(void* handle, float dropout_p, uint64_t seed, int32_t site, int64_t first,
+                         int64_t n, float* multipliers_host);
 
 /* Criterion: mean cross-entropy (labels i64 [rows], Something-Else) or mean BCE-with-logits (targets
  * f32 [rows, classes], Action Genome). loss_out (device float, may be NULL) receives the loss,

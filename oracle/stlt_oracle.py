@@ -210,9 +210,14 @@ def prepare_padded(raw_boxes: torch.Tensor, video_sizes: torch.Tensor, categorie
 # ---------------------------------------------------------------------------------------------------
 # model side (floating point): src/modelling/models.py:16-195
 # ---------------------------------------------------------------------------------------------------
-def _encoder_layer(x: torch.Tensor, masked: torch.Tensor, sd: Dict[str, torch.Tensor], p: str) -> torch.Tensor:
-    """One post-norm nn.TransformerEncoderLayer in eval mode (models.py:46-52,118-124 configure
-    it; the arithmetic is torch's): x [N, T, H]; masked [N, T, T] bool, True = not attended."""
+def _encoder_layer(x: torch.Tensor, masked: torch.Tensor, sd: Dict[str, torch.Tensor], p: str,
+                   drop: Dict[str, torch.Tensor] = None) -> torch.Tensor:
+    """One post-norm nn.TransformerEncoderLayer (models.py:46-52,118-124 configure it; the
+    arithmetic is torch's): x [N, T, H]; masked [N, T, T] bool, True = not attended. Eval mode unless
+    ``drop`` gives the dropout multipliers (0 or 1/(1-p)) of the layer's four dropout sites:
+    "attn" [N, heads, T, T] on the softmax output (nn.MultiheadAttention), "branch1" [N, T, H]
+    (dropout1), "ffn" [N, T, 4H] (between activation and linear2), "branch2" [N, T, H] (dropout2)."""
+    drop = drop or {}
     N, T, H = x.shape
     qkv = F.linear(x, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"])
     q, k, v = qkv.split(H, dim=-1)  # packed rows: Q; K; V
@@ -221,22 +226,34 @@ def _encoder_layer(x: torch.Tensor, masked: torch.Tensor, sd: Dict[str, torch.Te
     q, k, v = heads(q), heads(k), heads(v)
     scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(HEAD_DIM)
     scores = scores.masked_fill(masked.unsqueeze(1), float("-inf"))
-    ctx = torch.matmul(torch.softmax(scores, dim=-1), v)
+    probs = torch.softmax(scores, dim=-1)
+    if "attn" in drop:
+        probs = probs * drop["attn"]
+    ctx = torch.matmul(probs, v)
     ctx = ctx.transpose(1, 2).reshape(N, T, H)
     a = F.linear(ctx, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+    if "branch1" in drop:
+        a = a * drop["branch1"]
     x = F.layer_norm(x + a, (H,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], ENCODER_LN_EPS)
-    f = F.linear(F.gelu(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
-                 sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    hidden = F.gelu(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))
+    if "ffn" in drop:
+        hidden = hidden * drop["ffn"]
+    f = F.linear(hidden, sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    if "branch2" in drop:
+        f = f * drop["branch2"]
     return F.layer_norm(x + f, (H,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], ENCODER_LN_EPS)
 
 
 def stlt_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], num_spatial_layers: int = 4,
                  num_temporal_layers: int = 8, layer_norm_eps: float = 1e-12,
-                 dtype: torch.dtype = torch.float32, return_taps: bool = False):
-    """Stlt.forward (models.py:185-195) and callees, eval mode (dropout = identity).
+                 dtype: torch.dtype = torch.float32, return_taps: bool = False, dropout: Dict = None):
+    """Stlt.forward (models.py:185-195) and callees. Eval mode (dropout = identity) unless
+    ``dropout`` gives explicit multipliers: {"embed": [B,L,S,H], "frames": [B,L,H],
+    ("spatial", i): {...}, ("temporal", i): {...}} with the per-layer dicts of ``_encoder_layer``.
 
     ``sd`` is a reference-format state_dict. Returns logits [B, C] (or a dict of stage outputs).
     """
+    dropout = dropout or {}
     sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     cats = batch["categories"]
     boxes = batch["boxes"].to(dtype)
@@ -254,13 +271,16 @@ def stlt_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], nu
         e = e + F.linear(batch["scores"].to(dtype).unsqueeze(-1), sd[cbe + "score_embeddings.weight"],
                          sd[cbe + "score_embeddings.bias"])
     e = F.layer_norm(e, (H,), sd[cbe + "layer_norm.weight"], sd[cbe + "layer_norm.bias"], layer_norm_eps)
+    if "embed" in dropout:  # models.py:27,38
+        e = e * dropout["embed"]
     taps = {"embed": e}
 
     # SpatialTransformer.forward (models.py:57-81): B*L sequences of S tokens, key padding mask
     x = e.reshape(B * L, S, H)
     key_pad = (cats == 0).reshape(B * L, 1, S).expand(B * L, S, S)  # datasets.py:277
     for i in range(num_spatial_layers):
-        x = _encoder_layer(x, key_pad, sd, f"{bfe}layout_embedding.transformer.layers.{i}.")
+        x = _encoder_layer(x, key_pad, sd, f"{bfe}layout_embedding.transformer.layers.{i}.",
+                           dropout.get(("spatial", i)))
     taps["spatial"] = x.reshape(B, L, S, H)
     layout = x.reshape(B, L, S, H)[:, :, 0, :]  # models.py:79
 
@@ -268,6 +288,8 @@ def stlt_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], nu
     pos = sd[bfe + "position_embeddings.weight"][sd[bfe + "position_ids"][:, :L]]
     f = layout + pos + sd[bfe + "frame_type_embedding.weight"][ftypes]
     f = F.layer_norm(f, (H,), sd[bfe + "layer_norm.weight"], sd[bfe + "layer_norm.bias"], layer_norm_eps)
+    if "frames" in dropout:  # models.py:93,110
+        f = f * dropout["frames"]
     taps["frames"] = f
 
     # StltBackbone.forward (models.py:136-152): causal (model_utils.py:4-7) OR frame padding
@@ -275,7 +297,7 @@ def stlt_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], nu
     masked = causal.unsqueeze(0) | (ftypes == 0).unsqueeze(1)  # [B, L, L]
     z = f
     for i in range(num_temporal_layers):
-        z = _encoder_layer(z, masked, sd, f"backbone.transformer.layers.{i}.")
+        z = _encoder_layer(z, masked, sd, f"backbone.transformer.layers.{i}.", dropout.get(("temporal", i)))
     taps["temporal"] = z
 
     # Stlt.forward gather (models.py:189-192) + ClassificationHead (models.py:155-163)
@@ -303,14 +325,14 @@ def criterion(logits: torch.Tensor, labels: torch.Tensor, loss: str) -> torch.Te
 
 
 def loss_and_grads(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], labels: torch.Tensor,
-                   loss: str = "cross_entropy", dtype: torch.dtype = torch.float32):
+                   loss: str = "cross_entropy", dtype: torch.dtype = torch.float32, dropout: Dict = None):
     """loss.backward() of the reference loop (train.py:125-128) with dropout p = 0: returns
     (loss, logits, {name: grad}) by differentiating the restated forward. Tensors that do not reach
     the logits (orphan encoder_layer.*, score embedding without scores) have no entry, like
     ``param.grad is None`` in the reference."""
     leaves = {k: (v.detach().clone().to(dtype).requires_grad_(True) if v.is_floating_point() else v)
               for k, v in sd.items()}
-    logits = stlt_forward(leaves, batch, dtype=dtype)
+    logits = stlt_forward(leaves, batch, dtype=dtype, dropout=dropout)
     value = criterion(logits, labels, loss)
     names = [k for k, v in leaves.items() if v.is_floating_point()]
     grads = torch.autograd.grad(value, [leaves[k] for k in names], allow_unused=True)

@@ -45,7 +45,7 @@ __device__ __forceinline__ void stage_row(float* dst, const float (&src)[64]) {
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_ctx,
                      const long long* __restrict__ mask_src, long long num_seqs, int T, int G,
-                     int causal, __nv_bfloat16* __restrict__ d_qkv, long long num_items) {
+                     int causal, __nv_bfloat16* __restrict__ d_qkv, long long num_items, DropCfg drop) {
   extern __shared__ __align__(16) float smem_f[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,12 +118,20 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
       float sum = 0.f;
       for (int jj = 0; jj < T; ++jj) sum += __shfl_sync(0xffffffffu, e, seq_lane0 + jj);
       const float p = e / sum;
-      const float dp = masked ? 0.f : (p0 + p1) + (p2 + p3);
+      // dropout on the probabilities: O = (mask * P / (1-p)) V, so dV uses the dropped P and the
+      // gradient w.r.t. P is the masked, scaled dO V^T
+      float keep = 1.0f;
+      if (drop.thr16 != 0 && !masked) {
+        const unsigned long long el =
+            (static_cast<unsigned long long>(base + seq_lane0 + i) * kHeads + head) * 32ull + static_cast<unsigned>(j);
+        keep = drop_mul(drop_bits(drop.key, el >> 1), static_cast<int>(el & 1), drop);
+      }
+      const float dp = masked ? 0.f : ((p0 + p1) + (p2 + p3)) * keep;
       const float pd = p * dp;
       float dsum = 0.f;
       for (int jj = 0; jj < T; ++jj) dsum += __shfl_sync(0xffffffffu, pd, seq_lane0 + jj);
       if (active) {
-        Ps[(seq_lane0 + i) * PT + j] = p;
+        Ps[(seq_lane0 + i) * PT + j] = p * keep;
         Ss[(seq_lane0 + i) * PT + j] = p * (dp - dsum) * 0.125f;
       }
     }
@@ -161,7 +169,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 
 cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* d_ctx,
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
-                                 __nv_bfloat16* d_qkv, cudaStream_t stream) {
+                                 __nv_bfloat16* d_qkv, cudaStream_t stream, DropCfg drop) {
   if (T < 1 || T > 32) return cudaErrorInvalidValue;
   if (num_seqs == 0) return cudaSuccess;
   const int G = 32 / T;
@@ -176,7 +184,7 @@ cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* 
   cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   attention_bwd_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, smem, stream>>>(
-      qkv, d_ctx, mask_src, num_seqs, T, G, causal ? 1 : 0, d_qkv, items);
+      qkv, d_ctx, mask_src, num_seqs, T, G, causal ? 1 : 0, d_qkv, items, drop);
   return cudaGetLastError();
 }
 

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kSplit ? 128 : 256, 2)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_plane_elems,
                      const long long* __restrict__ mask_src, long long num_seqs, int T, int G,
                      int causal, __nv_bfloat16* __restrict__ out, long long out_plane_elems,
-                     long long num_items) {
+                     long long num_items, DropCfg drop) {
   constexpr int kWarps = kSplit ? 4 : 8;
   constexpr int kTiles = kSplit ? 6 : 3;  // Q, K, V (+ their lo planes)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -225,6 +225,24 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_plane_
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         inv_sum[mt][h] = sum > 0.f ? 1.0f / sum : 0.f;
+        if (!kSplit && drop.thr16 != 0) {
+          // dropout on the probabilities (nn.MultiheadAttention dropout, training only); the softmax
+          // denominator above is taken before the mask, as F.dropout(softmax(...)) does
+          const int row = mt * 16 + g + 8 * h;
+          const int seq0 = (row / T) * T;
+          const unsigned long long ebase =
+              (static_cast<unsigned long long>(base + row) * kHeads + head) * 32ull;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int kpos = nt * 8 + 2 * t + e - seq0;
+              if ((ok >> (nt * 2 + e)) & 1u) {
+                const unsigned long long el = ebase + static_cast<unsigned>(kpos);
+                s[mt][nt][2 * h + e] *= drop_mul(drop_bits(drop.key, el >> 1), static_cast<int>(el & 1), drop);
+              }
+            }
+        }
       }
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -322,7 +340,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_plane_
 template <bool kSplit>
 static cudaError_t launch_mma(const __nv_bfloat16* qkv, long long qkv_plane_rows,
                               const long long* mask_src, long long num_seqs, int T, bool causal,
-                              __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream) {
+                              __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream,
+                              DropCfg drop) {
   constexpr int kWarps = kSplit ? 4 : 8;
   constexpr int kTiles = kSplit ? 6 : 3;
   const int G = 32 / T;
@@ -341,7 +360,7 @@ static cudaError_t launch_mma(const __nv_bfloat16* qkv, long long qkv_plane_rows
   if (blocks > cap) blocks = cap;
   attention_mma_kernel<kSplit><<<static_cast<unsigned>(blocks), kWarps * 32, smem, stream>>>(
       qkv, qkv_plane_rows * kQkv, mask_src, num_seqs, T, G, causal ? 1 : 0, out,
-      out_plane_rows * kHidden, items);
+      out_plane_rows * kHidden, items, drop);
   return cudaGetLastError();
 }
 
@@ -349,12 +368,15 @@ static cudaError_t launch_mma(const __nv_bfloat16* qkv, long long qkv_plane_rows
 
 cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long qkv_plane_rows,
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
-                                 __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream) {
+                                 __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream,
+                                 DropCfg drop) {
   if (T < 1 || T > 32) return cudaErrorInvalidValue;
   if (num_seqs == 0) return cudaSuccess;
-  if (planes == 2)
-    return launch_mma<true>(qkv, qkv_plane_rows, mask_src, num_seqs, T, causal, out, out_plane_rows, stream);
-  return launch_mma<false>(qkv, 0, mask_src, num_seqs, T, causal, out, 0, stream);
+  if (planes == 2) {
+    if (drop.thr16 != 0) return cudaErrorInvalidValue;  // training runs the single-plane flavour
+    return launch_mma<true>(qkv, qkv_plane_rows, mask_src, num_seqs, T, causal, out, out_plane_rows, stream, drop);
+  }
+  return launch_mma<false>(qkv, 0, mask_src, num_seqs, T, causal, out, 0, stream, drop);
 }
 
 }  // namespace stlt

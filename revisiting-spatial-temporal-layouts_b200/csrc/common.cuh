@@ -50,6 +50,40 @@ __device__ __forceinline__ float bf16_residual(float x) {
   return x - __bfloat162float(__float2bfloat16_rn(x));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dropout (training step): stateless, counter-based masks so the backward pass regenerates the mask
+// of every site instead of storing it. Element e of a site is kept iff the 16-bit field (e & 1) of
+// hash(site key, e >> 1) is >= thr16 (drop probability thr16 / 65536); kept values are scaled by
+// 65536 / (65536 - thr16). thr16 == 0 disables the site. The hash is "lowbias32" (two xorshift-
+// multiply rounds), keyed per (seed, site) on the host (stlt_train.cu: site_key()).
+// ---------------------------------------------------------------------------------------------
+struct DropCfg {
+  uint32_t key;
+  uint32_t thr16;
+  float scale;
+};
+
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+
+// 32 mask bits for the element pair (2*pair, 2*pair + 1) of a site.
+__host__ __device__ __forceinline__ uint32_t drop_bits(uint32_t key, unsigned long long pair) {
+  uint32_t x = lowbias32(static_cast<uint32_t>(pair) ^ key);
+  x ^= static_cast<uint32_t>(pair >> 32) * 0x9e3779b9u;
+  return lowbias32(x);
+}
+
+// multiplier (0 or scale) of element `which` (0 / 1) of the pair
+__host__ __device__ __forceinline__ float drop_mul(uint32_t bits, int which, const DropCfg& d) {
+  return ((bits >> (16 * which)) & 0xffffu) >= d.thr16 ? d.scale : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -209,7 +209,7 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
              const float* __restrict__ box_b, const float* __restrict__ score_w,
              const float* __restrict__ score_b, const float* __restrict__ ln_g,
              const float* __restrict__ ln_b, float eps, long long tokens, ActOut out,
-             int* __restrict__ err_flag) {
+             int* __restrict__ err_flag, DropCfg drop) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -267,6 +267,7 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
     for (int i = 0; i < kEmbedTok; ++i) {
       if (t0 + i < tokens) {
         layer_norm_row(r[i], ln_g, ln_b, eps, lane);
+        drop_row(r[i], t0 + i, lane, drop);  // models.py:27,38 (training only)
         store_act(out, t0 + i, r[i], lane);
       }
     }
@@ -279,14 +280,15 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
 __global__ void __launch_bounds__(256)
 add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y,
               const float* __restrict__ g, const float* __restrict__ b, float eps, long long rows,
-              ActOut out, float* __restrict__ z_out) {
+              ActOut out, float* __restrict__ z_out, DropCfg drop) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
   for (long long row = warp0; row < rows; row += nwarps) {
     RowRegs r = load_row(x_in, row, lane);
     if (y != nullptr) {
-      const RowRegs a = load_row(y, row, lane);
+      RowRegs a = load_row(y, row, lane);
+      drop_row(a, row, lane, drop);  // dropout1 / dropout2 of nn.TransformerEncoderLayer (training only)
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
         r.v[k].x += a.v[k].x;
@@ -313,7 +315,7 @@ frame_embed_kernel(const float* __restrict__ spatial_x, int S,
                    const long long* __restrict__ frame_types, const float* __restrict__ pos_table,
                    const float* __restrict__ ft_table, int n_frame_types,
                    const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps, int L,
-                   long long frames, ActOut out, int* __restrict__ err_flag) {
+                   long long frames, ActOut out, int* __restrict__ err_flag, DropCfg drop) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -335,6 +337,7 @@ frame_embed_kernel(const float* __restrict__ spatial_x, int S,
       r.v[k].w = (r.v[k].w + p.v[k].w) + t.v[k].w;
     }
     layer_norm_row(r, ln_g, ln_b, eps, lane);
+    drop_row(r, f, lane, drop);  // models.py:93,110 (training only)
     store_act(out, f, r, lane);
   }
 }
@@ -460,30 +463,31 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
                          const float* cat_table, int unique_categories, const float* box_w,
                          const float* box_b, const float* score_w, const float* score_b,
                          const float* ln_g, const float* ln_b, float eps, long long tokens,
-                         ActOut out, int* err_flag, cudaStream_t stream) {
+                         ActOut out, int* err_flag, cudaStream_t stream, DropCfg drop) {
   if (tokens == 0) return cudaSuccess;
   embed_kernel<<<row_grid((tokens + kEmbedTok - 1) / kEmbedTok, 8), 256, 0, stream>>>(
       categories, reinterpret_cast<const float4*>(boxes), scores, cat_table, unique_categories,
-      box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag);
+      box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag, drop);
   return cudaGetLastError();
 }
 
 cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, const float* b,
-                          float eps, long long rows, ActOut out, cudaStream_t stream, float* z_out) {
+                          float eps, long long rows, ActOut out, cudaStream_t stream, float* z_out,
+                          DropCfg drop) {
   if (rows == 0) return cudaSuccess;
-  add_ln_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out);
+  add_ln_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out, drop);
   return cudaGetLastError();
 }
 
 cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* frame_types,
                                const float* pos_table, const float* ft_table, int n_frame_types,
                                const float* ln_g, const float* ln_b, float eps, int B, int L,
-                               ActOut out, int* err_flag, cudaStream_t stream) {
+                               ActOut out, int* err_flag, cudaStream_t stream, DropCfg drop) {
   const long long frames = static_cast<long long>(B) * L;
   if (frames == 0) return cudaSuccess;
   frame_embed_kernel<<<row_grid(frames, 8), 256, 0, stream>>>(spatial_x, S, frame_types, pos_table,
                                                               ft_table, n_frame_types, ln_g, ln_b,
-                                                              eps, L, frames, out, err_flag);
+                                                              eps, L, frames, out, err_flag, drop);
   return cudaGetLastError();
 }
 

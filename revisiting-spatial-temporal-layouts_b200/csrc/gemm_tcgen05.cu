@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias,
                     int m_tiles, int n_tiles, int k_blocks, int a_plane_rows, int b_plane_rows,
-                    int out_plane_rows) {
+                    int out_plane_rows, DropCfg drop) {
   constexpr int kStages = Cfg<kOut>::kStages;
   constexpr int kBufsPerWarp = Cfg<kOut>::kBufsPerWarp;
   constexpr bool kAMn = kLayout == GEMM_TN_RED;
@@ -324,6 +324,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
         }
+        if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
+          // FFN-inner dropout of nn.TransformerEncoderLayer (training): element = row * N + column
+          if (drop.thr16 != 0) {
+            const unsigned long long e0 =
+                static_cast<unsigned long long>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const uint32_t bits = drop_bits(drop.key, (e0 + j) >> 1);
+              f[j] *= drop_mul(bits, 0, drop);
+              f[j + 1] *= drop_mul(bits, 1, drop);
+            }
+          }
+        }
 
         if (kOut == GEMM_OUT_F32) {
           // 32 fp32 columns = 128 B per row -> one TMA store per chunk
@@ -442,7 +455,7 @@ static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sm
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, g.tm_a, g.tm_b, g.tm_out, g.bias, m_tiles, n_tiles,
-                            k_blocks, g.a_plane_rows, g.b_plane_rows, g.out_plane_rows);
+                            k_blocks, g.a_plane_rows, g.b_plane_rows, g.out_plane_rows, g.drop);
 }
 
 cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_sms) {

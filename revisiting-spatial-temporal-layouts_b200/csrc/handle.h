@@ -144,7 +144,7 @@ inline int make_tm(Handle* h, CUtensorMap* tm, const void* ptr, int dtype, long 
 // out = epilogue(A W^T + bias) on tcgen05. a/w point at plane 0; planes are a_plane_rows / n rows apart.
 inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_rows, long long a_plane_rows,
              const void* w, int n, int k, const float* bias, void* out, int terms, int out_kind,
-             int gelu) {
+             int gelu, DropCfg drop = DropCfg{0, 0, 1.f}) {
   GemmArgs g{};
   const int planes = terms == 3 ? 2 : 1;
   int rc = make_tm(h, &g.tm_a, a, 1, a_plane_rows * (planes - 1) + m_rows, k, 64, 128);
@@ -169,6 +169,7 @@ inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_r
   g.b_plane_rows = n;
   g.out_plane_rows = static_cast<int>(a_plane_rows);
   g.layout = GEMM_NT;
+  g.drop = drop;
   ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
@@ -206,6 +207,7 @@ inline int run_gemm_grad(Handle* h, cudaStream_t stream, int layout, const void*
   g.out_kind = out_kind;
   g.gelu = 0;
   g.layout = layout;
+  g.drop = DropCfg{0, 0, 1.f};
   ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * static_cast<double>(k));
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;

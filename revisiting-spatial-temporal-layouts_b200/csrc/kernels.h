@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace stlt {
 
 enum GemmOutKind : int {
@@ -36,6 +38,7 @@ struct GemmArgs {
   int b_plane_rows;    // row offset of the lo plane of W
   int out_plane_rows;  // row offset of the lo plane of the output (split only)
   int layout;          // GemmLayout; MN-major operands use box {64, 64} tensor maps
+  DropCfg drop;        // dropout on the activated output (GEMM_OUT_BF16_DUAL only; thr16 = 0: off)
 };
 
 int gemm_smem_bytes();
@@ -91,19 +94,20 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
                          const float* cat_table, int unique_categories, const float* box_w,
                          const float* box_b, const float* score_w, const float* score_b,
                          const float* ln_g, const float* ln_b, float eps, long long tokens,
-                         ActOut out, int* err_flag, cudaStream_t stream);
+                         ActOut out, int* err_flag, cudaStream_t stream, DropCfg drop = DropCfg{0, 0, 1.f});
 
 // x <- LayerNorm(x + y) (post-norm residual of nn.TransformerEncoderLayer); y may be null.
 // z_out (optional, training): receives the pre-LayerNorm sum x + y.
 cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, const float* b,
                           float eps, long long rows, ActOut out, cudaStream_t stream,
-                          float* z_out = nullptr);
+                          float* z_out = nullptr, DropCfg drop = DropCfg{0, 0, 1.f});
 
 // K7: frame tokens = LN(spatial CLS slot + position + frame type) (src/modelling/models.py:98-111).
 cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* frame_types,
                                const float* pos_table, const float* ft_table, int n_frame_types,
                                const float* ln_g, const float* ln_b, float eps, int B, int L,
-                               ActOut out, int* err_flag, cudaStream_t stream);
+                               ActOut out, int* err_flag, cudaStream_t stream,
+                               DropCfg drop = DropCfg{0, 0, 1.f});
 
 // K9: h[b] = x[b * L + lengths[b] - 1] (src/modelling/models.py:189-192).
 cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, int L, float* out,
@@ -124,9 +128,12 @@ cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long*
 
 // K3 on warp-level tensor-core tiles (attention_mma.cu). planes = 1: bf16 QKV [tokens, 2304] ->
 // bf16 context; planes = 2: hi/lo bf16 planes in and out (fp32-parity mode, 3-term split products).
+// drop (training, planes = 1 only): dropout on the attention probabilities; element index =
+// ((query token * 12 + head) * 32 + key position within the sequence).
 cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long qkv_plane_rows,
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
-                                 __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream);
+                                 __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream,
+                                 DropCfg drop = DropCfg{0, 0, 1.f});
 
 // fp32 -> bf16 plane(s) for weights.
 cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,
@@ -139,10 +146,11 @@ cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, 
 // every output may be null.
 cudaError_t launch_ln_bwd(const float* d_a, const float* d_b, const float* z, const float* gamma,
                           float eps, long long rows, float* dz_out, __nv_bfloat16* dzb_out,
-                          float* d_gamma, float* d_beta, float* d_bias, cudaStream_t stream);
+                          float* d_gamma, float* d_beta, float* d_bias, cudaStream_t stream,
+                          DropCfg drop = DropCfg{0, 0, 1.f});
 // In place d <- d * gelu'(u) on bf16 [rows, n] (u == null: no activation) + column sums into d_bias.
 cudaError_t launch_act_bwd_colsum(__nv_bfloat16* d, const __nv_bfloat16* u, long long rows, int n,
-                                  float* d_bias, cudaStream_t stream);
+                                  float* d_bias, cudaStream_t stream, DropCfg drop = DropCfg{0, 0, 1.f});
 cudaError_t launch_colsum_f32(const float* x, int rows, int n, float* out, cudaStream_t stream);
 // Adjoint of launch_gather_rows: dst_f[map(r)] += src_f[r]; dst_b[map(r)] = src_b[r].
 cudaError_t launch_scatter_rows(const float* src_f, float* dst_f, const __nv_bfloat16* src_b,
@@ -152,14 +160,15 @@ cudaError_t launch_frame_embed_bwd(const float* d_a, const float* d_b, const flo
                                    const long long* frame_types, const float* pos_table,
                                    const float* ft_table, int n_frame_types, const float* gamma,
                                    float eps, int B, int L, float* d_cls, float* d_pos, float* d_ft,
-                                   float* d_gamma, float* d_beta, cudaStream_t stream);
+                                   float* d_gamma, float* d_beta, cudaStream_t stream,
+                                   DropCfg drop = DropCfg{0, 0, 1.f});
 cudaError_t launch_embed_bwd(const float* d_a, const float* d_b, const long long* categories,
                              const float* boxes, const float* scores, const float* cat_table,
                              int unique_categories, const float* box_w, const float* box_b,
                              const float* score_w, const float* score_b, const float* gamma, float eps,
                              long long tokens, float* d_pre, float* d_cat, float* d_box_w,
                              float* d_box_b, float* d_score_w, float* d_score_b, float* d_gamma,
-                             float* d_beta, cudaStream_t stream);
+                             float* d_beta, cudaStream_t stream, DropCfg drop = DropCfg{0, 0, 1.f});
 cudaError_t launch_gelu_ln(const float* h1, const float* g, const float* b, float eps, long long rows,
                            float* out, cudaStream_t stream);
 cudaError_t launch_gelu_ln_bwd(const float* d_h2, const float* h1, const float* gamma, float eps,
@@ -179,6 +188,6 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
                          float bias_c2_sqrt, const float* sumsq, float max_norm, cudaStream_t stream);
 cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* d_ctx,
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
-                                 __nv_bfloat16* d_qkv, cudaStream_t stream);
+                                 __nv_bfloat16* d_qkv, cudaStream_t stream, DropCfg drop = DropCfg{0, 0, 1.f});
 
 }  // namespace stlt

@@ -82,6 +82,21 @@ __device__ __forceinline__ void store_act(const ActOut& out, long long row, cons
   }
 }
 
+// Dropout of one row held by a warp (element index = row * 768 + column).
+__device__ __forceinline__ void drop_row(RowRegs& r, long long row, int lane, const DropCfg& d) {
+  if (d.thr16 == 0) return;
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    const unsigned long long pair =
+        (static_cast<unsigned long long>(row) * kHidden + 4 * (lane + 32 * k)) >> 1;
+    const uint32_t b0 = drop_bits(d.key, pair), b1 = drop_bits(d.key, pair + 1);
+    r.v[k].x *= drop_mul(b0, 0, d);
+    r.v[k].y *= drop_mul(b0, 1, d);
+    r.v[k].z *= drop_mul(b1, 0, d);
+    r.v[k].w *= drop_mul(b1, 1, d);
+  }
+}
+
 inline int row_grid(long long rows, int warps_per_block, int blocks_per_sm = 16) {
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
   const long long cap = 148LL * blocks_per_sm;  // kernels are grid-stride

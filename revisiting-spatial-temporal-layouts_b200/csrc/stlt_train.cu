@@ -103,12 +103,31 @@ struct Ctx {
   cudaStream_t stream;
   uint8_t* ws;
   const TrainPlan* p;
+  float dropout_p;
+  uint64_t seed;
 };
+
+// Dropout sites (element indexing is documented at each kernel): 0 = category/box embedding output,
+// 1 = frame embedding output, 16 + 4 * layer + {0: attention probabilities, 1: dropout1 (attention
+// branch), 2: FFN inner, 3: dropout2 (FFN branch)} with the spatial layers numbered first.
+DropCfg site_cfg(float p, uint64_t seed, int site) {
+  DropCfg d{0u, 0u, 1.0f};
+  if (p <= 0.0f) return d;
+  uint32_t thr = static_cast<uint32_t>(std::lround(static_cast<double>(p) * 65536.0));
+  if (thr < 1) thr = 1;
+  if (thr > 65535) thr = 65535;
+  d.thr16 = thr;
+  d.scale = static_cast<float>(65536.0 / (65536.0 - thr));
+  d.key = lowbias32(static_cast<uint32_t>(seed) ^
+                    lowbias32(static_cast<uint32_t>(seed >> 32) ^ (static_cast<uint32_t>(site) * 0x9e3779b9u + 0x85ebca6bu)));
+  return d;
+}
+DropCfg layer_cfg(const Ctx& c, int layer, int which) { return site_cfg(c.dropout_p, c.seed, 16 + 4 * layer + which); }
 
 // ---- forward of one encoder layer, activations saved into `s` ------------------------------------
 // x: fp32 residual stream of the full phase (in/out unless the tail is compacted, in which case the
 // layer output is written to x_tail). next_xb: bf16 copy of the layer output (next layer's input).
-int fwd_layer(const Ctx& c, const LayerWeights& lw, const LayerSave& s, long long m_full,
+int fwd_layer(const Ctx& c, int layer, const LayerWeights& lw, const LayerSave& s, long long m_full,
               long long n_full, const long long* mask_src, long long num_seqs, int T, bool causal,
               bool compact, int gather_stride, const long long* lengths, int L, long long m_tail,
               long long n_tail, float* x, float* x_tail, float* y, __nv_bfloat16* next_xb) {
@@ -122,7 +141,8 @@ int fwd_layer(const Ctx& c, const LayerWeights& lw, const LayerSave& s, long lon
   if (rc) return rc;
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ATTENTION);
-    STLT_CUDA(h, launch_attention_mma(qkv, 1, m_full, mask_src, num_seqs, T, causal, att, m_full, c.stream));
+    STLT_CUDA(h, launch_attention_mma(qkv, 1, m_full, mask_src, num_seqs, T, causal, att, m_full, c.stream,
+                                      layer_cfg(c, layer, 0)));
   }
   h->launches++;
   float* xt = x;
@@ -140,11 +160,12 @@ int fwd_layer(const Ctx& c, const LayerWeights& lw, const LayerSave& s, long lon
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ADD_LN);
     ActOut o{xt, at<__nv_bfloat16>(c.ws, s.x1b), 1, m_tail};
-    STLT_CUDA(h, launch_add_ln(xt, y, lw.n1_g, lw.n1_b, eps, n_tail, o, c.stream, at<float>(c.ws, s.z1)));
+    STLT_CUDA(h, launch_add_ln(xt, y, lw.n1_g, lw.n1_b, eps, n_tail, o, c.stream, at<float>(c.ws, s.z1),
+                               layer_cfg(c, layer, 1)));
   }
   h->launches++;
   rc = run_gemm(h, c.stream, at<__nv_bfloat16>(c.ws, s.x1b), m_tail, m_tail, lw.l1_p, kFfn, kHidden, lw.l1_b,
-                at<__nv_bfloat16>(c.ws, s.hid), 1, GEMM_OUT_BF16_DUAL, 2);
+                at<__nv_bfloat16>(c.ws, s.hid), 1, GEMM_OUT_BF16_DUAL, 2, layer_cfg(c, layer, 2));
   if (rc) return rc;
   rc = run_gemm(h, c.stream, at<__nv_bfloat16>(c.ws, s.hid), m_tail, m_tail, lw.l2_p, kHidden, kFfn, lw.l2_b, y,
                 1, GEMM_OUT_F32, 0);
@@ -152,7 +173,8 @@ int fwd_layer(const Ctx& c, const LayerWeights& lw, const LayerSave& s, long lon
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ADD_LN);
     ActOut o{xt, next_xb, 1, m_tail};
-    STLT_CUDA(h, launch_add_ln(xt, y, lw.n2_g, lw.n2_b, eps, n_tail, o, c.stream, at<float>(c.ws, s.z2)));
+    STLT_CUDA(h, launch_add_ln(xt, y, lw.n2_g, lw.n2_b, eps, n_tail, o, c.stream, at<float>(c.ws, s.z2),
+                               layer_cfg(c, layer, 3)));
   }
   h->launches++;
   return STLT_OK;
@@ -164,7 +186,7 @@ int fwd_layer(const Ctx& c, const LayerWeights& lw, const LayerSave& s, long lon
 //      the residual part already added on the tail rows when the tail is compacted);
 //      fb = residual part (tail rows == full rows), or null when it was folded into fa.
 // Buffers: fa / fb may alias d_a / d_b (they are consumed first); fc, fd are scratch.
-int bwd_layer(const Ctx& c, const LayerWeights& lw, const LayerWeights& gw, const LayerSave& s,
+int bwd_layer(const Ctx& c, int layer, const LayerWeights& lw, const LayerWeights& gw, const LayerSave& s,
               long long m_full, long long n_full, const long long* mask_src, long long num_seqs, int T,
               bool causal, bool compact, int scatter_stride, const long long* lengths, int L,
               long long m_tail, long long n_tail, const float* d_a, const float* d_b, float* fa,
@@ -186,7 +208,7 @@ int bwd_layer(const Ctx& c, const LayerWeights& lw, const LayerWeights& gw, cons
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ADD_LN);
     STLT_CUDA(h, launch_ln_bwd(d_a, d_b, at<float>(ws, s.z2), lw.n2_g, eps, n_tail, fc, bz, grad_ptr(gw.n2_g),
-                               grad_ptr(gw.n2_b), grad_ptr(gw.l2_b), c.stream));
+                               grad_ptr(gw.n2_b), grad_ptr(gw.l2_b), c.stream, layer_cfg(c, layer, 3)));
   }
   h->launches++;
   // linear2: dH = dz2 W2 ; dW2 += dz2^T h
@@ -199,7 +221,7 @@ int bwd_layer(const Ctx& c, const LayerWeights& lw, const LayerWeights& gw, cons
   // GELU: dU = dH * gelu'(u) in place; d b1 = colsum(dU)
   {
     ProfileScope prof(h, c.stream, STLT_PROF_OTHER);
-    STLT_CUDA(h, launch_act_bwd_colsum(bh, u, n_tail, kFfn, grad_ptr(gw.l1_b), c.stream));
+    STLT_CUDA(h, launch_act_bwd_colsum(bh, u, n_tail, kFfn, grad_ptr(gw.l1_b), c.stream, layer_cfg(c, layer, 2)));
   }
   h->launches++;
   // linear1: dX1 = dU W1 -> fd ; dW1 += dU^T x1b
@@ -214,7 +236,7 @@ int bwd_layer(const Ctx& c, const LayerWeights& lw, const LayerWeights& gw, cons
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ADD_LN);
     STLT_CUDA(h, launch_ln_bwd(fc, fd, at<float>(ws, s.z1), lw.n1_g, eps, n_tail, fb, bz, grad_ptr(gw.n1_g),
-                               grad_ptr(gw.n1_b), grad_ptr(gw.out_b), c.stream));
+                               grad_ptr(gw.n1_b), grad_ptr(gw.out_b), c.stream, layer_cfg(c, layer, 1)));
   }
   h->launches++;
   // out-projection: dAtt = dz1 Wo ; dWo += dz1^T att
@@ -236,7 +258,7 @@ int bwd_layer(const Ctx& c, const LayerWeights& lw, const LayerWeights& gw, cons
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ATTENTION);
     STLT_CUDA(h, launch_attention_bwd(at<__nv_bfloat16>(ws, s.qkv), batt, mask_src, num_seqs, T, causal, bqkv,
-                                      c.stream));
+                                      c.stream, layer_cfg(c, layer, 0)));
   }
   h->launches++;
   if (gw.in_b) {
@@ -309,9 +331,7 @@ int stlt_forward_train(void* handle, void* stream_, const int64_t* categories_, 
     return fail(h, STLT_ERR_STATE, "training runs in bf16 mixed precision: pack the weights for STLT_PRECISION_BF16");
   int rc = check_shape(h, B, L, S);
   if (rc) return rc;
-  if (dropout_p != 0.0f)
-    return fail(h, STLT_ERR_INVALID, "dropout_p=%g: only p = 0 is implemented in this build", dropout_p);
-  (void)seed;
+  if (!(dropout_p >= 0.0f) || dropout_p >= 1.0f) return fail(h, STLT_ERR_INVALID, "dropout_p=%g outside [0, 1)", dropout_p);
   if (!categories_ || !boxes || !frame_types_ || !lengths_ || !workspace || !logits)
     return fail(h, STLT_ERR_INVALID, "null tensor pointer");
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
@@ -327,7 +347,7 @@ int stlt_forward_train(void* handle, void* stream_, const int64_t* categories_, 
   const long long* frame_types = reinterpret_cast<const long long*>(frame_types_);
   const long long* lengths = reinterpret_cast<const long long*>(lengths_);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  Ctx c{h, stream, ws, &p};
+  Ctx c{h, stream, ws, &p, dropout_p, seed};
   int* err_flag = at<int>(ws, p.off_err);
   h->launches = 0;
   STLT_CUDA(h, cudaMemsetAsync(err_flag, 0, sizeof(int), stream));
@@ -342,13 +362,13 @@ int stlt_forward_train(void* handle, void* stream_, const int64_t* categories_, 
     ActOut emb{x, at<__nv_bfloat16>(ws, p.sp[0].xb), 1, p.m_sp};
     STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories, h->w.box_w,
                               h->w.box_b, h->w.score_w, h->w.score_b, h->w.emb_g, h->w.emb_b,
-                              d.layer_norm_eps, p.n_sp, emb, err_flag, stream));
+                              d.layer_norm_eps, p.n_sp, emb, err_flag, stream, site_cfg(dropout_p, seed, 0)));
     h->launches++;
   }
   const int ns = d.num_spatial_layers, nt = d.num_temporal_layers;
   for (int i = 0; i < ns; ++i) {
     const bool last = i == ns - 1;
-    rc = fwd_layer(c, h->w.spatial[i], p.sp[i], p.m_sp, p.n_sp, categories, p.n_tm, S, false, last, S, nullptr,
+    rc = fwd_layer(c, i, h->w.spatial[i], p.sp[i], p.m_sp, p.n_sp, categories, p.n_tm, S, false, last, S, nullptr,
                    0, last ? p.m_tm : p.m_sp, last ? p.n_tm : p.n_sp, x, x_tail, y,
                    last ? nullptr : at<__nv_bfloat16>(ws, p.sp[i + 1].xb));
     if (rc) return rc;
@@ -363,13 +383,13 @@ int stlt_forward_train(void* handle, void* stream_, const int64_t* categories_, 
     ActOut fr{x, at<__nv_bfloat16>(ws, p.tm[0].xb), 1, p.m_tm};
     STLT_CUDA(h, launch_frame_embed(at<float>(ws, p.cls_x), 1, frame_types, h->w.pos_table, h->w.ft_table,
                                     d.num_frame_types, h->w.fr_g, h->w.fr_b, d.layer_norm_eps, B, L, fr,
-                                    err_flag, stream));
+                                    err_flag, stream, site_cfg(dropout_p, seed, 1)));
     h->launches++;
   }
   float* pooled = at<float>(ws, p.pooled);
   for (int i = 0; i < nt; ++i) {
     const bool last = i == nt - 1;
-    rc = fwd_layer(c, h->w.temporal[i], p.tm[i], p.m_tm, p.n_tm, frame_types, B, L, true, last, 0, lengths, L,
+    rc = fwd_layer(c, ns + i, h->w.temporal[i], p.tm[i], p.m_tm, p.n_tm, frame_types, B, L, true, last, 0, lengths, L,
                    last ? p.m_hd : p.m_tm, last ? B : p.n_tm, x, pooled, y,
                    last ? nullptr : at<__nv_bfloat16>(ws, p.tm[i + 1].xb));
     if (rc) return rc;
@@ -390,8 +410,8 @@ int stlt_forward_train(void* handle, void* stream_, const int64_t* categories_, 
 
 int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const float* boxes,
                   const float* scores, const int64_t* frame_types_, const int64_t* lengths_, int32_t B,
-                  int32_t L, int32_t S, void* workspace, size_t workspace_bytes, const float* d_logits,
-                  int32_t phases) {
+                  int32_t L, int32_t S, void* workspace, size_t workspace_bytes, float dropout_p,
+                  uint64_t seed, const float* d_logits, int32_t phases) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
   if (!h->bound || !h->grads_bound)
@@ -413,7 +433,7 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
   const long long* frame_types = reinterpret_cast<const long long*>(frame_types_);
   const long long* lengths = reinterpret_cast<const long long*>(lengths_);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  Ctx c{h, stream, ws, &p};
+  Ctx c{h, stream, ws, &p, dropout_p, seed};
   const Weights& w = h->w;
   const Weights& g = h->g;
   const int ns = d.num_spatial_layers, nt = d.num_temporal_layers;
@@ -457,7 +477,7 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
       bool fb_used = false;
       // the incoming gradient lives in f0 (+ f1); they are consumed by the first kernel, so the
       // layer's outputs go to the same pair and f2 / f3 are scratch
-      rc = bwd_layer(c, w.temporal[i], g.temporal[i], p.tm[i], p.m_tm, p.n_tm, frame_types, B, L, true, last, 0,
+      rc = bwd_layer(c, ns + i, w.temporal[i], g.temporal[i], p.tm[i], p.m_tm, p.n_tm, frame_types, B, L, true, last, 0,
                      lengths, L, last ? p.m_hd : p.m_tm, last ? B : p.n_tm, d_a, d_b, f0, f1, f2, f3, &fb_used);
       if (rc) return rc;
       d_a = f0;
@@ -468,7 +488,8 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
       ProfileScope prof(h, stream, STLT_PROF_OTHER);
       STLT_CUDA(h, launch_frame_embed_bwd(d_a, d_b, at<float>(ws, p.cls_x), frame_types, w.pos_table, w.ft_table,
                                           d.num_frame_types, w.fr_g, d.layer_norm_eps, B, L, f2, grad_ptr(g.pos_table),
-                                          grad_ptr(g.ft_table), grad_ptr(g.fr_g), grad_ptr(g.fr_b), stream));
+                                          grad_ptr(g.ft_table), grad_ptr(g.fr_g), grad_ptr(g.fr_b), stream,
+                                          site_cfg(dropout_p, seed, 1)));
       STLT_CUDA(h, cudaMemcpyAsync(d_cls, f2, static_cast<size_t>(p.n_tm) * kHidden * 4, cudaMemcpyDeviceToDevice,
                                    stream));
       h->launches++;
@@ -483,7 +504,7 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
     for (int i = ns - 1; i >= 0; --i) {
       const bool last = i == ns - 1;
       bool fb_used = false;
-      rc = bwd_layer(c, w.spatial[i], g.spatial[i], p.sp[i], p.m_sp, p.n_sp, categories, p.n_tm, S, false, last, S,
+      rc = bwd_layer(c, i, w.spatial[i], g.spatial[i], p.sp[i], p.m_sp, p.n_sp, categories, p.n_tm, S, false, last, S,
                      nullptr, 0, last ? p.m_tm : p.m_sp, last ? p.n_tm : p.n_sp, d_a, d_b, f0, f1, f2, f3, &fb_used);
       if (rc) return rc;
       d_a = f0;
@@ -497,9 +518,21 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
                                     grad_ptr(g.cat_table), grad_ptr(g.box_w), grad_ptr(g.box_b),
                                     has_scores ? grad_ptr(g.score_w) : nullptr,
                                     has_scores ? grad_ptr(g.score_b) : nullptr, grad_ptr(g.emb_g),
-                                    grad_ptr(g.emb_b), stream));
+                                    grad_ptr(g.emb_b), stream, site_cfg(dropout_p, seed, 0)));
       h->launches += 2;
     }
+  }
+  return STLT_OK;
+}
+
+int stlt_op_dropout_mask(void* handle, float dropout_p, uint64_t seed, int32_t site, int64_t first, int64_t n,
+                         float* multipliers_host) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !multipliers_host || n < 0 || first < 0) return fail(h, STLT_ERR_INVALID, "invalid argument");
+  const DropCfg d = site_cfg(dropout_p, seed, site);
+  for (int64_t i = 0; i < n; ++i) {
+    const unsigned long long e = static_cast<unsigned long long>(first + i);
+    multipliers_host[i] = d.thr16 == 0 ? 1.0f : drop_mul(drop_bits(d.key, e >> 1), static_cast<int>(e & 1), d);
   }
   return STLT_OK;
 }

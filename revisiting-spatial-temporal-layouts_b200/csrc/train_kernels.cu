@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1)
 ln_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ d_b,
               const float* __restrict__ z, const float* __restrict__ gamma, float eps, long long rows,
               float* __restrict__ dz_out, __nv_bfloat16* __restrict__ dzb_out,
-              float* __restrict__ d_gamma, float* __restrict__ d_beta, float* __restrict__ d_bias) {
+              float* __restrict__ d_gamma, float* __restrict__ d_beta, float* __restrict__ d_bias,
+              DropCfg drop) {
   __shared__ __align__(16) float scratch[kBwdWarps * kHidden];
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -156,8 +157,9 @@ ln_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ d_b,
     if (d_b != nullptr) acc_add(dy, load_row(d_b, row, lane));
     RowRegs zz = load_row(z, row, lane);
     ln_bwd_row(zz, dy, gamma, eps, lane, acc_g, acc_b);
+    if (dz_out != nullptr) store_row_f32(dz_out, row, dy, lane);  // residual branch: no dropout
+    drop_row(dy, row, lane, drop);  // branch through dropout1 / dropout2 into the producing linear
     acc_add(acc_z, dy);
-    if (dz_out != nullptr) store_row_f32(dz_out, row, dy, lane);
     if (dzb_out != nullptr) store_row_bf16(dzb_out, row, dy, lane);
   }
   flush_columns(acc_g, d_gamma, scratch);
@@ -172,7 +174,7 @@ ln_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ d_b,
 template <bool kGelu>
 __global__ void __launch_bounds__(384)
 act_bwd_colsum_kernel(__nv_bfloat16* __restrict__ d, const __nv_bfloat16* __restrict__ u, long long rows,
-                      int n, float* __restrict__ d_bias) {
+                      int n, float* __restrict__ d_bias, DropCfg drop) {
   const int c8 = threadIdx.x;  // 8-column group
   if (c8 * 8 >= n) return;
   float acc[8];
@@ -203,6 +205,12 @@ act_bwd_colsum_kernel(__nv_bfloat16* __restrict__ d, const __nv_bfloat16* __rest
           const float2 uu = __bfloat1622float2(up[j]);
           g.x *= gelu_erf_grad(uu.x);
           g.y *= gelu_erf_grad(uu.y);
+          if (drop.thr16 != 0) {  // FFN-inner dropout sits between the activation and linear2
+            const unsigned long long el = static_cast<unsigned long long>(r0 + i) * n + c8 * 8 + 2 * j;
+            const uint32_t bits = drop_bits(drop.key, el >> 1);
+            g.x *= drop_mul(bits, 0, drop);
+            g.y *= drop_mul(bits, 1, drop);
+          }
           o[j] = pack_bf16x2(g.x, g.y);
           // the bias gradient sums what the GEMMs will see (the rounded values)
           const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&o[j]);
@@ -275,7 +283,7 @@ frame_embed_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ 
                        int n_frame_types, const float* __restrict__ gamma, float eps, int L,
                        long long frames, float* __restrict__ d_cls, float* __restrict__ d_pos,
                        float* __restrict__ d_ft, float* __restrict__ d_gamma,
-                       float* __restrict__ d_beta) {
+                       float* __restrict__ d_beta, DropCfg drop) {
   __shared__ __align__(16) float scratch[kBwdWarps * kHidden];
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -297,6 +305,7 @@ frame_embed_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ 
     }
     RowRegs dy = load_row(d_a, f, lane);
     if (d_b != nullptr) acc_add(dy, load_row(d_b, f, lane));
+    drop_row(dy, f, lane, drop);  // dropout follows the LayerNorm (models.py:110)
     ln_bwd_row(zz, dy, gamma, eps, lane, acc_g, acc_b);
     store_row_f32(d_cls, f, dy, lane);
     float* dp = d_pos != nullptr ? d_pos + static_cast<long long>(l) * kHidden : nullptr;
@@ -334,7 +343,7 @@ embed_ln_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ d_b
                     const float* __restrict__ box_b, const float* __restrict__ score_w,
                     const float* __restrict__ score_b, const float* __restrict__ gamma, float eps,
                     long long tokens, float* __restrict__ d_pre, float* __restrict__ d_gamma,
-                    float* __restrict__ d_beta) {
+                    float* __restrict__ d_beta, DropCfg drop) {
   __shared__ __align__(16) float scratch[kBwdWarps * kHidden];
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -372,6 +381,7 @@ embed_ln_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ d_b
     }
     RowRegs dy = load_row(d_a, t, lane);
     if (d_b != nullptr) acc_add(dy, load_row(d_b, t, lane));
+    drop_row(dy, t, lane, drop);  // dropout follows the LayerNorm (models.py:38)
     ln_bwd_row(zz, dy, gamma, eps, lane, acc_g, acc_b);
     store_row_f32(d_pre, t, dy, lane);
   }
@@ -686,23 +696,24 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_ln_bwd(const float* d_a, const float* d_b, const float* z, const float* gamma,
                           float eps, long long rows, float* dz_out, __nv_bfloat16* dzb_out,
-                          float* d_gamma, float* d_beta, float* d_bias, cudaStream_t stream) {
+                          float* d_gamma, float* d_beta, float* d_bias, cudaStream_t stream,
+                          DropCfg drop) {
   if (rows == 0) return cudaSuccess;
   ln_bwd_kernel<<<row_grid(rows, kBwdWarps, 2), kBwdWarps * 32, 0, stream>>>(
-      d_a, d_b, z, gamma, eps, rows, dz_out, dzb_out, d_gamma, d_beta, d_bias);
+      d_a, d_b, z, gamma, eps, rows, dz_out, dzb_out, d_gamma, d_beta, d_bias, drop);
   return cudaGetLastError();
 }
 
 cudaError_t launch_act_bwd_colsum(__nv_bfloat16* d, const __nv_bfloat16* u, long long rows, int n,
-                                  float* d_bias, cudaStream_t stream) {
+                                  float* d_bias, cudaStream_t stream, DropCfg drop) {
   if (rows == 0) return cudaSuccess;
   if (n % 8 != 0 || n / 8 > 384) return cudaErrorInvalidValue;
   long long blocks = (rows + 3) / 4;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (u != nullptr)
-    act_bwd_colsum_kernel<true><<<static_cast<unsigned>(blocks), 384, 0, stream>>>(d, u, rows, n, d_bias);
+    act_bwd_colsum_kernel<true><<<static_cast<unsigned>(blocks), 384, 0, stream>>>(d, u, rows, n, d_bias, drop);
   else
-    act_bwd_colsum_kernel<false><<<static_cast<unsigned>(blocks), 384, 0, stream>>>(d, nullptr, rows, n, d_bias);
+    act_bwd_colsum_kernel<false><<<static_cast<unsigned>(blocks), 384, 0, stream>>>(d, nullptr, rows, n, d_bias, drop);
   return cudaGetLastError();
 }
 
@@ -726,12 +737,12 @@ cudaError_t launch_frame_embed_bwd(const float* d_a, const float* d_b, const flo
                                    const long long* frame_types, const float* pos_table,
                                    const float* ft_table, int n_frame_types, const float* gamma,
                                    float eps, int B, int L, float* d_cls, float* d_pos, float* d_ft,
-                                   float* d_gamma, float* d_beta, cudaStream_t stream) {
+                                   float* d_gamma, float* d_beta, cudaStream_t stream, DropCfg drop) {
   const long long frames = static_cast<long long>(B) * L;
   if (frames == 0) return cudaSuccess;
   frame_embed_bwd_kernel<<<row_grid(frames, kBwdWarps, 2), kBwdWarps * 32, 0, stream>>>(
       d_a, d_b, cls_x, frame_types, pos_table, ft_table, n_frame_types, gamma, eps, L, frames, d_cls,
-      d_pos, d_ft, d_gamma, d_beta);
+      d_pos, d_ft, d_gamma, d_beta, drop);
   return cudaGetLastError();
 }
 
@@ -741,12 +752,12 @@ cudaError_t launch_embed_bwd(const float* d_a, const float* d_b, const long long
                              const float* score_w, const float* score_b, const float* gamma, float eps,
                              long long tokens, float* d_pre, float* d_cat, float* d_box_w,
                              float* d_box_b, float* d_score_w, float* d_score_b, float* d_gamma,
-                             float* d_beta, cudaStream_t stream) {
+                             float* d_beta, cudaStream_t stream, DropCfg drop) {
   if (tokens == 0) return cudaSuccess;
   const float4* boxes4 = reinterpret_cast<const float4*>(boxes);
   embed_ln_bwd_kernel<<<row_grid(tokens, kBwdWarps, 2), kBwdWarps * 32, 0, stream>>>(
       d_a, d_b, categories, boxes4, scores, cat_table, unique_categories, box_w, box_b, score_w,
-      score_b, gamma, eps, tokens, d_pre, d_gamma, d_beta);
+      score_b, gamma, eps, tokens, d_pre, d_gamma, d_beta, drop);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int smem = unique_categories * kHidden * static_cast<int>(sizeof(float));

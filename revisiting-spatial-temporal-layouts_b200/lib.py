@@ -129,7 +129,9 @@ SIGNATURES = {
                                      c_int32, c_int32, c_int32, c_void_p, c_size_t, c_float, c_uint64,
                                      c_void_p]),
     "stlt_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_int32]),
+                                c_int32, c_int32, c_int32, c_void_p, c_size_t, c_float, c_uint64, c_void_p,
+                                c_int32]),
+    "stlt_op_dropout_mask": (c_int32, [c_void_p, c_float, c_uint64, c_int32, c_int64, c_int64, c_void_p]),
     "stlt_loss": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_float,
                             c_void_p, c_void_p]),
     "stlt_grad_sumsq": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -313,6 +313,8 @@ class Stlt(nn.Module):
             scores = self._as_input(batch, "scores", torch.float32, (B, L, S), device)
 
         dropout_p = float(getattr(self.config, "hidden_dropout_prob", 0.0)) if self.training else 0.0
+        if getattr(self.config, "load_backbone_path", None) and self.config.freeze_backbone:
+            dropout_p = 0.0  # the frozen backbone stays in eval mode (models.py:180-183); the head has no dropout
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad or dropout_p > 0.0:
             # training step (src/train.py:125-127): logits carry a grad_fn whose backward is
@@ -404,7 +406,8 @@ class Stlt(nn.Module):
             B, L, S, ws.data_ptr(), ws.numel(), dropout_p, seed, logits.data_ptr()))
         return logits
 
-    def _backward(self, inputs, ws: torch.Tensor, d_logits: Optional[torch.Tensor], phases: int) -> None:
+    def _backward(self, inputs, ws: torch.Tensor, d_logits: Optional[torch.Tensor], phases: int,
+                  dropout_p: float = 0.0, seed: int = 0) -> None:
         cats, boxes, scores, ftypes, lengths = inputs
         B, L, S = cats.shape
         lib = _lib.load_library()
@@ -412,8 +415,8 @@ class Stlt(nn.Module):
         _lib.check(self._handle, lib.stlt_backward(
             self._handle, stream, cats.data_ptr(), boxes.data_ptr(),
             scores.data_ptr() if scores is not None else None, ftypes.data_ptr(), lengths.data_ptr(),
-            B, L, S, ws.data_ptr(), ws.numel(), d_logits.data_ptr() if d_logits is not None else None,
-            phases))
+            B, L, S, ws.data_ptr(), ws.numel(), dropout_p, seed,
+            d_logits.data_ptr() if d_logits is not None else None, phases))
 
     def check_inputs(self) -> None:
         """Synchronises and raises if the last forward saw an out-of-range index (debug aid)."""
@@ -465,6 +468,7 @@ class _StltTrainFunction(torch.autograd.Function):
             inputs = (cats, boxes, scores, ftypes, lengths)
             logits = module._forward_train(inputs, ws, dropout_p, seed)
         ctx.module, ctx.names, ctx.ws, ctx.inputs = module, names, ws, inputs
+        ctx.dropout = (dropout_p, seed)
         ctx.param_shapes = [p.shape for p in params]
         return logits
 
@@ -495,7 +499,7 @@ class _StltTrainFunction(torch.autograd.Function):
             out.append(g)
         with torch.cuda.device(device):
             module._bind_grads(grads)
-            module._backward(ctx.inputs, ctx.ws, d_logits.contiguous().float(), _lib.BWD_ALL)
+            module._backward(ctx.inputs, ctx.ws, d_logits.contiguous().float(), _lib.BWD_ALL, *ctx.dropout)
         ctx.ws = None
         return (None,) * 8 + tuple(out)
 

@@ -160,8 +160,8 @@ class FusedTrainStep:
                 self._ws_key = (B, L, S)
             self.flat_grads.zero_()  # optimizer.zero_grad()
             self.step_count += 1
-            logits = model._forward_train(inputs, self._ws, self.dropout_p if model.training else 0.0,
-                                          self.seed + self.step_count)
+            drop = (self.dropout_p if model.training else 0.0, self.seed + self.step_count)
+            logits = model._forward_train(inputs, self._ws, *drop)
             d_logits = torch.empty_like(logits)
             # mean over the GLOBAL batch: local mean gradient scaled by 1/world, summed by the all-reduce
             _lib.check(model._handle, lib.stlt_loss(model._handle, stream, kind, logits.data_ptr(),
@@ -169,11 +169,11 @@ class FusedTrainStep:
                                                     self._loss.data_ptr(), d_logits.data_ptr()))
             t0, t1 = self.segments["t_nd"][0], self.segments["t_d"][1]
             s0 = self.segments["s_nd"][0]
-            model._backward(inputs, self._ws, d_logits, _lib.BWD_TEMPORAL)
+            model._backward(inputs, self._ws, d_logits, _lib.BWD_TEMPORAL, *drop)
             work = None
             if world > 1:  # bucket 1 travels over NVLink while the spatial stack's backward runs
                 work = dist.all_reduce(self.flat_grads[t0:t1], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            model._backward(inputs, self._ws, None, _lib.BWD_SPATIAL)
+            model._backward(inputs, self._ws, None, _lib.BWD_SPATIAL, *drop)
             if world > 1:
                 dist.all_reduce(self.flat_grads[s0:], op=dist.ReduceOp.SUM, group=self.group)
                 work.wait()
@@ -206,6 +206,9 @@ class FusedTrainStep:
         prec = _lib.PRECISION_BF16
         buf = model._packed[prec]
         _lib.check(model._handle, lib.stlt_pack_weights(model._handle, stream, prec, buf.data_ptr(), buf.numel()))
+        # copies packed for another precision are stale now (the parameter versions did not change)
+        model._packed_key = {prec: model._weights_key}
+        model._last_packed = prec
 
     def grad_norm(self) -> float:
         """Total gradient norm of the last step (synchronises; debugging / tests)."""

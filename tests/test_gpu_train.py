@@ -131,3 +131,91 @@ def test_fused_train_step_matches_oracle(layout):
         logits = model(to_cuda(batch))["stlt"].float().cpu()
         want = stlt_oracle.stlt_forward(ref_sd, batch)
     assert float((logits - want).abs().max() / want.abs().max()) < 3e-2
+
+
+def _site_mask(handle, p, seed, site, n):
+    import numpy as np
+    lib = L.load_library()
+    out = np.empty(n, dtype=np.float32)
+    L.check(handle, lib.stlt_op_dropout_mask(handle, p, seed, site, 0, n, out.ctypes.data))
+    return torch.from_numpy(out)
+
+
+def _replay_masks(handle, p, seed, batch, ns=4, nt=8):
+    """The multipliers the library applies at every dropout site, arranged for the oracle."""
+    B, Lf, S = batch["categories"].shape
+    H, F, heads = 768, 3072, 12
+    n_sp, n_tm = B * Lf * S, B * Lf
+    lengths = batch["lengths"]
+    masks = {"embed": _site_mask(handle, p, seed, 0, n_sp * H).view(B, Lf, S, H),
+             "frames": _site_mask(handle, p, seed, 1, n_tm * H).view(B, Lf, H)}
+
+    def layer(stack, i, layer_id, rows, seqs, T, last, place):
+        d = {}
+        attn = _site_mask(handle, p, seed, 16 + 4 * layer_id + 0, rows * heads * 32).view(seqs, T, heads, 32)
+        d["attn"] = attn[..., :T].permute(0, 2, 1, 3).contiguous()
+        for which, name, width in ((1, "branch1", H), (2, "ffn", F), (3, "branch2", H)):
+            if not last:
+                d[name] = _site_mask(handle, p, seed, 16 + 4 * layer_id + which, rows * width).view(seqs, T, width)
+            else:  # compacted rows of the pruned last layer; rows that are never read get 1
+                tail = _site_mask(handle, p, seed, 16 + 4 * layer_id + which, seqs_tail(stack) * width)
+                full = torch.ones(seqs, T, width)
+                place(full, tail.view(-1, width))
+                d[name] = full
+        masks[(stack, i)] = d
+
+    def seqs_tail(stack):
+        return n_tm if stack == "spatial" else B
+
+    def place_spatial(full, tail):   # row f of the tail = slot 0 of frame f
+        full[:, 0, :] = tail
+
+    def place_temporal(full, tail):  # row b of the tail = frame lengths[b]-1 of video b
+        full[torch.arange(B), lengths - 1, :] = tail
+
+    for i in range(ns):
+        layer("spatial", i, i, n_sp, n_tm, S, i == ns - 1, place_spatial)
+    for i in range(nt):
+        layer("temporal", i, ns + i, n_tm, B, Lf, i == nt - 1, place_temporal)
+    return masks
+
+
+@pytest.mark.parametrize("layout", ["something", "action_genome"])
+def test_dropout_forward_backward_match_oracle_under_identical_masks(layout):
+    """p = 0.1: the library regenerates its masks from (seed, site, element); the same multipliers are
+    replayed in the oracle, whose dropout placement restates torch's (MHA probabilities, dropout1,
+    FFN inner, dropout2, the two embedding dropouts)."""
+    cfg, sd, batch, labels, loss, g = _case(layout)
+    p, seed = 0.1, 1234
+    model = _model(cfg, sd)
+    model.train(True)
+    gb = to_cuda(batch)
+    B, Lf, S = batch["categories"].shape
+    model._ensure_handle(torch.device("cuda", 0))
+    stream = torch.cuda.current_stream().cuda_stream
+    model._sync_weights(torch.device("cuda", 0), stream, "bf16")
+    inputs = (gb["categories"], gb["boxes"], gb.get("scores"), gb["frame_types"], gb["lengths"])
+    ws = model._train_workspace(B, Lf, S, torch.device("cuda", 0))
+    logits = model._forward_train(inputs, ws, p, seed)
+    masks = _replay_masks(model._handle, p, seed, batch)
+    keep = torch.cat([m.flatten() for m in (masks["embed"], masks["frames"], masks[("spatial", 0)]["ffn"])])
+    rate = float((keep == 0).float().mean())
+    assert abs(rate - 0.1) < 3e-3, rate
+    assert abs(float(keep.max()) - 65536.0 / (65536 - 6554)) < 1e-6
+    want_loss, want_logits, want = stlt_oracle.loss_and_grads(sd, batch, labels, loss, dropout=masks)
+    err = float((logits.float().cpu() - want_logits).abs().max() / want_logits.abs().max())
+    print("dropout logits nerr", err)
+    assert err < 2e-2
+    # backward under the same masks
+    lg = want_logits.clone().requires_grad_(True)
+    stlt_oracle.criterion(lg, labels, loss).backward()
+    grads = {n: torch.zeros_like(q) for n, q in model.named_parameters() if n in want}
+    model._bind_grads(grads)
+    model._backward(inputs, ws, lg.grad.cuda().contiguous(), L.BWD_ALL, p, seed)
+    worst = sorted(((_rel(grads[n], want[n]), n) for n in grads), reverse=True)
+    print("dropout worst tensors:", worst[:4])
+    assert worst[0][0] < 3e-2, worst[:4]
+    # a different seed gives a different mask, the same seed the same logits
+    again = model._forward_train(inputs, ws, p, seed)
+    other = model._forward_train(inputs, ws, p, seed + 1)
+    assert torch.equal(again, logits) and not torch.equal(other, logits)
