@@ -48,6 +48,46 @@ def _phase_of(name: str) -> int:
     return 1 if ".layout_embedding." in name else 0
 
 
+SEGMENT_ORDER = ("t_nd", "t_d", "s_nd", "s_d", "sc_nd", "sc_d")
+
+
+def plan_flat_layout(named_parameters):
+    """Flat-buffer layout of the trainable parameters: [(name, param, offset)], {segment: (start, end)},
+    total. Segments: {temporal, spatial backward phase} x {no-decay, decay} and the score embedding
+    (which only gets a gradient when the batch carries ``scores``)."""
+    segs: Dict[str, List] = {k: [] for k in SEGMENT_ORDER}
+    for name, p in named_parameters:
+        if not p.requires_grad or ".encoder_layer." in name:
+            continue
+        nd = _is_no_decay(name, p)
+        if "score_embeddings" in name:
+            segs["sc_nd" if nd else "sc_d"].append((name, p))
+        else:
+            segs[("t" if _phase_of(name) == 0 else "s") + ("_nd" if nd else "_d")].append((name, p))
+    segments, layout, off = {}, [], 0
+    for key in SEGMENT_ORDER:
+        start = off
+        for name, p in segs[key]:
+            layout.append((name, p, off))
+            off += (p.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned
+        segments[key] = (start, off)
+    return layout, segments, off
+
+
+def all_reduce_buckets(flat_grads: torch.Tensor, segments, group=None, between=None):
+    """Sums the flat gradient over the data-parallel group in two contiguous buckets. ``between`` (the
+    second half of the backward pass) runs while the first bucket — the temporal-phase gradients, which
+    are final by then — is in flight."""
+    import torch.distributed as dist
+    t0, t1 = segments["t_nd"][0], segments["t_d"][1]
+    s0 = segments["s_nd"][0]
+    work = dist.all_reduce(flat_grads[t0:t1], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    if between is not None:
+        between()
+    dist.all_reduce(flat_grads[s0:], op=dist.ReduceOp.SUM, group=group)
+    work.wait()
+
+
 class FusedTrainStep:
     """Owns flat fp32 parameter / gradient / AdamW-state buffers of an ``Stlt`` module.
 
@@ -78,24 +118,7 @@ class FusedTrainStep:
         if device.type != "cuda":
             raise RuntimeError("FusedTrainStep needs the module on a CUDA device (there is no CPU path)")
         self.device = device
-        segs: Dict[str, List] = {k: [] for k in ("t_nd", "t_d", "s_nd", "s_d", "sc_nd", "sc_d")}
-        for name, p in model.named_parameters():
-            if not p.requires_grad or ".encoder_layer." in name:
-                continue
-            nd = _is_no_decay(name, p)
-            if "score_embeddings" in name:
-                segs["sc_nd" if nd else "sc_d"].append((name, p))
-            else:
-                segs[("t" if _phase_of(name) == 0 else "s") + ("_nd" if nd else "_d")].append((name, p))
-        self.segments = {}
-        off = 0
-        layout = []
-        for key in ("t_nd", "t_d", "s_nd", "s_d", "sc_nd", "sc_d"):
-            start = off
-            for name, p in segs[key]:
-                layout.append((name, p, off))
-                off += (p.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned
-            self.segments[key] = (start, off)
+        layout, self.segments, off = plan_flat_layout(model.named_parameters())
         self.total = off
         self.flat_params = torch.zeros(off, dtype=torch.float32, device=device)
         self.flat_grads = torch.zeros(off, dtype=torch.float32, device=device)
@@ -167,16 +190,12 @@ class FusedTrainStep:
             _lib.check(model._handle, lib.stlt_loss(model._handle, stream, kind, logits.data_ptr(),
                                                     labels.data_ptr(), B, C, 1.0 / world,
                                                     self._loss.data_ptr(), d_logits.data_ptr()))
-            t0, t1 = self.segments["t_nd"][0], self.segments["t_d"][1]
-            s0 = self.segments["s_nd"][0]
             model._backward(inputs, self._ws, d_logits, _lib.BWD_TEMPORAL, *drop)
-            work = None
+            spatial = lambda: model._backward(inputs, self._ws, None, _lib.BWD_SPATIAL, *drop)  # noqa: E731
             if world > 1:  # bucket 1 travels over NVLink while the spatial stack's backward runs
-                work = dist.all_reduce(self.flat_grads[t0:t1], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            model._backward(inputs, self._ws, None, _lib.BWD_SPATIAL, *drop)
-            if world > 1:
-                dist.all_reduce(self.flat_grads[s0:], op=dist.ReduceOp.SUM, group=self.group)
-                work.wait()
+                all_reduce_buckets(self.flat_grads, self.segments, self.group, between=spatial)
+            else:
+                spatial()
             sumsq_ptr = None
             if self.clip_val is not None:
                 self._sumsq.zero_()

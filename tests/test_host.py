@@ -92,10 +92,34 @@ def test_state_dict_contract():
     assert m.train(False) is m and not m.training
 
 
-def test_training_mode_is_not_silently_run():
+def test_training_mode_has_no_cpu_path_either():
     m = Stlt(StltModelConfig(num_classes=174, unique_categories=4))
-    with pytest.raises(NotImplementedError):
+    assert m.training
+    with pytest.raises(RuntimeError, match="no CPU path"):
         m(make_batch(1, "something"))
+
+
+def test_flat_training_layout_groups_parameters_like_the_reference_optimizer():
+    """plan_flat_layout: add_weight_decay's two groups (train_inference_utils.py:37-54), split by the
+    backward phase that produces the gradient; orphan tensors are not part of the optimizer."""
+    from stlt_b200.training import plan_flat_layout
+    m = Stlt(StltModelConfig(num_classes=174, unique_categories=4))
+    layout, segments, total = plan_flat_layout(m.named_parameters())
+    names = [n for n, _, _ in layout]
+    assert len(names) == len(set(names)) == 161  # 173 parameters - 12 orphan encoder_layer.* tensors
+    assert not any(".encoder_layer." in n for n in names)
+    offs = [o for _, _, o in layout]
+    assert offs == sorted(offs) and all(o % 4 == 0 for o in offs)
+    params = dict(m.named_parameters())
+    for n, p, o in layout:
+        key = next(k for k, (a, b) in segments.items() if a <= o < b)
+        assert key.endswith("_nd") == (p.dim() == 1 or n.endswith(".bias")), n
+        if "score_embeddings" in n:
+            assert key.startswith("sc")
+        else:
+            assert key.startswith("s_") == (".layout_embedding." in n), n
+    assert segments["t_nd"][0] == 0 and segments["sc_d"][1] == total
+    assert total >= sum(params[n].numel() for n in names)
 
 
 @pytest.mark.parametrize("layout,S,has_scores", [("something", 5, False), ("action_genome", 11, True)])
@@ -159,3 +183,44 @@ def test_two_rank_gloo_sharding_roundtrip(tmp_path):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "SHARD_OK" in res.stdout
+
+
+_TRAIN_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["STLT_ROOT"])
+import stlt_b200
+from stlt_b200.training import all_reduce_buckets, plan_flat_layout
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+model = stlt_b200.Stlt(stlt_b200.StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=1,
+                                                 num_temporal_layers=1))
+layout, segments, total = plan_flat_layout(model.named_parameters())
+# per-rank "gradients": the local-mean gradient already scaled by 1/world, as FusedTrainStep feeds the
+# all-reduce (stlt_loss grad_scale = 1/world), so the SUM over ranks is the global-batch mean
+g = torch.Generator().manual_seed(100 + rank)
+local = torch.randn(total, generator=g)
+flat = (local / world).clone()
+ran = []
+all_reduce_buckets(flat, segments, between=lambda: ran.append(True))
+assert ran == [True]
+want = sum(torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
+a, b = segments["t_nd"][0], segments["s_d"][1]
+assert torch.allclose(flat[a:b], want[a:b], atol=1e-6), rank
+# every trainable, non-orphan tensor lies inside one of the two buckets
+for name, p, off in layout:
+    assert 0 <= off and off + p.numel() <= total
+dist.barrier()
+if rank == 0:
+    print("ALLREDUCE_OK")
+"""
+
+
+def test_two_rank_gloo_gradient_buckets(tmp_path):
+    script = tmp_path / "train_worker.py"
+    script.write_text(_TRAIN_WORKER)
+    env = dict(os.environ, STLT_ROOT=str(ROOT), MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29519", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "ALLREDUCE_OK" in res.stdout
