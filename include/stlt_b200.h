@@ -267,6 +267,11 @@ int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w
  *             TMA reduce-add stores, work split stream-K over the token axis k; any k >= 1). */
 int stlt_op_gemm_grad(void* handle, void* stream, int32_t layout, const void* a, const void* b,
                       void* out, int32_t m_rows, int32_t n, int64_t k, int32_t out_kind);
+/* Attention backward: qkv bf16 [tokens][2304] (saved by the forward), d_ctx bf16 [tokens][768] ->
+ * d_qkv bf16 [tokens][2304]. impl 0 = CUDA cores, 1 = mma.sync tiles (the one the training step uses). */
+int stlt_op_attention_bwd(void* handle, void* stream, const void* qkv, const void* d_ctx,
+                          const int64_t* mask_src, int64_t num_seqs, int32_t seq_len, int32_t causal,
+                          void* d_qkv, int32_t impl);
 int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w,
                       const float* bias, float* out, int32_t m, int32_t n, int32_t k, int32_t gelu);
 int stlt_op_attention(void* handle, void* stream, const void* qkv, int32_t qkv_is_bf16,

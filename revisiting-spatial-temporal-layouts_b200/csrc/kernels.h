@@ -190,4 +190,11 @@ cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* 
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
                                  __nv_bfloat16* d_qkv, cudaStream_t stream, DropCfg drop = DropCfg{0, 0, 1.f});
 
+// Same on mma.sync tensor-core tiles (attention_bwd_mma.cu); the CUDA-core version above is kept as a
+// cross-check for the tests.
+cudaError_t launch_attention_bwd_mma(const __nv_bfloat16* qkv, const __nv_bfloat16* d_ctx,
+                                     const long long* mask_src, long long num_seqs, int T, bool causal,
+                                     __nv_bfloat16* d_qkv, cudaStream_t stream,
+                                     DropCfg drop = DropCfg{0, 0, 1.f});
+
 }  // namespace stlt

@@ -257,8 +257,8 @@ int bwd_layer(const Ctx& c, int layer, const LayerWeights& lw, const LayerWeight
   // attention: dQKV; d b_in = colsum(dQKV)
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ATTENTION);
-    STLT_CUDA(h, launch_attention_bwd(at<__nv_bfloat16>(ws, s.qkv), batt, mask_src, num_seqs, T, causal, bqkv,
-                                      c.stream, layer_cfg(c, layer, 0)));
+    STLT_CUDA(h, launch_attention_bwd_mma(at<__nv_bfloat16>(ws, s.qkv), batt, mask_src, num_seqs, T, causal, bqkv,
+                                          c.stream, layer_cfg(c, layer, 0)));
   }
   h->launches++;
   if (gw.in_b) {
@@ -534,6 +534,21 @@ int stlt_op_dropout_mask(void* handle, float dropout_p, uint64_t seed, int32_t s
     const unsigned long long e = static_cast<unsigned long long>(first + i);
     multipliers_host[i] = d.thr16 == 0 ? 1.0f : drop_mul(drop_bits(d.key, e >> 1), static_cast<int>(e & 1), d);
   }
+  return STLT_OK;
+}
+
+int stlt_op_attention_bwd(void* handle, void* stream, const void* qkv, const void* d_ctx,
+                          const int64_t* mask_src, int64_t num_seqs, int32_t seq_len, int32_t causal,
+                          void* d_qkv, int32_t impl) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !qkv || !d_ctx || !mask_src || !d_qkv) return fail(h, STLT_ERR_INVALID, "null argument");
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+  const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(d_ctx);
+  const long long* m = reinterpret_cast<const long long*>(mask_src);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(d_qkv);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (impl == 0) STLT_CUDA(h, launch_attention_bwd(q, d, m, num_seqs, seq_len, causal != 0, o, s));
+  else STLT_CUDA(h, launch_attention_bwd_mma(q, d, m, num_seqs, seq_len, causal != 0, o, s));
   return STLT_OK;
 }
 

@@ -63,3 +63,31 @@ def test_gemm_weight_gradient(handle, m, n, k):
                                           out.data_ptr(), m, n, k, 0))
     ref = init.double() + a.double().T @ b.double()
     assert nerr(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("T,num_seqs,causal", [(5, 13, False), (5, 4096, False), (11, 7, False), (17, 5, True),
+                                               (17, 700, True), (2, 3, True), (32, 2, True), (1, 9, False)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention_backward(handle, T, num_seqs, causal, impl):
+    """dQKV of masked multi-head attention vs torch autograd on the same bf16 inputs (fp32 math)."""
+    lib = L.load_library()
+    g = torch.Generator(device="cuda").manual_seed(T * 1000 + num_seqs)
+    tokens = num_seqs * T
+    qkv = torch.randn(tokens, 2304, device="cuda", generator=g).to(torch.bfloat16)
+    d_ctx = torch.randn(tokens, 768, device="cuda", generator=g).to(torch.bfloat16)
+    mask_src = (torch.rand(num_seqs, T, device="cuda", generator=g) > 0.3).long()
+    mask_src[:, 0] = 1  # slot / frame 0 is always valid
+    d_qkv = torch.full((tokens, 2304), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(handle, lib.stlt_op_attention_bwd(handle, _stream(), qkv.data_ptr(), d_ctx.data_ptr(),
+                                              mask_src.data_ptr(), num_seqs, T, int(causal), d_qkv.data_ptr(), impl))
+    x = qkv.float().view(num_seqs, T, 3, 12, 64).requires_grad_(True)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))  # [N, heads, T, 64]
+    scores = q @ k.transpose(-1, -2) / 8.0
+    masked = (mask_src == 0).view(num_seqs, 1, 1, T).expand(num_seqs, 12, T, T)
+    if causal:
+        masked = masked | torch.triu(torch.ones(T, T, dtype=torch.bool, device="cuda"), diagonal=1)
+    ctx = torch.softmax(scores.masked_fill(masked, float("-inf")), dim=-1) @ v
+    ctx.transpose(1, 2).reshape(tokens, 768).backward(d_ctx.float())
+    want = x.grad.view(tokens, 2304)
+    assert torch.isfinite(d_qkv.float()).all()
+    assert nerr(d_qkv, want) < 1.2e-2
