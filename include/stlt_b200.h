@@ -254,6 +254,28 @@ int stlt_adamw_step(void* handle, void* stream, float* params, const float* grad
                     float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int32_t step, const float* sumsq_or_null, float max_norm);
 
+/* ---- CACNF on precomputed appearance features (BASELINE.json configs[4]) ----
+ * Replaces CrossAttentionCentralNetFusion.forward (models.py:526-549) with the 3D-ResNet trunk factored
+ * out: `features` is what Resnet3D.forward_features returns (models.py:219-220), f32
+ * [batch, feature_channels, appearance_tokens] (e.g. [B, 2048, 2*4*4]). Inference only, bf16 GEMM
+ * operands. Weights are bound by their reference state_dict names ("backbone.layout_branch.*",
+ * "backbone.appearance_branch.{projector,cls_token,pos_embed,transformer}.*", "backbone.mm_fusion.*",
+ * "{layout,appearance,fusion}_classifier.*"); the ResNet trunk's and the two unused classifiers' entries
+ * are ignored. The Conv3d projector weight [768, C, 1, 1, 1] is passed with its trailing 1x1x1 flattened.
+ * The STLT part is packed with stlt_pack_weights(STLT_PRECISION_BF16), the rest with
+ * stlt_cacnf_pack_weights. Outputs: the four logits of `logit_names` (models.py:524), f32 [batch, classes]. */
+int stlt_cacnf_bind_weights(void* handle, const StltTensor* tensors, int32_t count,
+                            int32_t num_appearance_layers, int32_t num_fusion_layers,
+                            int32_t appearance_tokens, int32_t feature_channels);
+int stlt_cacnf_packed_weights_bytes(void* handle, size_t* bytes);
+int stlt_cacnf_pack_weights(void* handle, void* stream, void* packed, size_t bytes);
+int stlt_cacnf_workspace_bytes(void* handle, int32_t batch, int32_t frames, int32_t slots, size_t* bytes);
+int stlt_cacnf_forward(void* handle, void* stream, const int64_t* categories, const float* boxes,
+                       const float* scores_or_null, const int64_t* frame_types, const int64_t* lengths,
+                       const float* features, int32_t batch, int32_t frames, int32_t slots, void* workspace,
+                       size_t workspace_bytes, float* logits_stlt, float* logits_resnet3d, float* logits_caf,
+                       float* logits_ensemble);
+
 /* ---- single-operator entry points used by the parity tests -------------------------------- */
 
 /* out = epilogue(sum_terms A_t W_t^T + bias): A bf16 [terms>1 ? 2 : 1][m_rows][k], W bf16
@@ -272,6 +294,12 @@ int stlt_op_gemm_grad(void* handle, void* stream, int32_t layout, const void* a,
 int stlt_op_attention_bwd(void* handle, void* stream, const void* qkv, const void* d_ctx,
                           const int64_t* mask_src, int64_t num_seqs, int32_t seq_len, int32_t causal,
                           void* d_qkv, int32_t impl);
+/* Attention between two token streams (<= 64 queries / keys per sequence): Q from columns [0, 768) of
+ * q_qkv bf16 [num_seqs*q_len][2304], K / V from columns [768, 1536) / [1536, 2304) of kv_qkv bf16
+ * [num_seqs*kv_len][2304]; mask_src i64 per key token (0 = masked) or NULL. out bf16 [num_seqs*q_len][768]. */
+int stlt_op_attention_cross(void* handle, void* stream, const void* q_qkv, const void* kv_qkv,
+                            const int64_t* mask_src_or_null, int64_t num_seqs, int32_t q_len, int32_t kv_len,
+                            int32_t causal, void* out_bf16);
 int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w,
                       const float* bias, float* out, int32_t m, int32_t n, int32_t k, int32_t gelu);
 int stlt_op_attention(void* handle, void* stream, const void* qkv, int32_t qkv_is_bf16,

@@ -237,6 +237,40 @@ def golden_training(configs, models, train_utils, layout: str, batch_size: int, 
     print(f"train_{layout}.npz losses", losses, "grad norms", norms)
 
 
+def golden_cacnf(configs, models, batch_size: int, weight_seed: int, batch_seed: int):
+    """The unmodified reference CrossAttentionCentralNetFusion (models.py:504-549) in eval mode with
+    Resnet3D.forward_features replaced by synthetic precomputed features (the trunk needs a Kinetics
+    checkpoint and pixels, both outside this path; torch.load is stubbed for the constructor only)."""
+    import stlt_b200
+    from modelling import resnets3d
+    from stlt_b200.synthetic import make_appearance_features, make_batch, random_state_dict
+    orig_load = torch.load
+    torch.load = lambda *a, **k: {"state_dict": resnets3d.generate_model(model_depth=50, n_classes=1139).state_dict()}
+    try:
+        cfg = configs.MultimodalModelConfig(num_classes=174, unique_categories=4, appearance_num_frames=32,
+                                            resnet_model_path="synthetic")
+        torch.manual_seed(0)
+        ref = models.CrossAttentionCentralNetFusion(cfg)
+    finally:
+        torch.load = orig_load
+    ref.train(False)
+    full = ref.state_dict()
+    own = {k: v for k, v in full.items() if ".appearance_branch.resnet." not in k}
+    sd = random_state_dict(own, seed=weight_seed)
+    ref.load_state_dict({**full, **sd}, strict=True)
+    batch = make_batch(batch_size, layout="something", ragged=True, seed=batch_seed)
+    feats = make_appearance_features(batch_size, seed=batch_seed + 50)
+    ref.backbone.appearance_branch.resnet.forward_features = lambda b: feats
+    with torch.no_grad():
+        out = ref({**{k: v.clone() for k, v in batch.items()}, "video_frames": torch.zeros(batch_size, 1)})
+    res = {"batch_size": np.int64(batch_size), "weight_seed": np.int64(weight_seed), "batch_seed": np.int64(batch_seed),
+           "weights_checksum": np.float64(weights_checksum(sd)), "num_entries": np.int64(len(own))}
+    for k, v in out.items():
+        res["logits_" + k] = v.numpy()
+    np.savez_compressed(GOLDEN / "cacnf_something.npz", **res)
+    print("cacnf_something.npz", {k: float(v.abs().max()) for k, v in out.items()}, "entries", len(own))
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     configs, datasets, models, data_utils = import_reference()
@@ -245,6 +279,7 @@ def main():
     golden_dataset(configs, datasets, "action_genome", seed=22)
     golden_model(configs, models, "something", batch_size=3, weight_seed=1, batch_seed=3)
     golden_model(configs, models, "action_genome", batch_size=2, weight_seed=2, batch_seed=4)
+    golden_cacnf(configs, models, batch_size=3, weight_seed=8, batch_seed=9)
     from utils import train_inference_utils as train_utils
     golden_training(configs, models, train_utils, "something", batch_size=4, weight_seed=5, batch_seed=6)
     golden_training(configs, models, train_utils, "action_genome", batch_size=2, weight_seed=6, batch_seed=7)

@@ -371,3 +371,89 @@ def adamw_update(sd: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], st
         denom = st["v"].sqrt() / math.sqrt(1.0 - b2 ** step) + eps
         p.addcdiv_(st["m"], denom, value=-(lr / (1.0 - b1 ** step)))
     return total
+
+
+# ---------------------------------------------------------------------------------------------------
+# CACNF on precomputed appearance features: src/modelling/models.py:232-549
+# ---------------------------------------------------------------------------------------------------
+def _mha(xq: torch.Tensor, xkv: torch.Tensor, sd: Dict[str, torch.Tensor], p: str,
+         masked: torch.Tensor = None) -> torch.Tensor:
+    """nn.MultiheadAttention (eval) with separate query / key-value streams: xq [N, Tq, H], xkv
+    [N, Tk, H]; packed in-projection rows Q; K; V. masked [N, Tq, Tk] bool (True = not attended)."""
+    N, Tq, H = xq.shape
+    Tk = xkv.shape[1]
+    w, b = sd[p + "in_proj_weight"], sd[p + "in_proj_bias"]
+    q = F.linear(xq, w[:H], b[:H]).view(N, Tq, HEADS, HEAD_DIM).transpose(1, 2)
+    k = F.linear(xkv, w[H:2 * H], b[H:2 * H]).view(N, Tk, HEADS, HEAD_DIM).transpose(1, 2)
+    v = F.linear(xkv, w[2 * H:], b[2 * H:]).view(N, Tk, HEADS, HEAD_DIM).transpose(1, 2)
+    scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(HEAD_DIM)
+    if masked is not None:
+        scores = scores.masked_fill(masked.unsqueeze(1), float("-inf"))
+    ctx = torch.matmul(torch.softmax(scores, dim=-1), v).transpose(1, 2).reshape(N, Tq, H)
+    return F.linear(ctx, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+
+
+def _attn_layer(x, context, sd, p, eps, masked=None):
+    """CrossAttentionLayer / SelfAttentionLayer (models.py:328-373), eval: LN(attn(x, ctx) + x)."""
+    return F.layer_norm(_mha(x, context, sd, p + "attn.", masked) + x, (x.shape[-1],), sd[p + "ln.weight"],
+                        sd[p + "ln.bias"], eps)
+
+
+def _head(x, sd, p, eps):
+    """ClassificationHead / FusionHead (models.py:155-163, 286-294)."""
+    h = F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+    h = F.layer_norm(h, (h.shape[-1],), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], eps)
+    return F.linear(h, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+
+
+def cacnf_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], features: torch.Tensor,
+                  num_spatial_layers: int = 4, num_temporal_layers: int = 8, num_appearance_layers: int = 4,
+                  num_fusion_layers: int = 4, layer_norm_eps: float = 1e-12) -> Dict[str, torch.Tensor]:
+    """CrossAttentionCentralNetFusion.forward (models.py:526-549) in eval mode with the 3D-ResNet trunk
+    factored out: ``features`` = Resnet3D.forward_features(batch) [B, 2048, T', H', W'] (models.py:219-220).
+    ``sd`` is the reference CACNF state_dict (entries of the ResNet trunk are not needed)."""
+    H = HIDDEN
+    B, L, _ = batch["categories"].shape
+    lengths, ftypes = batch["lengths"], batch["frame_types"]
+    # layout branch = StltBackbone under another prefix (models.py:440, 452-453)
+    lb, lc = "backbone.layout_branch.", "layout_classifier."
+    stlt_sd = {"backbone." + k[len(lb):]: v for k, v in sd.items() if k.startswith(lb)}
+    stlt_sd.update({"prediction_head." + k[len(lc):]: v for k, v in sd.items() if k.startswith(lc)})
+    taps = stlt_forward(stlt_sd, batch, num_spatial_layers, num_temporal_layers, layer_norm_eps, return_taps=True)
+    layout = taps["temporal"]                                   # [B, L, H]
+    logits_stlt = taps["stlt"]                                  # layout_classifier(layout_hidden_state)
+
+    # appearance branch: TransformerResnet.forward_features (models.py:256-276)
+    ab = "backbone.appearance_branch."
+    feats = features.flatten(2).transpose(1, 2)                 # [B, P, 2048]
+    proj = F.linear(feats, sd[ab + "projector.weight"].flatten(1), sd[ab + "projector.bias"])  # 1x1x1 Conv3d
+    app = torch.cat((sd[ab + "cls_token"].expand(B, 1, H), proj), dim=1) + sd[ab + "pos_embed"].transpose(0, 1)
+    T = app.shape[1]
+    for i in range(num_appearance_layers):                      # post-norm, ReLU, eps 1e-5 (nn defaults)
+        p = f"{ab}transformer.layers.{i}."
+        a = _mha(app, app, sd, p + "self_attn.")
+        app = F.layer_norm(app + a, (H,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], ENCODER_LN_EPS)
+        f = F.linear(F.relu(F.linear(app, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+                     sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+        app = F.layer_norm(app + f, (H,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], ENCODER_LN_EPS)
+    logits_app = _head(app[:, 0], sd, "appearance_classifier.", layer_norm_eps)
+
+    # fusion: CrossAttentionFusionBackbone.forward (models.py:464-470), CrossModalModule (:395-431)
+    frame_pad = ftypes == 0                                      # src_key_padding_mask_frames
+    causal = torch.triu(torch.ones(L, L, dtype=torch.bool), diagonal=1)
+    self_mask = causal.unsqueeze(0) | frame_pad.unsqueeze(1)     # [B, L, L]
+    cross_mask = frame_pad.unsqueeze(1).expand(B, T, L)          # appearance queries x layout keys
+    for i in range(num_fusion_layers):
+        p = f"backbone.mm_fusion.{i}."
+        l1 = _attn_layer(layout, app, sd, p + "cross_attn.", layer_norm_eps)
+        a1 = _attn_layer(app, layout, sd, p + "cross_attn.", layer_norm_eps, cross_mask)
+        l2 = _attn_layer(l1, l1, sd, p + "layout_attn.", layer_norm_eps, self_mask)
+        a2 = _attn_layer(a1, a1, sd, p + "appearance_attn.", layer_norm_eps)
+        ff = F.linear(F.gelu(F.linear(l2, sd[p + "layout_ffn.linear1.weight"], sd[p + "layout_ffn.linear1.bias"])),
+                      sd[p + "layout_ffn.linear2.weight"], sd[p + "layout_ffn.linear2.bias"])
+        layout = F.layer_norm(ff + l2, (H,), sd[p + "layout_ffn.ln.weight"], sd[p + "layout_ffn.ln.bias"], layer_norm_eps)
+        app = _attn_layer(a2, a2, sd, p + "appearance_ffn.", layer_norm_eps)
+    fused = torch.cat((layout[torch.arange(B), lengths - 1], app[:, 0]), dim=-1)
+    logits_caf = _head(fused, sd, "fusion_classifier.", layer_norm_eps)
+    logits = (logits_stlt, logits_app, logits_caf)
+    return {"stlt": logits_stlt, "resnet3d": logits_app, "caf": logits_caf, "ensemble": sum(logits) / 3}

@@ -38,6 +38,22 @@ class StltModelConfig:
         )
 
 
+class CacnfModelConfig(StltModelConfig):
+    """Mirrors the reference MultimodalModelConfig (configs.py:150-175) + AppearanceModelConfig
+    (:128-147) for the CACNF path on precomputed features; no ``resnet_model_path`` is needed because
+    the 3D-ResNet trunk is outside this library."""
+
+    def __init__(self, **kwargs):
+        self.appearance_num_frames = kwargs.pop("appearance_num_frames", 32)
+        self.num_appearance_layers = kwargs.pop("num_appearance_layers", 4)
+        self.num_fusion_layers = kwargs.pop("num_fusion_layers", 4)
+        self.feature_channels = kwargs.pop("feature_channels", 2048)
+        kwargs.pop("resnet_model_path", None)
+        super().__init__(**kwargs)
+        self.stlt_config = self
+        self.appearance_config = self
+
+
 # Dataset-level constants of the two supported layouts (reference src/modelling/configs.py:30-88).
 SOMETHING_ELSE = {
     "unique_categories": 4, "num_classes": 174, "cls_id": 3, "object_ids": (1, 2),

@@ -323,6 +323,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         } else if (kGelu == 2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+        } else if (kGelu == 3) {  // ReLU (nn.TransformerEncoderLayer default, appearance branch of CACNF)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
           // FFN-inner dropout of nn.TransformerEncoderLayer (training): element = row * N + column
@@ -485,6 +488,7 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
   STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 1)
   STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 0)
   STLT_GEMM_CASE(1, GEMM_OUT_BF16_DUAL, 2)
+  STLT_GEMM_CASE(1, GEMM_OUT_BF16, 3)
 #undef STLT_GEMM_CASE
   return cudaErrorInvalidValue;
 }

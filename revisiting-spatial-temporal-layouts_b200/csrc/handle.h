@@ -40,6 +40,36 @@ struct Weights {
   std::vector<LayerWeights> spatial, temporal;
 };
 
+// ---- CACNF fusion path (stlt_cacnf.cu) ----
+struct MhaWeights {  // nn.MultiheadAttention: packed in-projection + out_proj
+  const float *in_w = nullptr, *in_b = nullptr, *out_w = nullptr, *out_b = nullptr;
+  const __nv_bfloat16 *in_p = nullptr, *out_p = nullptr;
+};
+struct AttnLayerWeights {  // CrossAttentionLayer / SelfAttentionLayer (models.py:328-373)
+  MhaWeights attn;
+  const float *ln_g = nullptr, *ln_b = nullptr;
+};
+struct FfnWeights {  // FeedforwardModule (models.py:313-325)
+  const float *l1_w = nullptr, *l1_b = nullptr, *l2_w = nullptr, *l2_b = nullptr, *ln_g = nullptr, *ln_b = nullptr;
+  const __nv_bfloat16 *l1_p = nullptr, *l2_p = nullptr;
+};
+struct FusionLayerWeights {  // CrossModalModule (models.py:376-431)
+  AttnLayerWeights cross, layout_attn, app_attn, app_ffn;
+  FfnWeights layout_ffn;
+};
+struct HeadWeights {  // ClassificationHead / FusionHead
+  const float *fc1_w = nullptr, *fc1_b = nullptr, *ln_g = nullptr, *ln_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;
+};
+struct CacnfWeights {
+  int app_layers = 0, fusion_layers = 0, app_tokens = 0, feat_channels = 0;
+  const float *proj_w = nullptr, *proj_b = nullptr, *cls_token = nullptr, *pos_embed = nullptr;
+  const __nv_bfloat16* proj_p = nullptr;
+  std::vector<LayerWeights> app;  // TransformerResnet.transformer (ReLU, eps 1e-5)
+  std::vector<FusionLayerWeights> fusion;
+  HeadWeights app_head, fusion_head;
+  bool bound = false, packed = false;
+};
+
 struct Handle {
   StltDims dims{};
   Weights w;
@@ -52,6 +82,10 @@ struct Handle {
   int launches = 0;
   EncodeTiledFn encode = nullptr;
   StltTaps taps{};
+  CacnfWeights cacnf;
+  // internal capture of the temporal stack's full output (all frames) for the fusion path
+  float* cap_tm_x = nullptr;
+  __nv_bfloat16* cap_tm_xb = nullptr;
   // optional per-category timing (CUDA events on the launching stream)
   bool pruning = true;  // run the row-wise tail of the last layer of each stack on the rows that are read
   bool profiling = false;

@@ -33,7 +33,7 @@ struct GemmArgs {
   int k;               // multiple of 64
   int terms;           // 1 (bf16) or 3 (fp32-parity split)
   int out_kind;        // GemmOutKind
-  int gelu;            // 0 none, 1 exact erf GELU (erff), 2 fast erf GELU (|erf err| < 7e-7)
+  int gelu;            // 0 none, 1 exact erf GELU (erff), 2 fast erf GELU (|erf err| < 7e-7), 3 ReLU
   int a_plane_rows;    // row offset of the lo plane of A
   int b_plane_rows;    // row offset of the lo plane of W
   int out_plane_rows;  // row offset of the lo plane of the output (split only)
@@ -189,6 +189,27 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
 cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* d_ctx,
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
                                  __nv_bfloat16* d_qkv, cudaStream_t stream, DropCfg drop = DropCfg{0, 0, 1.f});
+
+// ---- CACNF fusion path; attention_cross.cu / cacnf_kernels.cu ------------
+
+// Attention between two streams (<= 64 queries / keys per sequence). q: [*, ldq] bf16, Q at column
+// q_off + 64*head; kv: [*, ldkv] bf16 with K / V at k_off / v_off + 64*head. mask_src (i64 per key
+// token, may be null): key masked when 0. out: bf16 [num_seqs * Tq, 768].
+cudaError_t launch_attention_cross(const __nv_bfloat16* q, int ldq, int q_off, const __nv_bfloat16* kv,
+                                   int ldkv, int k_off, int v_off, const long long* mask_src,
+                                   long long num_seqs, int Tq, int Tk, bool causal, __nv_bfloat16* out,
+                                   cudaStream_t stream);
+// features f32 [B, C, P] (channel-major, as the 3D ResNet emits them) -> bf16 tokens [B * P, C]
+cudaError_t launch_features_to_tokens(const float* feat, __nv_bfloat16* out, int B, int C, int P,
+                                      cudaStream_t stream);
+// x[b, 0] = cls + pos[0]; x[b, 1 + s] = proj[b, s] + pos[1 + s]   (models.py:262-270)
+cudaError_t launch_app_embed(const float* proj, const float* cls, const float* pos, int B, int P, ActOut out,
+                             cudaStream_t stream);
+// dst[b, 0:768] = a[b * a_stride (+ lengths[b] - 1 if lengths)], dst[b, 768:1536] = c[b * c_stride]
+cudaError_t launch_gather_concat(const float* a, int a_stride, const long long* lengths, const float* c,
+                                 int c_stride, int B, float* dst, cudaStream_t stream);
+cudaError_t launch_mean3(const float* a, const float* b, const float* c, long long n, float* out,
+                         cudaStream_t stream);
 
 // Same on mma.sync tensor-core tiles (attention_bwd_mma.cu); the CUDA-core version above is kept as a
 // cross-check for the tests.

@@ -452,7 +452,8 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   // (models.py:192) are ever read, so the row-wise tail of the LAST layer of each stack runs on
   // those rows only. Taps that expose the full stack output switch the pruning off.
   const bool prune_sp = h->pruning && h->taps.spatial == nullptr && d.num_spatial_layers > 0;
-  const bool prune_tm = h->pruning && h->taps.temporal == nullptr && d.num_temporal_layers > 0;
+  const bool prune_tm = h->pruning && h->taps.temporal == nullptr && h->cap_tm_x == nullptr &&
+                        d.num_temporal_layers > 0;
 
   ActOut emb{sp.x, sp.xb, planes, sp.m_pad};
   {
@@ -525,6 +526,10 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   }
   if (h->taps.temporal)
     STLT_CUDA(h, cudaMemcpyAsync(h->taps.temporal, tm.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
+  if (h->cap_tm_x) {  // CACNF: the fusion layers consume every frame token (fp32 stream + bf16 GEMM operand)
+    STLT_CUDA(h, cudaMemcpyAsync(h->cap_tm_x, tm.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
+    STLT_CUDA(h, cudaMemcpyAsync(h->cap_tm_xb, tm.xb, n_tm * kHidden * 2, cudaMemcpyDeviceToDevice, stream));
+  }
 
   // ---- head (models.py:155-163,189-193) ----
   {

@@ -104,8 +104,12 @@ def random_state_dict(model_state: Dict[str, torch.Tensor], seed: int = 0) -> Di
         if name.endswith("embeddings.weight") and "score" not in name and "box_embedding" not in name \
                 or name.endswith("frame_type_embedding.weight"):
             t = torch.randn(shape, generator=g)
-        elif "norm" in name and name.endswith("weight"):
+        elif ("norm" in name or name.endswith(".ln.weight")) and name.endswith("weight"):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("cls_token") or name.endswith("pos_embed"):
+            t = 0.5 * torch.randn(shape, generator=g)
+        elif len(shape) > 2:  # Conv3d 1x1x1 projector of the CACNF appearance branch
+            t = torch.randn(shape, generator=g) * (0.7 / math.sqrt(shape[1] * math.prod(shape[2:])))
         elif name.endswith("bias"):
             t = 0.02 * torch.randn(shape, generator=g)
         elif len(shape) == 2:
@@ -114,3 +118,10 @@ def random_state_dict(model_state: Dict[str, torch.Tensor], seed: int = 0) -> Di
             t = torch.randn(shape, generator=g)
         out[name] = t.to(ref.dtype)
     return out
+
+
+def make_appearance_features(batch_size: int, seed: int = 0, channels: int = 2048, t: int = 2, hw: int = 4) -> torch.Tensor:
+    """Synthetic stand-in for Resnet3D.forward_features (reference models.py:219-220): post-ReLU
+    activations [B, 2048, T', H', W'] of a 32-frame 112x112 clip (2 x 4 x 4 positions)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.relu(torch.randn((batch_size, channels, t, hw, hw), generator=g)).to(torch.float32)

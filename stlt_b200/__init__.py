@@ -5,10 +5,13 @@ from pathlib import Path as _Path
 _PKG_DIR = _Path(__file__).resolve().parent.parent / "revisiting-spatial-temporal-layouts_b200"
 __path__.append(str(_PKG_DIR))
 
-from .configs import ACTION_GENOME, SOMETHING_ELSE, StltModelConfig  # noqa: E402
+from .configs import ACTION_GENOME, SOMETHING_ELSE, CacnfModelConfig, StltModelConfig  # noqa: E402
 from .module import Stlt, StltBackbone, models_factory  # noqa: E402
+from .cacnf import Cacnf  # noqa: E402
+
+models_factory["cacnf"] = Cacnf
 from .prepare import prepare_layout_batch  # noqa: E402
 from .data import LayoutStore, TopKCounter  # noqa: E402
 
-__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter",
+__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "Cacnf", "CacnfModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter",
            "SOMETHING_ELSE", "ACTION_GENOME"]
