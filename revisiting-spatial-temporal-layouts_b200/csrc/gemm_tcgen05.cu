@@ -80,29 +80,43 @@ struct Work {
   int tile, kb0, kb1;
 };
 
-// Work distribution of one CTA pair. Tile mode: whole tiles, round-robin. Stream-K mode: the
-// contiguous range [cur, end) of the linearised (tile, k-block) steps.
+// Work distribution of one CTA pair. Tile mode: whole tiles, round-robin. Stream-K mode (weight
+// gradients): the reduction axis (tokens) is cut into chunks of kChunk k-blocks and the (chunk, tile,
+// k-block) steps are linearised chunk-major; every pair owns an equal, contiguous range of steps. At any
+// moment all pairs therefore work inside the same one or two chunks: the 256-column operand slabs of
+// that row range are read from HBM once and shared by all output tiles through L2 (a tile-major order
+// re-read dY n_tiles times and X m_tiles times and was HBM-bound).
+constexpr int kChunk = 64;  // 64 k-blocks x 64 rows x (N + K) columns x 2 B: ~30 MB for the widest pair
+
 template <bool kStreamK>
 struct Sched {
-  int cur, end, total_kb, stride;
-  __device__ Sched(int cluster_id, int num_clusters, int num_tiles, int total_kb_) : total_kb(total_kb_) {
+  int cur, end, total_kb, stride, num_tiles;
+  __device__ Sched(int cluster_id, int num_clusters, int num_tiles_, int total_kb_)
+      : total_kb(total_kb_), num_tiles(num_tiles_) {
     if (kStreamK) {
-      const long long total = static_cast<long long>(num_tiles) * total_kb_;
+      const long long total = static_cast<long long>(num_tiles_) * total_kb_;
       cur = static_cast<int>(total * cluster_id / num_clusters);
       end = static_cast<int>(total * (cluster_id + 1) / num_clusters);
       stride = 0;
     } else {
       cur = cluster_id;
-      end = num_tiles;
+      end = num_tiles_;
       stride = num_clusters;
     }
   }
   __device__ bool next(Work& w) {
     if (cur >= end) return false;
     if (kStreamK) {
-      w.tile = cur / total_kb;
-      w.kb0 = cur - w.tile * total_kb;
-      const int n = min(total_kb - w.kb0, end - cur);
+      const int per_chunk = num_tiles * kChunk;           // steps of a full chunk
+      const int chunks = (total_kb + kChunk - 1) / kChunk;
+      int c = cur / per_chunk;
+      if (c > chunks - 1) c = chunks - 1;                 // the last chunk may be shorter
+      const int kc = min(kChunk, total_kb - c * kChunk);  // k-blocks of this chunk
+      const int rem = cur - c * per_chunk;
+      w.tile = rem / kc;
+      const int kb_in = rem - w.tile * kc;
+      const int n = min(kc - kb_in, end - cur);
+      w.kb0 = c * kChunk + kb_in;
       w.kb1 = w.kb0 + n;
       cur += n;
     } else {

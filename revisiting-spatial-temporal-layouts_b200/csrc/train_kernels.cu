@@ -285,6 +285,13 @@ frame_embed_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ 
                        float* __restrict__ d_ft, float* __restrict__ d_gamma,
                        float* __restrict__ d_beta, DropCfg drop) {
   __shared__ __align__(16) float scratch[kBwdWarps * kHidden];
+  // per-block accumulators of the two table gradients: [L + n_frame_types][768]; shared-memory atomics
+  // from the 8 warps, one global atomic per touched element per block at the end (the direct global
+  // version serialised ~35k adds on each of the few hot rows)
+  extern __shared__ __align__(16) float table_acc[];
+  const int table_rows = L + n_frame_types;
+  for (int i = threadIdx.x; i < table_rows * kHidden; i += blockDim.x) table_acc[i] = 0.f;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -308,23 +315,30 @@ frame_embed_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ 
     drop_row(dy, f, lane, drop);  // dropout follows the LayerNorm (models.py:110)
     ln_bwd_row(zz, dy, gamma, eps, lane, acc_g, acc_b);
     store_row_f32(d_cls, f, dy, lane);
-    float* dp = d_pos != nullptr ? d_pos + static_cast<long long>(l) * kHidden : nullptr;
-    float* dt = d_ft != nullptr ? d_ft + ft * kHidden : nullptr;
+    float* ap = table_acc + l * kHidden;
+    float* at = table_acc + (L + static_cast<int>(ft)) * kHidden;
 #pragma unroll
     for (int k = 0; k < kVec; ++k) {
       const int c = 4 * (lane + 32 * k);
-      if (dp != nullptr) {
-        atomicAdd(dp + c + 0, dy.v[k].x);
-        atomicAdd(dp + c + 1, dy.v[k].y);
-        atomicAdd(dp + c + 2, dy.v[k].z);
-        atomicAdd(dp + c + 3, dy.v[k].w);
-      }
-      if (dt != nullptr) {
-        atomicAdd(dt + c + 0, dy.v[k].x);
-        atomicAdd(dt + c + 1, dy.v[k].y);
-        atomicAdd(dt + c + 2, dy.v[k].z);
-        atomicAdd(dt + c + 3, dy.v[k].w);
-      }
+      atomicAdd(ap + c + 0, dy.v[k].x);
+      atomicAdd(ap + c + 1, dy.v[k].y);
+      atomicAdd(ap + c + 2, dy.v[k].z);
+      atomicAdd(ap + c + 3, dy.v[k].w);
+      atomicAdd(at + c + 0, dy.v[k].x);
+      atomicAdd(at + c + 1, dy.v[k].y);
+      atomicAdd(at + c + 2, dy.v[k].z);
+      atomicAdd(at + c + 3, dy.v[k].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < table_rows * kHidden; i += blockDim.x) {
+    const float v = table_acc[i];
+    if (v == 0.f) continue;
+    const int r = i / kHidden, c = i - r * kHidden;
+    if (r < L) {
+      if (d_pos != nullptr) atomicAdd(d_pos + static_cast<long long>(r) * kHidden + c, v);
+    } else if (d_ft != nullptr) {
+      atomicAdd(d_ft + static_cast<long long>(r - L) * kHidden + c, v);
     }
   }
   flush_columns(acc_g, d_gamma, scratch);
@@ -740,7 +754,10 @@ cudaError_t launch_frame_embed_bwd(const float* d_a, const float* d_b, const flo
                                    float* d_gamma, float* d_beta, cudaStream_t stream, DropCfg drop) {
   const long long frames = static_cast<long long>(B) * L;
   if (frames == 0) return cudaSuccess;
-  frame_embed_bwd_kernel<<<row_grid(frames, kBwdWarps, 2), kBwdWarps * 32, 0, stream>>>(
+  const int smem = (L + n_frame_types) * kHidden * static_cast<int>(sizeof(float));
+  cudaError_t e = cudaFuncSetAttribute(frame_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  frame_embed_bwd_kernel<<<row_grid(frames, kBwdWarps, 1), kBwdWarps * 32, smem, stream>>>(
       d_a, d_b, cls_x, frame_types, pos_table, ft_table, n_frame_types, gamma, eps, L, frames, d_cls,
       d_pos, d_ft, d_gamma, d_beta, drop);
   return cudaGetLastError();
