@@ -31,9 +31,8 @@
 //   GEMM_NT    (forward)        out[M,N]  = A[M,K] * B[N,K]^T + bias      A, B K-major
 //   GEMM_NN    (data gradient)  out[M,N]  = A[M,K] * B[K,N]                B MN-major (no transposed copy of W)
 //   GEMM_TN_RED(weight gradient) out[M,N] += A[K,M]^T * B[K,N]             A, B MN-major; the reduction runs
-//              over the token axis, the work is split stream-K style over all CTA pairs (each pair owns a
-//              contiguous range of (tile, k-block) steps) and every partial tile is added to the fp32
-//              output with a TMA reduce-add store, so no fix-up pass exists.
+//              over the token axis and is split into aligned k-slices, one (tile, slice) unit per CTA pair;
+//              every partial tile is added to the fp32 output with a TMA reduce-add store (no fix-up pass).
 // MN-major tiles are staged as 64-element (128 B) wide TMA boxes of 64 reduction rows: a 128-wide
 // operand is two boxes 8 KiB apart (descriptor LBO), 8-row groups are 1 KiB apart (SBO).
 //
@@ -80,51 +79,43 @@ struct Work {
   int tile, kb0, kb1;
 };
 
-// Work distribution of one CTA pair. Tile mode: whole tiles, round-robin. Stream-K mode (weight
-// gradients): the reduction axis (tokens) is cut into chunks of kChunk k-blocks and the (chunk, tile,
-// k-block) steps are linearised chunk-major; every pair owns an equal, contiguous range of steps. At any
-// moment all pairs therefore work inside the same one or two chunks: the 256-column operand slabs of
-// that row range are read from HBM once and shared by all output tiles through L2 (a tile-major order
-// re-read dY n_tiles times and X m_tiles times and was HBM-bound).
-constexpr int kChunk = 64;  // 64 k-blocks x 64 rows x (N + K) columns x 2 B: ~30 MB for the widest pair
-
-template <bool kStreamK>
+// Work distribution of one CTA pair. Tile mode: whole tiles, round-robin. Split-K mode (weight
+// gradients, few output tiles and a very long reduction over tokens): the reduction is cut into
+// S = floor(pairs / tiles) ALIGNED slices and every pair owns one (tile, slice) unit, accumulated in
+// TMEM over the whole slice and reduce-added once. All pairs of a slice sweep the same token rows at
+// the same time, so the 256-column operand slabs are read from HBM once and shared by the output tiles
+// through L2. (An equal-share stream-K split gave every pair a different k offset: ncu showed 4.8-6.3
+// GB of DRAM reads per launch against 1.3 GB of operands; chunking the reduction instead multiplied
+// the reduce-add traffic.)
+template <bool kSplitK>
 struct Sched {
-  int cur, end, total_kb, stride, num_tiles;
+  int cur, end, total_kb, stride, num_tiles, slices;
   __device__ Sched(int cluster_id, int num_clusters, int num_tiles_, int total_kb_)
       : total_kb(total_kb_), num_tiles(num_tiles_) {
-    if (kStreamK) {
-      const long long total = static_cast<long long>(num_tiles_) * total_kb_;
-      cur = static_cast<int>(total * cluster_id / num_clusters);
-      end = static_cast<int>(total * (cluster_id + 1) / num_clusters);
-      stride = 0;
-    } else {
-      cur = cluster_id;
-      end = num_tiles_;
-      stride = num_clusters;
+    slices = 1;
+    if (kSplitK) {
+      slices = num_clusters / num_tiles_;
+      if (slices < 1) slices = 1;
+      if (slices > total_kb_) slices = total_kb_;
     }
+    cur = cluster_id;
+    end = num_tiles_ * slices;
+    stride = num_clusters;
   }
   __device__ bool next(Work& w) {
     if (cur >= end) return false;
-    if (kStreamK) {
-      const int per_chunk = num_tiles * kChunk;           // steps of a full chunk
-      const int chunks = (total_kb + kChunk - 1) / kChunk;
-      int c = cur / per_chunk;
-      if (c > chunks - 1) c = chunks - 1;                 // the last chunk may be shorter
-      const int kc = min(kChunk, total_kb - c * kChunk);  // k-blocks of this chunk
-      const int rem = cur - c * per_chunk;
-      w.tile = rem / kc;
-      const int kb_in = rem - w.tile * kc;
-      const int n = min(kc - kb_in, end - cur);
-      w.kb0 = c * kChunk + kb_in;
-      w.kb1 = w.kb0 + n;
-      cur += n;
+    if (kSplitK) {
+      w.tile = cur % num_tiles;
+      const int slice = cur / num_tiles;
+      // even split; never empty because slices <= total_kb
+      w.kb0 = static_cast<int>(static_cast<long long>(total_kb) * slice / slices);
+      w.kb1 = static_cast<int>(static_cast<long long>(total_kb) * (slice + 1) / slices);
     } else {
       w.tile = cur;
       w.kb0 = 0;
       w.kb1 = total_kb;
-      cur += stride;
     }
+    cur += stride;
     return true;
   }
 };
@@ -150,7 +141,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   constexpr int kBufsPerWarp = Cfg<kOut>::kBufsPerWarp;
   constexpr bool kAMn = kLayout == GEMM_TN_RED;
   constexpr bool kBMn = kLayout != GEMM_NT;
-  constexpr bool kStreamK = kLayout == GEMM_TN_RED;
+  constexpr bool kStreamK = kLayout == GEMM_TN_RED;  // aligned split-K + reduce-add epilogue
   constexpr bool kBias = kLayout == GEMM_NT;
   static_assert(kLayout == GEMM_NT || kTerms == 1, "gradient GEMMs are single-term");
   static_assert(!kStreamK || kOut == GEMM_OUT_F32, "stream-K partials are reduce-added in fp32");
@@ -455,9 +446,12 @@ static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sm
   const int max_clusters = num_sms / kCluster;
   const int k_blocks = (g.k + BK - 1) / BK;
   int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
-  if (kLayout == GEMM_TN_RED) {  // stream-K: every pair gets an equal share of the (tile, k-block) steps
-    const long long steps = static_cast<long long>(pair_tiles) * k_blocks;
-    clusters = steps < max_clusters ? static_cast<int>(steps) : max_clusters;
+  if (kLayout == GEMM_TN_RED) {  // split-K: one (tile, k-slice) unit per pair, see Sched
+    int slices = max_clusters / pair_tiles;
+    if (slices < 1) slices = 1;
+    if (slices > k_blocks) slices = k_blocks;
+    const int units = pair_tiles * slices;
+    clusters = units < max_clusters ? units : max_clusters;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * kCluster);
