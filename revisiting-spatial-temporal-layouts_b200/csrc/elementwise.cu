@@ -277,8 +277,23 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
 // ------------------------------------------------------------------------------------------------
 // x <- LN(x + y): the two post-norm residual sites of every encoder layer.
 // ------------------------------------------------------------------------------------------------
+// bf16 branch output (bf16 inference mode): 96 x 16-byte loads per row instead of 192
+__device__ __forceinline__ RowRegs load_row_bf16(const __nv_bfloat16* base, long long row, int lane) {
+  RowRegs r;
+  const uint2* p = reinterpret_cast<const uint2*>(base + row * kHidden);
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    const uint2 v = __ldg(p + lane + 32 * k);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    r.v[k] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  return r;
+}
+
+template <typename TY>
 __global__ void __launch_bounds__(256)
-add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y,
+add_ln_kernel(const float* __restrict__ x_in, const TY* __restrict__ y,
               const float* __restrict__ g, const float* __restrict__ b, float eps, long long rows,
               ActOut out, float* __restrict__ z_out, DropCfg drop) {
   const int lane = threadIdx.x & 31;
@@ -287,7 +302,9 @@ add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y,
   for (long long row = warp0; row < rows; row += nwarps) {
     RowRegs r = load_row(x_in, row, lane);
     if (y != nullptr) {
-      RowRegs a = load_row(y, row, lane);
+      RowRegs a;
+      if constexpr (sizeof(TY) == 2) a = load_row_bf16(y, row, lane);
+      else a = load_row(y, row, lane);
       drop_row(a, row, lane, drop);  // dropout1 / dropout2 of nn.TransformerEncoderLayer (training only)
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
@@ -475,7 +492,15 @@ cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, con
                           float eps, long long rows, ActOut out, cudaStream_t stream, float* z_out,
                           DropCfg drop) {
   if (rows == 0) return cudaSuccess;
-  add_ln_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out, drop);
+  add_ln_kernel<float><<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out, drop);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_ln_bf16y(const float* x_in, const __nv_bfloat16* y, const float* g, const float* b,
+                                float eps, long long rows, ActOut out, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  add_ln_kernel<__nv_bfloat16><<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, nullptr,
+                                                                       DropCfg{0, 0, 1.f});
   return cudaGetLastError();
 }
 

@@ -87,6 +87,7 @@ struct Handle {
   float* cap_tm_x = nullptr;
   __nv_bfloat16* cap_tm_xb = nullptr;
   // optional per-category timing (CUDA events on the launching stream)
+  bool bf16_branch = true;  // bf16 mode: out-projection / linear2 outputs travel as bf16 (see run_tail_part)
   bool pruning = true;  // run the row-wise tail of the last layer of each stack on the rows that are read
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;

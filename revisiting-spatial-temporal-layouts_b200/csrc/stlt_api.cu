@@ -185,24 +185,30 @@ int run_tail_part(Handle* h, cudaStream_t stream, int precision, const LayerWeig
   const int terms = fp32 ? 3 : 1;
   const int planes = fp32 ? 2 : 1;
   const float eps = h->dims.encoder_norm_eps;
+  // bf16 mode: the branch outputs (out-projection, linear2) are stored as bf16 and widened again in the
+  // residual add; the residual stream itself stays fp32
+  const bool y16 = !fp32 && h->bf16_branch;
+  __nv_bfloat16* y_b = reinterpret_cast<__nv_bfloat16*>(ph.y);
   int rc = run_gemm(h, stream, ph.att, ph.m_pad, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.y,
-                    terms, GEMM_OUT_F32, 0);
+                    terms, y16 ? GEMM_OUT_BF16 : GEMM_OUT_F32, 0);
   if (rc) return rc;
   ActOut xo{ph.x, ph.xb, planes, ph.m_pad};
   {
     ProfileScope prof(h, stream, STLT_PROF_ADD_LN);
-    STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
+    if (y16) STLT_CUDA(h, launch_add_ln_bf16y(ph.x, y_b, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
+    else STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
   }
   h->launches++;
   rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.l1_p, kFfn, kHidden, lw.l1_b, ph.hid, terms,
                 fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, fp32 ? 1 : 2);
   if (rc) return rc;
   rc = run_gemm(h, stream, ph.hid, ph.m_pad, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.y, terms,
-                GEMM_OUT_F32, 0);
+                y16 ? GEMM_OUT_BF16 : GEMM_OUT_F32, 0);
   if (rc) return rc;
   {
     ProfileScope prof(h, stream, STLT_PROF_ADD_LN);
-    STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n2_g, lw.n2_b, eps, ph.m_valid, xo, stream));
+    if (y16) STLT_CUDA(h, launch_add_ln_bf16y(ph.x, y_b, lw.n2_g, lw.n2_b, eps, ph.m_valid, xo, stream));
+    else STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n2_g, lw.n2_b, eps, ph.m_valid, xo, stream));
   }
   h->launches++;
   return STLT_OK;
