@@ -497,10 +497,10 @@ cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, con
 }
 
 cudaError_t launch_add_ln_bf16y(const float* x_in, const __nv_bfloat16* y, const float* g, const float* b,
-                                float eps, long long rows, ActOut out, cudaStream_t stream) {
+                                float eps, long long rows, ActOut out, cudaStream_t stream, float* z_out,
+                                DropCfg drop) {
   if (rows == 0) return cudaSuccess;
-  add_ln_kernel<__nv_bfloat16><<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, nullptr,
-                                                                       DropCfg{0, 0, 1.f});
+  add_ln_kernel<__nv_bfloat16><<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out, drop);
   return cudaGetLastError();
 }
 

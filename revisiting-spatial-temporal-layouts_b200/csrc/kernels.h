@@ -105,7 +105,8 @@ cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, con
 // Same with the branch output y in bf16 (bf16 inference mode: the out-projection / linear2 GEMMs store
 // bf16, which halves their HBM write and this kernel's y read).
 cudaError_t launch_add_ln_bf16y(const float* x_in, const __nv_bfloat16* y, const float* g, const float* b,
-                                float eps, long long rows, ActOut out, cudaStream_t stream);
+                                float eps, long long rows, ActOut out, cudaStream_t stream,
+                                float* z_out = nullptr, DropCfg drop = DropCfg{0, 0, 1.f});
 
 // K7: frame tokens = LN(spatial CLS slot + position + frame type) (src/modelling/models.py:98-111).
 cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* frame_types,

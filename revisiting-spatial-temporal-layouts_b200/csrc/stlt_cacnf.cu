@@ -88,11 +88,12 @@ int in_proj(Handle* h, cudaStream_t s, const MhaWeights& w, const Stream& st) {
 // x <- LN(out_proj(ctx) + x)
 int out_proj_ln(Handle* h, cudaStream_t s, const MhaWeights& w, const float* g, const float* b, float eps,
                 const Stream& st) {
-  int rc = run_gemm(h, s, st.ctx, st.m, st.m, w.out_p, kHidden, kHidden, w.out_b, st.y, 1, GEMM_OUT_F32, 0);
+  // branch outputs travel as bf16 (as in the bf16 STLT path); the residual stream stays fp32
+  int rc = run_gemm(h, s, st.ctx, st.m, st.m, w.out_p, kHidden, kHidden, w.out_b, st.y, 1, GEMM_OUT_BF16, 0);
   if (rc) return rc;
   ProfileScope prof(h, s, STLT_PROF_ADD_LN);
   ActOut o{st.x, st.xb, 1, st.m};
-  STLT_CUDA(h, launch_add_ln(st.x, st.y, g, b, eps, st.n, o, s));
+  STLT_CUDA(h, launch_add_ln_bf16y(st.x, reinterpret_cast<const __nv_bfloat16*>(st.y), g, b, eps, st.n, o, s));
   h->launches++;
   return STLT_OK;
 }
@@ -115,11 +116,11 @@ int ffn_ln(Handle* h, cudaStream_t s, const __nv_bfloat16* l1_p, const float* l1
            __nv_bfloat16* hid) {
   int rc = run_gemm(h, s, st.xb, st.m, st.m, l1_p, kFfn, kHidden, l1_b, hid, 1, GEMM_OUT_BF16, act);
   if (rc) return rc;
-  rc = run_gemm(h, s, hid, st.m, st.m, l2_p, kHidden, kFfn, l2_b, st.y, 1, GEMM_OUT_F32, 0);
+  rc = run_gemm(h, s, hid, st.m, st.m, l2_p, kHidden, kFfn, l2_b, st.y, 1, GEMM_OUT_BF16, 0);
   if (rc) return rc;
   ProfileScope prof(h, s, STLT_PROF_ADD_LN);
   ActOut o{st.x, st.xb, 1, st.m};
-  STLT_CUDA(h, launch_add_ln(st.x, st.y, g, b, eps, st.n, o, s));
+  STLT_CUDA(h, launch_add_ln_bf16y(st.x, reinterpret_cast<const __nv_bfloat16*>(st.y), g, b, eps, st.n, o, s));
   h->launches++;
   return STLT_OK;
 }

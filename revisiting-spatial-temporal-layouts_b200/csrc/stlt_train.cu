@@ -155,26 +155,28 @@ int fwd_layer(const Ctx& c, int layer, const LayerWeights& lw, const LayerSave& 
     xt = x_tail;
   }
   (void)n_full;
-  rc = run_gemm(h, c.stream, att_c, m_tail, m_tail, lw.out_p, kHidden, kHidden, lw.out_b, y, 1, GEMM_OUT_F32, 0);
+  // the branch outputs (out-projection, linear2) travel as bf16, as in the bf16 inference path
+  const __nv_bfloat16* y_b = reinterpret_cast<const __nv_bfloat16*>(y);
+  rc = run_gemm(h, c.stream, att_c, m_tail, m_tail, lw.out_p, kHidden, kHidden, lw.out_b, y, 1, GEMM_OUT_BF16, 0);
   if (rc) return rc;
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ADD_LN);
     ActOut o{xt, at<__nv_bfloat16>(c.ws, s.x1b), 1, m_tail};
-    STLT_CUDA(h, launch_add_ln(xt, y, lw.n1_g, lw.n1_b, eps, n_tail, o, c.stream, at<float>(c.ws, s.z1),
-                               layer_cfg(c, layer, 1)));
+    STLT_CUDA(h, launch_add_ln_bf16y(xt, y_b, lw.n1_g, lw.n1_b, eps, n_tail, o, c.stream, at<float>(c.ws, s.z1),
+                                     layer_cfg(c, layer, 1)));
   }
   h->launches++;
   rc = run_gemm(h, c.stream, at<__nv_bfloat16>(c.ws, s.x1b), m_tail, m_tail, lw.l1_p, kFfn, kHidden, lw.l1_b,
                 at<__nv_bfloat16>(c.ws, s.hid), 1, GEMM_OUT_BF16_DUAL, 2, layer_cfg(c, layer, 2));
   if (rc) return rc;
   rc = run_gemm(h, c.stream, at<__nv_bfloat16>(c.ws, s.hid), m_tail, m_tail, lw.l2_p, kHidden, kFfn, lw.l2_b, y,
-                1, GEMM_OUT_F32, 0);
+                1, GEMM_OUT_BF16, 0);
   if (rc) return rc;
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ADD_LN);
     ActOut o{xt, next_xb, 1, m_tail};
-    STLT_CUDA(h, launch_add_ln(xt, y, lw.n2_g, lw.n2_b, eps, n_tail, o, c.stream, at<float>(c.ws, s.z2),
-                               layer_cfg(c, layer, 3)));
+    STLT_CUDA(h, launch_add_ln_bf16y(xt, y_b, lw.n2_g, lw.n2_b, eps, n_tail, o, c.stream, at<float>(c.ws, s.z2),
+                                     layer_cfg(c, layer, 3)));
   }
   h->launches++;
   return STLT_OK;
