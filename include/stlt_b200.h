@@ -290,10 +290,11 @@ int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w
 int stlt_op_gemm_grad(void* handle, void* stream, int32_t layout, const void* a, const void* b,
                       void* out, int32_t m_rows, int32_t n, int64_t k, int32_t out_kind);
 /* Attention backward: qkv bf16 [tokens][2304] (saved by the forward), d_ctx bf16 [tokens][768] ->
- * d_qkv bf16 [tokens][2304]. impl 0 = CUDA cores, 1 = mma.sync tiles (the one the training step uses). */
+ * d_qkv bf16 [tokens][2304]. impl 0 = CUDA cores, 1 = mma.sync tiles (the one the training step uses; it
+ * can also add the column sums of d_qkv — the in-projection bias gradient — to d_bias f32 [2304]). */
 int stlt_op_attention_bwd(void* handle, void* stream, const void* qkv, const void* d_ctx,
                           const int64_t* mask_src, int64_t num_seqs, int32_t seq_len, int32_t causal,
-                          void* d_qkv, int32_t impl);
+                          void* d_qkv, int32_t impl, void* d_bias_or_null);
 /* Attention between two token streams (<= 64 queries / keys per sequence): Q from columns [0, 768) of
  * q_qkv bf16 [num_seqs*q_len][2304], K / V from columns [768, 1536) / [1536, 2304) of kv_qkv bf16
  * [num_seqs*kv_len][2304]; mask_src i64 per key token (0 = masked) or NULL. out bf16 [num_seqs*q_len][768]. */

@@ -120,6 +120,15 @@ __device__ __forceinline__ void load_transposed(uint32_t m_base, int lane, uint3
       ldmatrix_x4_trans(sq_addr(m_base, ks * 16 + (q >> 1) * 8 + r, mt * 2 + (q & 1)), a[mt][ks]);
 }
 
+// per-thread column sums of an accumulator tile (rows mt*16 + g + 8h summed; columns dt*8 + 2t + e)
+__device__ __forceinline__ void add_columns(float (&acc)[16], const float (&o)[2][8][4]) {
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      acc[dt * 2 + e] += (o[0][dt][e] + o[0][dt][2 + e]) + (o[1][dt][e] + o[1][dt][2 + e]);
+}
+
 // accumulator tile -> bf16 rows of a 64-wide staging tile
 __device__ __forceinline__ void stage_out(uint32_t base, int g, int t, const float (&o)[2][8][4]) {
 #pragma unroll
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
 attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_ctx,
                          const long long* __restrict__ mask_src, long long num_seqs, int T, int G,
                          int causal, __nv_bfloat16* __restrict__ d_qkv, long long num_items,
-                         DropCfg drop) {
+                         DropCfg drop, float* __restrict__ d_bias) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,6 +186,15 @@ attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
   const long long gwarp = blockIdx.x * static_cast<long long>(kWarps) + warp;
   const long long nwarps = gridDim.x * static_cast<long long>(kWarps);
   const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  // Bias gradient of the packed in-projection = column sums of dQ | dK | dV. The launcher makes the
+  // total warp count a multiple of 12, so every item of this warp has the same head and the partial
+  // sums of its 3 x 64 columns stay in registers until the end (column dt*8 + 2t + e of each part).
+  float colacc[3][16];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) colacc[a][i] = 0.f;
+  const int my_head = static_cast<int>(gwarp % kHeads);
 
   for (long long item = gwarp; item < num_items; item += nwarps) {
     const long long grp = item / kHeads;
@@ -314,15 +332,18 @@ attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
     // dV = P~^T dO  -> staged in the V tile (V is dead after dP)
     load_transposed(p_base, lane, at);
     product_nn(at, o_base, lane, o);
+    add_columns(colacc[2], o);
     __syncwarp();
     stage_out(v_base, g, t, o);
     // dK = dS^T Q   -> staged in the dO tile (dead after dV)
     load_transposed(s_base, lane, at);
     product_nn(at, q_base, lane, o);
+    add_columns(colacc[1], o);
     __syncwarp();
     stage_out(o_base, g, t, o);
     // dQ = dS K     -> staged in the Q tile (dead after dK)
     product_nn(ds_a, k_base, lane, o);
+    add_columns(colacc[0], o);
     __syncwarp();
     stage_out(q_base, g, t, o);
     __syncwarp();
@@ -356,13 +377,28 @@ attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
     }
     __syncwarp();
   }
+
+  if (d_bias != nullptr) {
+    // sum over the 8 row groups (lanes that share t), then lanes 0..3 add their 16 columns of each part
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = colacc[a][i];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0 && v != 0.f)
+          atomicAdd(d_bias + a * kHidden + my_head * kHeadDim + (i >> 1) * 8 + 2 * t + (i & 1), v);
+      }
+  }
 }
 
 }  // namespace
 
 cudaError_t launch_attention_bwd_mma(const __nv_bfloat16* qkv, const __nv_bfloat16* d_ctx,
                                      const long long* mask_src, long long num_seqs, int T, bool causal,
-                                     __nv_bfloat16* d_qkv, cudaStream_t stream, DropCfg drop) {
+                                     __nv_bfloat16* d_qkv, cudaStream_t stream, DropCfg drop, float* d_bias) {
   if (T < 1 || T > 32) return cudaErrorInvalidValue;
   if (num_seqs == 0) return cudaSuccess;
   const int G = 32 / T;
@@ -378,8 +414,9 @@ cudaError_t launch_attention_bwd_mma(const __nv_bfloat16* qkv, const __nv_bfloat
   long long blocks = (items + kWarps - 1) / kWarps;
   const long long cap = 148LL * 2 * 8;
   if (blocks > cap) blocks = cap;
+  blocks = (blocks + 2) / 3 * 3;  // total warps a multiple of 12: a warp keeps one head (bias-gradient sums)
   attention_bwd_mma_kernel<<<static_cast<unsigned>(blocks), kWarps * 32, smem, stream>>>(
-      qkv, d_ctx, mask_src, num_seqs, T, G, causal ? 1 : 0, d_qkv, items, drop);
+      qkv, d_ctx, mask_src, num_seqs, T, G, causal ? 1 : 0, d_qkv, items, drop, d_bias);
   return cudaGetLastError();
 }
 

@@ -218,10 +218,10 @@ cudaError_t launch_mean3(const float* a, const float* b, const float* c, long lo
                          cudaStream_t stream);
 
 // Same on mma.sync tensor-core tiles (attention_bwd_mma.cu); the CUDA-core version above is kept as a
-// cross-check for the tests.
+// cross-check for the tests. d_bias (optional, f32 [2304]): += column sums of d_qkv (in-projection bias gradient).
 cudaError_t launch_attention_bwd_mma(const __nv_bfloat16* qkv, const __nv_bfloat16* d_ctx,
                                      const long long* mask_src, long long num_seqs, int T, bool causal,
                                      __nv_bfloat16* d_qkv, cudaStream_t stream,
-                                     DropCfg drop = DropCfg{0, 0, 1.f});
+                                     DropCfg drop = DropCfg{0, 0, 1.f}, float* d_bias = nullptr);
 
 }  // namespace stlt

@@ -259,15 +259,11 @@ int bwd_layer(const Ctx& c, int layer, const LayerWeights& lw, const LayerWeight
   // attention: dQKV; d b_in = colsum(dQKV)
   {
     ProfileScope prof(h, c.stream, STLT_PROF_ATTENTION);
+    // also accumulates d b_in = colsum(dQKV)
     STLT_CUDA(h, launch_attention_bwd_mma(at<__nv_bfloat16>(ws, s.qkv), batt, mask_src, num_seqs, T, causal, bqkv,
-                                          c.stream, layer_cfg(c, layer, 0)));
+                                          c.stream, layer_cfg(c, layer, 0), grad_ptr(gw.in_b)));
   }
   h->launches++;
-  if (gw.in_b) {
-    ProfileScope prof(h, c.stream, STLT_PROF_OTHER);
-    STLT_CUDA(h, launch_act_bwd_colsum(bqkv, nullptr, n_full, kQkv, grad_ptr(gw.in_b), c.stream));
-    h->launches++;
-  }
   // in-projection: dX = dQKV Win -> fa ; dWin += dQKV^T xb
   rc = run_gemm_grad(h, c.stream, GEMM_NN, bqkv, lw.in_p, fa, m_full, kHidden, kQkv, GEMM_OUT_F32);
   if (rc) return rc;
@@ -541,7 +537,7 @@ int stlt_op_dropout_mask(void* handle, float dropout_p, uint64_t seed, int32_t s
 
 int stlt_op_attention_bwd(void* handle, void* stream, const void* qkv, const void* d_ctx,
                           const int64_t* mask_src, int64_t num_seqs, int32_t seq_len, int32_t causal,
-                          void* d_qkv, int32_t impl) {
+                          void* d_qkv, int32_t impl, void* d_bias_or_null) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h || !qkv || !d_ctx || !mask_src || !d_qkv) return fail(h, STLT_ERR_INVALID, "null argument");
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
@@ -550,7 +546,8 @@ int stlt_op_attention_bwd(void* handle, void* stream, const void* qkv, const voi
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(d_qkv);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (impl == 0) STLT_CUDA(h, launch_attention_bwd(q, d, m, num_seqs, seq_len, causal != 0, o, s));
-  else STLT_CUDA(h, launch_attention_bwd_mma(q, d, m, num_seqs, seq_len, causal != 0, o, s));
+  else STLT_CUDA(h, launch_attention_bwd_mma(q, d, m, num_seqs, seq_len, causal != 0, o, s, DropCfg{0, 0, 1.f},
+                                             static_cast<float*>(d_bias_or_null)));
   return STLT_OK;
 }
 

@@ -149,7 +149,7 @@ SIGNATURES = {
     "stlt_op_gemm_grad": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_int32, c_int64, c_int32]),
     "stlt_op_attention_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
-                                        c_int32, c_void_p, c_int32]),
+                                        c_int32, c_void_p, c_int32, c_void_p]),
     "stlt_op_attention_cross": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                           c_int32, c_void_p]),
     "stlt_op_gemm_simt": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

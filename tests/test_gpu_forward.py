@@ -260,3 +260,30 @@ def test_full_size_batch_properties():
     with torch.no_grad():
         b16 = m(gb)["stlt"]
     assert nerr(b16[idx.cuda()].cpu(), want) < BF16_TOL
+
+
+def test_host_pipeline_delivers_every_batch_in_order():
+    """stlt_b200.pipeline.HostPipeline overlaps H2D / compute / D2H of neighbouring batches; results must
+    be the ones of the plain sequential loop, in order, for ragged batch sizes too."""
+    import stlt_b200
+    from stlt_b200.pipeline import HostPipeline
+    from stlt_b200.synthetic import make_batch, random_state_dict
+    cfg = stlt_b200.StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=1, num_temporal_layers=1)
+    torch.manual_seed(0)
+    model = stlt_b200.Stlt(cfg, precision="bf16")
+    model.load_state_dict(random_state_dict(model.state_dict(), seed=3))
+    model = model.cuda()
+    model.train(False)
+    sizes = [5, 9, 9, 2, 16, 16, 16, 1]
+    keys = ("categories", "boxes", "frame_types", "lengths")
+    host = [{k: v.pin_memory() for k, v in make_batch(b, "something", seed=40 + i).items() if k in keys}
+            for i, b in enumerate(sizes)]
+    with torch.no_grad():
+        want = [model({k: v.cuda() for k, v in hb.items()})["stlt"].cpu() for hb in host]
+    pipe = HostPipeline(model, "stlt", depth=2)
+    got = [t.clone() for t in pipe.run(iter(host))]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    got3 = [t.clone() for t in HostPipeline(model, "stlt", depth=3).run(iter(host))]
+    assert all(torch.equal(a, b) for a, b in zip(got3, want))

@@ -78,8 +78,10 @@ def test_attention_backward(handle, T, num_seqs, causal, impl):
     mask_src = (torch.rand(num_seqs, T, device="cuda", generator=g) > 0.3).long()
     mask_src[:, 0] = 1  # slot / frame 0 is always valid
     d_qkv = torch.full((tokens, 2304), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d_bias = torch.ones(2304, device="cuda")
     L.check(handle, lib.stlt_op_attention_bwd(handle, _stream(), qkv.data_ptr(), d_ctx.data_ptr(),
-                                              mask_src.data_ptr(), num_seqs, T, int(causal), d_qkv.data_ptr(), impl))
+                                              mask_src.data_ptr(), num_seqs, T, int(causal), d_qkv.data_ptr(), impl,
+                                              d_bias.data_ptr() if impl == 1 else None))
     x = qkv.float().view(num_seqs, T, 3, 12, 64).requires_grad_(True)
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))  # [N, heads, T, 64]
     scores = q @ k.transpose(-1, -2) / 8.0
@@ -91,3 +93,5 @@ def test_attention_backward(handle, T, num_seqs, causal, impl):
     want = x.grad.view(tokens, 2304)
     assert torch.isfinite(d_qkv.float()).all()
     assert nerr(d_qkv, want) < 1.2e-2
+    if impl == 1:  # fused in-projection bias gradient: accumulated on top of the existing value
+        assert nerr(d_bias - 1.0, want.sum(0)) < 5e-3
