@@ -11,8 +11,8 @@
 //   dV = P~^T dO, dK = dS^T Q          P~ and dS go through two 32 x 32 bf16 tiles in shared memory and
 //                                      come back transposed with ldmatrix.trans
 // The three gradient tiles are staged through dead input tiles and written as 16-byte vectors.
-#include "common.cuh"
 #include "kernels.h"
+#include "mma_tiles.cuh"
 
 namespace stlt {
 
@@ -23,36 +23,10 @@ constexpr int kSqTileBytes = 32 * 64;  // 32 rows x 32 bf16
 constexpr int kWarps = 4;
 constexpr int kWarpBytes = 4 * kTileBytes + 2 * kSqTileBytes;  // Q K V dO + P~ dS
 
-__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
-  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
-}
 // 32 x 32 bf16 tile, 64-byte rows, 16-byte chunks swizzled so that 8 consecutive rows of one chunk
 // column hit 8 different 16-byte bank groups
 __device__ __forceinline__ uint32_t sq_addr(uint32_t base, int row, int chunk) {
   return base + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr)
-               : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr)
-               : "memory");
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
-      "{%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // acc[32 x 32] = X[32 x 64] * Y[32 x 64]^T for two row-major 64-wide tiles (scores-shaped product)

@@ -11,47 +11,25 @@
 // S = Q K^T (16 x 64, fp32 fragments) -> masks (key padding from mask_src == 0, optional causal) ->
 // softmax with quad shuffles -> O = P V with P re-used from registers. Nothing but the bf16 context
 // leaves the SM.
-#include "common.cuh"
 #include "kernels.h"
+#include "mma_tiles.cuh"
 
 namespace stlt {
 
 namespace {
 
-constexpr int kTileBytes = 64 * 128;  // 64 rows x 64 bf16
 constexpr int kWarps = 4;
 
-__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
-  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
-}
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr)
-               : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr)
-               : "memory");
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
-      "{%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__global__ void __launch_bounds__(kWarps * 32, 2)
+// kRows = rows of the Q / K / V tiles (48 or 64): 48-row tiles hold the 33-token appearance stream in
+// 18 KB per warp, so three 4-warp blocks fit on an SM instead of two.
+template <int kRows>
+__global__ void __launch_bounds__(kWarps * 32, kRows <= 48 ? 3 : 2)
 attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
                        const __nv_bfloat16* __restrict__ kv, int ldkv, int k_off, int v_off,
                        const long long* __restrict__ mask_src, long long num_seqs, int Tq, int Tk,
                        int causal, __nv_bfloat16* __restrict__ out) {
+  constexpr int kTileBytes = kRows * 128;  // kRows x 64 bf16
+  constexpr int kKeyTiles = kRows / 8;     // 8-key accumulator tiles
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,7 +52,7 @@ attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
       const int chunk = lane & 7;
       const int r0 = lane >> 3;
 #pragma unroll 4
-      for (int it = 0; it < 16; ++it) {
+      for (int it = 0; it < kRows / 4; ++it) {
         const int row = it * 4 + r0;
         if (row < Tq)
           cp_async16(tile_addr(q_base, row, chunk), q + (seq * Tq + row) * ldq + q_off + head * kHeadDim + chunk * 8);
@@ -104,9 +82,9 @@ attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
 
     for (int mt = 0; mt < m_tiles; ++mt) {
       // ---- S = Q K^T for 16 queries x 64 keys ----
-      float s[8][4];
+      float s[kKeyTiles][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < kKeyTiles; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
 #pragma unroll
@@ -114,7 +92,7 @@ attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
         uint32_t a[4];
         ldmatrix_x4(tile_addr(q_base, mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kt * 2 + (lane >> 4)), a);
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {
+        for (int np = 0; np < kKeyTiles / 2; ++np) {
           if (np * 16 < Tk) {  // warp-uniform
             uint32_t b[4];
             ldmatrix_x4(tile_addr(k_base, (np * 2 + (lane >> 4)) * 8 + (lane & 7), kt * 2 + ((lane >> 3) & 1)), b);
@@ -124,14 +102,14 @@ attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
         }
       }
       // ---- masked softmax (fp32) ----
-      uint32_t p[4][4];
+      uint32_t p[kKeyTiles / 2][4];
       float inv_sum[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int row = mt * 16 + g + 8 * h;
         float m = -INFINITY;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < kKeyTiles; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int key = nt * 8 + 2 * t + e;
@@ -146,7 +124,7 @@ attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
         const float mm = (m == -INFINITY) ? 0.f : m;
         float sum = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < kKeyTiles; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const float pv = exp2f(s[nt][2 * h + e] - mm);
@@ -158,7 +136,7 @@ attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
         inv_sum[h] = sum > 0.f ? 1.0f / sum : 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kKeyTiles / 2; ++j) {
         p[j][0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
         p[j][1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
         p[j][2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
@@ -171,7 +149,7 @@ attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[dt][i] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kKeyTiles / 2; ++j) {
         if (j < k_steps) {  // warp-uniform
 #pragma unroll
           for (int dp = 0; dp < 4; ++dp) {
@@ -212,6 +190,26 @@ attention_cross_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_off,
   }
 }
 
+template <int kRows>
+static cudaError_t launch_rows(const __nv_bfloat16* q, int ldq, int q_off, const __nv_bfloat16* kv, int ldkv,
+                               int k_off, int v_off, const long long* mask_src, long long num_seqs, int Tq,
+                               int Tk, bool causal, __nv_bfloat16* out, cudaStream_t stream) {
+  const int smem = kWarps * 3 * kRows * 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_cross_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const long long items = num_seqs * kHeads;
+  long long blocks = (items + kWarps - 1) / kWarps;
+  const long long cap = 148LL * 3 * 8;
+  if (blocks > cap) blocks = cap;
+  attention_cross_kernel<kRows><<<static_cast<unsigned>(blocks), kWarps * 32, smem, stream>>>(
+      q, ldq, q_off, kv, ldkv, k_off, v_off, mask_src, num_seqs, Tq, Tk, causal ? 1 : 0, out);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_attention_cross(const __nv_bfloat16* q, int ldq, int q_off, const __nv_bfloat16* kv,
@@ -221,20 +219,9 @@ cudaError_t launch_attention_cross(const __nv_bfloat16* q, int ldq, int q_off, c
   if (Tq < 1 || Tq > 64 || Tk < 1 || Tk > 64) return cudaErrorInvalidValue;
   if (causal && Tq != Tk) return cudaErrorInvalidValue;
   if (num_seqs == 0) return cudaSuccess;
-  const int smem = kWarps * 3 * kTileBytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  const long long items = num_seqs * kHeads;
-  long long blocks = (items + kWarps - 1) / kWarps;
-  const long long cap = 148LL * 2 * 8;
-  if (blocks > cap) blocks = cap;
-  attention_cross_kernel<<<static_cast<unsigned>(blocks), kWarps * 32, smem, stream>>>(
-      q, ldq, q_off, kv, ldkv, k_off, v_off, mask_src, num_seqs, Tq, Tk, causal ? 1 : 0, out);
-  return cudaGetLastError();
+  if (Tq <= 48 && Tk <= 48)
+    return launch_rows<48>(q, ldq, q_off, kv, ldkv, k_off, v_off, mask_src, num_seqs, Tq, Tk, causal, out, stream);
+  return launch_rows<64>(q, ldq, q_off, kv, ldkv, k_off, v_off, mask_src, num_seqs, Tq, Tk, causal, out, stream);
 }
 
 }  // namespace stlt

@@ -20,45 +20,14 @@
 // The scores of sequences sharing a tile are computed and then masked away; at T = 5 that is
 // 30x30 computed for 6x(5x5) used, which is still ~4x fewer issued instructions per token than a
 // CUDA-core formulation, and the kernel is HBM-bound (reads 4.6 KB, writes 1.5 KB per token).
-#include "common.cuh"
 #include "kernels.h"
+#include "mma_tiles.cuh"
 
 namespace stlt {
 
 namespace {
 
 constexpr int kTileBytes = 32 * 128;  // 32 rows x 64 bf16
-
-__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
-  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr)
-               : "memory");
-}
-
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr)
-               : "memory");
-}
-
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
-                                         uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
-      "{%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 template <bool kSplit>
 __global__ void __launch_bounds__(kSplit ? 128 : 256, 2)

@@ -219,3 +219,53 @@ def test_dropout_forward_backward_match_oracle_under_identical_masks(layout):
     again = model._forward_train(inputs, ws, p, seed)
     other = model._forward_train(inputs, ws, p, seed + 1)
     assert torch.equal(again, logits) and not torch.equal(other, logits)
+
+
+@pytest.mark.parametrize("B,frames,objects", [(1, 1, 1), (5, 3, 2), (2, 16, 31)])
+def test_backward_edge_shapes(B, frames, objects):
+    """Tiny and maximal sequence shapes (L = 2, S = 2 ... S = 32), batch 1: gradients vs the oracle."""
+    import stlt_b200
+    from stlt_b200.synthetic import make_batch, random_state_dict
+    cfg = stlt_b200.StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=2, num_temporal_layers=2,
+                                    hidden_dropout_prob=0.0)
+    torch.manual_seed(0)
+    model = stlt_b200.Stlt(cfg, precision="bf16")
+    sd = random_state_dict(model.state_dict(), seed=11)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    model.train(True)
+    batch = make_batch(B, "something", ragged=True, seed=B + frames, num_frames=frames, max_objects=objects)
+    labels = torch.arange(B) % 174
+    want_loss, _, want = _oracle_small(sd, batch, labels)
+    out = model(to_cuda(batch))["stlt"]
+    torch.nn.functional.cross_entropy(out, labels.cuda()).backward()
+    worst = sorted(((_rel(p.grad, want[n]), n) for n, p in model.named_parameters() if n in want), reverse=True)
+    print("edge worst:", worst[:3])
+    assert worst[0][0] < 3e-2, worst[:3]
+
+
+def _oracle_small(sd, batch, labels):
+    leaves = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    logits = stlt_oracle.stlt_forward(leaves, batch, num_spatial_layers=2, num_temporal_layers=2)
+    value = stlt_oracle.criterion(logits, labels, "cross_entropy")
+    names = [k for k, v in leaves.items() if v.is_floating_point()]
+    grads = torch.autograd.grad(value, [leaves[k] for k in names], allow_unused=True)
+    return value.detach(), logits.detach(), {k: g for k, g in zip(names, grads) if g is not None}
+
+
+def test_frozen_backbone_trains_only_the_head():
+    """config.freeze_backbone semantics (reference models.py:170-176,180-183): no gradient for the backbone,
+    dropout off, head gradients unchanged."""
+    cfg, sd, batch, labels, loss, g = _case("something")
+    _, _, want = stlt_oracle.loss_and_grads(sd, batch, labels, loss)
+    model = _model(cfg, sd)
+    for p in model.backbone.parameters():
+        p.requires_grad = False
+    model.train(True)
+    out = model(to_cuda(batch))["stlt"]
+    torch.nn.functional.cross_entropy(out, labels.cuda()).backward()
+    for n, p in model.named_parameters():
+        if n.startswith("backbone."):
+            assert p.grad is None, n
+        else:
+            assert _rel(p.grad, want[n]) < 2e-2, n
