@@ -188,6 +188,13 @@ int stlt_get_profile(void* handle, StltProfile* out);
  * logits are bit-identical with pruning off; taps of the full stack outputs disable it. */
 int stlt_set_pruning(void* handle, int32_t enable);
 
+/* bf16 mode folds every encoder LayerNorm into the epilogues of the GEMMs around it (default on): the
+ * residual stream is kept pre-norm with per-row statistics, the in-projection / linear1 GEMMs read it with
+ * gamma-folded weights and normalise in their epilogue, the out-projection / linear2 GEMMs add the residual
+ * and accumulate the next statistics. 0 restores the separate residual + LayerNorm kernels (same results
+ * up to bf16 rounding; used by the tests as a cross-check). Has no effect in fp32 mode or with taps set. */
+int stlt_set_fused_ln(void* handle, int32_t enable);
+
 /* Test taps (NULL disables). The struct is copied. */
 int stlt_set_taps(void* handle, const StltTaps* taps);
 

@@ -332,7 +332,8 @@ frame_embed_kernel(const float* __restrict__ spatial_x, int S,
                    const long long* __restrict__ frame_types, const float* __restrict__ pos_table,
                    const float* __restrict__ ft_table, int n_frame_types,
                    const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps, int L,
-                   long long frames, ActOut out, int* __restrict__ err_flag, DropCfg drop) {
+                   long long frames, ActOut out, int* __restrict__ err_flag, DropCfg drop,
+                   const float* __restrict__ pre_g, const float* __restrict__ pre_b, float pre_eps) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -344,6 +345,8 @@ frame_embed_kernel(const float* __restrict__ spatial_x, int S,
       ft = 0;
     }
     RowRegs r = load_row(spatial_x, f * S, lane);  // slot 0 = CLS object (models.py:79)
+    // fused-LayerNorm path: the spatial stack hands over its PRE-norm output, normalise it here
+    if (pre_g != nullptr) layer_norm_row(r, pre_g, pre_b, pre_eps, lane);
     const RowRegs p = load_row(pos_table, l, lane);
     const RowRegs t = load_row(ft_table, ft, lane);
 #pragma unroll
@@ -388,7 +391,8 @@ gather_rows_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __restr
                    int planes, long long src_plane_rows, int stride,
                    const long long* __restrict__ lengths, int L, long long rows,
                    float* __restrict__ dst_x, __nv_bfloat16* __restrict__ dst_att,
-                   long long dst_plane_rows, int* __restrict__ err_flag) {
+                   long long dst_plane_rows, int* __restrict__ err_flag,
+                   const float2* __restrict__ src_stats, float2* __restrict__ dst_stats) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -404,6 +408,8 @@ gather_rows_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __restr
       }
       src = r * L + (len - 1);
     }
+    if (src_stats != nullptr && lane < kStatSlots)  // fused-LN path: the row's partial statistics travel along
+      dst_stats[r * kStatSlots + lane] = src_stats[src * kStatSlots + lane];
     const RowRegs x = load_row(src_x, src, lane);
     float4* px = reinterpret_cast<float4*>(dst_x + r * kHidden);
 #pragma unroll
@@ -433,6 +439,42 @@ __global__ void pack_bf16_kernel(const float4* __restrict__ src, uint2* __restri
       l.y = pack_bf16x2(bf16_residual(v.z), bf16_residual(v.w));
       lo[i] = l;
     }
+  }
+}
+
+// Fused-LayerNorm weights: Wf[n, k] = bf16(W[n, k] * gamma[k]), s[n] = sum_k Wf[n, k] (of the ROUNDED
+// values, so that mean * s cancels exactly what the MMA accumulates), c[n] = sum_k W[n, k] * beta[k] + bias[n].
+// One block per output row n.
+__global__ void __launch_bounds__(256)
+pack_folded_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ bias, int k, __nv_bfloat16* __restrict__ wf, float* __restrict__ s_out,
+                   float* __restrict__ c_out) {
+  const int n = blockIdx.x;
+  const float* row = w + static_cast<long long>(n) * k;
+  float s = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const float v = row[i];
+    const __nv_bfloat16 f = __float2bfloat16_rn(v * gamma[i]);
+    wf[static_cast<long long>(n) * k + i] = f;
+    s += __bfloat162float(f);
+    c = fmaf(v, beta[i], c);
+  }
+  s = warp_sum(s);
+  c = warp_sum(c);
+  __shared__ float ps[8], pc[8];
+  if ((threadIdx.x & 31) == 0) {
+    ps[threadIdx.x >> 5] = s;
+    pc[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tc = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      ts += ps[i];
+      tc += pc[i];
+    }
+    s_out[n] = ts;
+    c_out[n] = tc + bias[n];
   }
 }
 
@@ -507,12 +549,14 @@ cudaError_t launch_add_ln_bf16y(const float* x_in, const __nv_bfloat16* y, const
 cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* frame_types,
                                const float* pos_table, const float* ft_table, int n_frame_types,
                                const float* ln_g, const float* ln_b, float eps, int B, int L,
-                               ActOut out, int* err_flag, cudaStream_t stream, DropCfg drop) {
+                               ActOut out, int* err_flag, cudaStream_t stream, DropCfg drop,
+                               const float* pre_g, const float* pre_b, float pre_eps) {
   const long long frames = static_cast<long long>(B) * L;
   if (frames == 0) return cudaSuccess;
   frame_embed_kernel<<<row_grid(frames, 8), 256, 0, stream>>>(spatial_x, S, frame_types, pos_table,
                                                               ft_table, n_frame_types, ln_g, ln_b,
-                                                              eps, L, frames, out, err_flag, drop);
+                                                              eps, L, frames, out, err_flag, drop, pre_g,
+                                                              pre_b, pre_eps);
   return cudaGetLastError();
 }
 
@@ -526,11 +570,12 @@ cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, 
 cudaError_t launch_gather_rows(const float* src_x, const __nv_bfloat16* src_att, int planes,
                                long long src_plane_rows, int stride, const long long* lengths, int L,
                                long long rows, float* dst_x, __nv_bfloat16* dst_att,
-                               long long dst_plane_rows, int* err_flag, cudaStream_t stream) {
+                               long long dst_plane_rows, int* err_flag, cudaStream_t stream,
+                               const float2* src_stats, float2* dst_stats) {
   if (rows == 0) return cudaSuccess;
   gather_rows_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(src_x, src_att, planes, src_plane_rows,
                                                             stride, lengths, L, rows, dst_x, dst_att,
-                                                            dst_plane_rows, err_flag);
+                                                            dst_plane_rows, err_flag, src_stats, dst_stats);
   return cudaGetLastError();
 }
 
@@ -555,6 +600,12 @@ cudaError_t launch_topk_count(const float* logits, const long long* labels, int 
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   topk_count_kernel<<<blocks, 256, 0, stream>>>(logits, labels, rows, classes, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_folded(const float* w, const float* gamma, const float* beta, const float* bias, int n,
+                               int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream) {
+  pack_folded_kernel<<<n, 256, 0, stream>>>(w, gamma, beta, bias, k, wf, s_out, c_out);
   return cudaGetLastError();
 }
 

@@ -63,15 +63,19 @@ constexpr uint16_t kClusterMask = (1u << kCluster) - 1;
 // The split epilogue needs two staging tiles per warp (hi and lo plane), paid for with one stage.
 template <int kOut>
 struct Cfg {
-  static constexpr bool kTwoPlanes = kOut == GEMM_OUT_BF16_SPLIT || kOut == GEMM_OUT_BF16_DUAL;
-  static constexpr int kStages = kTwoPlanes ? 5 : 6;
-  static constexpr int kBufsPerWarp = kTwoPlanes ? 2 : 1;
+  static constexpr bool kTwoPlanes =
+      kOut == GEMM_OUT_BF16_SPLIT || kOut == GEMM_OUT_BF16_DUAL || kOut == GEMM_OUT_F32_BF16_DIRECT;
+  // fused-LN residual epilogue: outgoing fp32 tile, incoming z tile (+ outgoing bf16 tile unless DIRECT)
+  static constexpr int kStages = kOut == GEMM_OUT_F32_BF16 ? 4 : (kTwoPlanes ? 5 : 6);
+  static constexpr int kBufsPerWarp = kOut == GEMM_OUT_F32_BF16 ? 3 : (kTwoPlanes ? 2 : 1);
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + kEpiWarps * kBufsPerWarp * kEpiBufBytes + 256 /*barriers*/;
+      kStages * kStageBytes + kEpiWarps * kBufsPerWarp * kEpiBufBytes + 320 /*barriers*/;
 };
 static_assert(Cfg<GEMM_OUT_F32>::kSmemBytes <= 232448, "smem budget");
 static_assert(Cfg<GEMM_OUT_BF16_SPLIT>::kSmemBytes <= 232448, "smem budget");
 static_assert(Cfg<GEMM_OUT_BF16_DUAL>::kSmemBytes <= 232448, "smem budget");
+static_assert(Cfg<GEMM_OUT_F32_BF16>::kSmemBytes <= 232448, "smem budget");
+static_assert(Cfg<GEMM_OUT_F32_BF16_DIRECT>::kSmemBytes <= 232448, "smem budget");
 
 constexpr int kMnChunkBytes = 64 * BK * 2;  // one MN-major TMA box: 64 reduction rows x 128 B
 
@@ -125,18 +129,22 @@ struct __align__(8) Barriers {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t zin[kEpiWarps];  // RESID epilogue: per-warp "incoming z tile has landed"
   uint32_t tmem_base;
   uint32_t pad;
 };
 
 }  // namespace
 
-template <int kTerms, int kOut, int kGelu, int kLayout>
+template <int kTerms, int kOut, int kGelu, int kLayout, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias,
-                    int m_tiles, int n_tiles, int k_blocks, int a_plane_rows, int b_plane_rows,
-                    int out_plane_rows, DropCfg drop) {
+                    const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2,
+                    const float* __restrict__ bias, int m_tiles, int n_tiles, int k_blocks, int a_plane_rows,
+                    int b_plane_rows, int out_plane_rows, DropCfg drop, EpiArgs ep) {
+  static_assert(kEpi == GEMM_EPI_PLAIN || (kLayout == GEMM_NT && kTerms == 1), "fused-LN epilogues: bf16 forward only");
+  constexpr bool kResidOut = kOut == GEMM_OUT_F32_BF16 || kOut == GEMM_OUT_F32_BF16_DIRECT;
+  static_assert((kEpi == GEMM_EPI_RESID) == kResidOut, "RESID epilogue <-> fp32 + bf16 output");
   constexpr int kStages = Cfg<kOut>::kStages;
   constexpr int kBufsPerWarp = Cfg<kOut>::kBufsPerWarp;
   constexpr bool kAMn = kLayout == GEMM_TN_RED;
@@ -178,6 +186,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       mbar_init(&bars->tmem_full[i], 1);                     // leader's commit, multicast
       mbar_init(&bars->tmem_empty[i], kCluster * kEpiWarps);  // used in the leader: both epilogues
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&bars->zin[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -282,6 +291,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint8_t* ebuf = smem_epi + ew * kBufsPerWarp * kEpiBufBytes;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     const uint32_t row_smem = smem_u32(ebuf) + lane * 128;  // this thread's 128 B staging row
+    uint8_t* zbuf = ebuf + (kOut == GEMM_OUT_F32_BF16 ? 2 : 1) * kEpiBufBytes;  // RESID: incoming z tile (TMA load)
+    uint32_t zphase = 0;
     int it = 0;
     Sched<kStreamK> sched(cluster_id, num_clusters, num_tiles, total_kb);
     Work w;
@@ -294,6 +305,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const int col0 = n_blk * BN + half * 128;
       const int row0 = m_blk * BM + quarter * 32;
       const float4* bias4 = reinterpret_cast<const float4*>(bias + col0);  // warp-uniform reads
+      // fused LayerNorm: statistics of this thread's row (NORM_A: of the A row; RESID: of the z_prev row)
+      float mu = 0.f, rstd = 1.f;
+      float psum = 0.f, psq = 0.f;
+      if constexpr (kEpi != GEMM_EPI_PLAIN) {
+        if (store_ok && (kEpi == GEMM_EPI_NORM_A || ep.prev_norm)) {
+          // kStatSlots partial (sum, sum of squares) per row, one per 128-column slab of the producing GEMM,
+          // added in a fixed order: no atomics, bit-reproducible
+          const float4* st4 = reinterpret_cast<const float4*>(ep.stats_in + static_cast<size_t>(row0 + lane) * kStatSlots);
+          float sx = 0.f, sy = 0.f;
+#pragma unroll
+          for (int i = 0; i < kStatSlots / 2; ++i) {
+            const float4 v4 = __ldg(st4 + i);
+            sx += v4.x;
+            sy += v4.y;
+            sx += v4.z;
+            sy += v4.w;
+          }
+          mu = sx * (1.0f / kHidden);
+          rstd = rsqrtf(fmaxf(sy * (1.0f / kHidden) - mu * mu, 0.f) + ep.eps);
+        }
+      }
+      const float4* va4 = reinterpret_cast<const float4*>(ep.vec_a + col0);
+      const float4* vb4 = reinterpret_cast<const float4*>(ep.vec_b + col0);
+      if constexpr (kEpi == GEMM_EPI_RESID) {
+        // the residual input tile (32 rows x 32 fp32 columns) arrives by TMA, one chunk ahead of its use;
+        // z is updated in place, so the output tensor map also describes the input
+        if (store_ok && lane == 0) {
+          mbar_expect_tx(&bars->zin[ew], kEpiBufBytes);
+          tma_load_2d(&tm_out, &bars->zin[ew], zbuf, col0, row0);
+        }
+      }
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr =
@@ -309,13 +351,66 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         tmem_ld_wait_regs(v);
         if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
         float f[32];
+        if constexpr (kEpi == GEMM_EPI_NORM_A) {
+          // act(LN(z) W^T + b) from the raw product: rstd * (acc - mean * s[n]) + c[n]
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = kBias ? __ldg(bias4 + c * 8 + (j >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-          f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-          f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-          f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = __ldg(va4 + c * 8 + (j >> 2));
+            const float4 c4 = __ldg(vb4 + c * 8 + (j >> 2));
+            f[j + 0] = fmaf(rstd, fmaf(-mu, s4.x, __uint_as_float(v[j + 0])), c4.x);
+            f[j + 1] = fmaf(rstd, fmaf(-mu, s4.y, __uint_as_float(v[j + 1])), c4.y);
+            f[j + 2] = fmaf(rstd, fmaf(-mu, s4.z, __uint_as_float(v[j + 2])), c4.z);
+            f[j + 3] = fmaf(rstd, fmaf(-mu, s4.w, __uint_as_float(v[j + 3])), c4.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = kBias ? __ldg(bias4 + c * 8 + (j >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+        }
+        if constexpr (kEpi == GEMM_EPI_RESID) {
+          // z_new = x + branch, x = LN(z_prev) (or z_prev itself for the first layer of a stack); the row's
+          // partial (sum, sum of squares) over these 32 columns feeds the next LayerNorm
+          if (store_ok) {
+            mbar_wait(&bars->zin[ew], zphase);
+            zphase ^= 1u;
+            float4 zrow[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t addr = smem_u32(zbuf) + lane * 128 + ((static_cast<uint32_t>(j) ^ sw) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(zrow[j].x), "=f"(zrow[j].y), "=f"(zrow[j].z), "=f"(zrow[j].w)
+                           : "r"(addr)
+                           : "memory");
+            }
+            __syncwarp();  // every lane has read its row: the buffer may be refilled
+            if (c + 1 < 4 && lane == 0) {
+              mbar_expect_tx(&bars->zin[ew], kEpiBufBytes);
+              tma_load_2d(&tm_out, &bars->zin[ew], zbuf, col0 + (c + 1) * 32, row0);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 x = zrow[j >> 2];
+              if (ep.prev_norm) {
+                const float4 g4 = __ldg(va4 + c * 8 + (j >> 2));
+                const float4 b4 = __ldg(vb4 + c * 8 + (j >> 2));
+                x.x = fmaf((x.x - mu) * rstd, g4.x, b4.x);
+                x.y = fmaf((x.y - mu) * rstd, g4.y, b4.y);
+                x.z = fmaf((x.z - mu) * rstd, g4.z, b4.z);
+                x.w = fmaf((x.w - mu) * rstd, g4.w, b4.w);
+              }
+              f[j + 0] += x.x;
+              f[j + 1] += x.y;
+              f[j + 2] += x.z;
+              f[j + 3] += x.w;
+              psum += (f[j + 0] + f[j + 1]) + (f[j + 2] + f[j + 3]);
+              psq += (f[j + 0] * f[j + 0] + f[j + 1] * f[j + 1]) + (f[j + 2] * f[j + 2] + f[j + 3] * f[j + 3]);
+            }
+          }
         }
         uint32_t pre[kOut == GEMM_OUT_BF16_DUAL ? 16 : 1];  // pre-activation values (training)
         if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
@@ -346,7 +441,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           }
         }
 
-        if (kOut == GEMM_OUT_F32) {
+        if (kOut == GEMM_OUT_F32 || kResidOut) {
           // 32 fp32 columns = 128 B per row -> one TMA store per chunk
           if (lane == 0) tma_store_wait_read0();  // previous store has finished reading ebuf
           __syncwarp();
@@ -357,11 +452,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                          "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
                          : "memory");
           }
+          if constexpr (kOut == GEMM_OUT_F32_BF16) {
+            // bf16 copy (the next GEMM's A operand): two chunks fill one 128 B row of the third buffer; the
+            // wait_read0 above (before the fp32 tile was overwritten) also covers its previous store
+            const int hc = c & 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t addr = row_smem + kEpiBufBytes + ((static_cast<uint32_t>(hc * 4 + j) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                           "r"(pack_bf16x2(f[8 * j + 0], f[8 * j + 1])), "r"(pack_bf16x2(f[8 * j + 2], f[8 * j + 3])),
+                           "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
+                           : "memory");
+            }
+          }
+          if constexpr (kOut == GEMM_OUT_F32_BF16_DIRECT) {
+            // bf16 copy of the row: 64 contiguous bytes per thread, written straight from registers
+            if (store_ok) {
+              uint4* dst = reinterpret_cast<uint4*>(
+                  ep.zb_out + static_cast<size_t>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            }
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && store_ok) {
             if (kStreamK) tma_reduce_add_2d(&tm_out, ebuf, col0 + c * 32, row0);
             else tma_store_2d(&tm_out, ebuf, col0 + c * 32, row0);
+            if constexpr (kOut == GEMM_OUT_F32_BF16) {
+              if (c & 1) tma_store_2d(&tm_out2, ebuf + kEpiBufBytes, col0 + (c - 1) * 32, row0);
+            }
             tma_store_commit();
           }
         } else {
@@ -408,6 +530,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           }
         }
       }
+      if constexpr (kEpi == GEMM_EPI_RESID) {
+        if (store_ok)  // this thread's row, this warp's 128-column slab -> its own slot
+          ep.stats_out[static_cast<size_t>(row0 + lane) * kStatSlots + n_blk * 2 + half] = make_float2(psum, psq);
+      }
       // all TMEM reads of this accumulator have completed (last tmem_ld_wait_regs) -> release it
       tc_fence_before();
       __syncwarp();
@@ -430,9 +556,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 // -------------------------------------------------------------------------------------------------
 int gemm_smem_bytes() { return Cfg<GEMM_OUT_F32>::kSmemBytes; }
 
-template <int kTerms, int kOut, int kGelu, int kLayout = GEMM_NT>
+template <int kTerms, int kOut, int kGelu, int kLayout = GEMM_NT, int kEpi = GEMM_EPI_PLAIN>
 static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sms) {
-  auto kern = gemm_tcgen05_kernel<kTerms, kOut, kGelu, kLayout>;
+  auto kern = gemm_tcgen05_kernel<kTerms, kOut, kGelu, kLayout, kEpi>;
   constexpr int smem = Cfg<kOut>::kSmemBytes;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -465,8 +591,8 @@ static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sm
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, g.tm_a, g.tm_b, g.tm_out, g.bias, m_tiles, n_tiles,
-                            k_blocks, g.a_plane_rows, g.b_plane_rows, g.out_plane_rows, g.drop);
+  return cudaLaunchKernelEx(&cfg, kern, g.tm_a, g.tm_b, g.tm_out, g.tm_out2, g.bias, m_tiles, n_tiles,
+                            k_blocks, g.a_plane_rows, g.b_plane_rows, g.out_plane_rows, g.drop, g.epi);
 }
 
 cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_sms) {
@@ -486,6 +612,21 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
     return cudaErrorInvalidValue;
   }
   if (g.layout != GEMM_NT) return cudaErrorInvalidValue;
+  if (g.epilogue == GEMM_EPI_NORM_A) {
+    if (g.terms == 1 && g.out_kind == GEMM_OUT_BF16 && g.gelu == 0)
+      return launch_one<1, GEMM_OUT_BF16, 0, GEMM_NT, GEMM_EPI_NORM_A>(g, stream, num_sms);
+    if (g.terms == 1 && g.out_kind == GEMM_OUT_BF16 && g.gelu == 2)
+      return launch_one<1, GEMM_OUT_BF16, 2, GEMM_NT, GEMM_EPI_NORM_A>(g, stream, num_sms);
+    return cudaErrorInvalidValue;
+  }
+  if (g.epilogue == GEMM_EPI_RESID) {
+    if (g.terms == 1 && g.out_kind == GEMM_OUT_F32_BF16 && g.gelu == 0 && g.n == kHidden)
+      return launch_one<1, GEMM_OUT_F32_BF16, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
+    if (g.terms == 1 && g.out_kind == GEMM_OUT_F32_BF16_DIRECT && g.gelu == 0 && g.n == kHidden)
+      return launch_one<1, GEMM_OUT_F32_BF16_DIRECT, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
+    return cudaErrorInvalidValue;
+  }
+  if (g.epilogue != GEMM_EPI_PLAIN) return cudaErrorInvalidValue;
 #define STLT_GEMM_CASE(T, O, G) \
   if (g.terms == T && g.out_kind == O && g.gelu == G) return launch_one<T, O, G>(g, stream, num_sms);
   STLT_GEMM_CASE(1, GEMM_OUT_F32, 0)

@@ -29,6 +29,10 @@ struct LayerWeights {
   const float *n1_g = nullptr, *n1_b = nullptr, *n2_g = nullptr, *n2_b = nullptr;
   // packed bf16 planes (inside the caller-provided packed buffer)
   const __nv_bfloat16 *in_p = nullptr, *out_p = nullptr, *l1_p = nullptr, *l2_p = nullptr;
+  // fused-LayerNorm path (bf16 inference): in-projection folded with the PREVIOUS layer's norm2 (null for
+  // the first layer of a stack), linear1 folded with this layer's norm1; s / c epilogue vectors
+  const __nv_bfloat16 *in_f = nullptr, *l1_f = nullptr;
+  const float *in_s = nullptr, *in_c = nullptr, *l1_s = nullptr, *l1_c = nullptr;
 };
 
 struct Weights {
@@ -87,6 +91,7 @@ struct Handle {
   float* cap_tm_x = nullptr;
   __nv_bfloat16* cap_tm_xb = nullptr;
   // optional per-category timing (CUDA events on the launching stream)
+  bool fused_ln = true;     // bf16 mode: LayerNorm folded into the GEMM epilogues (stlt_set_fused_ln)
   bool bf16_branch = true;  // bf16 mode: out-projection / linear2 outputs travel as bf16 (see run_tail_part)
   bool pruning = true;  // run the row-wise tail of the last layer of each stack on the rows that are read
   bool profiling = false;
@@ -205,6 +210,52 @@ inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_r
   g.out_plane_rows = static_cast<int>(a_plane_rows);
   g.layout = GEMM_NT;
   g.drop = drop;
+  g.epilogue = GEMM_EPI_PLAIN;
+  g.epi = EpiArgs{};
+  g.tm_out2 = g.tm_out;
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
+  STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
+  h->launches++;
+  return STLT_OK;
+}
+
+// Projection GEMM with a fused-LayerNorm epilogue (bf16 inference path):
+//   GEMM_EPI_NORM_A: out bf16 [m_rows, n] = act(LN(z) W^T + b) from A = bf16(z) and gamma-folded weights
+//   GEMM_EPI_RESID : z_out fp32 [m_rows, 768] (+ bf16 copy zb_out) = (prev_norm ? LN(z_prev) : z_prev) + A W^T + bias
+inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const void* a, long long m_rows,
+                          const void* w, int n, int k, const float* bias, void* out, void* out_bf16, int gelu,
+                          const EpiArgs& epi) {
+  GemmArgs g{};
+  int rc = make_tm(h, &g.tm_a, a, 1, m_rows, k, 64, 128);
+  if (rc) return rc;
+  rc = make_tm(h, &g.tm_b, w, 1, n, k, 64, 128);
+  if (rc) return rc;
+  if (epilogue == GEMM_EPI_RESID) {
+    rc = make_tm(h, &g.tm_out, out, 0, m_rows, n, 32, 32);
+    if (rc) return rc;
+    rc = make_tm(h, &g.tm_out2, out_bf16, 1, m_rows, n, 64, 32);
+    // short reductions (out-projection) are paced by the epilogue's HBM traffic: TMA-staged bf16 copy;
+    // long ones (linear2) by the mainloop: spend the shared memory on a fifth stage instead
+    g.out_kind = k <= kHidden ? GEMM_OUT_F32_BF16 : GEMM_OUT_F32_BF16_DIRECT;
+  } else {
+    rc = make_tm(h, &g.tm_out, out, 1, m_rows, n, 64, 32);
+    g.tm_out2 = g.tm_out;
+    g.out_kind = GEMM_OUT_BF16;
+  }
+  if (rc) return rc;
+  g.bias = bias;
+  g.m_rows = static_cast<int>(m_rows);
+  g.n = n;
+  g.k = k;
+  g.terms = 1;
+  g.gelu = gelu;
+  g.a_plane_rows = static_cast<int>(m_rows);
+  g.b_plane_rows = n;
+  g.out_plane_rows = static_cast<int>(m_rows);
+  g.layout = GEMM_NT;
+  g.drop = DropCfg{0, 0, 1.f};
+  g.epilogue = epilogue;
+  g.epi = epi;
   ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
@@ -243,6 +294,9 @@ inline int run_gemm_grad(Handle* h, cudaStream_t stream, int layout, const void*
   g.gelu = 0;
   g.layout = layout;
   g.drop = DropCfg{0, 0, 1.f};
+  g.epilogue = GEMM_EPI_PLAIN;
+  g.epi = EpiArgs{};
+  g.tm_out2 = g.tm_out;
   ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * static_cast<double>(k));
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;

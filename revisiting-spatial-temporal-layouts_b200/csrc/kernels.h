@@ -15,6 +15,35 @@ enum GemmOutKind : int {
   GEMM_OUT_BF16 = 1,        // bf16 [M, N]
   GEMM_OUT_BF16_SPLIT = 2,  // bf16 hi plane [M, N] followed by lo plane [M, N]
   GEMM_OUT_BF16_DUAL = 3,   // bf16 act(z) [M, N] followed by bf16 z [M, N] (training: GELU input kept)
+  GEMM_OUT_F32_BF16 = 4,    // fp32 [M, N] (tm_out) and a bf16 copy [M, N] (tm_out2): fused-LayerNorm residual epilogue
+  // same outputs, the bf16 copy written straight from registers (ep.zb_out): one staging tile less per warp buys
+  // a fifth pipeline stage, which pays for long reductions (linear2, K = 3072)
+  GEMM_OUT_F32_BF16_DIRECT = 5,
+};
+
+// LayerNorm fused into the projection GEMMs (bf16 inference path, see DESIGN.md "fused LayerNorm"): the
+// residual stream is kept PRE-norm (z, fp32 + a bf16 copy) together with per-row (sum, sum of squares).
+enum GemmEpilogue : int {
+  GEMM_EPI_PLAIN = 0,
+  // A = bf16(z) un-normalised, W pre-multiplied by gamma: out = act(rstd * (acc - mean * s[n]) + c[n]),
+  // s[n] = sum_k (W gamma)[n,k], c[n] = (W beta)[n] + bias[n]  ==  act(LN(z) W^T + bias)
+  GEMM_EPI_NORM_A = 1,
+  // z_new = (prev_norm ? LN(z_prev) : z_prev) + acc + bias[n]; writes z_new (fp32 + bf16) and adds the row's
+  // (sum, sum of squares) over this CTA's columns to stats_out. N must be 768 (the LayerNorm width).
+  GEMM_EPI_RESID = 2,
+};
+
+constexpr int kStatSlots = 6;  // 768 columns / 128-column slabs: partial row statistics per slab
+
+struct EpiArgs {
+  const float2* stats_in;  // [M][kStatSlots]; NORM_A: stats of the A rows; RESID: of the z_prev rows (prev_norm only)
+  const float* vec_a;      // NORM_A: s[N]; RESID: gamma of the LayerNorm applied to z_prev
+  const float* vec_b;      // NORM_A: c[N]; RESID: beta of that LayerNorm
+  const float* z_prev;     // RESID: fp32 [M, 768]; may alias the fp32 output (in place)
+  float2* stats_out;       // RESID: [M][kStatSlots], every slot is written (no zeroing needed)
+  __nv_bfloat16* zb_out;   // RESID: bf16 copy of the new z [M, 768]
+  float eps;
+  int prev_norm;
 };
 
 enum GemmLayout : int {
@@ -39,6 +68,9 @@ struct GemmArgs {
   int out_plane_rows;  // row offset of the lo plane of the output (split only)
   int layout;          // GemmLayout; MN-major operands use box {64, 64} tensor maps
   DropCfg drop;        // dropout on the activated output (GEMM_OUT_BF16_DUAL only; thr16 = 0: off)
+  int epilogue;        // GemmEpilogue
+  EpiArgs epi;
+  CUtensorMap tm_out2; // bf16 [M, N] box {64, 32} (GEMM_OUT_F32_BF16 only)
 };
 
 int gemm_smem_bytes();
@@ -113,7 +145,8 @@ cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* f
                                const float* pos_table, const float* ft_table, int n_frame_types,
                                const float* ln_g, const float* ln_b, float eps, int B, int L,
                                ActOut out, int* err_flag, cudaStream_t stream,
-                               DropCfg drop = DropCfg{0, 0, 1.f});
+                               DropCfg drop = DropCfg{0, 0, 1.f}, const float* pre_g = nullptr,
+                               const float* pre_b = nullptr, float pre_eps = 0.f);
 
 // K9: h[b] = x[b * L + lengths[b] - 1] (src/modelling/models.py:189-192).
 cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, int L, float* out,
@@ -123,7 +156,8 @@ cudaError_t launch_gather_last(const float* x, const long long* lengths, int B, 
 cudaError_t launch_gather_rows(const float* src_x, const __nv_bfloat16* src_att, int planes,
                                long long src_plane_rows, int stride, const long long* lengths, int L,
                                long long rows, float* dst_x, __nv_bfloat16* dst_att,
-                               long long dst_plane_rows, int* err_flag, cudaStream_t stream);
+                               long long dst_plane_rows, int* err_flag, cudaStream_t stream,
+                               const float2* src_stats = nullptr, float2* dst_stats = nullptr);
 
 // K3: masked multi-head attention over short sequences held in shared memory.
 //   qkv: [tokens, 2304] fp32 (fp32-parity mode; bf16 input is handled by launch_attention_mma); key j of a sequence is masked when mask_src[token_j] == 0,
@@ -140,6 +174,10 @@ cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
                                  __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream,
                                  DropCfg drop = DropCfg{0, 0, 1.f});
+
+// gamma-folded bf16 weights + the two epilogue vectors of GEMM_EPI_NORM_A (see GemmEpilogue).
+cudaError_t launch_pack_folded(const float* w, const float* gamma, const float* beta, const float* bias, int n,
+                               int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream);
 
 // fp32 -> bf16 plane(s) for weights.
 cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,

@@ -104,6 +104,8 @@ struct WorkspacePlan {
   BufSet tm;  // temporal phase: B*L frame tokens (also the CLS-only tail of the last spatial layer)
   BufSet hd;  // B extract-frame tokens (tail of the last temporal layer)
   size_t off_err, off_head, total;
+  // fused-LayerNorm path: per-row (sum, sum of squares) accumulators of every LayerNorm site
+  size_t off_stats, stats_bytes;
 };
 
 size_t plan_bufset(BufSet* b, size_t off, long long rows, int precision, bool with_qkv) {
@@ -120,7 +122,7 @@ size_t plan_bufset(BufSet* b, size_t off, long long rows, int precision, bool wi
   return off;
 }
 
-WorkspacePlan plan_workspace(int B, int L, int S, int precision) {
+WorkspacePlan plan_workspace(int B, int L, int S, int precision, int ns = 0, int nt = 0) {
   WorkspacePlan p{};
   size_t off = 0;
   p.off_err = off;
@@ -130,6 +132,14 @@ WorkspacePlan plan_workspace(int B, int L, int S, int precision) {
   off = plan_bufset(&p.hd, off, B, precision, false);
   p.off_head = off;
   off += align1k(static_cast<size_t>(B) * kHidden * 4 * 3);
+  // fused-LayerNorm statistics (bf16 mode): 2 sites per spatial layer over the object tokens, 2 per temporal
+  // layer + 6 compaction sites over the frame tokens
+  p.off_stats = off;
+  p.stats_bytes = 0;
+  if (precision == STLT_PRECISION_BF16)
+    p.stats_bytes = (static_cast<size_t>(2 * ns) * p.sp.m_pad + static_cast<size_t>(2 * nt + 6) * p.tm.m_pad) *
+                    kStatSlots * sizeof(float2);
+  off += align1k(p.stats_bytes);
   p.total = off;
   return p;
 }
@@ -214,6 +224,89 @@ int run_tail_part(Handle* h, cudaStream_t stream, int precision, const LayerWeig
   return STLT_OK;
 }
 
+
+// ---- fused-LayerNorm forward (bf16 mode; DESIGN.md "LayerNorm fused into the GEMM epilogues") ----------
+// The residual stream of a stack is kept PRE-norm: ph.x holds z (fp32), ph.xb its bf16 copy, and a float2 per
+// row holds (sum, sum of squares) of z. `pending` describes the LayerNorm that still has to be applied to z
+// (null gamma: z is already a normalised activation, i.e. the embedding output).
+struct PendingNorm {
+  const float2* stats = nullptr;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+};
+
+// in-projection (+ deferred LayerNorm of its input) and attention over the full phase
+int fused_attention_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, const Phase& ph,
+                         const PendingNorm& in, const long long* mask_src, long long num_seqs, int T, bool causal) {
+  int rc;
+  if (in.gamma == nullptr) {
+    rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv, 1, GEMM_OUT_BF16, 0);
+  } else {
+    EpiArgs e{in.stats, lw.in_s, lw.in_c, nullptr, nullptr, nullptr, h->dims.encoder_norm_eps, 1};
+    rc = run_gemm_fused(h, stream, GEMM_EPI_NORM_A, ph.xb, ph.m_pad, lw.in_f, kQkv, kHidden, nullptr, ph.qkv, nullptr, 0, e);
+  }
+  if (rc) return rc;
+  ActOut att{nullptr, ph.att, 1, ph.m_pad};
+  {
+    ProfileScope prof(h, stream, STLT_PROF_ATTENTION);
+    STLT_CUDA(h, launch_attention(ph.qkv, true, mask_src, num_seqs, T, causal, att, stream));
+  }
+  h->launches++;
+  return STLT_OK;
+}
+
+// out-projection + residual, linear1 (+ LN1, GELU), linear2 + residual; LN2 stays pending (stats in s2)
+int fused_tail_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, const Phase& ph, const PendingNorm& in,
+                    float2* s1, float2* s2) {
+  const float eps = h->dims.encoder_norm_eps;
+  EpiArgs e1{in.stats, in.gamma, in.beta, ph.x, s1, ph.xb, eps, in.gamma != nullptr ? 1 : 0};
+  int rc = run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.att, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.x, ph.xb, 0, e1);
+  if (rc) return rc;
+  EpiArgs e2{s1, lw.l1_s, lw.l1_c, nullptr, nullptr, nullptr, eps, 1};
+  rc = run_gemm_fused(h, stream, GEMM_EPI_NORM_A, ph.xb, ph.m_pad, lw.l1_f, kFfn, kHidden, nullptr, ph.hid, nullptr, 2, e2);
+  if (rc) return rc;
+  EpiArgs e3{s1, lw.n1_g, lw.n1_b, ph.x, s2, ph.xb, eps, 1};
+  return run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.hid, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.x, ph.xb, 0, e3);
+}
+
+// One stack of post-norm encoder layers; the last layer's row-wise tail runs on the compacted rows of `tail`
+// (gathered with `stride` / `lengths`). On return tail.x holds the PRE-norm output of the stack on those rows
+// and *out the LayerNorm still to be applied to it.
+int fused_stack(Handle* h, cudaStream_t stream, const std::vector<LayerWeights>& layers, const Phase& full,
+                const Phase& tail, const long long* mask_src, long long num_seqs, int T, bool causal, int stride,
+                const long long* lengths, int L, float2* stats_full, float2* stats_tail, int* err_flag,
+                PendingNorm* out) {
+  const int n = static_cast<int>(layers.size());
+  PendingNorm pending;  // layer 0 reads the (already normalised) embedding output
+  for (int i = 0; i < n; ++i) {
+    const LayerWeights& lw = layers[i];
+    int rc = fused_attention_part(h, stream, lw, full, pending, mask_src, num_seqs, T, causal);
+    if (rc) return rc;
+    if (i < n - 1) {
+      float2* s1 = stats_full + static_cast<size_t>(2 * i) * full.m_pad * kStatSlots;
+      float2* s2 = s1 + full.m_pad * kStatSlots;
+      rc = fused_tail_part(h, stream, lw, full, pending, s1, s2);
+      if (rc) return rc;
+      pending = PendingNorm{s2, lw.n2_g, lw.n2_b};
+    } else {
+      float2* sc_in = stats_tail;
+      float2* sc1 = stats_tail + tail.m_pad * kStatSlots;
+      float2* sc2 = sc1 + tail.m_pad * kStatSlots;
+      {
+        ProfileScope prof(h, stream, STLT_PROF_OTHER);
+        STLT_CUDA(h, launch_gather_rows(full.x, full.att, 1, full.m_pad, stride, lengths, L, tail.m_valid, tail.x,
+                                        tail.att, tail.m_pad, err_flag, stream, pending.stats, sc_in));
+      }
+      h->launches++;
+      PendingNorm tail_in{pending.gamma ? sc_in : nullptr, pending.gamma, pending.beta};
+      rc = fused_tail_part(h, stream, lw, tail, tail_in, sc1, sc2);
+      if (rc) return rc;
+      *out = PendingNorm{sc2, lw.n2_g, lw.n2_b};
+    }
+  }
+  return STLT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -294,6 +387,8 @@ int stlt_packed_weights_bytes(void* handle, int32_t precision, size_t* bytes) {
   const size_t per_layer = static_cast<size_t>(kHidden) * (kQkv + kHidden + 2 * kFfn);
   const size_t layers = h->dims.num_spatial_layers + h->dims.num_temporal_layers;
   *bytes = layers * per_layer * planes * 2;
+  if (precision == STLT_PRECISION_BF16)  // fused-LayerNorm copies: folded in-proj / linear1 + their s, c vectors
+    *bytes += layers * (static_cast<size_t>(kHidden) * (kQkv + kFfn) * 2 + static_cast<size_t>(kQkv + kFfn) * 2 * 4);
   return STLT_OK;
 }
 
@@ -326,6 +421,38 @@ int stlt_pack_weights(void* handle, void* stream_, int32_t precision, void* pack
   };
   for (auto& lw : h->w.spatial) STLT_CUDA(h, pack_layer(lw));
   for (auto& lw : h->w.temporal) STLT_CUDA(h, pack_layer(lw));
+  if (precision == STLT_PRECISION_BF16) {
+    // fused-LayerNorm section (see GemmEpilogue): per layer [in_f | l1_f] bf16, then [in_s in_c l1_s l1_c] f32
+    auto fold_stack = [&](std::vector<LayerWeights>& stack) -> cudaError_t {
+      for (size_t i = 0; i < stack.size(); ++i) {
+        LayerWeights& lw = stack[i];
+        __nv_bfloat16* in_f = cur;
+        __nv_bfloat16* l1_f = in_f + static_cast<size_t>(kQkv) * kHidden;
+        float* vec = reinterpret_cast<float*>(l1_f + static_cast<size_t>(kFfn) * kHidden);
+        cur = reinterpret_cast<__nv_bfloat16*>(vec + 2 * (kQkv + kFfn));
+        lw.in_f = nullptr;
+        lw.in_s = lw.in_c = nullptr;
+        cudaError_t e;
+        if (i > 0) {  // the in-projection reads LN2 of the previous layer
+          const LayerWeights& prev = stack[i - 1];
+          e = launch_pack_folded(lw.in_w, prev.n2_g, prev.n2_b, lw.in_b, kQkv, kHidden, in_f, vec, vec + kQkv, stream);
+          if (e != cudaSuccess) return e;
+          lw.in_f = in_f;
+          lw.in_s = vec;
+          lw.in_c = vec + kQkv;
+        }
+        float* v1 = vec + 2 * kQkv;
+        e = launch_pack_folded(lw.l1_w, lw.n1_g, lw.n1_b, lw.l1_b, kFfn, kHidden, l1_f, v1, v1 + kFfn, stream);
+        if (e != cudaSuccess) return e;
+        lw.l1_f = l1_f;
+        lw.l1_s = v1;
+        lw.l1_c = v1 + kFfn;
+      }
+      return cudaSuccess;
+    };
+    STLT_CUDA(h, fold_stack(h->w.spatial));
+    STLT_CUDA(h, fold_stack(h->w.temporal));
+  }
   h->packed_precision = precision;
   h->packed_ptr = packed;
   return STLT_OK;
@@ -336,7 +463,7 @@ int stlt_workspace_bytes(void* handle, int32_t B, int32_t L, int32_t S, int32_t 
   Handle* h = static_cast<Handle*>(handle);
   if (!h || !bytes) return fail(h, STLT_ERR_INVALID, "null argument");
   if (B < 0 || L < 1 || S < 1) return fail(h, STLT_ERR_INVALID, "invalid batch shape");
-  *bytes = plan_workspace(B, L, S, precision).total;
+  *bytes = plan_workspace(B, L, S, precision, h->dims.num_spatial_layers, h->dims.num_temporal_layers).total;
   return STLT_OK;
 }
 
@@ -428,7 +555,7 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     return fail(h, STLT_ERR_INVALID, "null tensor pointer");
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
     return fail(h, STLT_ERR_INVALID, "workspace must be 1024-byte aligned");
-  const WorkspacePlan p = plan_workspace(B, L, S, precision);
+  const WorkspacePlan p = plan_workspace(B, L, S, precision, d.num_spatial_layers, d.num_temporal_layers);
   if (workspace_bytes < p.total)
     return fail(h, STLT_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, p.total);
   if (p.sp.m_pad > 0x7fffffffLL / 2) return fail(h, STLT_ERR_INVALID, "batch too large for one call");
@@ -460,6 +587,58 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   const bool prune_sp = h->pruning && h->taps.spatial == nullptr && d.num_spatial_layers > 0;
   const bool prune_tm = h->pruning && h->taps.temporal == nullptr && h->cap_tm_x == nullptr &&
                         d.num_temporal_layers > 0;
+
+  const bool fused = !fp32 && h->fused_ln && h->pruning && d.num_spatial_layers > 0 && d.num_temporal_layers > 0 &&
+                     h->taps.embed == nullptr && h->taps.spatial == nullptr && h->taps.frames == nullptr &&
+                     h->taps.temporal == nullptr && h->taps.pooled == nullptr && h->cap_tm_x == nullptr &&
+                     h->w.spatial[0].l1_f != nullptr;
+  if (fused) {
+    // ---- bf16 path with LayerNorm folded into the GEMM epilogues (no add_ln launches) ----
+    float2* stats = reinterpret_cast<float2*>(ws + p.off_stats);
+    float2* st_sp = stats;
+    float2* st_tm = st_sp + static_cast<size_t>(2 * d.num_spatial_layers) * p.sp.m_pad * kStatSlots;
+    float2* st_c_sp = st_tm + static_cast<size_t>(2 * d.num_temporal_layers) * p.tm.m_pad * kStatSlots;  // 3 compaction sites
+    float2* st_c_tm = st_c_sp + 3 * p.tm.m_pad * kStatSlots;                                               // 3 more (B rows)
+    ActOut emb{sp.x, sp.xb, 1, sp.m_pad};
+    {
+      ProfileScope prof(h, stream, STLT_PROF_OTHER);
+      STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories, h->w.box_w, h->w.box_b,
+                                h->w.score_w, h->w.score_b, h->w.emb_g, h->w.emb_b, d.layer_norm_eps, n_sp, emb,
+                                err_flag, stream));
+    }
+    h->launches++;
+    PendingNorm sp_out;
+    int rc = fused_stack(h, stream, h->w.spatial, sp, tm, categories, n_tm, S, false, S, nullptr, 0, st_sp, st_c_sp,
+                         err_flag, &sp_out);
+    if (rc) return rc;
+    {
+      ProfileScope prof(h, stream, STLT_PROF_OTHER);
+      ActOut fr{tm.x, tm.xb, 1, tm.m_pad};
+      // the spatial stack's LayerNorm-2 is applied on the fly (row statistics recomputed in registers)
+      STLT_CUDA(h, launch_frame_embed(tm.x, 1, frame_types, h->w.pos_table, h->w.ft_table, d.num_frame_types,
+                                      h->w.fr_g, h->w.fr_b, d.layer_norm_eps, B, L, fr, err_flag, stream,
+                                      DropCfg{0, 0, 1.f}, sp_out.gamma, sp_out.beta, d.encoder_norm_eps));
+    }
+    h->launches++;
+    PendingNorm tm_out;
+    rc = fused_stack(h, stream, h->w.temporal, tm, hd, frame_types, B, L, true, 0, lengths, L, st_tm, st_c_tm, err_flag,
+                     &tm_out);
+    if (rc) return rc;
+    float* h1f = reinterpret_cast<float*>(ws + p.off_head);
+    float* h2f = h1f + static_cast<size_t>(B) * kHidden;
+    float* pooledf = h2f + static_cast<size_t>(B) * kHidden;
+    {
+      ProfileScope prof(h, stream, STLT_PROF_OTHER);
+      ActOut po{pooledf, nullptr, 1, 0};
+      STLT_CUDA(h, launch_add_ln(hd.x, nullptr, tm_out.gamma, tm_out.beta, d.encoder_norm_eps, B, po, stream));
+      STLT_CUDA(h, launch_gemm_simt(pooledf, h->w.fc1_w, h->w.fc1_b, h1f, B, kHidden, kHidden, true, stream));
+      ActOut ho{h2f, nullptr, 1, 0};
+      STLT_CUDA(h, launch_add_ln(h1f, nullptr, h->w.head_g, h->w.head_b, d.layer_norm_eps, B, ho, stream));
+      STLT_CUDA(h, launch_gemm_simt(h2f, h->w.fc2_w, h->w.fc2_b, logits, B, d.num_classes, kHidden, false, stream));
+      h->launches += 4;
+    }
+    return STLT_OK;
+  }
 
   ActOut emb{sp.x, sp.xb, planes, sp.m_pad};
   {
@@ -555,6 +734,13 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     STLT_CUDA(h, launch_gemm_simt(h2, h->w.fc2_w, h->w.fc2_b, logits, B, d.num_classes, kHidden, false, stream));
     h->launches++;
   }
+  return STLT_OK;
+}
+
+int stlt_set_fused_ln(void* handle, int32_t enable) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  h->fused_ln = enable != 0;
   return STLT_OK;
 }
 

@@ -221,6 +221,7 @@ class Stlt(nn.Module):
         self._handle = handle
         self._handle_device = device
         _lib.check(handle, lib.stlt_set_pruning(handle, int(self._pruning)))
+        _lib.check(handle, lib.stlt_set_fused_ln(handle, int(getattr(self, "_fused_ln", True))))
         self._weights_key = None
         self._packed.clear()
         self._packed_key.clear()
@@ -464,6 +465,12 @@ class Stlt(nn.Module):
         self._pruning = bool(enable)
         if self._handle is not None:
             _lib.check(self._handle, _lib.load_library().stlt_set_pruning(self._handle, int(self._pruning)))
+
+    def set_fused_layer_norm(self, enable: bool) -> None:
+        """bf16 mode: LayerNorm folded into the GEMM epilogues (default on). Off = separate add+LN kernels."""
+        self._fused_ln = bool(enable)
+        if self._handle is not None:
+            _lib.check(self._handle, _lib.load_library().stlt_set_fused_ln(self._handle, int(self._fused_ln)))
 
     def set_profiling(self, enable: bool) -> None:
         """Per-category CUDA-event timing of the kernels launched by forward (bench / profiles)."""

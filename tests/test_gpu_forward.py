@@ -162,6 +162,7 @@ def test_last_layer_pruning_is_bit_identical(precision):
     sd = random_state_dict(Stlt(cfg).state_dict(), seed=61)
     m = _model(cfg, sd, precision)
     batch = to_cuda(make_batch(37, "action_genome", ragged=True, seed=62))
+    m.set_fused_layer_norm(False)  # the LayerNorm-fused bf16 path only exists in its pruned form
     with torch.no_grad():
         pruned = m(batch)["stlt"].clone()
         n_pruned = m.last_launch_count()
@@ -327,3 +328,32 @@ def test_cuda_graph_replay_matches_eager(precision):
     end.record()
     torch.cuda.synchronize()
     print(f"batch-8 forward {precision}: graph {g_ms:.3f} ms, eager {start.elapsed_time(end) / 50:.3f} ms")
+
+
+@pytest.mark.parametrize("layout", ["something", "action_genome"])
+def test_fused_layer_norm_path_matches_unfused_and_oracle(layout):
+    """bf16 mode folds the encoder LayerNorms into the GEMM epilogues (pre-norm residual stream + row
+    statistics). A/B against the separate add+LN kernels and against the oracle on the golden case."""
+    import stlt_b200
+    from oracle import stlt_oracle
+    from tests.util import golden_model_case, nerr, to_cuda
+    cfg, sd, batch, g = golden_model_case(layout)
+    model = stlt_b200.Stlt(cfg, precision="bf16")
+    model.load_state_dict(sd)
+    model = model.cuda()
+    model.train(False)
+    gb = to_cuda(batch)
+    with torch.no_grad():
+        model.set_fused_layer_norm(True)
+        fused = model(gb)["stlt"].float().cpu()
+        n_fused = model.last_launch_count()
+        model.set_fused_layer_norm(False)
+        plain = model(gb)["stlt"].float().cpu()
+        n_plain = model.last_launch_count()
+        want = stlt_oracle.stlt_forward(sd, batch)
+    print(layout, "fused vs oracle", nerr(fused, want), "plain vs oracle", nerr(plain, want), "fused vs plain",
+          nerr(fused, plain), "launches", n_fused, n_plain)
+    assert n_fused == n_plain - 23  # 24 residual + LayerNorm launches gone, one LayerNorm of the pooled rows added
+    assert nerr(fused, want) < 2e-2 and nerr(plain, want) < 2e-2
+    assert torch.equal(fused.argmax(-1), want.argmax(-1))
+    assert nerr(fused, torch.from_numpy(g["logits"])) < 2e-2
