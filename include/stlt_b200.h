@@ -148,6 +148,17 @@ int stlt_build_batch(void* handle, void* stream, const StltLayoutStore* store, c
 int stlt_topk_count(void* handle, void* stream, const float* logits, const int64_t* labels, int32_t rows,
                     int32_t classes, uint64_t* counters);
 
+/* §8(f) rank 4, multi-label head — replaces EvaluatorActionGenome.process (src/utils/evaluation.py:76-83):
+ * predictions_out[r] = sigmoid(logits[r]), ground_truths_out[r] = labels[r] for `rows` rows (the caller passes
+ * the write position inside its [total_instances, classes] device buffers), no synchronisation. */
+int stlt_map_accumulate(void* handle, void* stream, const float* logits, const float* labels, int32_t rows,
+                        int32_t classes, float* predictions_out, float* ground_truths_out);
+/* Replaces charades_map / map (src/utils/evaluation.py:100-132) on the device: per-class average precision
+ * (f64 [classes]; nan for a class without positives) and their mean (f64 [1], np.mean semantics). Rows whose
+ * ground truth is all zero rank last (-inf). At most 32768 instances. */
+int stlt_charades_map(void* handle, void* stream, const float* predictions, const float* ground_truths,
+                      int32_t instances, int32_t classes, double* ap_out, double* map_out);
+
 /* Replaces Stlt.forward (models.py:185-195) in eval mode.
  *   categories i64 [B, L, S]; boxes f32 [B, L, S, 4]; scores f32 [B, L, S] or NULL (presence
  *   toggles the score embedding, models.py:33-35); frame_types i64 [B, L]; lengths i64 [B].

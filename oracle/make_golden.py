@@ -271,6 +271,29 @@ def golden_cacnf(configs, models, batch_size: int, weight_seed: int, batch_seed:
     print("cacnf_something.npz", {k: float(v.abs().max()) for k, v in out.items()}, "entries", len(own))
 
 
+def golden_charades_map():
+    """The reference's own charades_map (src/utils/evaluation.py:126-132) on seeded scores / multi-hot labels,
+    including videos without labels (the -inf fix) and one class without positives (nan)."""
+    from utils import evaluation
+    if not hasattr(np, "NINF"):  # the reference targets numpy < 2 (evaluation.py:130 uses np.NINF)
+        np.NINF = -np.inf
+    g = torch.Generator().manual_seed(31)
+    n, c = 777, 157
+    logits = torch.randn((n, c), generator=g) * 2
+    labels = (torch.rand((n, c), generator=g) < 0.04).float()
+    labels[::13] = 0          # videos without any action
+    labels[:, 5] = 0          # a class that never occurs
+    pred = torch.sigmoid(logits).numpy().astype(np.float64)
+    m_ap, _, aps = evaluation.charades_map(pred, labels.numpy().astype(np.float64))
+    labels2 = labels.clone()
+    labels2[:, 5] = (torch.rand(n, generator=g) < 0.1).float()
+    labels2[::13] = 0
+    m_ap2, _, aps2 = evaluation.charades_map(pred, labels2.numpy().astype(np.float64))
+    np.savez_compressed(GOLDEN / "charades_map.npz", logits=logits.numpy(), labels=labels.numpy(), labels2=labels2.numpy(),
+                        map=np.float64(m_ap), aps=aps, map2=np.float64(m_ap2), aps2=aps2)
+    print("charades_map.npz", m_ap, m_ap2)
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     configs, datasets, models, data_utils = import_reference()
@@ -280,6 +303,7 @@ def main():
     golden_model(configs, models, "something", batch_size=3, weight_seed=1, batch_seed=3)
     golden_model(configs, models, "action_genome", batch_size=2, weight_seed=2, batch_seed=4)
     golden_cacnf(configs, models, batch_size=3, weight_seed=8, batch_seed=9)
+    golden_charades_map()
     from utils import train_inference_utils as train_utils
     golden_training(configs, models, train_utils, "something", batch_size=4, weight_seed=5, batch_seed=6)
     golden_training(configs, models, train_utils, "action_genome", batch_size=2, weight_seed=6, batch_seed=7)

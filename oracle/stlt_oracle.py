@@ -457,3 +457,28 @@ def cacnf_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], f
     logits_caf = _head(fused, sd, "fusion_classifier.", layer_norm_eps)
     logits = (logits_stlt, logits_app, logits_caf)
     return {"stlt": logits_stlt, "resnet3d": logits_app, "caf": logits_caf, "ensemble": sum(logits) / 3}
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-label evaluation: src/utils/evaluation.py:100-132
+# ---------------------------------------------------------------------------------------------------
+def charades_map(predictions, ground_truths):
+    """charades_map + map (evaluation.py:100-132) restated with numpy: rows without any positive label are
+    ranked last (-inf), per class AP = mean over positives of (positives so far / rank), classes without
+    positives give nan (and np.mean then makes the mAP nan). Returns (mAP, per-class AP)."""
+    import numpy as np
+    pred = np.array(predictions, dtype=np.float64, copy=True)
+    gt = np.asarray(ground_truths, dtype=np.float64)
+    pred[gt.sum(axis=1) == 0, :] = -np.inf
+    aps = []
+    for c in range(pred.shape[1]):
+        order = np.argsort(-pred[:, c])
+        tp = gt[order, c] == 1
+        n_pos = int(tp.sum())
+        if n_pos < 1:
+            aps.append(float("nan"))
+            continue
+        ranks = np.arange(1, len(tp) + 1, dtype=np.float64)
+        aps.append(float((np.cumsum(tp)[tp] / ranks[tp]).sum() / n_pos))
+    aps = np.array(aps)
+    return float(np.mean(aps)), aps

@@ -121,6 +121,12 @@ cudaError_t launch_build_batch(const BatchStore& st, const long long* video_inde
 cudaError_t launch_topk_count(const float* logits, const long long* labels, int rows, int classes,
                               unsigned long long* counters, cudaStream_t stream);
 
+// Multi-label evaluator (src/utils/evaluation.py:61-132): sigmoid + label accumulation, Charades mAP.
+cudaError_t launch_map_accumulate(const float* logits, const float* labels, long long n, float* pred, float* gt,
+                                  cudaStream_t stream);
+cudaError_t launch_charades_map(const float* pred, const float* gt, int n, int classes, double* ap_out,
+                                double* map_out, cudaStream_t stream);
+
 // K1: category + box (+score) embedding and LayerNorm (src/modelling/models.py:29-39).
 cudaError_t launch_embed(const long long* categories, const float* boxes, const float* scores,
                          const float* cat_table, int unique_categories, const float* box_w,

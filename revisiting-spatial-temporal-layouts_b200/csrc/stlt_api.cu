@@ -531,6 +531,30 @@ int stlt_topk_count(void* handle, void* stream, const float* logits, const int64
   return STLT_OK;
 }
 
+int stlt_map_accumulate(void* handle, void* stream, const float* logits, const float* labels, int32_t rows,
+                        int32_t classes, float* predictions_out, float* ground_truths_out) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  if (rows < 0 || classes < 1) return fail(h, STLT_ERR_INVALID, "invalid shape");
+  if (rows == 0) return STLT_OK;
+  if (!logits || !labels || !predictions_out || !ground_truths_out) return fail(h, STLT_ERR_INVALID, "null pointer");
+  STLT_CUDA(h, launch_map_accumulate(logits, labels, static_cast<long long>(rows) * classes, predictions_out,
+                                     ground_truths_out, static_cast<cudaStream_t>(stream)));
+  return STLT_OK;
+}
+
+int stlt_charades_map(void* handle, void* stream, const float* predictions, const float* ground_truths,
+                      int32_t instances, int32_t classes, double* ap_out, double* map_out) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  if (!predictions || !ground_truths || !ap_out || !map_out) return fail(h, STLT_ERR_INVALID, "null pointer");
+  if (instances < 1 || instances > 32768 || classes < 1)
+    return fail(h, STLT_ERR_INVALID, "instances must be in [1, 32768] (one shared-memory sort per class)");
+  STLT_CUDA(h, launch_charades_map(predictions, ground_truths, instances, classes, ap_out, map_out,
+                                   static_cast<cudaStream_t>(stream)));
+  return STLT_OK;
+}
+
 int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* categories_,
                  const float* boxes, const float* scores, const int64_t* frame_types_,
                  const int64_t* lengths_, int32_t B, int32_t L, int32_t S, void* workspace,

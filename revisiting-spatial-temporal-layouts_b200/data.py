@@ -155,3 +155,60 @@ class TopKCounter:
         top1, top5 = self.counters.tolist()  # the only synchronisation
         return {f"{name}_top1_accuracy": top1 / self.total_instances,
                 f"{name}_top5_accuracy": top5 / self.total_instances}
+
+
+class CharadesMapEvaluator:
+    """Device-resident EvaluatorActionGenome (reference src/utils/evaluation.py:61-98): ``process`` appends
+    sigmoid(logits) and the multi-hot labels to device buffers without synchronising, ``evaluate`` runs the
+    Charades mAP (evaluation.py:100-132) on the device and reads back one number."""
+
+    def __init__(self, total_instances: int, total_classes: int, logit_names=("stlt",), device="cuda"):
+        self.total_instances, self.total_classes, self.logit_names = total_instances, total_classes, logit_names
+        self.device = torch.device(device)
+        self.predictions = torch.zeros((total_instances, total_classes), dtype=torch.float32, device=self.device)
+        self.ground_truths = torch.zeros((total_instances, total_classes), dtype=torch.float32, device=self.device)
+        self.best_mean_average_precision = 0.0
+        self.index = 0
+
+    def reset(self):
+        self.index = 0
+        self.predictions.zero_()
+        self.ground_truths.zero_()
+
+    def process(self, logits, labels: torch.Tensor) -> None:
+        x = logits["stlt"] if isinstance(logits, dict) else logits  # Action Genome only for STLT (evaluation.py:77)
+        if x.dtype != torch.float32 or x.device.type != "cuda":
+            raise TypeError("logits must be CUDA float32 [rows, classes]")
+        size = x.shape[0]
+        if self.index + size > self.total_instances:
+            raise ValueError("more rows than total_instances")
+        x = x.contiguous()
+        y = labels.to(device=self.device, dtype=torch.float32).contiguous()
+        lib = _lib.load_library()
+        with torch.cuda.device(self.device):
+            handle = _prep_handle(self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(handle, lib.stlt_map_accumulate(handle, stream, x.data_ptr(), y.data_ptr(), size,
+                                                       self.total_classes, self.predictions[self.index].data_ptr(),
+                                                       self.ground_truths[self.index].data_ptr()))
+        self.index += size
+
+    def evaluate(self) -> Dict[str, float]:
+        ap = torch.empty(self.total_classes, dtype=torch.float64, device=self.device)
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        lib = _lib.load_library()
+        with torch.cuda.device(self.device):
+            handle = _prep_handle(self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(handle, lib.stlt_charades_map(handle, stream, self.predictions.data_ptr(),
+                                                     self.ground_truths.data_ptr(), self.total_instances,
+                                                     self.total_classes, ap.data_ptr(), out.data_ptr()))
+        self.average_precisions = ap
+        return {"map": float(out.item())}  # the only synchronisation
+
+    def is_best(self) -> bool:
+        metrics = self.evaluate()
+        if metrics["map"] > self.best_mean_average_precision:
+            self.best_mean_average_precision = metrics["map"]
+            return True
+        return False

@@ -11,7 +11,7 @@ from .cacnf import Cacnf  # noqa: E402
 
 models_factory["cacnf"] = Cacnf
 from .prepare import prepare_layout_batch  # noqa: E402
-from .data import LayoutStore, TopKCounter  # noqa: E402
+from .data import CharadesMapEvaluator, LayoutStore, TopKCounter  # noqa: E402
 
-__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "Cacnf", "CacnfModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter",
+__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "Cacnf", "CacnfModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter", "CharadesMapEvaluator",
            "SOMETHING_ELSE", "ACTION_GENOME"]

@@ -104,3 +104,30 @@ def test_topk_counter_matches_reference_evaluator_semantics():
     assert m["stlt_top1_accuracy"] == top1 / 1000 and m["stlt_top5_accuracy"] == top5 / 1000
     counter.reset()
     assert counter.evaluate()["stlt_top1_accuracy"] == 0
+
+
+def test_charades_map_evaluator_matches_reference_golden():
+    """Device EvaluatorActionGenome: sigmoid + label accumulation over ragged batches, mAP on the device, vs
+    the reference's charades_map (tests/golden/charades_map.npz) and the oracle."""
+    import numpy as np
+    from oracle import stlt_oracle
+    from stlt_b200 import CharadesMapEvaluator
+    from tests.util import load_golden
+    g = load_golden("charades_map.npz")
+    logits, n = torch.from_numpy(g["logits"]).cuda(), g["logits"].shape[0]
+    for labels_key, map_key, aps_key in (("labels2", "map2", "aps2"), ("labels", "map", "aps")):
+        labels = torch.from_numpy(g[labels_key]).cuda()
+        ev = CharadesMapEvaluator(n, logits.shape[1])
+        i = 0
+        for size in (100, 1, 333, 343):
+            ev.process({"stlt": logits[i:i + size]}, labels[i:i + size])
+            i += size
+        assert i == n
+        got = ev.evaluate()["map"]
+        aps = ev.average_precisions.cpu().numpy()
+        want, want_aps = float(g[map_key]), g[aps_key]
+        assert np.allclose(aps, want_aps, rtol=1e-6, atol=0, equal_nan=True), np.nanmax(np.abs(aps - want_aps))
+        assert (np.isnan(got) and np.isnan(want)) or abs(got - want) < 1e-6
+        assert torch.equal(ev.ground_truths, labels)
+        assert float((ev.predictions - torch.sigmoid(logits)).abs().max()) < 2e-7
+    assert ev.is_best() is False  # nan mAP never counts as an improvement (nan > 0 is False), as in the reference

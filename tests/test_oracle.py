@@ -110,3 +110,17 @@ def test_live_reference_default_init_and_dataset():
         want = ref({k: v.clone() for k, v in batch.items()})["stlt"]
         got = O.stlt_forward(ref.state_dict(), batch)
     assert nerr(got, want) < 2e-5
+
+
+def test_oracle_charades_map_matches_reference_golden():
+    """oracle.charades_map vs the reference's charades_map output (tests/golden/charades_map.npz)."""
+    import numpy as np
+    from oracle import stlt_oracle
+    from tests.util import load_golden
+    g = load_golden("charades_map.npz")
+    pred = torch.sigmoid(torch.from_numpy(g["logits"])).numpy().astype(np.float64)
+    m_ap, aps = stlt_oracle.charades_map(pred, g["labels"])
+    assert np.isnan(m_ap) and np.isnan(g["map"])  # class 5 has no positives: np.mean propagates the nan
+    assert np.allclose(aps, g["aps"], rtol=1e-12, atol=0, equal_nan=True)
+    m_ap2, aps2 = stlt_oracle.charades_map(pred, g["labels2"])
+    assert abs(m_ap2 - float(g["map2"])) < 1e-12 and np.allclose(aps2, g["aps2"], rtol=1e-12)
