@@ -218,7 +218,7 @@ class FusedTrainStep:
             self._repack(stream)
         self._keepalive = (inputs, labels, d_logits, logits)
         self.last_logits = logits
-        return self._loss[0]
+        return self._loss[0].clone()  # a fresh device scalar: the accumulator is reused by the next step
 
     def _repack(self, stream: int) -> None:
         model, lib = self.model, _lib.load_library()
