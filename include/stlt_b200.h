@@ -262,8 +262,11 @@ int stlt_op_dropout_mask(void* handle, float dropout_p, uint64_t seed, int32_t s
 int stlt_loss(void* handle, void* stream, int32_t kind, const float* logits, const void* labels,
               int32_t rows, int32_t classes, float grad_scale, float* loss_out, float* d_logits_out);
 
-/* sumsq_inout[0] += sum(grads^2) over a flat fp32 buffer (the squared total norm of clip_grad_norm_). */
-int stlt_grad_sumsq(void* handle, void* stream, const float* grads, int64_t n, float* sumsq_inout);
+/* sumsq_out[0] = sum(grads^2) over a flat fp32 buffer (the squared total norm of clip_grad_norm_), reduced in
+ * a fixed order so that data-parallel ranks derive bit-identical clip coefficients from their all-reduced
+ * gradients. scratch: caller-owned device floats (up to 1184 are used). */
+int stlt_grad_sumsq(void* handle, void* stream, const float* grads, int64_t n, float* sumsq_out, float* scratch,
+                    int32_t scratch_floats);
 
 /* One AdamW step on flat fp32 buffers (torch.optim.AdamW semantics, decoupled weight decay, bias
  * correction for `step` >= 1). If sumsq is given, gradients are first scaled by

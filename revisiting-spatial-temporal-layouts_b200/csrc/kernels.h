@@ -232,7 +232,9 @@ cudaError_t launch_cross_entropy(const float* logits, const long long* labels, i
                                  float grad_scale, float* loss, float* d_logits, cudaStream_t stream);
 cudaError_t launch_bce_logits(const float* logits, const float* targets, long long n, float grad_scale,
                               float* loss, float* d_logits, cudaStream_t stream);
-cudaError_t launch_sumsq(const float* g, long long n, float* out, cudaStream_t stream);
+// out[0] = sum(g^2), deterministic (fixed reduction order); scratch: >= 1 floats, up to 1184 are used
+cudaError_t launch_sumsq(const float* g, long long n, float* out, float* scratch, int scratch_len,
+                         cudaStream_t stream);
 cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr,
                          float beta1, float beta2, float eps, float weight_decay, float bias_c1,
                          float bias_c2_sqrt, const float* sumsq, float max_norm, cudaStream_t stream);

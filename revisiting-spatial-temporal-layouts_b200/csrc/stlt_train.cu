@@ -571,11 +571,12 @@ int stlt_loss(void* handle, void* stream, int32_t kind, const float* logits, con
   return STLT_OK;
 }
 
-int stlt_grad_sumsq(void* handle, void* stream, const float* grads, int64_t n, float* sumsq_inout) {
+int stlt_grad_sumsq(void* handle, void* stream, const float* grads, int64_t n, float* sumsq_out, float* scratch,
+                    int32_t scratch_floats) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
-  if (n < 0 || !grads || !sumsq_inout) return fail(h, STLT_ERR_INVALID, "invalid argument");
-  STLT_CUDA(h, launch_sumsq(grads, n, sumsq_inout, static_cast<cudaStream_t>(stream)));
+  if (n < 0 || !grads || !sumsq_out || !scratch || scratch_floats < 1) return fail(h, STLT_ERR_INVALID, "invalid argument");
+  STLT_CUDA(h, launch_sumsq(grads, n, sumsq_out, scratch, scratch_floats, static_cast<cudaStream_t>(stream)));
   return STLT_OK;
 }
 

@@ -676,9 +676,11 @@ bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ ta
 // clip_grad_norm_ (src/train.py:129) + AdamW (torch.optim.AdamW as configured at src/train.py:102-104)
 // on flat fp32 buffers.
 // ------------------------------------------------------------------------------------------------
+// Deterministic two-stage reduction: data-parallel ranks must derive bit-identical clip coefficients from
+// their (identical, all-reduced) gradients, otherwise their parameters drift apart.
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float4* __restrict__ g, long long n4, const float* __restrict__ tail, int n_tail,
-             float* __restrict__ out) {
+sumsq_partial_kernel(const float4* __restrict__ g, long long n4, const float* __restrict__ tail, int n_tail,
+                     float* __restrict__ partials) {
   float s = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += gridDim.x * static_cast<long long>(blockDim.x)) {
@@ -693,7 +695,21 @@ sumsq_kernel(const float4* __restrict__ g, long long n4, const float* __restrict
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += part[i];
-    atomicAdd(out, t);
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_final_kernel(const float* __restrict__ partials, int count, float* __restrict__ out) {
+  __shared__ double part[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += 256) s += static_cast<double>(partials[i]);
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 256; ++i) t += part[i];
+    out[0] = static_cast<float>(t);
   }
 }
 
@@ -852,15 +868,20 @@ cudaError_t launch_bce_logits(const float* logits, const float* targets, long lo
   return cudaGetLastError();
 }
 
-cudaError_t launch_sumsq(const float* g, long long n, float* out, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  if ((reinterpret_cast<uintptr_t>(g) & 15) != 0) return cudaErrorInvalidValue;
+cudaError_t launch_sumsq(const float* g, long long n, float* out, float* scratch, int scratch_len,
+                         cudaStream_t stream) {
+  if (n == 0) return cudaMemsetAsync(out, 0, sizeof(float), stream);
+  if ((reinterpret_cast<uintptr_t>(g) & 15) != 0 || scratch_len < 1) return cudaErrorInvalidValue;
   const long long n4 = n / 4;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > scratch_len) blocks = scratch_len;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(g), n4, g + n4 * 4, static_cast<int>(n - n4 * 4), out);
+  sumsq_partial_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(g), n4, g + n4 * 4, static_cast<int>(n - n4 * 4), scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sumsq_final_kernel<<<1, 256, 0, stream>>>(scratch, static_cast<int>(blocks), out);
   return cudaGetLastError();
 }
 

@@ -132,6 +132,7 @@ class FusedTrainStep:
                 p.data = view
                 self.grad_views[name] = self.flat_grads[o:o + p.numel()].view(p.shape)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=device)
+        self._sumsq_scratch = torch.zeros(2048, dtype=torch.float32, device=device)
         self._loss = torch.zeros(1, dtype=torch.float32, device=device)
         self._bound_scores = None
 
@@ -198,9 +199,9 @@ class FusedTrainStep:
                 spatial()
             sumsq_ptr = None
             if self.clip_val is not None:
-                self._sumsq.zero_()
                 _lib.check(model._handle, lib.stlt_grad_sumsq(model._handle, stream, self.flat_grads.data_ptr(),
-                                                              self.total, self._sumsq.data_ptr()))
+                                                              self.total, self._sumsq.data_ptr(),
+                                                              self._sumsq_scratch.data_ptr(), self._sumsq_scratch.numel()))
                 sumsq_ptr = self._sumsq.data_ptr()
             lr = self.lr * self.lr_lambda(self.step_count - 1)
             for key in ("t_nd", "t_d", "s_nd", "s_d", "sc_nd", "sc_d"):

@@ -330,3 +330,21 @@ def test_training_converges_on_a_learnable_synthetic_task():
     print("loss first/last 5:", losses[:5].tolist(), losses[-5:].tolist())
     assert torch.isfinite(losses).all()
     assert losses[-5:].mean() < 0.5 * losses[:5].mean()
+
+
+def test_two_gpu_data_parallel_step_equals_single_process(tmp_path):
+    """NCCL data parallelism (mean over the GLOBAL batch: 1/world folded into d loss, SUM all-reduce in two
+    buckets): after 3 steps two ranks on half batches hold the parameters of one process on the whole batch."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = Path(__file__).resolve().parent / "dp_worker.py"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29547", str(worker)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "DP_OK" in res.stdout
