@@ -424,7 +424,7 @@ def run_cacnf(args, rank, local_rank, world, torch, dist):
     from stlt_b200.synthetic import make_appearance_features, make_batch, random_state_dict
     cfg = stlt_b200.CacnfModelConfig(num_classes=174, unique_categories=4)
     torch.manual_seed(0)
-    model = stlt_b200.Cacnf(cfg)
+    model = stlt_b200.Cacnf(cfg, precision=args.dtype)
     model.load_state_dict(random_state_dict(model.state_dict(), seed=0))
     model = model.to("cuda")
     model.train(False)
@@ -500,7 +500,8 @@ def run_cacnf(args, rank, local_rank, world, torch, dist):
         line = {
             "metric": "cacnf_inference_videos_per_sec", "value": videos / (ms * 1e-3), "unit": "videos/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "f32 (3xbf16 split MMA)", "data": "synthetic",
             "config": {"workload": f"CACNF inference on precomputed ResNet3D features [B, 2048, 2x4x4] + Something-Else layouts "
                                    f"(17 x 5), batch {B} per GPU, dense layouts, random-init weights",
                        "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",

@@ -278,20 +278,20 @@ int stlt_adamw_step(void* handle, void* stream, float* params, const float* grad
 /* ---- CACNF on precomputed appearance features (BASELINE.json configs[4]) ----
  * Replaces CrossAttentionCentralNetFusion.forward (models.py:526-549) with the 3D-ResNet trunk factored
  * out: `features` is what Resnet3D.forward_features returns (models.py:219-220), f32
- * [batch, feature_channels, appearance_tokens] (e.g. [B, 2048, 2*4*4]). Inference only, bf16 GEMM
- * operands. Weights are bound by their reference state_dict names ("backbone.layout_branch.*",
+ * [batch, feature_channels, appearance_tokens] (e.g. [B, 2048, 2*4*4]). Inference only; both precision modes
+ * of the STLT path (STLT_PRECISION_BF16, or STLT_PRECISION_FP32 = 3-term split, logits within 1e-4). Weights are bound by their reference state_dict names ("backbone.layout_branch.*",
  * "backbone.appearance_branch.{projector,cls_token,pos_embed,transformer}.*", "backbone.mm_fusion.*",
  * "{layout,appearance,fusion}_classifier.*"); the ResNet trunk's and the two unused classifiers' entries
  * are ignored. The Conv3d projector weight [768, C, 1, 1, 1] is passed with its trailing 1x1x1 flattened.
- * The STLT part is packed with stlt_pack_weights(STLT_PRECISION_BF16), the rest with
- * stlt_cacnf_pack_weights. Outputs: the four logits of `logit_names` (models.py:524), f32 [batch, classes]. */
+ * The STLT part is packed with stlt_pack_weights, the rest with stlt_cacnf_pack_weights (same precision). Outputs: the four logits of `logit_names` (models.py:524), f32 [batch, classes]. */
 int stlt_cacnf_bind_weights(void* handle, const StltTensor* tensors, int32_t count,
                             int32_t num_appearance_layers, int32_t num_fusion_layers,
                             int32_t appearance_tokens, int32_t feature_channels);
-int stlt_cacnf_packed_weights_bytes(void* handle, size_t* bytes);
-int stlt_cacnf_pack_weights(void* handle, void* stream, void* packed, size_t bytes);
-int stlt_cacnf_workspace_bytes(void* handle, int32_t batch, int32_t frames, int32_t slots, size_t* bytes);
-int stlt_cacnf_forward(void* handle, void* stream, const int64_t* categories, const float* boxes,
+int stlt_cacnf_packed_weights_bytes(void* handle, int32_t precision, size_t* bytes);
+int stlt_cacnf_pack_weights(void* handle, void* stream, int32_t precision, void* packed, size_t bytes);
+int stlt_cacnf_workspace_bytes(void* handle, int32_t batch, int32_t frames, int32_t slots, int32_t precision,
+                               size_t* bytes);
+int stlt_cacnf_forward(void* handle, void* stream, int32_t precision, const int64_t* categories, const float* boxes,
                        const float* scores_or_null, const int64_t* frame_types, const int64_t* lengths,
                        const float* features, int32_t batch, int32_t frames, int32_t slots, void* workspace,
                        size_t workspace_bytes, float* logits_stlt, float* logits_resnet3d, float* logits_caf,

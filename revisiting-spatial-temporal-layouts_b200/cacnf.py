@@ -83,8 +83,14 @@ class _FusionHead(nn.Module):  # models.py:286-291
 
 
 class Cacnf(nn.Module):
-    def __init__(self, config):
+    """``precision``: "bf16" (default) or "fp32" (3-term bf16 split on tcgen05, logits within 1e-4 of the fp32
+    reference), as for ``Stlt``."""
+
+    def __init__(self, config, precision: str = "bf16"):
         super().__init__()
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        self.precision = precision
         if config.hidden_size != 768 or config.num_attention_heads != 12:
             raise ValueError("the sm_100a kernels are specialised for hidden_size=768, 12 heads")
         if config.appearance_num_frames > 32:
@@ -134,7 +140,8 @@ class Cacnf(nn.Module):
     def _sync_weights(self, device, stream):
         lib = _lib.load_library()
         named = list(self.named_parameters())
-        key = tuple((p.data_ptr(), p._version) for _, p in named)
+        prec = _lib.PRECISIONS[self.precision]
+        key = (prec,) + tuple((p.data_ptr(), p._version) for _, p in named)
         if key == self._weights_key:
             return
         arr = (_lib.StltTensor * len(named))()
@@ -155,14 +162,14 @@ class Cacnf(nn.Module):
                                                              c.num_fusion_layers, c.appearance_num_frames,
                                                              c.feature_channels))
         n1, n2 = ctypes.c_size_t(), ctypes.c_size_t()
-        _lib.check(self._handle, lib.stlt_packed_weights_bytes(self._handle, _lib.PRECISION_BF16, ctypes.byref(n1)))
-        _lib.check(self._handle, lib.stlt_cacnf_packed_weights_bytes(self._handle, ctypes.byref(n2)))
+        _lib.check(self._handle, lib.stlt_packed_weights_bytes(self._handle, prec, ctypes.byref(n1)))
+        _lib.check(self._handle, lib.stlt_cacnf_packed_weights_bytes(self._handle, prec, ctypes.byref(n2)))
         a = (n1.value + 1023) // 1024 * 1024
         if self._packed is None or self._packed.numel() < a + n2.value or self._packed.device != device:
             self._packed = torch.empty(a + n2.value, dtype=torch.uint8, device=device)
-        _lib.check(self._handle, lib.stlt_pack_weights(self._handle, stream, _lib.PRECISION_BF16,
-                                                       self._packed.data_ptr(), n1.value))
-        _lib.check(self._handle, lib.stlt_cacnf_pack_weights(self._handle, stream, self._packed.data_ptr() + a, n2.value))
+        _lib.check(self._handle, lib.stlt_pack_weights(self._handle, stream, prec, self._packed.data_ptr(), n1.value))
+        _lib.check(self._handle, lib.stlt_cacnf_pack_weights(self._handle, stream, prec, self._packed.data_ptr() + a,
+                                                             n2.value))
         self._weights_key = key
 
     def forward(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -193,12 +200,13 @@ class Cacnf(nn.Module):
             stream = torch.cuda.current_stream(device).cuda_stream
             self._sync_weights(device, stream)
             nbytes = ctypes.c_size_t()
-            _lib.check(self._handle, lib.stlt_cacnf_workspace_bytes(self._handle, B, L, S, ctypes.byref(nbytes)))
+            prec = _lib.PRECISIONS[self.precision]
+            _lib.check(self._handle, lib.stlt_cacnf_workspace_bytes(self._handle, B, L, S, prec, ctypes.byref(nbytes)))
             if self._workspace is None or self._workspace.numel() < nbytes.value or self._workspace.device != device:
                 self._workspace = torch.empty(max(nbytes.value, 1024), dtype=torch.uint8, device=device)
             out = [torch.empty((B, c.num_classes), dtype=torch.float32, device=device) for _ in range(4)]
             _lib.check(self._handle, lib.stlt_cacnf_forward(
-                self._handle, stream, cats.data_ptr(), boxes.data_ptr(),
+                self._handle, stream, prec, cats.data_ptr(), boxes.data_ptr(),
                 scores.data_ptr() if scores is not None else None, ftypes.data_ptr(), lengths.data_ptr(),
                 feats.data_ptr(), B, L, S, self._workspace.data_ptr(), self._workspace.numel(),
                 *(t.data_ptr() for t in out)))

@@ -10,7 +10,8 @@ namespace {
 // [B][C][P] f32 -> [B * P][C] bf16 through a padded shared-memory tile (64 channels x P positions).
 // Reads are 128-byte rows of P = 32 floats, writes are 128-byte runs of 64 bf16.
 __global__ void __launch_bounds__(256)
-features_to_tokens_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__ out, int C, int P) {
+features_to_tokens_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__ out, int C, int P,
+                          long long lo_plane_elems) {
   __shared__ float tile[64][33];
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * 64;
@@ -24,8 +25,11 @@ features_to_tokens_kernel(const float* __restrict__ feat, __nv_bfloat16* __restr
   for (int e = threadIdx.x; e < P * 32; e += 256) {
     const int s = e >> 5, cp = e & 31;
     if (c0 + 2 * cp + 1 < C + 1) {
-      const uint32_t v = pack_bf16x2(tile[2 * cp][s], tile[2 * cp + 1][s]);
-      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * P + s) * C + c0 + 2 * cp) = v;
+      const float a = tile[2 * cp][s], d = tile[2 * cp + 1][s];
+      __nv_bfloat16* dst = out + (static_cast<long long>(b) * P + s) * C + c0 + 2 * cp;
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(a, d);
+      if (lo_plane_elems != 0)  // fp32-parity mode: residual plane
+        *reinterpret_cast<uint32_t*>(dst + lo_plane_elems) = pack_bf16x2(bf16_residual(a), bf16_residual(d));
     }
   }
 }
@@ -87,11 +91,11 @@ __global__ void mean3_kernel(const float* __restrict__ a, const float* __restric
 }  // namespace
 
 cudaError_t launch_features_to_tokens(const float* feat, __nv_bfloat16* out, int B, int C, int P,
-                                      cudaStream_t stream) {
+                                      cudaStream_t stream, long long lo_plane_rows) {
   if (B == 0) return cudaSuccess;
   if (P < 1 || P > 32 || C % 2 != 0) return cudaErrorInvalidValue;
   dim3 grid((C + 63) / 64, B);
-  features_to_tokens_kernel<<<grid, 256, 0, stream>>>(feat, out, C, P);
+  features_to_tokens_kernel<<<grid, 256, 0, stream>>>(feat, out, C, P, lo_plane_rows * C);
   return cudaGetLastError();
 }
 

@@ -638,6 +638,7 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
   STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 0)
   STLT_GEMM_CASE(1, GEMM_OUT_BF16_DUAL, 2)
   STLT_GEMM_CASE(1, GEMM_OUT_BF16, 3)
+  STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 3)
 #undef STLT_GEMM_CASE
   return cudaErrorInvalidValue;
 }

@@ -71,7 +71,8 @@ struct CacnfWeights {
   std::vector<LayerWeights> app;  // TransformerResnet.transformer (ReLU, eps 1e-5)
   std::vector<FusionLayerWeights> fusion;
   HeadWeights app_head, fusion_head;
-  bool bound = false, packed = false;
+  bool bound = false;
+  int packed_precision = -1;
 };
 
 struct Handle {

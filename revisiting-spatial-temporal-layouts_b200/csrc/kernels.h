@@ -250,10 +250,12 @@ cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* 
 cudaError_t launch_attention_cross(const __nv_bfloat16* q, int ldq, int q_off, const __nv_bfloat16* kv,
                                    int ldkv, int k_off, int v_off, const long long* mask_src,
                                    long long num_seqs, int Tq, int Tk, bool causal, __nv_bfloat16* out,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, int planes = 1, long long q_plane_rows = 0,
+                                   long long kv_plane_rows = 0, long long out_plane_rows = 0);
 // features f32 [B, C, P] (channel-major, as the 3D ResNet emits them) -> bf16 tokens [B * P, C]
+// lo_plane_rows != 0 (fp32-parity mode): also writes the bf16 residual plane that many rows further
 cudaError_t launch_features_to_tokens(const float* feat, __nv_bfloat16* out, int B, int C, int P,
-                                      cudaStream_t stream);
+                                      cudaStream_t stream, long long lo_plane_rows = 0);
 // x[b, 0] = cls + pos[0]; x[b, 1 + s] = proj[b, s] + pos[1 + s]   (models.py:262-270)
 cudaError_t launch_app_embed(const float* proj, const float* cls, const float* pos, int B, int P, ActOut out,
                              cudaStream_t stream);

@@ -737,7 +737,10 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     STLT_CUDA(h, cudaMemcpyAsync(h->taps.temporal, tm.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
   if (h->cap_tm_x) {  // CACNF: the fusion layers consume every frame token (fp32 stream + bf16 GEMM operand)
     STLT_CUDA(h, cudaMemcpyAsync(h->cap_tm_x, tm.x, n_tm * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
-    STLT_CUDA(h, cudaMemcpyAsync(h->cap_tm_xb, tm.xb, n_tm * kHidden * 2, cudaMemcpyDeviceToDevice, stream));
+    for (int pl = 0; pl < planes; ++pl)  // same padded row count on both sides (pad128(B * L))
+      STLT_CUDA(h, cudaMemcpyAsync(h->cap_tm_xb + static_cast<size_t>(pl) * tm.m_pad * kHidden,
+                                   tm.xb + static_cast<size_t>(pl) * tm.m_pad * kHidden, n_tm * kHidden * 2,
+                                   cudaMemcpyDeviceToDevice, stream));
   }
 
   // ---- head (models.py:155-163,189-193) ----

@@ -33,8 +33,9 @@ struct CacnfPlan {
   size_t total;
 };
 
-CacnfPlan plan_cacnf(Handle* h, int B, int L, int S, size_t stlt_bytes) {
+CacnfPlan plan_cacnf(Handle* h, int B, int L, int S, size_t stlt_bytes, int precision) {
   const CacnfWeights& w = h->cacnf;
+  const size_t pl = precision == STLT_PRECISION_FP32 ? 2 : 1;  // bf16 planes (hi / lo in fp32-parity mode)
   CacnfPlan p{};
   const int T = w.app_tokens + 1;
   p.n_l = static_cast<long long>(B) * L;
@@ -45,19 +46,19 @@ CacnfPlan plan_cacnf(Handle* h, int B, int L, int S, size_t stlt_bytes) {
   size_t off = 0;
   p.stlt_ws = take(off, stlt_bytes);
   p.stlt_bytes = stlt_bytes;
-  p.feat_tok = take(off, static_cast<size_t>(m_p) * w.feat_channels * 2);
+  p.feat_tok = take(off, static_cast<size_t>(m_p) * w.feat_channels * 2 * pl);
   p.proj = take(off, static_cast<size_t>(m_p) * kHidden * 4);
   p.xl = take(off, static_cast<size_t>(p.m_l) * kHidden * 4);
-  p.xlb = take(off, static_cast<size_t>(p.m_l) * kHidden * 2);
+  p.xlb = take(off, static_cast<size_t>(p.m_l) * kHidden * 2 * pl);
   p.xa = take(off, static_cast<size_t>(p.m_a) * kHidden * 4);
-  p.xab = take(off, static_cast<size_t>(p.m_a) * kHidden * 2);
-  p.qkv_l = take(off, static_cast<size_t>(p.m_l) * kQkv * 2);
-  p.qkv_a = take(off, static_cast<size_t>(p.m_a) * kQkv * 2);
-  p.ctx_l = take(off, static_cast<size_t>(p.m_l) * kHidden * 2);
-  p.ctx_a = take(off, static_cast<size_t>(p.m_a) * kHidden * 2);
+  p.xab = take(off, static_cast<size_t>(p.m_a) * kHidden * 2 * pl);
+  p.qkv_l = take(off, static_cast<size_t>(p.m_l) * kQkv * 2 * pl);
+  p.qkv_a = take(off, static_cast<size_t>(p.m_a) * kQkv * 2 * pl);
+  p.ctx_l = take(off, static_cast<size_t>(p.m_l) * kHidden * 2 * pl);
+  p.ctx_a = take(off, static_cast<size_t>(p.m_a) * kHidden * 2 * pl);
   p.y_l = take(off, static_cast<size_t>(p.m_l) * kHidden * 4);
   p.y_a = take(off, static_cast<size_t>(p.m_a) * kHidden * 4);
-  p.hid = take(off, static_cast<size_t>(p.m_l > p.m_a ? p.m_l : p.m_a) * kFfn * 2);
+  p.hid = take(off, static_cast<size_t>(p.m_l > p.m_a ? p.m_l : p.m_a) * kFfn * 2 * pl);
   p.pooled = take(off, static_cast<size_t>(B) * kHidden * 4);
   p.h1 = take(off, static_cast<size_t>(B) * kHidden * 4);
   p.h2 = take(off, static_cast<size_t>(B) * kHidden * 4);
@@ -74,26 +75,32 @@ T* at(uint8_t* ws, size_t off) {
 
 struct Stream {  // one token stream of the fusion stage
   float* x;
-  __nv_bfloat16* xb;
-  __nv_bfloat16* qkv;
-  __nv_bfloat16* ctx;
+  __nv_bfloat16* xb;   // [planes][m][768]
+  __nv_bfloat16* qkv;  // [planes][m][2304]
+  __nv_bfloat16* ctx;  // [planes][m][768]
   float* y;
   long long m, n;  // padded / valid rows
+  int planes;      // 1 = bf16 mode, 2 = fp32-parity mode (hi / lo planes, 3-term GEMMs)
 };
 
 int in_proj(Handle* h, cudaStream_t s, const MhaWeights& w, const Stream& st) {
-  return run_gemm(h, s, st.xb, st.m, st.m, w.in_p, kQkv, kHidden, w.in_b, st.qkv, 1, GEMM_OUT_BF16, 0);
+  const bool f = st.planes == 2;
+  return run_gemm(h, s, st.xb, st.m, st.m, w.in_p, kQkv, kHidden, w.in_b, st.qkv, f ? 3 : 1,
+                  f ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, 0);
 }
 
 // x <- LN(out_proj(ctx) + x)
 int out_proj_ln(Handle* h, cudaStream_t s, const MhaWeights& w, const float* g, const float* b, float eps,
                 const Stream& st) {
-  // branch outputs travel as bf16 (as in the bf16 STLT path); the residual stream stays fp32
-  int rc = run_gemm(h, s, st.ctx, st.m, st.m, w.out_p, kHidden, kHidden, w.out_b, st.y, 1, GEMM_OUT_BF16, 0);
+  // bf16 mode: branch outputs travel as bf16 (as in the bf16 STLT path); the residual stream stays fp32
+  const bool f = st.planes == 2;
+  int rc = run_gemm(h, s, st.ctx, st.m, st.m, w.out_p, kHidden, kHidden, w.out_b, st.y, f ? 3 : 1,
+                    f ? GEMM_OUT_F32 : GEMM_OUT_BF16, 0);
   if (rc) return rc;
   ProfileScope prof(h, s, STLT_PROF_ADD_LN);
-  ActOut o{st.x, st.xb, 1, st.m};
-  STLT_CUDA(h, launch_add_ln_bf16y(st.x, reinterpret_cast<const __nv_bfloat16*>(st.y), g, b, eps, st.n, o, s));
+  ActOut o{st.x, st.xb, st.planes, st.m};
+  if (f) STLT_CUDA(h, launch_add_ln(st.x, st.y, g, b, eps, st.n, o, s));
+  else STLT_CUDA(h, launch_add_ln_bf16y(st.x, reinterpret_cast<const __nv_bfloat16*>(st.y), g, b, eps, st.n, o, s));
   h->launches++;
   return STLT_OK;
 }
@@ -102,10 +109,10 @@ int self_attention(Handle* h, cudaStream_t s, const Stream& st, long long num_se
                    bool causal) {
   ProfileScope prof(h, s, STLT_PROF_ATTENTION);
   if (T <= 32)
-    STLT_CUDA(h, launch_attention_mma(st.qkv, 1, st.m, mask_src, num_seqs, T, causal, st.ctx, st.m, s));
+    STLT_CUDA(h, launch_attention_mma(st.qkv, st.planes, st.m, mask_src, num_seqs, T, causal, st.ctx, st.m, s));
   else
     STLT_CUDA(h, launch_attention_cross(st.qkv, kQkv, 0, st.qkv, kQkv, kHidden, 2 * kHidden, mask_src, num_seqs, T, T,
-                                        causal, st.ctx, s));
+                                        causal, st.ctx, s, st.planes, st.m, st.m, st.m));
   h->launches++;
   return STLT_OK;
 }
@@ -114,13 +121,17 @@ int self_attention(Handle* h, cudaStream_t s, const Stream& st, long long num_se
 int ffn_ln(Handle* h, cudaStream_t s, const __nv_bfloat16* l1_p, const float* l1_b, const __nv_bfloat16* l2_p,
            const float* l2_b, const float* g, const float* b, float eps, int act, const Stream& st,
            __nv_bfloat16* hid) {
-  int rc = run_gemm(h, s, st.xb, st.m, st.m, l1_p, kFfn, kHidden, l1_b, hid, 1, GEMM_OUT_BF16, act);
+  const bool f = st.planes == 2;
+  if (f && act == 2) act = 1;  // fp32-parity mode: exact erf GELU
+  int rc = run_gemm(h, s, st.xb, st.m, st.m, l1_p, kFfn, kHidden, l1_b, hid, f ? 3 : 1,
+                    f ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, act);
   if (rc) return rc;
-  rc = run_gemm(h, s, hid, st.m, st.m, l2_p, kHidden, kFfn, l2_b, st.y, 1, GEMM_OUT_BF16, 0);
+  rc = run_gemm(h, s, hid, st.m, st.m, l2_p, kHidden, kFfn, l2_b, st.y, f ? 3 : 1, f ? GEMM_OUT_F32 : GEMM_OUT_BF16, 0);
   if (rc) return rc;
   ProfileScope prof(h, s, STLT_PROF_ADD_LN);
-  ActOut o{st.x, st.xb, 1, st.m};
-  STLT_CUDA(h, launch_add_ln_bf16y(st.x, reinterpret_cast<const __nv_bfloat16*>(st.y), g, b, eps, st.n, o, s));
+  ActOut o{st.x, st.xb, st.planes, st.m};
+  if (f) STLT_CUDA(h, launch_add_ln(st.x, st.y, g, b, eps, st.n, o, s));
+  else STLT_CUDA(h, launch_add_ln_bf16y(st.x, reinterpret_cast<const __nv_bfloat16*>(st.y), g, b, eps, st.n, o, s));
   h->launches++;
   return STLT_OK;
 }
@@ -277,9 +288,11 @@ int stlt_op_attention_cross(void* handle, void* stream, const void* q_qkv, const
   return STLT_OK;
 }
 
-int stlt_cacnf_packed_weights_bytes(void* handle, size_t* bytes) {
+int stlt_cacnf_packed_weights_bytes(void* handle, int32_t precision, size_t* bytes) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h || !bytes) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (precision != STLT_PRECISION_FP32 && precision != STLT_PRECISION_BF16)
+    return fail(h, STLT_ERR_INVALID, "unknown precision %d", precision);
   const CacnfWeights& w = h->cacnf;
   if (!w.bound) return fail(h, STLT_ERR_STATE, "stlt_cacnf_bind_weights has not been called");
   const size_t mha = static_cast<size_t>(kHidden) * (kQkv + kHidden);
@@ -287,25 +300,26 @@ int stlt_cacnf_packed_weights_bytes(void* handle, size_t* bytes) {
   size_t elems = static_cast<size_t>(kHidden) * w.feat_channels;
   elems += static_cast<size_t>(w.app_layers) * (mha + ffn);
   elems += static_cast<size_t>(w.fusion_layers) * (4 * mha + ffn);
-  *bytes = elems * 2;
+  *bytes = elems * 2 * (precision == STLT_PRECISION_FP32 ? 2 : 1);
   return STLT_OK;
 }
 
-int stlt_cacnf_pack_weights(void* handle, void* stream_, void* packed, size_t bytes) {
+int stlt_cacnf_pack_weights(void* handle, void* stream_, int32_t precision, void* packed, size_t bytes) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h || !packed) return fail(h, STLT_ERR_INVALID, "null argument");
   size_t need = 0;
-  int rc = stlt_cacnf_packed_weights_bytes(handle, &need);
+  int rc = stlt_cacnf_packed_weights_bytes(handle, precision, &need);
   if (rc) return rc;
   if (bytes < need) return fail(h, STLT_ERR_INVALID, "packed buffer too small: %zu < %zu", bytes, need);
   if ((reinterpret_cast<uintptr_t>(packed) & 127) != 0) return fail(h, STLT_ERR_INVALID, "packed buffer must be 128-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CacnfWeights& w = h->cacnf;
   __nv_bfloat16* cur = static_cast<__nv_bfloat16*>(packed);
+  const int planes = precision == STLT_PRECISION_FP32 ? 2 : 1;
   auto pack = [&](const float* src, long long n, const __nv_bfloat16** dst) -> cudaError_t {
     *dst = cur;
-    cudaError_t e = launch_pack_bf16(src, cur, n, 1, stream);
-    cur += n;
+    cudaError_t e = launch_pack_bf16(src, cur, n, planes, stream);
+    cur += n * planes;
     return e;
   };
   const long long H = kHidden, F = kFfn;
@@ -324,22 +338,22 @@ int stlt_cacnf_pack_weights(void* handle, void* stream_, void* packed, size_t by
     STLT_CUDA(h, pack(f.layout_ffn.l1_w, F * H, &f.layout_ffn.l1_p));
     STLT_CUDA(h, pack(f.layout_ffn.l2_w, H * F, &f.layout_ffn.l2_p));
   }
-  w.packed = true;
+  w.packed_precision = precision;
   return STLT_OK;
 }
 
-int stlt_cacnf_workspace_bytes(void* handle, int32_t B, int32_t L, int32_t S, size_t* bytes) {
+int stlt_cacnf_workspace_bytes(void* handle, int32_t B, int32_t L, int32_t S, int32_t precision, size_t* bytes) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h || !bytes) return fail(h, STLT_ERR_INVALID, "null argument");
   if (!h->cacnf.bound) return fail(h, STLT_ERR_STATE, "stlt_cacnf_bind_weights has not been called");
   size_t stlt_bytes = 0;
-  int rc = stlt_workspace_bytes(handle, B, L, S, STLT_PRECISION_BF16, &stlt_bytes);
+  int rc = stlt_workspace_bytes(handle, B, L, S, precision, &stlt_bytes);
   if (rc) return rc;
-  *bytes = plan_cacnf(h, B, L, S, stlt_bytes).total;
+  *bytes = plan_cacnf(h, B, L, S, stlt_bytes, precision).total;
   return STLT_OK;
 }
 
-int stlt_cacnf_forward(void* handle, void* stream_, const int64_t* categories, const float* boxes,
+int stlt_cacnf_forward(void* handle, void* stream_, int32_t precision, const int64_t* categories, const float* boxes,
                        const float* scores, const int64_t* frame_types_, const int64_t* lengths_,
                        const float* features, int32_t B, int32_t L, int32_t S, void* workspace,
                        size_t workspace_bytes, float* logits_stlt, float* logits_resnet3d, float* logits_caf,
@@ -347,16 +361,21 @@ int stlt_cacnf_forward(void* handle, void* stream_, const int64_t* categories, c
   Handle* h = static_cast<Handle*>(handle);
   if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
   CacnfWeights& w = h->cacnf;
-  if (!w.bound || !w.packed) return fail(h, STLT_ERR_STATE, "CACNF weights are not bound / packed");
+  if (precision != STLT_PRECISION_FP32 && precision != STLT_PRECISION_BF16)
+    return fail(h, STLT_ERR_INVALID, "unknown precision %d", precision);
+  if (!w.bound || w.packed_precision != precision)
+    return fail(h, STLT_ERR_STATE, "CACNF weights are not bound / packed for precision %d", precision);
   if (B < 0) return fail(h, STLT_ERR_INVALID, "negative batch size");
   if (B == 0) return STLT_OK;
   if (!features || !workspace || !logits_stlt || !logits_resnet3d || !logits_caf || !logits_ensemble)
     return fail(h, STLT_ERR_INVALID, "null tensor pointer");
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(h, STLT_ERR_INVALID, "workspace must be 1024-byte aligned");
   size_t stlt_bytes = 0;
-  int rc = stlt_workspace_bytes(handle, B, L, S, STLT_PRECISION_BF16, &stlt_bytes);
+  int rc = stlt_workspace_bytes(handle, B, L, S, precision, &stlt_bytes);
   if (rc) return rc;
-  const CacnfPlan p = plan_cacnf(h, B, L, S, stlt_bytes);
+  const CacnfPlan p = plan_cacnf(h, B, L, S, stlt_bytes, precision);
+  const bool fp32 = precision == STLT_PRECISION_FP32;
+  const int planes = fp32 ? 2 : 1;
   if (workspace_bytes < p.total) return fail(h, STLT_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, p.total);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -366,9 +385,9 @@ int stlt_cacnf_forward(void* handle, void* stream_, const int64_t* categories, c
   const float eps_enc = h->dims.encoder_norm_eps, eps_fus = h->dims.layer_norm_eps;
 
   Stream sl{at<float>(ws, p.xl), at<__nv_bfloat16>(ws, p.xlb), at<__nv_bfloat16>(ws, p.qkv_l),
-            at<__nv_bfloat16>(ws, p.ctx_l), at<float>(ws, p.y_l), p.m_l, p.n_l};
+            at<__nv_bfloat16>(ws, p.ctx_l), at<float>(ws, p.y_l), p.m_l, p.n_l, planes};
   Stream sa{at<float>(ws, p.xa), at<__nv_bfloat16>(ws, p.xab), at<__nv_bfloat16>(ws, p.qkv_a),
-            at<__nv_bfloat16>(ws, p.ctx_a), at<float>(ws, p.y_a), p.m_a, p.n_a};
+            at<__nv_bfloat16>(ws, p.ctx_a), at<float>(ws, p.y_a), p.m_a, p.n_a, planes};
   __nv_bfloat16* hid = at<__nv_bfloat16>(ws, p.hid);
   float* pooled = at<float>(ws, p.pooled);
   float* h1 = at<float>(ws, p.h1);
@@ -377,7 +396,7 @@ int stlt_cacnf_forward(void* handle, void* stream_, const int64_t* categories, c
   // ---- layout branch: the STLT path; keeps every frame token, emits the layout logits ("stlt") ----
   h->cap_tm_x = sl.x;
   h->cap_tm_xb = sl.xb;
-  rc = stlt_forward(handle, stream_, STLT_PRECISION_BF16, categories, boxes, scores, frame_types_, lengths_, B, L, S,
+  rc = stlt_forward(handle, stream_, precision, categories, boxes, scores, frame_types_, lengths_, B, L, S,
                     ws + p.stlt_ws, p.stlt_bytes, logits_stlt, nullptr, nullptr);
   h->cap_tm_x = nullptr;
   h->cap_tm_xb = nullptr;
@@ -386,16 +405,17 @@ int stlt_cacnf_forward(void* handle, void* stream_, const int64_t* categories, c
   // ---- appearance branch (models.py:256-276) ----
   {
     ProfileScope prof(h, stream, STLT_PROF_OTHER);
-    STLT_CUDA(h, launch_features_to_tokens(features, at<__nv_bfloat16>(ws, p.feat_tok), B, w.feat_channels, P, stream));
+    STLT_CUDA(h, launch_features_to_tokens(features, at<__nv_bfloat16>(ws, p.feat_tok), B, w.feat_channels, P, stream,
+                                           fp32 ? pad128(static_cast<long long>(B) * P) : 0));
     h->launches++;
   }
   const long long m_p = pad128(static_cast<long long>(B) * P);
   rc = run_gemm(h, stream, at<__nv_bfloat16>(ws, p.feat_tok), m_p, m_p, w.proj_p, kHidden, w.feat_channels, w.proj_b,
-                at<float>(ws, p.proj), 1, GEMM_OUT_F32, 0);
+                at<float>(ws, p.proj), fp32 ? 3 : 1, GEMM_OUT_F32, 0);
   if (rc) return rc;
   {
     ProfileScope prof(h, stream, STLT_PROF_OTHER);
-    ActOut o{sa.x, sa.xb, 1, sa.m};
+    ActOut o{sa.x, sa.xb, planes, sa.m};
     STLT_CUDA(h, launch_app_embed(at<float>(ws, p.proj), w.cls_token, w.pos_embed, B, P, o, stream));
   }
   for (const LayerWeights& lw : w.app) {
@@ -421,9 +441,9 @@ int stlt_cacnf_forward(void* handle, void* stream_, const int64_t* categories, c
     {
       ProfileScope prof(h, stream, STLT_PROF_ATTENTION);
       STLT_CUDA(h, launch_attention_cross(sl.qkv, kQkv, 0, sa.qkv, kQkv, kHidden, 2 * kHidden, nullptr, B, L, T, false,
-                                          sl.ctx, stream));
+                                          sl.ctx, stream, planes, sl.m, sa.m, sl.m));
       STLT_CUDA(h, launch_attention_cross(sa.qkv, kQkv, 0, sl.qkv, kQkv, kHidden, 2 * kHidden, frame_types, B, T, L,
-                                          false, sa.ctx, stream));
+                                          false, sa.ctx, stream, planes, sa.m, sl.m, sa.m));
       h->launches += 2;
     }
     if ((rc = out_proj_ln(h, stream, f.cross.attn, f.cross.ln_g, f.cross.ln_b, eps_fus, sl))) return rc;

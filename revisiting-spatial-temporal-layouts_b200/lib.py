@@ -141,10 +141,10 @@ SIGNATURES = {
     "stlt_adamw_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_float, c_float, c_float, c_int32, c_void_p, c_float]),
     "stlt_cacnf_bind_weights": (c_int32, [c_void_p, POINTER(StltTensor), c_int32, c_int32, c_int32, c_int32, c_int32]),
-    "stlt_cacnf_packed_weights_bytes": (c_int32, [c_void_p, POINTER(c_size_t)]),
-    "stlt_cacnf_pack_weights": (c_int32, [c_void_p, c_void_p, c_void_p, c_size_t]),
-    "stlt_cacnf_workspace_bytes": (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(c_size_t)]),
-    "stlt_cacnf_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "stlt_cacnf_packed_weights_bytes": (c_int32, [c_void_p, c_int32, POINTER(c_size_t)]),
+    "stlt_cacnf_pack_weights": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_size_t]),
+    "stlt_cacnf_workspace_bytes": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_size_t)]),
+    "stlt_cacnf_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
     "stlt_op_gemm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
