@@ -261,7 +261,9 @@ def roofline_from_profile(prof, steps, precision, peaks, peak_src):
             traffic = None
     out = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": traffic, "kernel": "gemm_tcgen05_kernel (all projection GEMMs of a step)",
+        "traffic": traffic,
+        "kernel": "gemm_tcgen05_kernel (all projection GEMMs of a step" +
+                  ("; in bf16 mode their epilogues also carry the residual adds and LayerNorms)" if precision == "bf16" else ")"),
         "launches_per_step": gemm["launches"] / max(steps, 1), "kernel_ms_per_step": ms,
         "algorithmic_flops_per_step": algorithmic,
         "peak_source": f"bf16 dense sustained, {peak_src}",
