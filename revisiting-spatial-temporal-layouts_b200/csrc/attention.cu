@@ -137,8 +137,15 @@ attention_kernel(const TIn* __restrict__ qkv, const long long* __restrict__ mask
 cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long* mask_src,
                              long long num_seqs, int T, bool causal, ActOut out,
                              cudaStream_t stream) {
-  if (T < 1 || T > 32) return cudaErrorInvalidValue;
+  if (T < 1 || T > 64) return cudaErrorInvalidValue;
   if (num_seqs == 0) return cudaSuccess;
+  if (T > 32) {
+    // 33..64 tokens per sequence: one warp per (sequence, head) on the 48 / 64-row tiles of attention_cross.cu
+    if (!qkv_is_bf16) return cudaErrorInvalidValue;
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(qkv);
+    return launch_attention_cross(p, kQkv, 0, p, kQkv, kHidden, 2 * kHidden, mask_src, num_seqs, T, T, causal, out.xb,
+                                  stream, out.planes, out.plane_rows, out.plane_rows, out.plane_rows);
+  }
   const int G = 32 / T;
   const int R = G * T;
   const long long groups = (num_seqs + G - 1) / G;

@@ -357,3 +357,21 @@ def test_fused_layer_norm_path_matches_unfused_and_oracle(layout):
     assert nerr(fused, want) < 2e-2 and nerr(plain, want) < 2e-2
     assert torch.equal(fused.argmax(-1), want.argmax(-1))
     assert nerr(fused, torch.from_numpy(g["logits"])) < 2e-2
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_long_sequences_up_to_64_tokens(precision, tol):
+    """33..64 frames / slots per sequence take the 48 / 64-row attention tiles (the reference's position table
+    allows 256 frames; its CLIs sample 16)."""
+    cfg = StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=2, num_temporal_layers=2)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=71)
+    m = _model(cfg, sd, precision)
+    for frames, objects in ((39, 4), (63, 2), (16, 40)):
+        batch = make_batch(3, "something", ragged=True, seed=frames, num_frames=frames, max_objects=objects)
+        with torch.no_grad():
+            want = O.stlt_forward(sd, batch, num_spatial_layers=2, num_temporal_layers=2)
+            got = m(to_cuda(batch))["stlt"].cpu()
+        assert nerr(got, want) < tol, (frames, objects, nerr(got, want))
+    with pytest.raises(Exception, match="64"), torch.no_grad():
+        m(to_cuda(make_batch(1, "something", num_frames=64)))
