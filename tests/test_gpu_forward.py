@@ -375,3 +375,30 @@ def test_long_sequences_up_to_64_tokens(precision, tol):
         assert nerr(got, want) < tol, (frames, objects, nerr(got, want))
     with pytest.raises(Exception, match="64"), torch.no_grad():
         m(to_cuda(make_batch(1, "something", num_frames=64)))
+
+
+def test_random_shapes_fuzz_bf16_and_fp32():
+    """Random (batch, frames, slots, layout) combinations — odd tile counts, single-frame videos, S = 1, scores on /
+    off — through both precision modes (the bf16 one on the LayerNorm-fused epilogues) vs the oracle."""
+    import random
+    rng = random.Random(1234)
+    for trial in range(14):
+        layout = rng.choice(["something", "action_genome"])
+        spec = stlt_b200.SOMETHING_ELSE if layout == "something" else stlt_b200.ACTION_GENOME
+        ns, nt = rng.choice([(1, 1), (2, 1), (1, 3), (2, 2)])
+        cfg = StltModelConfig(num_classes=spec["num_classes"], unique_categories=spec["unique_categories"],
+                              num_spatial_layers=ns, num_temporal_layers=nt)
+        torch.manual_seed(0)
+        sd = random_state_dict(Stlt(cfg).state_dict(), seed=100 + trial)
+        B = rng.choice([1, 2, 7, 26, 77, 130])
+        frames = rng.choice([1, 2, 5, 16, 31])
+        objects = rng.choice([0, 1, 4, 10, 31]) if frames * B < 2000 else 4
+        batch = make_batch(B, layout, ragged=True, seed=trial, num_frames=frames, max_objects=objects)
+        with torch.no_grad():
+            want = O.stlt_forward(sd, batch, num_spatial_layers=ns, num_temporal_layers=nt)
+        for precision, tol in (("bf16", BF16_TOL), ("fp32", FP32_TOL)):
+            m = _model(cfg, sd, precision)
+            with torch.no_grad():
+                got = m(to_cuda(batch))["stlt"].cpu()
+            err = nerr(got, want)
+            assert torch.isfinite(got).all() and err < tol, (trial, layout, B, frames, objects, ns, nt, precision, err)
