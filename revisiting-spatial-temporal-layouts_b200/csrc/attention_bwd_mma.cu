@@ -379,11 +379,10 @@ cudaError_t launch_attention_bwd_mma(const __nv_bfloat16* qkv, const __nv_bfloat
   const long long groups = (num_seqs + G - 1) / G;
   const long long items = groups * kHeads;
   const int smem = kWarps * kWarpBytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static unsigned long long smem_done = 0;  // per instantiation, one bit per device
+  {
+    cudaError_t e = ensure_dynamic_smem(attention_bwd_mma_kernel, smem, &smem_done);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   long long blocks = (items + kWarps - 1) / kWarps;
   const long long cap = 148LL * 2 * 8;

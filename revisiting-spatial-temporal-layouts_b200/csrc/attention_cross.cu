@@ -252,12 +252,10 @@ static cudaError_t launch_rows(const __nv_bfloat16* q, int ldq, int q_off, const
                                int Tk, bool causal, __nv_bfloat16* out, long long q_plane, long long kv_plane,
                                long long out_plane, cudaStream_t stream) {
   const int smem = kWarps * (kSplit ? 6 : 3) * kRows * 128;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_cross_kernel<kRows, kSplit>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static unsigned long long smem_done = 0;  // per instantiation, one bit per device
+  {
+    cudaError_t e = ensure_dynamic_smem(attention_cross_kernel<kRows, kSplit>, smem, &smem_done);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const long long items = num_seqs * kHeads;
   long long blocks = (items + kWarps - 1) / kWarps;

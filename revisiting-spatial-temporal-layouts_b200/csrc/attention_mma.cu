@@ -317,12 +317,10 @@ static cudaError_t launch_mma(const __nv_bfloat16* qkv, long long qkv_plane_rows
   const long long groups = (num_seqs + G - 1) / G;
   const long long items = groups * kHeads;
   const int smem = kWarps * kTiles * kTileBytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<kSplit>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static unsigned long long smem_done = 0;  // per instantiation, one bit per device
+  {
+    cudaError_t e = ensure_dynamic_smem(attention_mma_kernel<kSplit>, smem, &smem_done);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   long long blocks = (items + kWarps - 1) / kWarps;
   const long long cap = 148LL * 2 * 8;  // 2 CTAs resident per SM, several waves; grid-stride inside

@@ -17,6 +17,21 @@ constexpr int kFfn = 3072;     // src/modelling/models.py:49 (hidden_size * 4)
 constexpr int kQkv = 3 * kHidden;
 
 // ---------------------------------------------------------------------------------------------
+// host: opt a kernel into > 48 KB of dynamic shared memory, once per (kernel instantiation, device)
+// ---------------------------------------------------------------------------------------------
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*done_mask & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) *done_mask |= bit;  // the attribute is per device: a second GPU in the process needs its own call
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------
 // small math helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) {

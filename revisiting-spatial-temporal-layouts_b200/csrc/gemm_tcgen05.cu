@@ -569,11 +569,10 @@ template <int kTerms, int kOut, int kGelu, int kLayout = GEMM_NT, int kEpi = GEM
 static cudaError_t launch_one(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   auto kern = gemm_tcgen05_kernel<kTerms, kOut, kGelu, kLayout, kEpi>;
   constexpr int smem = Cfg<kOut>::kSmemBytes;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static unsigned long long smem_done = 0;  // per instantiation, one bit per device
+  {
+    cudaError_t e = ensure_dynamic_smem(kern, smem, &smem_done);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int m_tiles = g.m_rows / BM;
   const int n_tiles = g.n / BN;

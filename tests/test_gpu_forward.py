@@ -402,3 +402,23 @@ def test_random_shapes_fuzz_bf16_and_fp32():
                 got = m(to_cuda(batch))["stlt"].cpu()
             err = nerr(got, want)
             assert torch.isfinite(got).all() and err < tol, (trial, layout, B, frames, objects, ns, nt, precision, err)
+
+
+def test_two_devices_in_one_process():
+    """One handle per device; kernel attributes (dynamic shared memory opt-in) are per device too."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=1, num_temporal_layers=1)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=81)
+    batch = make_batch(9, "something", ragged=True, seed=82)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        for precision in ("bf16", "fp32"):
+            m = Stlt(cfg, precision=precision)
+            m.load_state_dict(sd)
+            m = m.to(dev)
+            m.train(False)
+            with torch.no_grad():
+                outs.append(m({k: v.to(dev) for k, v in batch.items()})["stlt"].cpu())
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
