@@ -154,6 +154,25 @@ __device__ __forceinline__ float gelu_erf_grad_fast(float u) {
   return fmaf(u * 0.3989422804014327f, g, cdf);
 }
 
+// Two elements at a time in packed fp16 (see gelu_erf_fast_h2): the result multiplies a bf16 gradient.
+__device__ __forceinline__ __half2 gelu_erf_grad_fast_h2(__half2 u) {
+  const __half2 au = __habs2(u);
+  const __half2 a = __hmin2(au, __float2half2_rn(5.9f));
+  __half2 q = __float2half2_rn(5.204604041e-04f);
+  q = __hfma2(q, a, __float2half2_rn(-7.397519993e-03f));
+  q = __hfma2(q, a, __float2half2_rn(5.256125276e-02f));
+  q = __hfma2(q, a, __float2half2_rn(4.592546886e-01f));
+  q = __hfma2(q, a, __float2half2_rn(1.151091390e+00f));
+  const __half2 e = h2exp2(__hneg2(__hmul2(q, a)));                                   // erfc(|u| / sqrt 2)
+  // exp(-u^2 / 2) with |u| clamped like the erf argument (beyond 5.9 the term is < 1e-7 anyway)
+  const __half2 g = h2exp2(__hmul2(__float2half2_rn(-0.72134752044f), __hmul2(a, a)));
+  const __half2 half_erf = __hfma2(__float2half2_rn(-0.5f), e, __float2half2_rn(0.5f));  // 0.5 * erf(|u| / sqrt 2)
+  // cdf = 0.5 + sign(u) * half_erf
+  const __half2 sgn = __hsub2(__hgt2(u, __float2half2_rn(0.f)), __hlt2(u, __float2half2_rn(0.f)));
+  const __half2 cdf = __hfma2(sgn, half_erf, __float2half2_rn(0.5f));
+  return __hfma2(__hmul2(u, __float2half2_rn(0.3989422804014327f)), g, cdf);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Backward of x_out = LN(z), z = x + y (the two post-norm residual sites of an encoder layer,
 // src/modelling/models.py:46-52 -> nn.TransformerEncoderLayer): dz feeds both the residual branch
@@ -222,8 +241,9 @@ act_bwd_colsum_kernel(__nv_bfloat16* __restrict__ d, const __nv_bfloat16* __rest
         float2 g = __bfloat1622float2(dp[j]);
         if (kGelu) {
           const float2 uu = __bfloat1622float2(up[j]);
-          g.x *= gelu_erf_grad_fast(uu.x);
-          g.y *= gelu_erf_grad_fast(uu.y);
+          const float2 dg = __half22float2(gelu_erf_grad_fast_h2(__floats2half2_rn(uu.x, uu.y)));
+          g.x *= dg.x;
+          g.y *= dg.y;
           if (drop.thr16 != 0) {  // FFN-inner dropout sits between the activation and linear2
             const unsigned long long el = static_cast<unsigned long long>(r0 + i) * n + c8 * 8 + 2 * j;
             const uint32_t bits = drop_bits(drop.key, el >> 1);
