@@ -125,6 +125,8 @@ class StltBackbone(nn.Module):
         super().__init__()
         self.frames_embeddings = _FramesEmbeddings(config)
         self.transformer = _Encoder(_EncoderLayer(config.hidden_size), config.num_temporal_layers)
+        object.__setattr__(self, "_config", config)   # not part of the state_dict
+        object.__setattr__(self, "_runner", None)
 
     @classmethod
     def from_pretrained(cls, config):  # models.py:130-134
@@ -132,10 +134,29 @@ class StltBackbone(nn.Module):
         model.load_state_dict(torch.load(config.load_backbone_path, map_location="cpu"))
         return model
 
-    def forward(self, batch):
-        raise NotImplementedError(
-            "StltBackbone is a parameter holder; call Stlt.forward (the backbone-only output is "
-            "available through Stlt.forward_with_taps()['temporal']).")
+    def forward(self, batch, precision: str = "fp32"):
+        """Reference StltBackbone.forward (models.py:136-152): the temporal stack's output for every frame,
+        seq-first [L, B, H] as the reference returns it (its fusion models index it with lengths - 1).
+        Inference only; runs the same library path as ``Stlt`` (this module's parameters + an unused head)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("StltBackbone.forward is inference-only here: use Stlt for training, or call "
+                                      "it under torch.no_grad() in eval mode")
+        runner = self._runner
+        device = batch["categories"].device
+        if runner is None or runner.precision != precision or next(runner.prediction_head.parameters()).device != device:
+            runner = Stlt.__new__(Stlt)
+            nn.Module.__init__(runner)
+            runner.config, runner.precision = self._config, precision
+            runner.backbone = self                      # shares the parameters, no copy
+            runner.prediction_head = _ClassificationHead(self._config).to(device)
+            runner.logit_names = ("stlt",)
+            runner._handle = runner._handle_device = runner._weights_key = runner._workspace = runner._keepalive = None
+            runner._packed, runner._packed_key, runner._pruning = {}, {}, True
+            runner.train(False)
+            object.__setattr__(self, "_runner", runner)
+        with torch.no_grad():
+            out = runner.forward_with_taps(batch)["temporal"]   # [B, L, H]
+        return out.transpose(0, 1)
 
 
 class _ClassificationHead(nn.Module):  # reference models.py:155-160

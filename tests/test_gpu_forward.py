@@ -422,3 +422,17 @@ def test_two_devices_in_one_process():
             with torch.no_grad():
                 outs.append(m({k: v.to(dev) for k, v in batch.items()})["stlt"].cpu())
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+def test_backbone_forward_returns_every_frame_seq_first():
+    """StltBackbone.forward (reference models.py:136-152): [L, B, H], what the reference fusion models consume."""
+    cfg, sd, batch, g = golden_model_case("something")
+    m = _model(cfg, sd, "fp32")
+    with torch.no_grad():
+        out = m.backbone(to_cuda(batch))
+    B, L, _ = batch["categories"].shape
+    assert tuple(out.shape) == (L, B, 768)
+    for b in range(B):
+        n = int(batch["lengths"][b])
+        assert nerr(out[:n, b], torch.from_numpy(g["temporal"][b, :n])) < FP32_TOL
+    assert len(m.state_dict()) == 174 and len(m.backbone.state_dict()) == 168  # the runner adds nothing
