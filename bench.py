@@ -376,7 +376,6 @@ def run_train(args, rank, local_rank, world, torch, dist):
     sampler.start()
     ms, _ = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
-    launches_fwd_bwd = None
     prof_ms, prof = timed(step_resident, args.steps, 1, profile=True)
     e2e_ms, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
     videos = B * world * args.steps

@@ -135,26 +135,9 @@ __device__ __forceinline__ float gelu_erf_grad(float u) {
          u * 0.3989422804014327f * __expf(-0.5f * u * u);
 }
 
-// Same with the single-branch erf of gelu_erf_fast (common.cuh; |erf error| < 7e-7) and ex2.approx:
-// two MUFU + ~14 ALU instructions per element instead of erff()'s divergent branches, which made the
-// bf16 GELU-backward pass compute-bound (ncu: 81 % SM throughput at 3.8 TB/s).
-__device__ __forceinline__ float gelu_erf_grad_fast(float u) {
-  const float au = fabsf(u);
-  const float a = fminf(au, 5.9f);
-  float q = 5.204604041e-04f;
-  q = fmaf(q, a, -7.397519993e-03f);
-  q = fmaf(q, a, 5.256125276e-02f);
-  q = fmaf(q, a, 4.592546886e-01f);
-  q = fmaf(q, a, 1.151091390e+00f);
-  float e, g;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q * a));                  // erfc(|u| / sqrt 2)
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(-0.72134752044f * u * u));  // exp(-u^2 / 2)
-  const float erf_abs = 1.0f - e;
-  const float cdf = 0.5f + copysignf(0.5f * erf_abs, u);
-  return fmaf(u * 0.3989422804014327f, g, cdf);
-}
-
-// Two elements at a time in packed fp16 (see gelu_erf_fast_h2): the result multiplies a bf16 gradient.
+// GELU derivative, two elements at a time in packed fp16 (single-branch erf as in gelu_erf_fast_h2 + ex2 for the
+// Gaussian term): erff() + expf() made the bf16 GELU-backward pass compute-bound (ncu: 81 % SM throughput at 3.8 TB/s).
+// The result multiplies a bf16 gradient, fp16's 11 mantissa bits are ample.
 __device__ __forceinline__ __half2 gelu_erf_grad_fast_h2(__half2 u) {
   const __half2 au = __habs2(u);
   const __half2 a = __hmin2(au, __float2half2_rn(5.9f));
