@@ -421,7 +421,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
         } else if (kGelu == 2) {
-          if constexpr (kOut == GEMM_OUT_BF16) {  // inference: packed fp16 math, the output is bf16 anyway
+          if constexpr (kOut == GEMM_OUT_BF16 || kOut == GEMM_OUT_BF16_DUAL) {  // packed fp16 math, the output is bf16 anyway
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float2 r = __half22float2(gelu_erf_fast_h2(__floats2half2_rn(f[j], f[j + 1])));
