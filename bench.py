@@ -601,6 +601,18 @@ def main():
         }
         flops = FLOPS_PER_VIDEO[args.layout] * args.batch
         res["model_tflops"] = flops / (ms / args.steps * 1e-3) / 1e12
+        if precision == "bf16":
+            # the same K steps with the LayerNorms in their own kernels (stlt_set_fused_ln(0)): the GEMM launches
+            # then contain nothing but the projections, which is the figure comparable to a plain GEMM roofline
+            model.set_fused_layer_norm(False)
+            u_ms, u_prof = time_resident(model, batch_dev, args.steps, 2, world, torch, dist, profile=True)
+            model.set_fused_layer_norm(True)
+            u_roof = roofline_from_profile(u_prof, args.steps, precision, peaks, peak_src)
+            res["separate_layernorm_kernels"] = {
+                "value": args.batch * world * args.steps / (u_ms * 1e-3), "unit": "videos/s", "ms_per_step": u_ms / args.steps,
+                "gemm_roofline_frac": u_roof["frac"], "gemm_ms_per_step": u_roof["kernel_ms_per_step"],
+                "add_ln_ms_per_step": u_prof["add_ln"]["ms"] / args.steps,
+                "note": "profiled pass (per-launch CUDA events), LayerNorm fusion off"}
         return res, clocks
 
     main_res, clocks = measure(args.dtype, with_clocks=True)
@@ -633,7 +645,8 @@ def main():
             "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
             "cpu_baseline": cpu, "clocks": clocks, "model_tflops": main_res["model_tflops"],
             "breakdown_ms_per_step": main_res["breakdown_ms_per_step"],
-            "profiled_pass_ms_per_step": main_res["profiled_pass_ms_per_step"], "secondary": secondary,
+            "profiled_pass_ms_per_step": main_res["profiled_pass_ms_per_step"],
+            "separate_layernorm_kernels": main_res.get("separate_layernorm_kernels"), "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
