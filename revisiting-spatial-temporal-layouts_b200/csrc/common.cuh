@@ -107,8 +107,9 @@ __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
 // 32 mask bits for the element pair (2*pair, 2*pair + 1) of a site.
 __host__ __device__ __forceinline__ uint32_t drop_bits(uint32_t key, unsigned long long pair) {
   uint32_t x = lowbias32(static_cast<uint32_t>(pair) ^ key);
-  x ^= static_cast<uint32_t>(pair >> 32) * 0x9e3779b9u;
-  return lowbias32(x);
+  const uint32_t hi = static_cast<uint32_t>(pair >> 32);
+  if (hi != 0) x = lowbias32(x ^ (hi * 0x9e3779b9u));  // sites with more than 2^33 elements only
+  return x;
 }
 
 // multiplier (0 or scale) of element `which` (0 / 1) of the pair
