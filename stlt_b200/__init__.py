@@ -12,6 +12,9 @@ from .cacnf import Cacnf  # noqa: E402
 models_factory["cacnf"] = Cacnf
 from .prepare import prepare_layout_batch  # noqa: E402
 from .data import CharadesMapEvaluator, LayoutStore, TopKCounter  # noqa: E402
+from .pipeline import HostPipeline  # noqa: E402
+from .training import FusedTrainStep, linear_schedule_with_warmup  # noqa: E402
 
-__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "Cacnf", "CacnfModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter", "CharadesMapEvaluator",
+__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "Cacnf", "CacnfModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter", "CharadesMapEvaluator", "HostPipeline", "FusedTrainStep",
+           "linear_schedule_with_warmup",
            "SOMETHING_ELSE", "ACTION_GENOME"]
