@@ -271,6 +271,41 @@ def golden_cacnf(configs, models, batch_size: int, weight_seed: int, batch_seed:
     print("cacnf_something.npz", {k: float(v.abs().max()) for k, v in out.items()}, "entries", len(own))
 
 
+def golden_caf_lcf(configs, models, batch_size: int, weight_seed: int, batch_seed: int):
+    """The unmodified reference CrossAttentionFusion (CAF) and LateConcatenationFusion (LCF) modules, eval mode,
+    ResNet features injected as in golden_cacnf."""
+    import stlt_b200
+    from modelling import resnets3d
+    from stlt_b200.synthetic import make_appearance_features, make_batch, random_state_dict
+    batch = make_batch(batch_size, layout="something", ragged=True, seed=batch_seed)
+    feats = make_appearance_features(batch_size, seed=batch_seed + 50)
+    res = {"batch_size": np.int64(batch_size), "weight_seed": np.int64(weight_seed), "batch_seed": np.int64(batch_seed)}
+    for name, cls in (("caf", models.CrossAttentionFusion), ("lcf", models.LateConcatenationFusion)):
+        orig_load = torch.load
+        torch.load = lambda *a, **k: {"state_dict": resnets3d.generate_model(model_depth=50, n_classes=1139).state_dict()}
+        try:
+            cfg = configs.MultimodalModelConfig(num_classes=174, unique_categories=4, appearance_num_frames=32,
+                                                resnet_model_path="synthetic")
+            torch.manual_seed(0)
+            ref = cls(cfg)
+        finally:
+            torch.load = orig_load
+        ref.train(False)
+        full = ref.state_dict()
+        own = {k: v for k, v in full.items() if ".resnet." not in k}
+        sd = random_state_dict(own, seed=weight_seed)
+        ref.load_state_dict({**full, **sd}, strict=True)
+        branch = ref.caf_backbone.appearance_branch if name == "caf" else ref.appearance_branch
+        branch.resnet.forward_features = lambda b: feats
+        with torch.no_grad():
+            out = ref({**{k: v.clone() for k, v in batch.items()}, "video_frames": torch.zeros(batch_size, 1)})
+        res[f"logits_{name}"] = out[name].numpy()
+        res[f"checksum_{name}"] = np.float64(weights_checksum(sd))
+        res[f"entries_{name}"] = np.int64(len(own))
+        print(name, float(out[name].abs().max()), len(own))
+    np.savez_compressed(GOLDEN / "caf_lcf_something.npz", **res)
+
+
 def golden_charades_map():
     """The reference's own charades_map (src/utils/evaluation.py:126-132) on seeded scores / multi-hot labels,
     including videos without labels (the -inf fix) and one class without positives (nan)."""
@@ -304,6 +339,7 @@ def main():
     golden_model(configs, models, "action_genome", batch_size=2, weight_seed=2, batch_seed=4)
     golden_cacnf(configs, models, batch_size=3, weight_seed=8, batch_seed=9)
     golden_charades_map()
+    golden_caf_lcf(configs, models, batch_size=3, weight_seed=12, batch_seed=13)
     from utils import train_inference_utils as train_utils
     golden_training(configs, models, train_utils, "something", batch_size=4, weight_seed=5, batch_seed=6)
     golden_training(configs, models, train_utils, "action_genome", batch_size=2, weight_seed=6, batch_seed=7)

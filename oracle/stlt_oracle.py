@@ -482,3 +482,36 @@ def charades_map(predictions, ground_truths):
         aps.append(float((np.cumsum(tp)[tp] / ranks[tp]).sum() / n_pos))
     aps = np.array(aps)
     return float(np.mean(aps)), aps
+
+
+def caf_forward(sd, batch, features, **kw):
+    """CrossAttentionFusion.forward (models.py:486-501): the CACNF backbone + the fusion classifier."""
+    remap = {}
+    for k, v in sd.items():
+        if k.startswith("caf_backbone."):
+            remap["backbone." + k[len("caf_backbone."):]] = v
+        elif k.startswith("classifier."):
+            remap["fusion_classifier." + k[len("classifier."):]] = v
+    _add_zero_heads(remap)
+    return {"caf": cacnf_forward(remap, batch, features, **kw)["caf"]}
+
+
+def lcf_forward(sd, batch, features, **kw):
+    """LateConcatenationFusion.forward (models.py:305-323): layout state [lengths - 1] ++ appearance CLS state ->
+    FusionHead, i.e. the CACNF data flow without fusion layers."""
+    remap = {}
+    for k, v in sd.items():
+        if k.startswith("layout_branch.") or k.startswith("appearance_branch."):
+            remap["backbone." + k] = v
+        elif k.startswith("classifier."):
+            remap["fusion_classifier." + k[len("classifier."):]] = v
+    _add_zero_heads(remap)
+    return {"lcf": cacnf_forward(remap, batch, features, num_fusion_layers=0, **kw)["caf"]}
+
+
+def _add_zero_heads(sd):
+    c = sd["fusion_classifier.fc2.weight"].shape[0]
+    for p in ("layout_classifier.", "appearance_classifier."):
+        sd[p + "fc1.weight"], sd[p + "fc1.bias"] = torch.zeros(HIDDEN, HIDDEN), torch.zeros(HIDDEN)
+        sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"] = torch.ones(HIDDEN), torch.zeros(HIDDEN)
+        sd[p + "fc2.weight"], sd[p + "fc2.bias"] = torch.zeros(c, HIDDEN), torch.zeros(c)

@@ -86,27 +86,48 @@ class Cacnf(nn.Module):
     """``precision``: "bf16" (default) or "fp32" (3-term bf16 split on tcgen05, logits within 1e-4 of the fp32
     reference), as for ``Stlt``."""
 
+    # reference state_dict prefix -> name the library binds (identity for CACNF; see Caf / Lcf below)
+    _NAME_MAP = ()
+    _FUSION_LAYERS = None  # None: config.num_fusion_layers
+
     def __init__(self, config, precision: str = "bf16"):
         super().__init__()
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         self.precision = precision
+        self._build(config)
+
+    def _build(self, config):
         if config.hidden_size != 768 or config.num_attention_heads != 12:
             raise ValueError("the sm_100a kernels are specialised for hidden_size=768, 12 heads")
         if config.appearance_num_frames > 32:
             raise ValueError("at most 32 appearance positions (+1 CLS token) are supported")
         self.config = config
-        self.backbone = _FusionBackbone(config)
-        self.layout_classifier = _ClassificationHead(config)
-        self.appearance_classifier = _ClassificationHead(config)
-        self.fusion_classifier = _FusionHead(config)
-        self.logit_names = ("stlt", "resnet3d", "caf", "ensemble")
+        self._make_parameters(config)
         self._handle = None
         self._handle_device = None
         self._weights_key = None
         self._packed = None
         self._workspace = None
         self._keepalive = None
+
+    def _make_parameters(self, config):
+        self.backbone = _FusionBackbone(config)
+        self.layout_classifier = _ClassificationHead(config)
+        self.appearance_classifier = _ClassificationHead(config)
+        self.fusion_classifier = _FusionHead(config)
+        self.logit_names = ("stlt", "resnet3d", "caf", "ensemble")
+
+    def _bound_tensors(self):
+        """(library name, tensor) for every tensor the library binds."""
+        out = []
+        for name, p in self.named_parameters():
+            for src, dst in self._NAME_MAP:
+                if name.startswith(src):
+                    name = dst + name[len(src):]
+                    break
+            out.append((name, p))
+        return out
 
     def __del__(self):
         try:
@@ -139,7 +160,7 @@ class Cacnf(nn.Module):
 
     def _sync_weights(self, device, stream):
         lib = _lib.load_library()
-        named = list(self.named_parameters())
+        named = self._bound_tensors()
         prec = _lib.PRECISIONS[self.precision]
         key = (prec,) + tuple((p.data_ptr(), p._version) for _, p in named)
         if key == self._weights_key:
@@ -158,8 +179,9 @@ class Cacnf(nn.Module):
             for d, s in enumerate(shape):
                 arr[i].shape[d] = s
         c = self.config
+        fusion_layers = c.num_fusion_layers if self._FUSION_LAYERS is None else self._FUSION_LAYERS
         _lib.check(self._handle, lib.stlt_cacnf_bind_weights(self._handle, arr, len(named), c.num_appearance_layers,
-                                                             c.num_fusion_layers, c.appearance_num_frames,
+                                                             fusion_layers, c.appearance_num_frames,
                                                              c.feature_channels))
         n1, n2 = ctypes.c_size_t(), ctypes.c_size_t()
         _lib.check(self._handle, lib.stlt_packed_weights_bytes(self._handle, prec, ctypes.byref(n1)))
@@ -211,7 +233,10 @@ class Cacnf(nn.Module):
                 feats.data_ptr(), B, L, S, self._workspace.data_ptr(), self._workspace.numel(),
                 *(t.data_ptr() for t in out)))
             self._keepalive = (cats, boxes, ftypes, lengths, scores, feats)
-        return {k: v for k, v in zip(self.logit_names, out)}
+        return self._select_logits(dict(zip(("stlt", "resnet3d", "caf", "ensemble"), out)))
+
+    def _select_logits(self, logits):
+        return logits
 
     def set_profiling(self, enable: bool) -> None:
         _lib.check(self._handle, _lib.load_library().stlt_set_profiling(self._handle, int(enable)))
@@ -221,3 +246,63 @@ class Cacnf(nn.Module):
         _lib.check(self._handle, _lib.load_library().stlt_get_profile(self._handle, ctypes.byref(prof)))
         return {name: {"ms": prof.ms[i], "flops": prof.flops[i], "launches": int(prof.launches[i])}
                 for i, name in enumerate(_lib.PROF_CATEGORIES)}
+
+
+class _UnusedHeads(nn.Module):
+    """The library's CACNF entry point always evaluates the layout / appearance classifiers; the two-logit-less
+    variants below feed it zero heads that are NOT part of their state_dict."""
+
+    def _add_unused_heads(self, config):
+        for prefix in ("layout_classifier", "appearance_classifier"):
+            head = _ClassificationHead(config)
+            for name, p in head.named_parameters():
+                self.register_buffer(f"_unused_{prefix}_{name.replace('.', '_')}", torch.zeros_like(p), persistent=False)
+
+    def _unused_head_tensors(self):
+        out = []
+        for prefix in ("layout_classifier", "appearance_classifier"):
+            for name in ("fc1.weight", "fc1.bias", "layer_norm.weight", "layer_norm.bias", "fc2.weight", "fc2.bias"):
+                out.append((f"{prefix}.{name}", getattr(self, f"_unused_{prefix}_{name.replace('.', '_')}")))
+        return out
+
+
+class Caf(Cacnf, _UnusedHeads):
+    """Drop-in for the reference ``CrossAttentionFusion`` (CAF, models.py:486-501) on precomputed features:
+    the CACNF backbone with the fusion classifier only; state_dict prefixes ``caf_backbone.`` / ``classifier.``."""
+
+    _NAME_MAP = (("caf_backbone.", "backbone."), ("classifier.", "fusion_classifier."))
+
+    def _make_parameters(self, config):
+        self.caf_backbone = _FusionBackbone(config)
+        self.classifier = _FusionHead(config)
+        self._add_unused_heads(config)
+        self.logit_names = ("caf",)
+
+    def _bound_tensors(self):
+        return super()._bound_tensors() + self._unused_head_tensors()
+
+    def _select_logits(self, logits):
+        return {"caf": logits["caf"]}
+
+
+class Lcf(Cacnf, _UnusedHeads):
+    """Drop-in for the reference ``LateConcatenationFusion`` (LCF, models.py:297-323) on precomputed features:
+    layout state [lengths - 1] and appearance CLS state concatenated into the fusion head — the CACNF pipeline with
+    zero fusion layers; state_dict prefixes ``layout_branch.`` / ``appearance_branch.`` / ``classifier.``."""
+
+    _NAME_MAP = (("layout_branch.", "backbone.layout_branch."), ("appearance_branch.", "backbone.appearance_branch."),
+                 ("classifier.", "fusion_classifier."))
+    _FUSION_LAYERS = 0
+
+    def _make_parameters(self, config):
+        self.layout_branch = StltBackbone(config)
+        self.appearance_branch = _AppearanceBranch(config)
+        self.classifier = _FusionHead(config)
+        self._add_unused_heads(config)
+        self.logit_names = ("lcf",)
+
+    def _bound_tensors(self):
+        return super()._bound_tensors() + self._unused_head_tensors()
+
+    def _select_logits(self, logits):
+        return {"lcf": logits["caf"]}

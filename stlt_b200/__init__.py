@@ -7,14 +7,14 @@ __path__.append(str(_PKG_DIR))
 
 from .configs import ACTION_GENOME, SOMETHING_ELSE, CacnfModelConfig, StltModelConfig  # noqa: E402
 from .module import Stlt, StltBackbone, models_factory  # noqa: E402
-from .cacnf import Cacnf  # noqa: E402
+from .cacnf import Cacnf, Caf, Lcf  # noqa: E402
 
-models_factory["cacnf"] = Cacnf
+models_factory.update({"cacnf": Cacnf, "caf": Caf, "lcf": Lcf})
 from .prepare import prepare_layout_batch  # noqa: E402
 from .data import CharadesMapEvaluator, LayoutStore, TopKCounter  # noqa: E402
 from .pipeline import HostPipeline  # noqa: E402
 from .training import FusedTrainStep, linear_schedule_with_warmup  # noqa: E402
 
-__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "Cacnf", "CacnfModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter", "CharadesMapEvaluator", "HostPipeline", "FusedTrainStep",
+__all__ = ["Stlt", "StltBackbone", "StltModelConfig", "Cacnf", "Caf", "Lcf", "CacnfModelConfig", "models_factory", "prepare_layout_batch", "LayoutStore", "TopKCounter", "CharadesMapEvaluator", "HostPipeline", "FusedTrainStep",
            "linear_schedule_with_warmup",
            "SOMETHING_ELSE", "ACTION_GENOME"]

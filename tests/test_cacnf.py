@@ -107,3 +107,44 @@ def test_attention_cross_kernel(Tq, Tk, causal, masked):
     want = (torch.softmax(scores, -1) @ v).transpose(1, 2).reshape(N * Tq, 768)
     assert nerr(out, want) < 1e-2
     lib.stlt_destroy(h)
+
+
+def _variant_case(name):
+    import stlt_b200
+    from stlt_b200.synthetic import make_appearance_features, make_batch, random_state_dict
+    g = load_golden("caf_lcf_something.npz")
+    cfg = stlt_b200.CacnfModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(0)
+    model = (stlt_b200.Caf if name == "caf" else stlt_b200.Lcf)(cfg)
+    sd = random_state_dict(model.state_dict(), seed=int(g["weight_seed"]))
+    assert len(sd) == int(g[f"entries_{name}"])
+    assert abs(weights_checksum(sd) - float(g[f"checksum_{name}"])) < 1e-6 * float(g[f"checksum_{name}"])
+    batch = make_batch(int(g["batch_size"]), layout="something", ragged=True, seed=int(g["batch_seed"]))
+    feats = make_appearance_features(int(g["batch_size"]), seed=int(g["batch_seed"]) + 50)
+    return model, sd, batch, feats, torch.from_numpy(g[f"logits_{name}"])
+
+
+@pytest.mark.parametrize("name", ["caf", "lcf"])
+def test_oracle_caf_lcf_match_reference_golden(name):
+    model, sd, batch, feats, want = _variant_case(name)
+    fn = stlt_oracle.caf_forward if name == "caf" else stlt_oracle.lcf_forward
+    with torch.no_grad():
+        got = fn(dict(sd), batch, feats)[name]
+    assert nerr(got, want) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["caf", "lcf"])
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("fp32", 1e-4)])
+def test_caf_lcf_gpu_match_reference_golden(name, precision, tol):
+    model, sd, batch, feats, want = _variant_case(name)
+    model.load_state_dict(sd)
+    model.precision = precision
+    model = model.cuda()
+    model.train(False)
+    with torch.no_grad():
+        out = model({**to_cuda(batch), "video_features": feats.cuda()})
+    assert list(out) == [name]
+    err = nerr(out[name], want)
+    print(name, precision, err)
+    assert err < tol
