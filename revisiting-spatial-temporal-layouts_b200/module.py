@@ -337,7 +337,9 @@ class Stlt(nn.Module):
         dropout_p = float(getattr(self.config, "hidden_dropout_prob", 0.0)) if self.training else 0.0
         if getattr(self.config, "load_backbone_path", None) and self.config.freeze_backbone:
             dropout_p = 0.0  # the frozen backbone stays in eval mode (models.py:180-183); the head has no dropout
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        # The autograd / mixed-precision training path is taken in train mode only. In eval mode the logits come
+        # from the inference path in the configured precision and carry no grad_fn, with or without torch.no_grad().
+        needs_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad or dropout_p > 0.0:
             # training step (src/train.py:125-127): logits carry a grad_fn whose backward is
             # stlt_backward; the reference's own criterion / clip_grad_norm_ / AdamW then work as is

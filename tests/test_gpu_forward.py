@@ -139,6 +139,27 @@ def test_forward_batch8_config1_fp32_and_bf16_top1():
     assert torch.equal(again, got)
 
 
+def test_eval_mode_uses_inference_path_with_or_without_no_grad():
+    """Eval mode returns the configured-precision inference logits (no grad_fn) whether or not the caller wraps
+    the call in torch.no_grad() (src/inference.py:60-77 does, an ad-hoc notebook call may not); train mode
+    returns logits with a grad_fn (src/train.py:125-127)."""
+    cfg = StltModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=41)
+    batch = to_cuda(make_batch(6, "something", ragged=True, seed=42))
+    m = _model(cfg, sd, "fp32")
+    with torch.no_grad():
+        a = m(batch)["stlt"]
+    b = m(batch)["stlt"]
+    assert b.grad_fn is None and not b.requires_grad
+    assert torch.equal(a, b)
+    m.train(True)
+    m.config.hidden_dropout_prob = 0.0
+    c = m(batch)["stlt"]
+    assert c.grad_fn is not None
+    assert nerr(c.detach(), a) < BF16_TOL
+
+
 def test_forward_default_init_clone_layers():
     """Default init (all encoder layers identical clones, zero padding rows), non-128-multiple M."""
     cfg = StltModelConfig(num_classes=174, unique_categories=4)
