@@ -200,75 +200,190 @@ __global__ void topk_count_kernel(const float* __restrict__ logits, const long l
 // ------------------------------------------------------------------------------------------------
 // K1: CategoryBoxEmbeddings.forward (src/modelling/models.py:29-39)
 // ------------------------------------------------------------------------------------------------
-constexpr int kEmbedTok = 4;  // tokens per warp iteration: parameter loads are amortised over them
+// The pre-LayerNorm row is affine in u = (box, score, 1):  x[col] = E[cat][col] + sum_q u_q V_q[col], so its
+// LayerNorm statistics need no reduction over the 768 columns at run time:
+//   mean = mean(E[cat]) + sum_q u_q mean(V_q)                      -> removed by centring E, V_q once
+//   var  = u^T G_cat u / 768, G_cat = Gram matrix of the centred vectors (w0..w3, score_w, E[cat] + bias)
+// `embed_stats_kernel` (one CTA per category, fp64 accumulation) writes mean(E[cat]) and the 21 Gram entries;
+// `embed_kernel` then has thread t of 192 own columns 4t..4t+3 with their centred parameters resident in
+// registers, evaluates the 6x6 quadratic form for 8 tokens in lanes 0-7 of every warp, and streams the 4.6 KB
+// per token out as 512-byte warp stores. No shared memory, no barrier, no cross-lane reduction.
+constexpr int kEmbedTok = 8;
+constexpr int kEmbedThreads = kHidden / 4;  // 192
+constexpr int kEmbedCatStride = 24;         // floats per category: mean(E[cat]), 21 quadratic-form coefficients
+constexpr int kEmbedGlobal = 8;             // after the categories: mean of w0..w3, score_w, bias
 
 __global__ void __launch_bounds__(256)
+embed_stats_kernel(const float* __restrict__ cat_table, int unique_categories,
+                   const float* __restrict__ box_w, const float* __restrict__ box_b,
+                   const float* __restrict__ score_w, const float* __restrict__ score_b,
+                   float* __restrict__ stats) {
+  __shared__ double red[8][21];
+  __shared__ double mean_s[7];
+  const int cat = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* erow = cat_table + static_cast<long long>(cat) * kHidden;
+  // pass 1: column means of the seven vectors (w0..w3, score_w, bias, E[cat])
+  double m[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int col = tid; col < kHidden; col += 256) {
+    for (int q = 0; q < 4; ++q) m[q] += box_w[col * 4 + q];
+    if (score_w != nullptr) m[4] += score_w[col];
+    m[5] += box_b[col] + (score_b != nullptr ? score_b[col] : 0.f);
+    m[6] += erow[col];
+  }
+  for (int i = 0; i < 7; ++i) {
+    for (int o = 16; o > 0; o >>= 1) m[i] += __shfl_xor_sync(0xffffffffu, m[i], o);
+    if (lane == 0) red[warp][i] = m[i];
+  }
+  __syncthreads();
+  if (tid < 7) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w][tid];
+    mean_s[tid] = t / kHidden;
+  }
+  __syncthreads();
+  // pass 2: Gram matrix of the centred vectors v = (w0, w1, w2, w3, score_w, E[cat] + bias)
+  double g[21];
+  for (int i = 0; i < 21; ++i) g[i] = 0;
+  for (int col = tid; col < kHidden; col += 256) {
+    double v[6];
+    for (int q = 0; q < 4; ++q) v[q] = box_w[col * 4 + q] - mean_s[q];
+    v[4] = score_w != nullptr ? score_w[col] - mean_s[4] : 0.0;
+    v[5] = (erow[col] - mean_s[6]) + ((box_b[col] + (score_b != nullptr ? score_b[col] : 0.f)) - mean_s[5]);
+    int k = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) g[k++] += v[i] * v[j];
+  }
+  __syncthreads();  // red is reused
+  for (int i = 0; i < 21; ++i) {
+    for (int o = 16; o > 0; o >>= 1) g[i] += __shfl_xor_sync(0xffffffffu, g[i], o);
+    if (lane == 0) red[warp][i] = g[i];
+  }
+  __syncthreads();
+  float* out = stats + static_cast<long long>(cat) * kEmbedCatStride;
+  if (tid < 21) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w][tid];
+    // position of entry tid in the upper triangle: off-diagonal terms appear twice in u^T G u
+    int i = 0, rem = tid;
+    while (rem >= 6 - i) { rem -= 6 - i; ++i; }
+    out[1 + tid] = static_cast<float>((rem == 0 ? 1.0 : 2.0) * t / kHidden);
+  }
+  if (tid == 21) out[0] = static_cast<float>(mean_s[6]);
+  if (tid == 22 || tid == 23) out[tid] = 0.f;
+  if (cat == 0 && tid < kEmbedGlobal)
+    stats[static_cast<long long>(unique_categories) * kEmbedCatStride + tid] =
+        tid < 6 ? static_cast<float>(mean_s[tid]) : 0.f;
+}
+
+__global__ void __launch_bounds__(kEmbedThreads, 4)
 embed_kernel(const long long* __restrict__ categories, const float4* __restrict__ boxes,
              const float* __restrict__ scores, const float* __restrict__ cat_table,
              int unique_categories, const float* __restrict__ box_w,
              const float* __restrict__ box_b, const float* __restrict__ score_w,
              const float* __restrict__ score_b, const float* __restrict__ ln_g,
              const float* __restrict__ ln_b, float eps, long long tokens, ActOut out,
-             int* __restrict__ err_flag, DropCfg drop) {
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
-  const float4* bw4 = reinterpret_cast<const float4*>(box_w);  // [768][4]: one float4 per feature
+             int* __restrict__ err_flag, DropCfg drop, const float* __restrict__ stats) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int c = 4 * tid;
+  // resident, centred parameters of this thread's four columns
+  const float* glob = stats + static_cast<long long>(unique_categories) * kEmbedCatStride;
+  const float4 mw = *reinterpret_cast<const float4*>(glob);
+  const float msw = glob[4], mb = glob[5];
+  float4 w[4];  // box_w is [768][4]: one float4 per feature
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    w[q] = __ldg(reinterpret_cast<const float4*>(box_w) + c + q);
+    w[q].x -= mw.x; w[q].y -= mw.y; w[q].z -= mw.z; w[q].w -= mw.w;
+  }
+  float4 bias = __ldg(reinterpret_cast<const float4*>(box_b + c));
+  float4 sw = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (scores != nullptr) {
+    sw = __ldg(reinterpret_cast<const float4*>(score_w + c));  // [768][1]
+    sw.x -= msw; sw.y -= msw; sw.z -= msw; sw.w -= msw;
+    const float4 sb = __ldg(reinterpret_cast<const float4*>(score_b + c));
+    bias.x += sb.x; bias.y += sb.y; bias.z += sb.z; bias.w += sb.w;
+  }
+  bias.x -= mb; bias.y -= mb; bias.z -= mb; bias.w -= mb;
+  const float4 gam = __ldg(reinterpret_cast<const float4*>(ln_g + c));
+  const float4 bet = __ldg(reinterpret_cast<const float4*>(ln_b + c));
+
   const long long groups = (tokens + kEmbedTok - 1) / kEmbedTok;
-  for (long long grp = warp0; grp < groups; grp += nwarps) {
+  for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
     const long long t0 = grp * kEmbedTok;
-    long long cat[kEmbedTok];
-    float4 box[kEmbedTok];
-    float score[kEmbedTok];
-    RowRegs r[kEmbedTok];
+    // ---- row statistics of token t0 + (lane & 7) from the category's quadratic form ----
+    long long tl = t0 + (lane & 7);
+    if (tl >= tokens) tl = tokens - 1;  // tail: recompute the last token
+    long long cat_l = __ldg(categories + tl);
+    if (cat_l < 0 || cat_l >= unique_categories) {
+      if (tid < kEmbedTok) atomicExch(err_flag, 1);  // lanes 0-7 of warp 0 cover the group's eight tokens
+      cat_l = 0;
+    }
+    const float4 box_l = __ldg(boxes + tl);
+    const float sc_l = scores != nullptr ? __ldg(scores + tl) : 0.f;
+    float mean_l, rstd_l;
+    {
+      const float4* gq = reinterpret_cast<const float4*>(stats + cat_l * kEmbedCatStride);
+      float coef[kEmbedCatStride];
+#pragma unroll
+      for (int k = 0; k < kEmbedCatStride / 4; ++k) {
+        const float4 v = __ldg(gq + k);
+        coef[4 * k + 0] = v.x; coef[4 * k + 1] = v.y; coef[4 * k + 2] = v.z; coef[4 * k + 3] = v.w;
+      }
+      mean_l = coef[0];
+      const float u[6] = {box_l.x, box_l.y, box_l.z, box_l.w, sc_l, 1.f};
+      float var = 0.f;
+      int k = 1;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float inner = 0.f;
+#pragma unroll
+        for (int j = i; j < 6; ++j) inner += coef[k++] * u[j];
+        var += inner * u[i];
+      }
+      rstd_l = 1.0f / sqrtf(fmaxf(var, 0.f) + eps);
+    }
+    const int cat_i = static_cast<int>(cat_l);
 #pragma unroll
     for (int i = 0; i < kEmbedTok; ++i) {
-      const long long t = t0 + i < tokens ? t0 + i : tokens - 1;  // tail: recompute the last token
-      cat[i] = categories[t];
-      if (cat[i] < 0 || cat[i] >= unique_categories) {
-        if (lane == 0) atomicExch(err_flag, 1);
-        cat[i] = 0;
-      }
-      box[i] = __ldg(boxes + t);
-      score[i] = scores != nullptr ? __ldg(scores + t) : 0.f;
-      r[i] = load_row(cat_table, cat[i], lane);
-    }
+      const long long t = t0 + i;
+      if (t >= tokens) break;
+      const int cat = __shfl_sync(0xffffffffu, cat_i, i);
+      const float mean = __shfl_sync(0xffffffffu, mean_l, i);
+      const float rstd = __shfl_sync(0xffffffffu, rstd_l, i);
+      const float4 box = __ldg(boxes + t);
+      const float4 row = __ldg(reinterpret_cast<const float4*>(cat_table + static_cast<long long>(cat) * kHidden + c));
+      float v[4] = {bias.x - mean, bias.y - mean, bias.z - mean, bias.w - mean};
 #pragma unroll
-    for (int k = 0; k < kVec; ++k) {
-      const int c = 4 * (lane + 32 * k);
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(box_b + c));
-      float4 w[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = __ldg(bw4 + c + q);
-      float4 sw = make_float4(0.f, 0.f, 0.f, 0.f), sb = sw;
+      for (int q = 0; q < 4; ++q) v[q] += box.x * w[q].x + box.y * w[q].y + box.z * w[q].z + box.w * w[q].w;
       if (scores != nullptr) {
-        sw = __ldg(reinterpret_cast<const float4*>(score_w + c));  // [768][1]
-        sb = __ldg(reinterpret_cast<const float4*>(score_b + c));
+        const float sc = __ldg(scores + t);
+        v[0] += sc * sw.x; v[1] += sc * sw.y; v[2] += sc * sw.z; v[3] += sc * sw.w;
       }
-#pragma unroll
-      for (int i = 0; i < kEmbedTok; ++i) {
-        float e[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          e[q] += box[i].x * w[q].x + box[i].y * w[q].y + box[i].z * w[q].z + box[i].w * w[q].w;
-        if (scores != nullptr) {
-          e[0] += score[i] * sw.x + sb.x;
-          e[1] += score[i] * sw.y + sb.y;
-          e[2] += score[i] * sw.z + sb.z;
-          e[3] += score[i] * sw.w + sb.w;
+      float4 y;
+      y.x = (row.x + v[0]) * rstd * gam.x + bet.x;
+      y.y = (row.y + v[1]) * rstd * gam.y + bet.y;
+      y.z = (row.z + v[2]) * rstd * gam.z + bet.z;
+      y.w = (row.w + v[3]) * rstd * gam.w + bet.w;
+      if (drop.thr16 != 0) {  // models.py:27,38 (training only); element index = token * 768 + column
+        const unsigned long long pair = (static_cast<unsigned long long>(t) * kHidden + c) >> 1;
+        const uint32_t b0 = drop_bits(drop.key, pair), b1 = drop_bits(drop.key, pair + 1);
+        y.x *= drop_mul(b0, 0, drop);
+        y.y *= drop_mul(b0, 1, drop);
+        y.z *= drop_mul(b1, 0, drop);
+        y.w *= drop_mul(b1, 1, drop);
+      }
+      if (out.x != nullptr) *reinterpret_cast<float4*>(out.x + t * kHidden + c) = y;
+      if (out.xb != nullptr) {
+        uint2 h;
+        h.x = pack_bf16x2(y.x, y.y);
+        h.y = pack_bf16x2(y.z, y.w);
+        *reinterpret_cast<uint2*>(out.xb + t * kHidden + c) = h;
+        if (out.planes == 2) {
+          uint2 l;
+          l.x = pack_bf16x2(bf16_residual(y.x), bf16_residual(y.y));
+          l.y = pack_bf16x2(bf16_residual(y.z), bf16_residual(y.w));
+          *reinterpret_cast<uint2*>(out.xb + (out.plane_rows + t) * kHidden + c) = l;
         }
-        r[i].v[k].x += e[0];
-        r[i].v[k].y += e[1];
-        r[i].v[k].z += e[2];
-        r[i].v[k].w += e[3];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kEmbedTok; ++i) {
-      if (t0 + i < tokens) {
-        layer_norm_row(r[i], ln_g, ln_b, eps, lane);
-        drop_row(r[i], t0 + i, lane, drop);  // models.py:27,38 (training only)
-        store_act(out, t0 + i, r[i], lane);
       }
     }
   }
@@ -518,15 +633,27 @@ cudaError_t launch_masks(const long long* categories, const long long* frame_typ
   return cudaGetLastError();
 }
 
+size_t embed_scratch_bytes(int unique_categories) {
+  return (static_cast<size_t>(unique_categories) * kEmbedCatStride + kEmbedGlobal) * sizeof(float);
+}
+
 cudaError_t launch_embed(const long long* categories, const float* boxes, const float* scores,
                          const float* cat_table, int unique_categories, const float* box_w,
                          const float* box_b, const float* score_w, const float* score_b,
                          const float* ln_g, const float* ln_b, float eps, long long tokens,
-                         ActOut out, int* err_flag, cudaStream_t stream, DropCfg drop) {
+                         ActOut out, int* err_flag, cudaStream_t stream, float* scratch,
+                         size_t scratch_bytes, DropCfg drop) {
   if (tokens == 0) return cudaSuccess;
-  embed_kernel<<<row_grid((tokens + kEmbedTok - 1) / kEmbedTok, 8), 256, 0, stream>>>(
+  if (scratch == nullptr || scratch_bytes < embed_scratch_bytes(unique_categories) || unique_categories < 1)
+    return cudaErrorInvalidValue;
+  embed_stats_kernel<<<unique_categories, 256, 0, stream>>>(
+      cat_table, unique_categories, box_w, box_b, scores != nullptr ? score_w : nullptr,
+      scores != nullptr ? score_b : nullptr, scratch);
+  long long blocks = (tokens + kEmbedTok - 1) / kEmbedTok;
+  if (blocks > 148LL * 4 * 8) blocks = 148LL * 4 * 8;  // 4 resident CTAs per SM, grid-stride inside
+  embed_kernel<<<static_cast<unsigned>(blocks), kEmbedThreads, 0, stream>>>(
       categories, reinterpret_cast<const float4*>(boxes), scores, cat_table, unique_categories,
-      box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag, drop);
+      box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag, drop, scratch);
   return cudaGetLastError();
 }
 

@@ -132,7 +132,11 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
                          const float* cat_table, int unique_categories, const float* box_w,
                          const float* box_b, const float* score_w, const float* score_b,
                          const float* ln_g, const float* ln_b, float eps, long long tokens,
-                         ActOut out, int* err_flag, cudaStream_t stream, DropCfg drop = DropCfg{0, 0, 1.f});
+                         ActOut out, int* err_flag, cudaStream_t stream, float* scratch, size_t scratch_bytes,
+                         DropCfg drop = DropCfg{0, 0, 1.f});
+// `scratch` (>= embed_scratch_bytes, any buffer that is dead until the kernel after the embedding) receives the
+// per-category LayerNorm statistics tables that embed_stats_kernel derives from the live parameters on every call.
+size_t embed_scratch_bytes(int unique_categories);
 
 // x <- LayerNorm(x + y) (post-norm residual of nn.TransformerEncoderLayer); y may be null.
 // z_out (optional, training): receives the pre-LayerNorm sum x + y.

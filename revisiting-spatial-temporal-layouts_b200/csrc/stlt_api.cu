@@ -168,6 +168,9 @@ Phase make_phase(uint8_t* ws, const BufSet& b, long long m_valid) {
   return ph;
 }
 
+// The FFN hidden buffer is dead until the first linear1: the embedding kernel's statistics tables live there.
+size_t embed_scratch(const Phase& ph) { return static_cast<size_t>(ph.m_pad) * kFfn * 2; }
+
 // First half of a post-norm nn.TransformerEncoderLayer (eval mode): in-projection + attention.
 // Needs every token of the sequences (keys / values), so it always runs on the full phase.
 int run_attention_part(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw,
@@ -628,9 +631,9 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
       ProfileScope prof(h, stream, STLT_PROF_OTHER);
       STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories, h->w.box_w, h->w.box_b,
                                 h->w.score_w, h->w.score_b, h->w.emb_g, h->w.emb_b, d.layer_norm_eps, n_sp, emb,
-                                err_flag, stream));
+                                err_flag, stream, reinterpret_cast<float*>(sp.hid), embed_scratch(sp)));
     }
-    h->launches++;
+    h->launches += 2;  // embed_stats_kernel + embed_kernel
     PendingNorm sp_out;
     int rc = fused_stack(h, stream, h->w.spatial, sp, tm, categories, n_tm, S, false, S, nullptr, 0, st_sp, st_c_sp,
                          err_flag, &sp_out);
@@ -669,9 +672,10 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     ProfileScope prof(h, stream, STLT_PROF_OTHER);
     STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories,
                               h->w.box_w, h->w.box_b, h->w.score_w, h->w.score_b, h->w.emb_g,
-                              h->w.emb_b, d.layer_norm_eps, n_sp, emb, err_flag, stream));
+                              h->w.emb_b, d.layer_norm_eps, n_sp, emb, err_flag, stream,
+                              reinterpret_cast<float*>(sp.hid), embed_scratch(sp)));
   }
-  h->launches++;
+  h->launches += 2;  // embed_stats_kernel + embed_kernel
   if (h->taps.embed)
     STLT_CUDA(h, cudaMemcpyAsync(h->taps.embed, sp.x, n_sp * kHidden * 4, cudaMemcpyDeviceToDevice, stream));
 

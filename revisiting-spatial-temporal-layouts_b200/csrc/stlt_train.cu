@@ -360,8 +360,10 @@ int stlt_forward_train(void* handle, void* stream_, const int64_t* categories_, 
     ActOut emb{x, at<__nv_bfloat16>(ws, p.sp[0].xb), 1, p.m_sp};
     STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories, h->w.box_w,
                               h->w.box_b, h->w.score_w, h->w.score_b, h->w.emb_g, h->w.emb_b,
-                              d.layer_norm_eps, p.n_sp, emb, err_flag, stream, site_cfg(dropout_p, seed, 0)));
-    h->launches++;
+                              d.layer_norm_eps, p.n_sp, emb, err_flag, stream, y,
+                              static_cast<size_t>(p.m_sp) * kHidden * 4,  // y is dead until the first out-projection
+                              site_cfg(dropout_p, seed, 0)));
+    h->launches += 2;  // embed_stats_kernel + embed_kernel
   }
   const int ns = d.num_spatial_layers, nt = d.num_temporal_layers;
   for (int i = 0; i < ns; ++i) {
