@@ -218,61 +218,63 @@ embed_stats_kernel(const float* __restrict__ cat_table, int unique_categories,
                    const float* __restrict__ box_w, const float* __restrict__ box_b,
                    const float* __restrict__ score_w, const float* __restrict__ score_b,
                    float* __restrict__ stats) {
-  __shared__ double red[8][21];
-  __shared__ double mean_s[7];
+  // One sweep over the 768 columns in fp64: raw first and second moments of v = (w0, w1, w2, w3, score_w,
+  // E[cat] + bias) plus the sums of E[cat] and of the bias alone; the centred Gram matrix is
+  // (sum v_i v_j - sum v_i sum v_j / n) / n (exact to ~1e-16 relative in fp64).
+  constexpr int kAcc = 6 + 21 + 2;
+  __shared__ double red[8][kAcc];
   const int cat = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* erow = cat_table + static_cast<long long>(cat) * kHidden;
-  // pass 1: column means of the seven vectors (w0..w3, score_w, bias, E[cat])
-  double m[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (int col = tid; col < kHidden; col += 256) {
-    for (int q = 0; q < 4; ++q) m[q] += box_w[col * 4 + q];
-    if (score_w != nullptr) m[4] += score_w[col];
-    m[5] += box_b[col] + (score_b != nullptr ? score_b[col] : 0.f);
-    m[6] += erow[col];
+  double a[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) a[i] = 0;
+#pragma unroll
+  for (int r = 0; r < kHidden / 256; ++r) {
+    const int col = tid + 256 * r;
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(box_w) + col);
+    const double bias = static_cast<double>(box_b[col]) + (score_b != nullptr ? score_b[col] : 0.f);
+    const double e = erow[col];
+    const double v[6] = {w4.x, w4.y, w4.z, w4.w, score_w != nullptr ? score_w[col] : 0.f, e + bias};
+    int k = 6;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      a[i] += v[i];
+#pragma unroll
+      for (int j = i; j < 6; ++j) a[k++] += v[i] * v[j];
+    }
+    a[27] += e;
+    a[28] += bias;
   }
-  for (int i = 0; i < 7; ++i) {
-    for (int o = 16; o > 0; o >>= 1) m[i] += __shfl_xor_sync(0xffffffffu, m[i], o);
-    if (lane == 0) red[warp][i] = m[i];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+    if (lane == 0) red[warp][i] = a[i];
   }
   __syncthreads();
-  if (tid < 7) {
+  if (tid < kAcc) {
     double t = 0;
+#pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w][tid];
-    mean_s[tid] = t / kHidden;
+    red[0][tid] = t;  // column tid is only touched by thread tid
   }
   __syncthreads();
-  // pass 2: Gram matrix of the centred vectors v = (w0, w1, w2, w3, score_w, E[cat] + bias)
-  double g[21];
-  for (int i = 0; i < 21; ++i) g[i] = 0;
-  for (int col = tid; col < kHidden; col += 256) {
-    double v[6];
-    for (int q = 0; q < 4; ++q) v[q] = box_w[col * 4 + q] - mean_s[q];
-    v[4] = score_w != nullptr ? score_w[col] - mean_s[4] : 0.0;
-    v[5] = (erow[col] - mean_s[6]) + ((box_b[col] + (score_b != nullptr ? score_b[col] : 0.f)) - mean_s[5]);
-    int k = 0;
-    for (int i = 0; i < 6; ++i)
-      for (int j = i; j < 6; ++j) g[k++] += v[i] * v[j];
-  }
-  __syncthreads();  // red is reused
-  for (int i = 0; i < 21; ++i) {
-    for (int o = 16; o > 0; o >>= 1) g[i] += __shfl_xor_sync(0xffffffffu, g[i], o);
-    if (lane == 0) red[warp][i] = g[i];
-  }
-  __syncthreads();
+  const double* tot = red[0];
   float* out = stats + static_cast<long long>(cat) * kEmbedCatStride;
   if (tid < 21) {
-    double t = 0;
-    for (int w = 0; w < 8; ++w) t += red[w][tid];
-    // position of entry tid in the upper triangle: off-diagonal terms appear twice in u^T G u
+    // entry tid of the upper triangle -> (i, j); off-diagonal terms appear twice in u^T G u
     int i = 0, rem = tid;
     while (rem >= 6 - i) { rem -= 6 - i; ++i; }
-    out[1 + tid] = static_cast<float>((rem == 0 ? 1.0 : 2.0) * t / kHidden);
+    const int j = i + rem;
+    const double g = (tot[6 + tid] - tot[i] * tot[j] / kHidden) / kHidden;
+    out[1 + tid] = static_cast<float>(rem == 0 ? g : 2.0 * g);
   }
-  if (tid == 21) out[0] = static_cast<float>(mean_s[6]);
+  if (tid == 21) out[0] = static_cast<float>(tot[27] / kHidden);
   if (tid == 22 || tid == 23) out[tid] = 0.f;
-  if (cat == 0 && tid < kEmbedGlobal)
-    stats[static_cast<long long>(unique_categories) * kEmbedCatStride + tid] =
-        tid < 6 ? static_cast<float>(mean_s[tid]) : 0.f;
+  if (cat == 0 && tid < kEmbedGlobal) {
+    const double m = tid < 5 ? tot[tid] : (tid == 5 ? tot[28] : 0.0);
+    stats[static_cast<long long>(unique_categories) * kEmbedCatStride + tid] = static_cast<float>(m / kHidden);
+  }
 }
 
 __global__ void __launch_bounds__(kEmbedThreads, 4)

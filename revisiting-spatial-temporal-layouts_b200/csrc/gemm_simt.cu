@@ -1,7 +1,7 @@
 // fp32 CUDA-core GEMM: out[M, N] = act(A[M, K] * W[N, K]^T + bias[N]).
 // Used for the classifier head fc1 / fc2 (src/modelling/models.py:155-163; 0.02 % of the FLOPs,
 // kept off the tensor cores per the north star) and as an independent numerical cross-check of the
-// tcgen05 GEMM in the parity tests. 64x64 tile, 16-wide K steps, 4x4 outputs per thread.
+// tcgen05 GEMM in the parity tests. 128x64 tile, 32-wide K steps prefetched into registers, 8x8 outputs per thread.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -9,59 +9,99 @@ namespace stlt {
 
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TM = 128, TN = 64, TK = 32, kThreads = 128;
 
+// Thread (ty, tx) of a 16 x 8 grid owns rows {4ty..4ty+3, 64+4ty..} x columns {4tx..4tx+3, 32+4tx..}: an 8x8
+// register tile (64 FFMA per four 16-byte shared-memory loads) whose loads are bank-conflict free.
 template <bool kGelu>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kThreads, 3)
 gemm_simt_kernel(const float* __restrict__ a, const float* __restrict__ w,
                  const float* __restrict__ bias, float* __restrict__ out, int m, int n, int k) {
-  __shared__ float As[TK][TM + 4];
-  __shared__ float Ws[TK][TN + 4];
+  __shared__ __align__(16) float As[TK][TM + 4];
+  __shared__ __align__(16) float Ws[TK][TN + 4];
   const int tid = threadIdx.x;
-  const int tx = tid & 15;  // column group
-  const int ty = tid >> 4;  // row group
+  const int tx = tid & 7;
+  const int ty = tid >> 3;
   const int m0 = blockIdx.y * TM;
   const int n0 = blockIdx.x * TN;
-  const int lr = tid >> 2;        // 0..63: tile row loaded by this thread
-  const int lk = (tid & 3) * 4;   // 0,4,8,12: k offset loaded by this thread
+  const int lr = tid >> 3;        // 0..15 (+16 per vector): tile row loaded by this thread
+  const int lk = (tid & 7) * 4;   // k offset loaded by this thread: a row's 32 k-values are one 128-byte line
+  const int sw_store = 4 * (((tid & 7) >> 1) & 3);  // = 4 * ((k >> 3) & 3) for k = lk .. lk + 3
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  float acc[4][4];
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
+  // the next k-slab travels from global memory to registers while the current one is multiplied
+  float4 va[TM / 16], vw[TN / 16];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < TM / 16; ++h) {
+      const int row = m0 + lr + 16 * h;
+      va[h] = row < m ? __ldg(reinterpret_cast<const float4*>(a + (long long)row * k + k0 + lk)) : zero;
+    }
+#pragma unroll
+    for (int h = 0; h < TN / 16; ++h) {
+      const int row = n0 + lr + 16 * h;
+      vw[h] = row < n ? __ldg(reinterpret_cast<const float4*>(w + (long long)row * k + k0 + lk)) : zero;
+    }
+  };
+  fetch(0);
   for (int k0 = 0; k0 < k; k0 += TK) {
-    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vw = va;
-    if (m0 + lr < m) va = __ldg(reinterpret_cast<const float4*>(a + (long long)(m0 + lr) * k + k0 + lk));
-    if (n0 + lr < n) vw = __ldg(reinterpret_cast<const float4*>(w + (long long)(n0 + lr) * k + k0 + lk));
-    As[lk + 0][lr] = va.x; As[lk + 1][lr] = va.y; As[lk + 2][lr] = va.z; As[lk + 3][lr] = va.w;
-    Ws[lk + 0][lr] = vw.x; Ws[lk + 1][lr] = vw.y; Ws[lk + 2][lr] = vw.z; Ws[lk + 3][lr] = vw.w;
+    // transposed stores: the 4-row groups are XOR-permuted per 8 k-values so that the eight k-offsets of a warp
+    // hit different banks (the row pitch of 132 / 68 floats alone separates only two of them)
+#pragma unroll
+    for (int h = 0; h < TM / 16; ++h) {
+      const int r = (lr + 16 * h) ^ sw_store;
+      As[lk + 0][r] = va[h].x; As[lk + 1][r] = va[h].y; As[lk + 2][r] = va[h].z; As[lk + 3][r] = va[h].w;
+    }
+#pragma unroll
+    for (int h = 0; h < TN / 16; ++h) {
+      const int r = (lr + 16 * h) ^ sw_store;
+      Ws[lk + 0][r] = vw[h].x; Ws[lk + 1][r] = vw[h].y; Ws[lk + 2][r] = vw[h].z; Ws[lk + 3][r] = vw[h].w;
+    }
     __syncthreads();
+    if (k0 + TK < k) fetch(k0 + TK);
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 wv = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
-      const float ar[4] = {av.x, av.y, av.z, av.w};
-      const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+      const int sw = 4 * ((kk >> 3) & 3);
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][(ty * 4) ^ sw]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ((ty * 4) ^ sw)]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk][(tx * 4) ^ sw]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[kk][32 + ((tx * 4) ^ sw)]);
+      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
     if (row >= m) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = n0 + tx * 4 + j;
-      if (col >= n) continue;
-      float v = acc[i][j] + (bias != nullptr ? __ldg(bias + col) : 0.f);
-      if (kGelu) v = gelu_erf(v);
-      out[(long long)row * n + col] = v;
+    for (int jh = 0; jh < 2; ++jh) {
+      const int col = n0 + jh * 32 + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = acc[i][jh * 4 + j] + ((bias != nullptr && col + j < n) ? __ldg(bias + col + j) : 0.f);
+        if (kGelu) v[j] = gelu_erf(v[j]);
+      }
+      float* dst = out + (long long)row * n + col;
+      if (col + 3 < n && (n & 3) == 0) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < n) dst[j] = v[j];
+      }
     }
   }
 }
@@ -74,9 +114,9 @@ cudaError_t launch_gemm_simt(const float* a, const float* w, const float* bias, 
   if (k % TK != 0) return cudaErrorInvalidValue;
   dim3 grid((n + TN - 1) / TN, (m + TM - 1) / TM);
   if (gelu)
-    gemm_simt_kernel<true><<<grid, 256, 0, stream>>>(a, w, bias, out, m, n, k);
+    gemm_simt_kernel<true><<<grid, kThreads, 0, stream>>>(a, w, bias, out, m, n, k);
   else
-    gemm_simt_kernel<false><<<grid, 256, 0, stream>>>(a, w, bias, out, m, n, k);
+    gemm_simt_kernel<false><<<grid, kThreads, 0, stream>>>(a, w, bias, out, m, n, k);
   return cudaGetLastError();
 }
 
