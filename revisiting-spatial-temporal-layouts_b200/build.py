@@ -19,7 +19,7 @@ LIB_PATH = PKG_DIR / "libstlt_b200.so"
 BUILD_DIR = PKG_DIR / "build"
 SOURCES = ["gemm_tcgen05.cu", "gemm_simt.cu", "elementwise.cu", "attention.cu", "attention_mma.cu",
            "attention_bwd.cu", "attention_bwd_mma.cu", "train_kernels.cu", "stlt_api.cu", "stlt_train.cu",
-           "attention_cross.cu", "cacnf_kernels.cu", "stlt_cacnf.cu", "eval_kernels.cu"]
+           "attention_cross.cu", "attention_long.cu", "cacnf_kernels.cu", "stlt_cacnf.cu", "eval_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

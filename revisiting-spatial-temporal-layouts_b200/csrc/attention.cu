@@ -137,8 +137,14 @@ attention_kernel(const TIn* __restrict__ qkv, const long long* __restrict__ mask
 cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long* mask_src,
                              long long num_seqs, int T, bool causal, ActOut out,
                              cudaStream_t stream) {
-  if (T < 1 || T > 64) return cudaErrorInvalidValue;
+  if (T < 1 || T > 256) return cudaErrorInvalidValue;
   if (num_seqs == 0) return cudaSuccess;
+  if (T > 64) {
+    // 65..256 tokens per sequence: one CTA per (sequence, head), online softmax over 64-key blocks (attention_long.cu)
+    if (!qkv_is_bf16) return cudaErrorInvalidValue;
+    return launch_attention_long(static_cast<const __nv_bfloat16*>(qkv), out.planes, out.plane_rows, mask_src, num_seqs,
+                                 T, causal, out.xb, out.plane_rows, stream);
+  }
   if (T > 32) {
     // 33..64 tokens per sequence: one warp per (sequence, head) on the 48 / 64-row tiles of attention_cross.cu
     if (!qkv_is_bf16) return cudaErrorInvalidValue;

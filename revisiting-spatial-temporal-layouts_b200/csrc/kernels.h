@@ -185,6 +185,12 @@ cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long
                                  __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream,
                                  DropCfg drop = DropCfg{0, 0, 1.f});
 
+// K3 for 65..256-token sequences (attention_long.cu): one CTA per (sequence, head), Q / K / V staged once in shared
+// memory, online softmax over 64-key blocks. planes as in launch_attention_mma; inference only.
+cudaError_t launch_attention_long(const __nv_bfloat16* qkv, int planes, long long qkv_plane_rows,
+                                  const long long* mask_src, long long num_seqs, int T, bool causal,
+                                  __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream);
+
 // gamma-folded bf16 weights + the two epilogue vectors of GEMM_EPI_NORM_A (see GemmEpilogue).
 cudaError_t launch_pack_folded(const float* w, const float* gamma, const float* beta, const float* bias, int n,
                                int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream);

@@ -574,7 +574,7 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   if (B < 0) return fail(h, STLT_ERR_INVALID, "negative batch size");
   if (L < 1 || L > d.max_positions)
     return fail(h, STLT_ERR_INVALID, "frames=%d outside [1, %d] (position table)", L, d.max_positions);
-  if (L > 64) return fail(h, STLT_ERR_INVALID, "frames=%d > 64 is not supported by the attention kernels", L);
+  if (L > 256) return fail(h, STLT_ERR_INVALID, "frames=%d > 256 is not supported by the attention kernels", L);
   if (S < 1 || S > 64) return fail(h, STLT_ERR_INVALID, "slots=%d outside [1, 64]", S);
   h->launches = 0;
   if (B == 0) return STLT_OK;

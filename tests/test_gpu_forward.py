@@ -394,8 +394,25 @@ def test_long_sequences_up_to_64_tokens(precision, tol):
             want = O.stlt_forward(sd, batch, num_spatial_layers=2, num_temporal_layers=2)
             got = m(to_cuda(batch))["stlt"].cpu()
         assert nerr(got, want) < tol, (frames, objects, nerr(got, want))
-    with pytest.raises(Exception, match="64"), torch.no_grad():
-        m(to_cuda(make_batch(1, "something", num_frames=64)))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_long_sequences_up_to_the_position_table(precision, tol):
+    """65..256 frames (the reference's position table, models.py:88-96) take attention_long.cu: one CTA per
+    (sequence, head), online softmax over 64-key blocks, causal blocks skipped. Ragged lengths, so the padded
+    frames exercise the key mask inside and across key blocks; L = 256 is the maximum the reference accepts."""
+    cfg = StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=1, num_temporal_layers=2)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=72)
+    m = _model(cfg, sd, precision)
+    for frames in (64, 100, 129, 255):
+        batch = make_batch(3, "something", ragged=True, seed=frames, num_frames=frames, max_objects=2)
+        with torch.no_grad():
+            want = O.stlt_forward(sd, batch, num_spatial_layers=1, num_temporal_layers=2)
+            got = m(to_cuda(batch))["stlt"].cpu()
+        assert nerr(got, want) < tol, (frames, nerr(got, want))
+    with pytest.raises(Exception, match="256"), torch.no_grad():
+        m(to_cuda(make_batch(1, "something", num_frames=256)))
 
 
 def test_random_shapes_fuzz_bf16_and_fp32():

@@ -164,6 +164,43 @@ def test_attention(handle, T, causal, n_seqs, flavour):
     assert nerr(got, ref) < tol
 
 
+@pytest.mark.parametrize("T,causal,n_seqs", [(65, True, 9), (128, False, 5), (200, True, 7), (256, True, 3),
+                                             (256, False, 2), (97, False, 40)])
+@pytest.mark.parametrize("flavour", ["mma_bf16", "mma_split"])
+def test_attention_long_sequences(handle, T, causal, n_seqs, flavour):
+    """65..256 tokens per sequence (attention_long.cu: online softmax over 64-key blocks) vs fp64 torch; random
+    key masks, so whole key blocks can be masked for some rows."""
+    lib = L.load_library()
+    g = torch.Generator(device="cuda").manual_seed(T * 11 + n_seqs)
+    tokens = n_seqs * T
+    rows = tokens + 5
+    qkv = torch.randn(tokens, 2304, device="cuda", generator=g)
+    if flavour == "mma_bf16":
+        qkv_in = qkv.to(torch.bfloat16)
+        qkv = qkv_in.float()
+        planes, tol = 1, 4e-3
+    else:
+        hi, lo = _split(qkv)
+        qkv_in = torch.zeros(2 * rows, 2304, dtype=torch.bfloat16, device="cuda")
+        qkv_in[:tokens] = hi
+        qkv_in[rows: rows + tokens] = lo
+        planes, tol = 2, 3e-5
+    mask_src = torch.randint(0, 3, (n_seqs, T), device="cuda", generator=g)
+    mask_src[:, 0] = 2  # first key always valid (first frame)
+    mask_src[0, 1:70] = 0  # a run of masked keys longer than a key block
+    mask_src = mask_src.view(-1).contiguous()
+    out = torch.zeros(planes * rows, 768, dtype=torch.bfloat16, device="cuda")
+    L.check(handle, lib.stlt_op_attention(handle, _stream(), qkv_in.data_ptr(), 1, mask_src.data_ptr(),
+                                          n_seqs, T, int(causal), out.data_ptr(), planes, rows))
+    torch.cuda.synchronize()
+    got = out[:tokens].float()
+    if planes == 2:
+        got = got + out[rows: rows + tokens].float()
+    ref = _attention_ref(qkv, mask_src == 0, T, causal)
+    assert torch.isfinite(got).all()
+    assert nerr(got, ref) < tol
+
+
 @pytest.mark.parametrize("rows,with_y,planes", [(1000, True, 2), (77, False, 1), (3, True, 1)])
 def test_add_layer_norm(handle, rows, with_y, planes):
     lib = L.load_library()
