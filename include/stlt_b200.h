@@ -163,7 +163,9 @@ int stlt_charades_map(void* handle, void* stream, const float* predictions, cons
  *   categories i64 [B, L, S]; boxes f32 [B, L, S, 4]; scores f32 [B, L, S] or NULL (presence
  *   toggles the score embedding, models.py:33-35); frame_types i64 [B, L]; lengths i64 [B].
  *   logits_out f32 [B, num_classes]. mask_*_out (u8, optional) receive the padding masks the
- *   reference collater would have produced (categories == 0, frame_types == 0). */
+ *   reference collater would have produced (categories == 0, frame_types == 0).
+ *   Shapes: B >= 0 (0 is a no-op), 1 <= L <= min(256, max_positions) (the position table, models.py:88-96),
+ *   1 <= S <= 64; anything else returns STLT_ERR_INVALID. */
 int stlt_forward(void* handle, void* stream, int32_t precision, const int64_t* categories,
                  const float* boxes, const float* scores_or_null, const int64_t* frame_types,
                  const int64_t* lengths, int32_t batch, int32_t frames, int32_t slots,
