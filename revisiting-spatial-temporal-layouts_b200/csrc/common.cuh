@@ -72,6 +72,31 @@ __device__ __forceinline__ __half2 gelu_erf_fast_h2(__half2 x) {
   return __hmul2(__float2half2_rn(0.5f), __hadd2(x, h));  // 0.5 * x * (1 + erf(x / sqrt 2))
 }
 
+// GELU and its derivative together (training forward: the FFN1 epilogue stores act(u) and gelu'(u), both already
+// multiplied by the FFN-inner dropout mask, so the backward pass never re-evaluates the activation): the erfc term is
+// shared, the derivative costs one more ex2 and a few HFMA2. cdf = 0.5 + sign(u) * 0.5 * erf(|u| / sqrt 2).
+__device__ __forceinline__ void gelu_erf_and_grad_fast_h2(__half2 x, __half2& act, __half2& grad) {
+  const __half2 ax = __habs2(x);
+  const __half2 a = __hmin2(ax, __float2half2_rn(5.9f));
+  __half2 q = __float2half2_rn(5.204604041e-04f);
+  q = __hfma2(q, a, __float2half2_rn(-7.397519993e-03f));
+  q = __hfma2(q, a, __float2half2_rn(5.256125276e-02f));
+  q = __hfma2(q, a, __float2half2_rn(4.592546886e-01f));
+  q = __hfma2(q, a, __float2half2_rn(1.151091390e+00f));
+  const __half2 e = h2exp2(__hneg2(__hmul2(q, a)));       // erfc(|x| / sqrt 2)
+  const __half2 h = __hfma2(__hneg2(ax), e, ax);          // |x| * erf(|x| / sqrt 2)
+  act = __hmul2(__float2half2_rn(0.5f), __hadd2(x, h));
+  const __half2 pdf = h2exp2(__hmul2(__float2half2_rn(-0.72134752044f), __hmul2(a, a)));  // exp(-x^2 / 2)
+  const __half2 half_erf = __hfma2(__float2half2_rn(-0.5f), e, __float2half2_rn(0.5f));   // >= 0
+  // copy the sign of x onto half_erf (both halves)
+  const uint32_t xb = *reinterpret_cast<const uint32_t*>(&x);
+  uint32_t hb = *reinterpret_cast<const uint32_t*>(&half_erf);
+  hb ^= xb & 0x80008000u;
+  const __half2 signed_half_erf = *reinterpret_cast<const __half2*>(&hb);
+  const __half2 cdf = __hadd2(signed_half_erf, __float2half2_rn(0.5f));
+  grad = __hfma2(__hmul2(x, __float2half2_rn(0.3989422804014327f)), pdf, cdf);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits)
   return *reinterpret_cast<uint32_t*>(&v);

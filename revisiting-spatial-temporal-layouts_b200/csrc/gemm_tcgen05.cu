@@ -142,7 +142,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2,
                     const float* __restrict__ bias, int m_tiles, int n_tiles, int k_blocks, int a_plane_rows,
                     int b_plane_rows, int out_plane_rows, DropCfg drop, EpiArgs ep) {
-  static_assert(kEpi == GEMM_EPI_PLAIN || (kLayout == GEMM_NT && kTerms == 1), "fused-LN epilogues: bf16 forward only");
+  static_assert(kEpi == GEMM_EPI_PLAIN || kEpi == GEMM_EPI_ACT_BWD || (kLayout == GEMM_NT && kTerms == 1),
+                "fused-LN epilogues: bf16 forward only");
+  static_assert(kEpi != GEMM_EPI_ACT_BWD || (kLayout == GEMM_NN && kOut == GEMM_OUT_BF16 && kGelu == 0),
+                "ACT_BWD: bf16 data gradient");
   constexpr bool kResidOut = kOut == GEMM_OUT_F32_BF16 || kOut == GEMM_OUT_F32_BF16_DIRECT;
   static_assert((kEpi == GEMM_EPI_RESID) == kResidOut, "RESID epilogue <-> fp32 + bf16 output");
   constexpr int kStages = Cfg<kOut>::kStages;
@@ -336,6 +339,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           tma_load_2d(&tm_out, &bars->zin[ew], zbuf, col0, row0);
         }
       }
+      // ACT_BWD: this thread's 32 activation-gradient factors of a chunk (64 B of its row), fetched one chunk ahead
+      uint4 ubuf[kEpi == GEMM_EPI_ACT_BWD ? 2 : 1][4];
+      const uint4* urow = nullptr;
+      if constexpr (kEpi == GEMM_EPI_ACT_BWD) {
+        urow = reinterpret_cast<const uint4*>(ep.act_in + static_cast<size_t>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0);
+        if (store_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ubuf[0][j] = __ldg(urow + j);
+        }
+      }
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr =
@@ -350,6 +363,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         uint32_t(&v)[32] = vbuf[c & 1];
         tmem_ld_wait_regs(v);
         if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
+        if constexpr (kEpi == GEMM_EPI_ACT_BWD) {
+          if (c + 1 < 4 && store_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ubuf[(c + 1) & 1][j] = __ldg(urow + (c + 1) * 4 + j);
+          }
+        }
         float f[32];
         if constexpr (kEpi == GEMM_EPI_NORM_A) {
           // act(LN(z) W^T + b) from the raw product: rstd * (acc - mean * s[n]) + c[n]
@@ -412,16 +431,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             }
           }
         }
-        uint32_t pre[kOut == GEMM_OUT_BF16_DUAL ? 16 : 1];  // pre-activation values (training)
-        if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
+        if constexpr (kEpi == GEMM_EPI_ACT_BWD) {
+          // d u = d h * (gelu'(u) * dropout mask): the factor was stored by the forward FFN1 epilogue
+          const uint32_t* gw = reinterpret_cast<const uint32_t*>(ubuf[c & 1]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pre[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+          for (int j = 0; j < 32; j += 2) {
+            const float2 gg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[j >> 1]));
+            f[j] *= gg.x;
+            f[j + 1] *= gg.y;
+          }
         }
-        if (kGelu == 1) {
+        uint32_t pre[kOut == GEMM_OUT_BF16_DUAL ? 16 : 1];  // second plane (training): gelu'(u) * dropout mask
+        if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
+          static_assert(kOut != GEMM_OUT_BF16_DUAL || kGelu == 2, "DUAL output: fast erf GELU");
+          // act(u) and gelu'(u) in one evaluation, both under the FFN-inner dropout mask of
+          // nn.TransformerEncoderLayer (element = row * N + column); the backward GEMM (GEMM_EPI_ACT_BWD)
+          // multiplies by the second plane and never sees u
+          const unsigned long long e0 =
+              static_cast<unsigned long long>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            __half2 act, grad;
+            gelu_erf_and_grad_fast_h2(__floats2half2_rn(f[j], f[j + 1]), act, grad);
+            float2 a2 = __half22float2(act), g2 = __half22float2(grad);
+            if (drop.thr16 != 0) {
+              const uint32_t bits = drop_bits(drop.key, (e0 + j) >> 1);
+              const float m0 = drop_mul(bits, 0, drop), m1 = drop_mul(bits, 1, drop);
+              a2.x *= m0; a2.y *= m1;
+              g2.x *= m0; g2.y *= m1;
+            }
+            f[j] = a2.x;
+            f[j + 1] = a2.y;
+            pre[j >> 1] = pack_bf16x2(g2.x, g2.y);
+          }
+        } else if (kGelu == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
         } else if (kGelu == 2) {
-          if constexpr (kOut == GEMM_OUT_BF16 || kOut == GEMM_OUT_BF16_DUAL) {  // packed fp16 math, the output is bf16 anyway
+          if constexpr (kOut == GEMM_OUT_BF16) {  // packed fp16 math, the output is bf16 anyway
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float2 r = __half22float2(gelu_erf_fast_h2(__floats2half2_rn(f[j], f[j + 1])));
@@ -435,19 +482,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         } else if (kGelu == 3) {  // ReLU (nn.TransformerEncoderLayer default, appearance branch of CACNF)
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
-          // FFN-inner dropout of nn.TransformerEncoderLayer (training): element = row * N + column
-          if (drop.thr16 != 0) {
-            const unsigned long long e0 =
-                static_cast<unsigned long long>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const uint32_t bits = drop_bits(drop.key, (e0 + j) >> 1);
-              f[j] *= drop_mul(bits, 0, drop);
-              f[j + 1] *= drop_mul(bits, 1, drop);
-            }
-          }
         }
 
         if (kOut == GEMM_OUT_F32 || kResidOut) {
@@ -529,6 +563,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           if (hc == 1) {
             fence_proxy_async_smem();
             __syncwarp();
+            if constexpr (kEpi == GEMM_EPI_ACT_BWD) {
+              // bias gradient of linear1: column sums of the ROUNDED values the weight-gradient GEMM will read, taken
+              // from the staging tile (lane l owns columns 2l, 2l + 1 of this 64-column slab; a row is one
+              // conflict-free 128-byte read)
+              int nvalid = ep.valid_rows - row0;
+              nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+              if (store_ok && nvalid > 0 && ep.colsum_out != nullptr) {
+                float sx = 0.f, sy = 0.f;
+                const uint32_t cbase = smem_u32(ebuf) + (lane & 3) * 4;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  if (r < nvalid) {
+                    uint32_t wv;
+                    asm volatile("ld.shared.b32 %0, [%1];"
+                                 : "=r"(wv)
+                                 : "r"(cbase + r * 128 + (((static_cast<uint32_t>(lane) >> 2) ^ (r & 7)) << 4))
+                                 : "memory");
+                    const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv));
+                    sx += v2.x;
+                    sy += v2.y;
+                  }
+                }
+                float* dst = ep.colsum_out + col0 + (c - 1) * 32 + 2 * lane;
+                atomicAdd(dst, sx);
+                atomicAdd(dst + 1, sy);
+              }
+            }
             if (lane == 0 && store_ok) {
               tma_store_2d(&tm_out, ebuf, col0 + (c - 1) * 32, row0);
               if (kOut == GEMM_OUT_BF16_SPLIT || kOut == GEMM_OUT_BF16_DUAL)
@@ -610,6 +671,11 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
   if (g.layout == GEMM_NN) {
     if (g.terms == 1 && g.gelu == 0 && g.out_kind == GEMM_OUT_F32)
       return launch_one<1, GEMM_OUT_F32, 0, GEMM_NN>(g, stream, num_sms);
+    if (g.epilogue == GEMM_EPI_ACT_BWD) {
+      if (g.terms == 1 && g.gelu == 0 && g.out_kind == GEMM_OUT_BF16 && g.epi.act_in != nullptr)
+        return launch_one<1, GEMM_OUT_BF16, 0, GEMM_NN, GEMM_EPI_ACT_BWD>(g, stream, num_sms);
+      return cudaErrorInvalidValue;
+    }
     if (g.terms == 1 && g.gelu == 0 && g.out_kind == GEMM_OUT_BF16)
       return launch_one<1, GEMM_OUT_BF16, 0, GEMM_NN>(g, stream, num_sms);
     return cudaErrorInvalidValue;

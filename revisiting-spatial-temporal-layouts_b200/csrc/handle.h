@@ -266,8 +266,11 @@ inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const vo
 // Gradient GEMMs of the training step (bf16 operands, fp32 accumulation):
 //   GEMM_NN     out[m_rows, n]  = A[m_rows, k] * B[k, n]       (out fp32 or bf16; rows padded to 128)
 //   GEMM_TN_RED out[m_rows, n] += A[k, m_rows]^T * B[k, n]      (out fp32; k = token count, any value)
+// act_in != null (GEMM_NN, bf16 output): GEMM_EPI_ACT_BWD, i.e. out = (A B) * gelu'(act_in) * dropout mask and
+// colsum += column sums of the first valid_rows rows of out.
 inline int run_gemm_grad(Handle* h, cudaStream_t stream, int layout, const void* a, const void* b, void* out,
-                  long long m_rows, int n, long long k, int out_kind) {
+                  long long m_rows, int n, long long k, int out_kind, const __nv_bfloat16* act_in = nullptr,
+                  float* colsum = nullptr, long long valid_rows = 0, DropCfg drop = DropCfg{0, 0, 1.f}) {
   GemmArgs g{};
   int rc;
   if (layout == GEMM_NN) {
@@ -294,9 +297,16 @@ inline int run_gemm_grad(Handle* h, cudaStream_t stream, int layout, const void*
   g.out_kind = out_kind;
   g.gelu = 0;
   g.layout = layout;
-  g.drop = DropCfg{0, 0, 1.f};
+  g.drop = drop;
   g.epilogue = GEMM_EPI_PLAIN;
   g.epi = EpiArgs{};
+  if (act_in != nullptr) {
+    if (layout != GEMM_NN || out_kind != GEMM_OUT_BF16) return fail(h, STLT_ERR_INVALID, "run_gemm_grad: ACT_BWD needs NN / bf16");
+    g.epilogue = GEMM_EPI_ACT_BWD;
+    g.epi.act_in = act_in;
+    g.epi.colsum_out = colsum;
+    g.epi.valid_rows = static_cast<int>(valid_rows);
+  }
   g.tm_out2 = g.tm_out;
   ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * static_cast<double>(k));
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));

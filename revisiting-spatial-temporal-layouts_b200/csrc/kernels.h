@@ -14,7 +14,7 @@ enum GemmOutKind : int {
   GEMM_OUT_F32 = 0,         // fp32 [M, N]
   GEMM_OUT_BF16 = 1,        // bf16 [M, N]
   GEMM_OUT_BF16_SPLIT = 2,  // bf16 hi plane [M, N] followed by lo plane [M, N]
-  GEMM_OUT_BF16_DUAL = 3,   // bf16 act(z) [M, N] followed by bf16 z [M, N] (training: GELU input kept)
+  GEMM_OUT_BF16_DUAL = 3,   // bf16 act(z) [M, N] followed by bf16 act'(z) [M, N], both under the dropout mask (training)
   GEMM_OUT_F32_BF16 = 4,    // fp32 [M, N] (tm_out) and a bf16 copy [M, N] (tm_out2): fused-LayerNorm residual epilogue
   // same outputs, the bf16 copy written straight from registers (ep.zb_out): one staging tile less per warp buys
   // a fifth pipeline stage, which pays for long reductions (linear2, K = 3072)
@@ -31,6 +31,11 @@ enum GemmEpilogue : int {
   // z_new = (prev_norm ? LN(z_prev) : z_prev) + acc + bias[n]; writes z_new (fp32 + bf16) and adds the row's
   // (sum, sum of squares) over this CTA's columns to stats_out. N must be 768 (the LayerNorm width).
   GEMM_EPI_RESID = 2,
+  // training, data gradient of linear2 (GEMM_NN, bf16 output): out = acc * act_in, act_in = gelu'(u) * dropout mask
+  // as stored by the forward FFN1 epilogue (second plane of GEMM_OUT_BF16_DUAL), i.e. the gradient w.r.t. the GELU
+  // input, and colsum_out[n] += sum over the valid rows of the rounded output (the bias gradient of linear1).
+  // Replaces a separate elementwise pass over the [M, 3072] gradient.
+  GEMM_EPI_ACT_BWD = 3,
 };
 
 constexpr int kStatSlots = 6;  // 768 columns / 128-column slabs: partial row statistics per slab
@@ -44,6 +49,9 @@ struct EpiArgs {
   __nv_bfloat16* zb_out;   // RESID: bf16 copy of the new z [M, 768]
   float eps;
   int prev_norm;
+  const __nv_bfloat16* act_in;  // ACT_BWD: gelu'(u) * dropout mask, bf16 [M, N]
+  float* colsum_out;            // ACT_BWD: [N] fp32, accumulated with atomics (may be null)
+  int valid_rows;               // ACT_BWD: rows >= valid_rows are tile padding and stay out of the column sums
 };
 
 enum GemmLayout : int {
@@ -208,9 +216,6 @@ cudaError_t launch_ln_bwd(const float* d_a, const float* d_b, const float* z, co
                           float eps, long long rows, float* dz_out, __nv_bfloat16* dzb_out,
                           float* d_gamma, float* d_beta, float* d_bias, cudaStream_t stream,
                           DropCfg drop = DropCfg{0, 0, 1.f});
-// In place d <- d * gelu'(u) on bf16 [rows, n] (u == null: no activation) + column sums into d_bias.
-cudaError_t launch_act_bwd_colsum(__nv_bfloat16* d, const __nv_bfloat16* u, long long rows, int n,
-                                  float* d_bias, cudaStream_t stream, DropCfg drop = DropCfg{0, 0, 1.f});
 cudaError_t launch_colsum_f32(const float* x, int rows, int n, float* out, cudaStream_t stream);
 // Adjoint of launch_gather_rows: dst_f[map(r)] += src_f[r]; dst_b[map(r)] = src_b[r].
 cudaError_t launch_scatter_rows(const float* src_f, float* dst_f, const __nv_bfloat16* src_b,

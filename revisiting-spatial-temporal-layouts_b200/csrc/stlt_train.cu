@@ -213,19 +213,16 @@ int bwd_layer(const Ctx& c, int layer, const LayerWeights& lw, const LayerWeight
                                grad_ptr(gw.n2_b), grad_ptr(gw.l2_b), c.stream, layer_cfg(c, layer, 3)));
   }
   h->launches++;
-  // linear2: dH = dz2 W2 ; dW2 += dz2^T h
-  rc = run_gemm_grad(h, c.stream, GEMM_NN, bz, lw.l2_p, bh, m_tail, kFfn, kHidden, GEMM_OUT_BF16);
+  // linear2 + GELU: dU = (dz2 W2) * [gelu'(u) * dropout mask] (the factor the forward epilogue stored in the second
+  // plane of hid) and d b1 = colsum(dU) in the GEMM epilogue
+  // (GEMM_EPI_ACT_BWD); dW2 += dz2^T h
+  rc = run_gemm_grad(h, c.stream, GEMM_NN, bz, lw.l2_p, bh, m_tail, kFfn, kHidden, GEMM_OUT_BF16, u,
+                     grad_ptr(gw.l1_b), n_tail);
   if (rc) return rc;
   if (gw.l2_w) {
     rc = run_gemm_grad(h, c.stream, GEMM_TN_RED, bz, hid, grad_ptr(gw.l2_w), kHidden, kFfn, n_tail, GEMM_OUT_F32);
     if (rc) return rc;
   }
-  // GELU: dU = dH * gelu'(u) in place; d b1 = colsum(dU)
-  {
-    ProfileScope prof(h, c.stream, STLT_PROF_OTHER);
-    STLT_CUDA(h, launch_act_bwd_colsum(bh, u, n_tail, kFfn, grad_ptr(gw.l1_b), c.stream, layer_cfg(c, layer, 2)));
-  }
-  h->launches++;
   // linear1: dX1 = dU W1 -> fd ; dW1 += dU^T x1b
   rc = run_gemm_grad(h, c.stream, GEMM_NN, bh, lw.l1_p, fd, m_tail, kHidden, kFfn, GEMM_OUT_F32);
   if (rc) return rc;

@@ -135,27 +135,6 @@ __device__ __forceinline__ float gelu_erf_grad(float u) {
          u * 0.3989422804014327f * __expf(-0.5f * u * u);
 }
 
-// GELU derivative, two elements at a time in packed fp16 (single-branch erf as in gelu_erf_fast_h2 + ex2 for the
-// Gaussian term): erff() + expf() made the bf16 GELU-backward pass compute-bound (ncu: 81 % SM throughput at 3.8 TB/s).
-// The result multiplies a bf16 gradient, fp16's 11 mantissa bits are ample.
-__device__ __forceinline__ __half2 gelu_erf_grad_fast_h2(__half2 u) {
-  const __half2 au = __habs2(u);
-  const __half2 a = __hmin2(au, __float2half2_rn(5.9f));
-  __half2 q = __float2half2_rn(5.204604041e-04f);
-  q = __hfma2(q, a, __float2half2_rn(-7.397519993e-03f));
-  q = __hfma2(q, a, __float2half2_rn(5.256125276e-02f));
-  q = __hfma2(q, a, __float2half2_rn(4.592546886e-01f));
-  q = __hfma2(q, a, __float2half2_rn(1.151091390e+00f));
-  const __half2 e = h2exp2(__hneg2(__hmul2(q, a)));                                   // erfc(|u| / sqrt 2)
-  // exp(-u^2 / 2) with |u| clamped like the erf argument (beyond 5.9 the term is < 1e-7 anyway)
-  const __half2 g = h2exp2(__hmul2(__float2half2_rn(-0.72134752044f), __hmul2(a, a)));
-  const __half2 half_erf = __hfma2(__float2half2_rn(-0.5f), e, __float2half2_rn(0.5f));  // 0.5 * erf(|u| / sqrt 2)
-  // cdf = 0.5 + sign(u) * half_erf
-  const __half2 sgn = __hsub2(__hgt2(u, __float2half2_rn(0.f)), __hlt2(u, __float2half2_rn(0.f)));
-  const __half2 cdf = __hfma2(sgn, half_erf, __float2half2_rn(0.5f));
-  return __hfma2(__hmul2(u, __float2half2_rn(0.3989422804014327f)), g, cdf);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Backward of x_out = LN(z), z = x + y (the two post-norm residual sites of an encoder layer,
 // src/modelling/models.py:46-52 -> nn.TransformerEncoderLayer): dz feeds both the residual branch
@@ -189,67 +168,6 @@ ln_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ d_b,
 }
 
 // ------------------------------------------------------------------------------------------------
-// d_u = d_h * gelu'(u) in place on a bf16 [rows, n] tensor (kGelu), and the column sums of the
-// result (bias gradient of linear1 / of the packed in-projection). Thread t owns columns 8t..8t+7.
-// ------------------------------------------------------------------------------------------------
-template <bool kGelu>
-__global__ void __launch_bounds__(384)
-act_bwd_colsum_kernel(__nv_bfloat16* __restrict__ d, const __nv_bfloat16* __restrict__ u, long long rows,
-                      int n, float* __restrict__ d_bias, DropCfg drop) {
-  const int c8 = threadIdx.x;  // 8-column group
-  if (c8 * 8 >= n) return;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const long long pitch = n / 8;
-  uint4* d4 = reinterpret_cast<uint4*>(d);
-  const uint4* u4 = reinterpret_cast<const uint4*>(u);
-  constexpr int kUnroll = 4;
-  for (long long r0 = static_cast<long long>(blockIdx.x) * kUnroll; r0 < rows;
-       r0 += static_cast<long long>(gridDim.x) * kUnroll) {
-    uint4 dv[kUnroll], uv[kUnroll];
-#pragma unroll
-    for (int i = 0; i < kUnroll; ++i) {
-      const bool ok = r0 + i < rows;
-      dv[i] = ok ? d4[(r0 + i) * pitch + c8] : make_uint4(0, 0, 0, 0);
-      if (kGelu) uv[i] = ok ? __ldg(u4 + (r0 + i) * pitch + c8) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int i = 0; i < kUnroll; ++i) {
-      const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&dv[i]);
-      const __nv_bfloat162* up = reinterpret_cast<const __nv_bfloat162*>(&uv[i]);
-      uint32_t o[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 g = __bfloat1622float2(dp[j]);
-        if (kGelu) {
-          const float2 uu = __bfloat1622float2(up[j]);
-          const float2 dg = __half22float2(gelu_erf_grad_fast_h2(__floats2half2_rn(uu.x, uu.y)));
-          g.x *= dg.x;
-          g.y *= dg.y;
-          if (drop.thr16 != 0) {  // FFN-inner dropout sits between the activation and linear2
-            const unsigned long long el = static_cast<unsigned long long>(r0 + i) * n + c8 * 8 + 2 * j;
-            const uint32_t bits = drop_bits(drop.key, el >> 1);
-            g.x *= drop_mul(bits, 0, drop);
-            g.y *= drop_mul(bits, 1, drop);
-          }
-          o[j] = pack_bf16x2(g.x, g.y);
-          // the bias gradient sums what the GEMMs will see (the rounded values)
-          const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&o[j]);
-          g = __bfloat1622float2(rb);
-        }
-        acc[2 * j] += g.x;
-        acc[2 * j + 1] += g.y;
-      }
-      if (kGelu && r0 + i < rows) d4[(r0 + i) * pitch + c8] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-  }
-  if (d_bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(d_bias + c8 * 8 + j, acc[j]);
-  }
-}
-
 // fp32 column sums of a [rows, n] fp32 tensor (bias gradients of the classifier head).
 __global__ void colsum_f32_kernel(const float* __restrict__ x, int rows, int n, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -753,19 +671,6 @@ cudaError_t launch_ln_bwd(const float* d_a, const float* d_b, const float* z, co
   if (rows == 0) return cudaSuccess;
   ln_bwd_kernel<<<row_grid(rows, kBwdWarps, 2), kBwdWarps * 32, 0, stream>>>(
       d_a, d_b, z, gamma, eps, rows, dz_out, dzb_out, d_gamma, d_beta, d_bias, drop);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_act_bwd_colsum(__nv_bfloat16* d, const __nv_bfloat16* u, long long rows, int n,
-                                  float* d_bias, cudaStream_t stream, DropCfg drop) {
-  if (rows == 0) return cudaSuccess;
-  if (n % 8 != 0 || n / 8 > 384) return cudaErrorInvalidValue;
-  long long blocks = (rows + 3) / 4;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (u != nullptr)
-    act_bwd_colsum_kernel<true><<<static_cast<unsigned>(blocks), 384, 0, stream>>>(d, u, rows, n, d_bias, drop);
-  else
-    act_bwd_colsum_kernel<false><<<static_cast<unsigned>(blocks), 384, 0, stream>>>(d, nullptr, rows, n, d_bias, drop);
   return cudaGetLastError();
 }
 
