@@ -106,6 +106,101 @@ gemm_simt_kernel(const float* __restrict__ a, const float* __restrict__ w,
   }
 }
 
+// Head gradients of the training step (fc1 / fc2 of ClassificationHead, models.py:155-163):
+//   out[i, j] (+)= sum_k A(i, k) * B[k * ldb + j],  A(i, k) = a[i * lda + k] (kAKContig) or a[k * lda + i].
+// Same 128x64 tile, 8x8 register tile and swizzled [k][m] shared-memory layout as gemm_simt_kernel; operands are
+// fetched element-wise (coalesced along their contiguous axis; the 174-column logits gradient is not 16-byte aligned)
+// into registers one k-slab ahead. Weight gradients (few output tiles, reduction over the batch) are split over
+// blockIdx.z and accumulated with atomics.
+template <bool kAKContig>
+__global__ void __launch_bounds__(kThreads, 2)
+gemm_grad_simt_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b, long long ldb,
+                      float* __restrict__ out, int m, int n, int k, int k_per_split, int atomic) {
+  __shared__ __align__(16) float As[TK][TM + 4];
+  __shared__ __align__(16) float Ws[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 7;
+  const int ty = tid >> 3;
+  const int m0 = blockIdx.y * TM;
+  const int n0 = blockIdx.x * TN;
+  const int kz0 = blockIdx.z * k_per_split;
+  const int kz1 = kz0 + k_per_split < k ? kz0 + k_per_split : k;
+  constexpr int kAPer = TM * TK / kThreads;  // 32
+  constexpr int kBPer = TN * TK / kThreads;  // 16
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float va[kAPer], vb[kBPer];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < kAPer; ++r) {
+      const int e = tid + kThreads * r;
+      const int kk = kAKContig ? (e & (TK - 1)) : (e / TM);
+      const int ii = kAKContig ? (e / TK) : (e & (TM - 1));
+      const int gi = m0 + ii, gk = k0 + kk;
+      const bool ok = gi < m && gk < kz1;
+      va[r] = ok ? __ldg(kAKContig ? a + gi * lda + gk : a + gk * lda + gi) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < kBPer; ++r) {
+      const int e = tid + kThreads * r;
+      const int kk = e / TN, jj = e & (TN - 1);
+      const int gj = n0 + jj, gk = k0 + kk;
+      vb[r] = (gj < n && gk < kz1) ? __ldg(b + gk * ldb + gj) : 0.f;
+    }
+  };
+  fetch(kz0);
+  for (int k0 = kz0; k0 < kz1; k0 += TK) {
+#pragma unroll
+    for (int r = 0; r < kAPer; ++r) {
+      const int e = tid + kThreads * r;
+      const int kk = kAKContig ? (e & (TK - 1)) : (e / TM);
+      const int ii = kAKContig ? (e / TK) : (e & (TM - 1));
+      As[kk][ii ^ (4 * ((kk >> 3) & 3))] = va[r];
+    }
+#pragma unroll
+    for (int r = 0; r < kBPer; ++r) {
+      const int e = tid + kThreads * r;
+      const int kk = e / TN, jj = e & (TN - 1);
+      Ws[kk][jj ^ (4 * ((kk >> 3) & 3))] = vb[r];
+    }
+    __syncthreads();
+    if (k0 + TK < kz1) fetch(k0 + TK);
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      const int sw = 4 * ((kk >> 3) & 3);
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][(ty * 4) ^ sw]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ((ty * 4) ^ sw)]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk][(tx * 4) ^ sw]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[kk][32 + ((tx * 4) ^ sw)]);
+      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (row >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = n0 + (j >> 2) * 32 + tx * 4 + (j & 3);
+      if (col >= n) continue;
+      float* o = out + static_cast<long long>(row) * n + col;
+      if (atomic) atomicAdd(o, acc[i][j]);
+      else *o = acc[i][j];
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_gemm_simt(const float* a, const float* w, const float* bias, float* out, int m,
@@ -117,6 +212,31 @@ cudaError_t launch_gemm_simt(const float* a, const float* w, const float* bias, 
     gemm_simt_kernel<true><<<grid, kThreads, 0, stream>>>(a, w, bias, out, m, n, k);
   else
     gemm_simt_kernel<false><<<grid, kThreads, 0, stream>>>(a, w, bias, out, m, n, k);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_strided(const float* a, long long sai, long long sak, const float* b,
+                                long long sbk, long long sbj, float* out, int m, int n, int k,
+                                bool accumulate, cudaStream_t stream) {
+  if (m == 0 || n == 0) return cudaSuccess;
+  if (sbj != 1 || (sai != 1 && sak != 1)) return cudaErrorInvalidValue;  // B row-major [K, N]; A contiguous along M or K
+  const int tiles = ((n + TN - 1) / TN) * ((m + TM - 1) / TM);
+  // accumulating calls (weight gradients: few tiles, long reduction) are split along k until the grid is ~one wave
+  int splits = 1;
+  if (accumulate) {
+    splits = (148 * 2 + tiles - 1) / tiles;
+    const int max_splits = (k + 4 * TK - 1) / (4 * TK);  // at least four k-slabs per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int k_per_split = (k + splits - 1) / splits;
+  k_per_split = (k_per_split + TK - 1) / TK * TK;
+  splits = (k + k_per_split - 1) / k_per_split;
+  dim3 grid((n + TN - 1) / TN, (m + TM - 1) / TM, splits);
+  if (sak == 1)
+    gemm_grad_simt_kernel<true><<<grid, kThreads, 0, stream>>>(a, sai, b, sbk, out, m, n, k, k_per_split, accumulate ? 1 : 0);
+  else
+    gemm_grad_simt_kernel<false><<<grid, kThreads, 0, stream>>>(a, sak, b, sbk, out, m, n, k, k_per_split, accumulate ? 1 : 0);
   return cudaGetLastError();
 }
 

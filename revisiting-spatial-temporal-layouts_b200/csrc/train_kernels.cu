@@ -488,59 +488,6 @@ gelu_ln_bwd_kernel(const float* __restrict__ d_h2, const float* __restrict__ h1,
   flush_columns(acc_b, d_beta, scratch);
 }
 
-// Generic strided fp32 GEMM for the head gradients (M = batch rows, tiny N / K):
-//   out[i, j] (+)= sum_k A[i * sai + k * sak] * B[k * sbk + j * sbj]
-// 64 x 64 output tile, 16-deep k slices in shared memory, 4 x 4 micro-tile per thread.
-__global__ void __launch_bounds__(256)
-gemm_strided_kernel(const float* __restrict__ a, long long sai, long long sak,
-                    const float* __restrict__ b, long long sbk, long long sbj, float* __restrict__ out,
-                    int m, int n, int k, int accumulate) {
-  __shared__ float as[16][64 + 1];
-  __shared__ float bs[16][64 + 1];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < k; k0 += 16) {
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      int kk, ii;
-      if (sak == 1) { kk = e & 15; ii = e >> 4; } else { ii = e & 63; kk = e >> 6; }
-      const int gi = i0 + ii, gk = k0 + kk;
-      as[kk][ii] = (gi < m && gk < k) ? a[gi * sai + gk * sak] : 0.f;
-    }
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      int kk, jj;
-      if (sbk == 1) { kk = e & 15; jj = e >> 4; } else { jj = e & 63; kk = e >> 6; }
-      const int gj = j0 + jj, gk = k0 + kk;
-      bs[kk][jj] = (gj < n && gk < k) ? b[gk * sbk + gj * sbj] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float av[4], bv[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        av[p] = as[kk][ty + 16 * p];
-        bv[p] = bs[kk][tx + 16 * p];
-      }
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int gi = i0 + ty + 16 * p, gj = j0 + tx + 16 * q;
-      if (gi < m && gj < n) {
-        float* o = out + static_cast<long long>(gi) * n + gj;
-        *o = accumulate ? *o + acc[p][q] : acc[p][q];
-      }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Losses of the reference Criterion (src/utils/train_inference_utils.py:64-76), mean reduction, and
 // their gradients w.r.t. the logits. One warp per row.
@@ -745,15 +692,6 @@ cudaError_t launch_gelu_ln_bwd(const float* d_h2, const float* h1, const float* 
   if (rows == 0) return cudaSuccess;
   gelu_ln_bwd_kernel<<<row_grid(rows, kBwdWarps, 2), kBwdWarps * 32, 0, stream>>>(
       d_h2, h1, gamma, eps, rows, d_h1, d_gamma, d_beta);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_gemm_strided(const float* a, long long sai, long long sak, const float* b,
-                                long long sbk, long long sbj, float* out, int m, int n, int k,
-                                bool accumulate, cudaStream_t stream) {
-  if (m == 0 || n == 0) return cudaSuccess;
-  dim3 grid((n + 63) / 64, (m + 63) / 64);
-  gemm_strided_kernel<<<grid, 256, 0, stream>>>(a, sai, sak, b, sbk, sbj, out, m, n, k, accumulate ? 1 : 0);
   return cudaGetLastError();
 }
 
