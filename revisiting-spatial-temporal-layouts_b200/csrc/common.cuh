@@ -39,6 +39,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// 2^x on both halves: ex2.approx.f16x2 is two MUFU.EX2.F16 and a PRMT; cuda_fp16's h2exp2() widens to fp32 and back
+// (two conversions, two MUFU.EX2, one pack).
+__device__ __forceinline__ __half2 ex2_h2(__half2 x) {
+  uint32_t r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&x)));
+  return *reinterpret_cast<__half2*>(&r);
+}
+
 // Single-branch erf-GELU for the bf16 epilogue: erf(z) = 1 - 2^(-a*q(a)), a = |x| (degree-4 minimax
 // fit of -log2(erfc(z))/z, z = a/sqrt(2); |erf error| < 7e-7 in fp32, far below bf16 rounding).
 // ~11 instructions and one MUFU.EX2 per element instead of erff()'s two divergent branches.
@@ -67,7 +75,7 @@ __device__ __forceinline__ __half2 gelu_erf_fast_h2(__half2 x) {
   q = __hfma2(q, a, __float2half2_rn(5.256125276e-02f));
   q = __hfma2(q, a, __float2half2_rn(4.592546886e-01f));
   q = __hfma2(q, a, __float2half2_rn(1.151091390e+00f));
-  const __half2 e = h2exp2(__hneg2(__hmul2(q, a)));       // erfc(|x| / sqrt 2)
+  const __half2 e = ex2_h2(__hneg2(__hmul2(q, a)));       // erfc(|x| / sqrt 2)
   const __half2 h = __hfma2(__hneg2(ax), e, ax);          // |x| * erf(|x| / sqrt 2)
   return __hmul2(__float2half2_rn(0.5f), __hadd2(x, h));  // 0.5 * x * (1 + erf(x / sqrt 2))
 }
@@ -83,10 +91,10 @@ __device__ __forceinline__ void gelu_erf_and_grad_fast_h2(__half2 x, __half2& ac
   q = __hfma2(q, a, __float2half2_rn(5.256125276e-02f));
   q = __hfma2(q, a, __float2half2_rn(4.592546886e-01f));
   q = __hfma2(q, a, __float2half2_rn(1.151091390e+00f));
-  const __half2 e = h2exp2(__hneg2(__hmul2(q, a)));       // erfc(|x| / sqrt 2)
+  const __half2 e = ex2_h2(__hneg2(__hmul2(q, a)));       // erfc(|x| / sqrt 2)
   const __half2 h = __hfma2(__hneg2(ax), e, ax);          // |x| * erf(|x| / sqrt 2)
   act = __hmul2(__float2half2_rn(0.5f), __hadd2(x, h));
-  const __half2 pdf = h2exp2(__hmul2(__float2half2_rn(-0.72134752044f), __hmul2(a, a)));  // exp(-x^2 / 2)
+  const __half2 pdf = ex2_h2(__hmul2(__float2half2_rn(-0.72134752044f), __hmul2(a, a)));  // exp(-x^2 / 2)
   const __half2 half_erf = __hfma2(__float2half2_rn(-0.5f), e, __float2half2_rn(0.5f));   // >= 0
   // copy the sign of x onto half_erf (both halves)
   const uint32_t xb = *reinterpret_cast<const uint32_t*>(&x);

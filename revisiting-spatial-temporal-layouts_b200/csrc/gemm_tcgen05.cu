@@ -449,21 +449,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           // multiplies by the second plane and never sees u
           const unsigned long long e0 =
               static_cast<unsigned long long>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32;
+          // pair indices below 2^32 (every shape this model produces) take drop_bits' single hash round without
+          // its per-pair test of the high word; the choice is uniform over the launch
+          const bool idx32 = (static_cast<unsigned long long>(m_tiles) * BM * (static_cast<unsigned>(n_tiles) * BN) >> 33) == 0;
+          const uint32_t p0 = static_cast<uint32_t>(e0 >> 1);
+          auto activate = [&](auto bits_of) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            __half2 act, grad;
-            gelu_erf_and_grad_fast_h2(__floats2half2_rn(f[j], f[j + 1]), act, grad);
-            float2 a2 = __half22float2(act), g2 = __half22float2(grad);
-            if (drop.thr16 != 0) {
-              const uint32_t bits = drop_bits(drop.key, (e0 + j) >> 1);
-              const float m0 = drop_mul(bits, 0, drop), m1 = drop_mul(bits, 1, drop);
-              a2.x *= m0; a2.y *= m1;
-              g2.x *= m0; g2.y *= m1;
+            for (int j = 0; j < 32; j += 2) {
+              __half2 act, grad;
+              gelu_erf_and_grad_fast_h2(__floats2half2_rn(f[j], f[j + 1]), act, grad);
+              float2 a2 = __half22float2(act), g2 = __half22float2(grad);
+              if (drop.thr16 != 0) {
+                const uint32_t bits = bits_of(j);
+                const float m0 = drop_mul(bits, 0, drop), m1 = drop_mul(bits, 1, drop);
+                a2.x *= m0; a2.y *= m1;
+                g2.x *= m0; g2.y *= m1;
+              }
+              f[j] = a2.x;
+              f[j + 1] = a2.y;
+              pre[j >> 1] = pack_bf16x2(g2.x, g2.y);
             }
-            f[j] = a2.x;
-            f[j + 1] = a2.y;
-            pre[j >> 1] = pack_bf16x2(g2.x, g2.y);
-          }
+          };
+          if (idx32) activate([&](int j) { return lowbias32((p0 + (j >> 1)) ^ drop.key); });
+          else activate([&](int j) { return drop_bits(drop.key, (e0 + j) >> 1); });
         } else if (kGelu == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
