@@ -370,7 +370,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           }
         }
         float f[32];
-        if constexpr (kEpi == GEMM_EPI_NORM_A) {
+        // NORM_A with a bf16 output: evaluated eight columns at a time inside the staging-store loop below
+        constexpr bool kNormInStore = kEpi == GEMM_EPI_NORM_A && kOut == GEMM_OUT_BF16 && (kGelu == 0 || kGelu == 2);
+        if constexpr (kNormInStore) {
+        } else if constexpr (kEpi == GEMM_EPI_NORM_A) {
           // act(LN(z) W^T + b) from the raw product: rstd * (acc - mean * s[n]) + c[n]
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -441,48 +444,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             f[j + 1] *= gg.y;
           }
         }
-        uint32_t pre[kOut == GEMM_OUT_BF16_DUAL ? 16 : 1];  // second plane (training): gelu'(u) * dropout mask
+        // GEMM_OUT_BF16_DUAL (training forward of linear1): act(u) and gelu'(u) in one evaluation, both under the
+        // FFN-inner dropout mask of nn.TransformerEncoderLayer (element = row * N + column); the backward GEMM
+        // (GEMM_EPI_ACT_BWD) multiplies by the second plane and never sees u. Evaluated eight columns at a time right
+        // before their two 16-byte staging stores (below), so that only one group of results is live at a time.
+        const unsigned long long dual_e0 =
+            static_cast<unsigned long long>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32;
+        // pair indices below 2^32 (every shape this model produces) take drop_bits' single hash round without its
+        // per-pair test of the high word; the choice is uniform over the launch
+        const bool dual_idx32 =
+            (static_cast<unsigned long long>(m_tiles) * BM * (static_cast<unsigned>(n_tiles) * BN) >> 33) == 0;
+        auto dual_group = [&](int g8, uint32_t (&ap)[4], uint32_t (&gp)[4], auto bits_of) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = 8 * g8 + 2 * q;
+            __half2 act, grad;
+            gelu_erf_and_grad_fast_h2(__floats2half2_rn(f[j], f[j + 1]), act, grad);
+            float2 a2 = __half22float2(act), g2 = __half22float2(grad);
+            if (drop.thr16 != 0) {
+              const uint32_t bits = bits_of(j);
+              const float m0 = drop_mul(bits, 0, drop), m1 = drop_mul(bits, 1, drop);
+              a2.x *= m0; a2.y *= m1;
+              g2.x *= m0; g2.y *= m1;
+            }
+            ap[q] = pack_bf16x2(a2.x, a2.y);
+            gp[q] = pack_bf16x2(g2.x, g2.y);
+          }
+        };
         if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
           static_assert(kOut != GEMM_OUT_BF16_DUAL || kGelu == 2, "DUAL output: fast erf GELU");
-          // act(u) and gelu'(u) in one evaluation, both under the FFN-inner dropout mask of
-          // nn.TransformerEncoderLayer (element = row * N + column); the backward GEMM (GEMM_EPI_ACT_BWD)
-          // multiplies by the second plane and never sees u
-          const unsigned long long e0 =
-              static_cast<unsigned long long>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32;
-          // pair indices below 2^32 (every shape this model produces) take drop_bits' single hash round without
-          // its per-pair test of the high word; the choice is uniform over the launch
-          const bool idx32 = (static_cast<unsigned long long>(m_tiles) * BM * (static_cast<unsigned>(n_tiles) * BN) >> 33) == 0;
-          const uint32_t p0 = static_cast<uint32_t>(e0 >> 1);
-          auto activate = [&](auto bits_of) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              __half2 act, grad;
-              gelu_erf_and_grad_fast_h2(__floats2half2_rn(f[j], f[j + 1]), act, grad);
-              float2 a2 = __half22float2(act), g2 = __half22float2(grad);
-              if (drop.thr16 != 0) {
-                const uint32_t bits = bits_of(j);
-                const float m0 = drop_mul(bits, 0, drop), m1 = drop_mul(bits, 1, drop);
-                a2.x *= m0; a2.y *= m1;
-                g2.x *= m0; g2.y *= m1;
-              }
-              f[j] = a2.x;
-              f[j + 1] = a2.y;
-              pre[j >> 1] = pack_bf16x2(g2.x, g2.y);
-            }
-          };
-          if (idx32) activate([&](int j) { return lowbias32((p0 + (j >> 1)) ^ drop.key); });
-          else activate([&](int j) { return drop_bits(drop.key, (e0 + j) >> 1); });
         } else if (kGelu == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
         } else if (kGelu == 2) {
-          if constexpr (kOut == GEMM_OUT_BF16) {  // packed fp16 math, the output is bf16 anyway
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 r = __half22float2(gelu_erf_fast_h2(__floats2half2_rn(f[j], f[j + 1])));
-              f[j] = r.x;
-              f[j + 1] = r.y;
-            }
+          if constexpr (kOut == GEMM_OUT_BF16) {
+            // packed fp16 math (the output is bf16 anyway), evaluated eight columns at a time right before their
+            // staging store below: fewer live registers, more independent work between the stores
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
@@ -547,16 +544,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t addr = row_smem + ((static_cast<uint32_t>(hc * 4 + j) ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                         "r"(pack_bf16x2(f[8 * j + 0], f[8 * j + 1])),
-                         "r"(pack_bf16x2(f[8 * j + 2], f[8 * j + 3])),
-                         "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])),
-                         "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
-                         : "memory");
             if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kEpiBufBytes),
-                           "r"(pre[4 * j + 0]), "r"(pre[4 * j + 1]), "r"(pre[4 * j + 2]),
-                           "r"(pre[4 * j + 3])
+              uint32_t ap[4], gp[4];
+              if (dual_idx32)
+                dual_group(j, ap, gp, [&](int e) { return lowbias32((static_cast<uint32_t>(dual_e0 >> 1) + (e >> 1)) ^ drop.key); });
+              else
+                dual_group(j, ap, gp, [&](int e) { return drop_bits(drop.key, (dual_e0 + e) >> 1); });
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ap[0]), "r"(ap[1]), "r"(ap[2]),
+                           "r"(ap[3])
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kEpiBufBytes), "r"(gp[0]), "r"(gp[1]),
+                           "r"(gp[2]), "r"(gp[3])
+                           : "memory");
+            } else if constexpr (kNormInStore || (kOut == GEMM_OUT_BF16 && kGelu == 2)) {
+              float gv[8];
+              if constexpr (kNormInStore) {
+                // act(LN(z) W^T + b) from the raw product: rstd * (acc - mean * s[n]) + c[n]
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const float4 s4 = __ldg(va4 + c * 8 + 2 * j + q);
+                  const float4 c4 = __ldg(vb4 + c * 8 + 2 * j + q);
+                  const int e = 8 * j + 4 * q;
+                  gv[4 * q + 0] = fmaf(rstd, fmaf(-mu, s4.x, __uint_as_float(v[e + 0])), c4.x);
+                  gv[4 * q + 1] = fmaf(rstd, fmaf(-mu, s4.y, __uint_as_float(v[e + 1])), c4.y);
+                  gv[4 * q + 2] = fmaf(rstd, fmaf(-mu, s4.z, __uint_as_float(v[e + 2])), c4.z);
+                  gv[4 * q + 3] = fmaf(rstd, fmaf(-mu, s4.w, __uint_as_float(v[e + 3])), c4.w);
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) gv[q] = f[8 * j + q];
+              }
+              uint32_t ap[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if constexpr (kGelu == 2) {
+                  const float2 r = __half22float2(gelu_erf_fast_h2(__floats2half2_rn(gv[2 * q], gv[2 * q + 1])));
+                  ap[q] = pack_bf16x2(r.x, r.y);
+                } else {
+                  ap[q] = pack_bf16x2(gv[2 * q], gv[2 * q + 1]);
+                }
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ap[0]), "r"(ap[1]), "r"(ap[2]),
+                           "r"(ap[3])
+                           : "memory");
+            } else {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                           "r"(pack_bf16x2(f[8 * j + 0], f[8 * j + 1])),
+                           "r"(pack_bf16x2(f[8 * j + 2], f[8 * j + 3])),
+                           "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])),
+                           "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
                            : "memory");
             }
             if (kOut == GEMM_OUT_BF16_SPLIT) {
