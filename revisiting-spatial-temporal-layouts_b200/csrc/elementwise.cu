@@ -210,14 +210,14 @@ __global__ void topk_count_kernel(const float* __restrict__ logits, const long l
 // per token out as 512-byte warp stores. No shared memory, no barrier, no cross-lane reduction.
 constexpr int kEmbedTok = 8;
 constexpr int kEmbedThreads = kHidden / 4;  // 192
-constexpr int kEmbedCatStride = 24;         // floats per category: mean(E[cat]), 21 quadratic-form coefficients
+constexpr int kEmbedCatStride = 24;         // doubles per category: mean(E[cat]), 21 quadratic-form coefficients
 constexpr int kEmbedGlobal = 8;             // after the categories: mean of w0..w3, score_w, bias
 
 __global__ void __launch_bounds__(256)
 embed_stats_kernel(const float* __restrict__ cat_table, int unique_categories,
                    const float* __restrict__ box_w, const float* __restrict__ box_b,
                    const float* __restrict__ score_w, const float* __restrict__ score_b,
-                   float* __restrict__ stats) {
+                   double* __restrict__ stats) {
   // One sweep over the 768 columns in fp64: raw first and second moments of v = (w0, w1, w2, w3, score_w,
   // E[cat] + bias) plus the sums of E[cat] and of the bias alone; the centred Gram matrix is
   // (sum v_i v_j - sum v_i sum v_j / n) / n (exact to ~1e-16 relative in fp64).
@@ -260,20 +260,20 @@ embed_stats_kernel(const float* __restrict__ cat_table, int unique_categories,
   }
   __syncthreads();
   const double* tot = red[0];
-  float* out = stats + static_cast<long long>(cat) * kEmbedCatStride;
+  double* out = stats + static_cast<long long>(cat) * kEmbedCatStride;
   if (tid < 21) {
     // entry tid of the upper triangle -> (i, j); off-diagonal terms appear twice in u^T G u
     int i = 0, rem = tid;
     while (rem >= 6 - i) { rem -= 6 - i; ++i; }
     const int j = i + rem;
     const double g = (tot[6 + tid] - tot[i] * tot[j] / kHidden) / kHidden;
-    out[1 + tid] = static_cast<float>(rem == 0 ? g : 2.0 * g);
+    out[1 + tid] = rem == 0 ? g : 2.0 * g;
   }
-  if (tid == 21) out[0] = static_cast<float>(tot[27] / kHidden);
-  if (tid == 22 || tid == 23) out[tid] = 0.f;
+  if (tid == 21) out[0] = tot[27] / kHidden;
+  if (tid == 22 || tid == 23) out[tid] = 0.0;
   if (cat == 0 && tid < kEmbedGlobal) {
     const double m = tid < 5 ? tot[tid] : (tid == 5 ? tot[28] : 0.0);
-    stats[static_cast<long long>(unique_categories) * kEmbedCatStride + tid] = static_cast<float>(m / kHidden);
+    stats[static_cast<long long>(unique_categories) * kEmbedCatStride + tid] = m / kHidden;
   }
 }
 
@@ -284,13 +284,14 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
              const float* __restrict__ box_b, const float* __restrict__ score_w,
              const float* __restrict__ score_b, const float* __restrict__ ln_g,
              const float* __restrict__ ln_b, float eps, long long tokens, ActOut out,
-             int* __restrict__ err_flag, DropCfg drop, const float* __restrict__ stats) {
+             int* __restrict__ err_flag, DropCfg drop, const double* __restrict__ stats) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int c = 4 * tid;
   // resident, centred parameters of this thread's four columns
-  const float* glob = stats + static_cast<long long>(unique_categories) * kEmbedCatStride;
-  const float4 mw = *reinterpret_cast<const float4*>(glob);
-  const float msw = glob[4], mb = glob[5];
+  const double* glob = stats + static_cast<long long>(unique_categories) * kEmbedCatStride;
+  const float4 mw = make_float4(static_cast<float>(glob[0]), static_cast<float>(glob[1]), static_cast<float>(glob[2]),
+                                static_cast<float>(glob[3]));
+  const float msw = static_cast<float>(glob[4]), mb = static_cast<float>(glob[5]);
   float4 w[4];  // box_w is [768][4]: one float4 per feature
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -324,25 +325,21 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
     const float sc_l = scores != nullptr ? __ldg(scores + tl) : 0.f;
     float mean_l, rstd_l;
     {
-      const float4* gq = reinterpret_cast<const float4*>(stats + cat_l * kEmbedCatStride);
-      float coef[kEmbedCatStride];
-#pragma unroll
-      for (int k = 0; k < kEmbedCatStride / 4; ++k) {
-        const float4 v = __ldg(gq + k);
-        coef[4 * k + 0] = v.x; coef[4 * k + 1] = v.y; coef[4 * k + 2] = v.z; coef[4 * k + 3] = v.w;
-      }
-      mean_l = coef[0];
-      const float u[6] = {box_l.x, box_l.y, box_l.z, box_l.w, sc_l, 1.f};
-      float var = 0.f;
+      // the quadratic form is evaluated in fp64 (22 loads and 27 DFMA per token, in one lane): its terms may cancel,
+      // and this way the variance is as exact as a two-pass reduction
+      const double* gq = stats + cat_l * kEmbedCatStride;
+      mean_l = static_cast<float>(gq[0]);
+      const double u[6] = {box_l.x, box_l.y, box_l.z, box_l.w, sc_l, 1.0};
+      double var = 0.0;
       int k = 1;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        float inner = 0.f;
+        double inner = 0.0;
 #pragma unroll
-        for (int j = i; j < 6; ++j) inner += coef[k++] * u[j];
+        for (int j = i; j < 6; ++j) inner += gq[k++] * u[j];
         var += inner * u[i];
       }
-      rstd_l = 1.0f / sqrtf(fmaxf(var, 0.f) + eps);
+      rstd_l = 1.0f / sqrtf(fmaxf(static_cast<float>(var), 0.f) + eps);
     }
     const int cat_i = static_cast<int>(cat_l);
 #pragma unroll
@@ -636,7 +633,7 @@ cudaError_t launch_masks(const long long* categories, const long long* frame_typ
 }
 
 size_t embed_scratch_bytes(int unique_categories) {
-  return (static_cast<size_t>(unique_categories) * kEmbedCatStride + kEmbedGlobal) * sizeof(float);
+  return (static_cast<size_t>(unique_categories) * kEmbedCatStride + kEmbedGlobal) * sizeof(double);
 }
 
 cudaError_t launch_embed(const long long* categories, const float* boxes, const float* scores,
@@ -650,12 +647,13 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
     return cudaErrorInvalidValue;
   embed_stats_kernel<<<unique_categories, 256, 0, stream>>>(
       cat_table, unique_categories, box_w, box_b, scores != nullptr ? score_w : nullptr,
-      scores != nullptr ? score_b : nullptr, scratch);
+      scores != nullptr ? score_b : nullptr, reinterpret_cast<double*>(scratch));
   long long blocks = (tokens + kEmbedTok - 1) / kEmbedTok;
   if (blocks > 148LL * 4 * 8) blocks = 148LL * 4 * 8;  // 4 resident CTAs per SM, grid-stride inside
   embed_kernel<<<static_cast<unsigned>(blocks), kEmbedThreads, 0, stream>>>(
       categories, reinterpret_cast<const float4*>(boxes), scores, cat_table, unique_categories,
-      box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag, drop, scratch);
+      box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag, drop,
+      reinterpret_cast<const double*>(scratch));
   return cudaGetLastError();
 }
 

@@ -224,3 +224,34 @@ def test_two_rank_gloo_gradient_buckets(tmp_path):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "ALLREDUCE_OK" in res.stdout
+
+
+def test_embedding_layernorm_statistics_identity():
+    """The identity embed_stats_kernel / embed_kernel rely on (csrc/elementwise.cu): the pre-LayerNorm row of
+    CategoryBoxEmbeddings (models.py:29-39) is affine in u = (box, score, 1), so its mean is removed by centring the
+    tables and its biased variance is u^T G_cat u / 768 with G_cat the Gram matrix of the centred vectors — checked
+    here in numpy against the direct two-pass statistics (the CUDA kernels are checked on the GPU against the
+    reference's embedding activations)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    H, U = 768, 7
+    E = rng.normal(size=(U, H))
+    W = rng.uniform(-0.5, 0.5, size=(H, 4))
+    b = 0.02 * rng.normal(size=H)
+    sw = rng.uniform(-1, 1, size=H)
+    sb = 0.02 * rng.normal(size=H)
+    for cat in range(U):
+        for _ in range(5):
+            box = rng.uniform(0, 1, size=4)
+            score = rng.uniform(0.5, 1)
+            x = E[cat] + W @ box + b + score * sw + sb
+            mean, var = x.mean(), x.var()
+            V = np.stack([W[:, 0], W[:, 1], W[:, 2], W[:, 3], sw, E[cat] + b + sb])  # [6, H]
+            Vc = V - V.mean(axis=1, keepdims=True)
+            G = Vc @ Vc.T / H
+            u = np.array([*box, score, 1.0])
+            assert abs(V.mean(axis=1) @ u - mean) < 1e-12
+            assert abs(u @ G @ u - var) < 1e-12 * max(1.0, var)
+            # the upper-triangle form the kernel evaluates (off-diagonal coefficients doubled)
+            tri = sum((G[i, j] * (1.0 if i == j else 2.0)) * u[i] * u[j] for i in range(6) for j in range(i, 6))
+            assert abs(tri - var) < 1e-12 * max(1.0, var)
