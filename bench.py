@@ -155,6 +155,16 @@ def cpu_oracle_throughput(layout: str, batch: int, seconds: float, warmup: int =
             "steps": len(times), "cores": torch.get_num_threads(), "host_cpus": os.cpu_count()}
 
 
+def inference_config(layout: str, batch: int, world: int, L: int, S: int, num_classes: int) -> dict:
+    """`config` of the inference workload; the reference arm reports the same one (it times a bounded sample of it)."""
+    return {
+        "workload": f"STLT inference, {layout} shape (L={L} frames x S={S} slots, "
+                    f"{num_classes} classes), batch {batch} per GPU, dense layouts, random-init weights",
+        "global_batch": batch * world, "parallelism": f"batch-sharded x{world}, no collective",
+        "l2_policy": "activations (GBs per step) far exceed the 126 MB L2; no explicit flush",
+    }
+
+
 def run_reference(args, rank: int):
     """Reference arm: the reference's CPU implementation of the path, timed on the host cores.
     The reference is a Python/PyTorch repo that is not present on the GPU box, so this runs the
@@ -167,10 +177,12 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": "stlt_inference_videos_per_sec", "value": r["value"], "unit": "videos/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"STLT inference, {args.layout} shape (17 frames x {5 if args.layout == 'something' else 11} slots), "
-                               f"CPU fp32, {sample}-video sample per step"},
+        # same config as the B200 arm; each step is a bounded sample of that workload on the host cores
+        "config": inference_config(args.layout, args.batch, args.gpus, 17, 5 if args.layout == "something" else 11,
+                                   174 if args.layout == "something" else 157),
         "cpu_baseline": {"value": r["value"], "unit": "videos/s", "cores": r["cores"], "kind": "port",
-                         "sample": f"{r['steps']} forwards of {sample} videos (dense layouts), host cpus {r['host_cpus']}"},
+                         "sample": f"{r['steps']} CPU fp32 forwards of {sample} videos of that workload (dense layouts) "
+                                   f"through oracle/stlt_oracle.py on rank 0, host cpus {r['host_cpus']}"},
         "e2e": {"value": r["value"], "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -636,12 +648,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.dtype == "bf16" else "f32 (3xbf16 split MMA)", "data": "synthetic",
-            "config": {
-                "workload": f"STLT inference, {args.layout} shape (L={L} frames x S={S} slots, "
-                            f"{spec['num_classes']} classes), batch {args.batch} per GPU, dense layouts, random-init weights",
-                "global_batch": args.batch * world, "parallelism": f"batch-sharded x{world}, no collective",
-                "l2_policy": "activations (GBs per step) far exceed the 126 MB L2; no explicit flush",
-            },
+            "config": inference_config(args.layout, args.batch, world, L, S, spec["num_classes"]),
             "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
             "cpu_baseline": cpu, "clocks": clocks, "model_tflops": main_res["model_tflops"],
             "breakdown_ms_per_step": main_res["breakdown_ms_per_step"],
