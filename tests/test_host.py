@@ -255,3 +255,23 @@ def test_embedding_layernorm_statistics_identity():
             # the upper-triangle form the kernel evaluates (off-diagonal coefficients doubled)
             tri = sum((G[i, j] * (1.0 if i == j else 2.0)) * u[i] * u[j] for i in range(6) for j in range(i, 6))
             assert abs(tri - var) < 1e-12 * max(1.0, var)
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """`bench.py --impl reference` launched like the B200 arm (torchrun, N = 2): rank 0 alone runs the CPU arm and
+    prints ONE JSON line carrying the B200 arm's metric / unit / config; the other rank exits 0 without work."""
+    import json
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="4")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29523", str(ROOT / "bench.py"),
+           "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, res.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "stlt_inference_videos_per_sec" and d["unit"] == "videos/s"
+    assert d["n_gpus"] == 2 and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"]["workload"].startswith("STLT inference, something shape (L=17 frames x S=5 slots, 174 classes), batch 4096")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
