@@ -167,6 +167,31 @@ def golden_model(configs, models, layout: str, batch_size: int, weight_seed: int
     print(f"stlt_{layout}.npz logits", tuple(logits.shape), "max|logit|", float(logits.abs().max()))
 
 
+def golden_model_long(configs, models, frames: int, batch_size: int, weight_seed: int, batch_seed: int):
+    """Long-sequence case: more sampled frames than the CLIs' default 16 (the position table allows 256,
+    models.py:88-96); 2 spatial + 2 temporal layers keep the fixture and the CPU test small. Logits only."""
+    import stlt_b200
+    from stlt_b200.synthetic import make_batch, random_state_dict
+    spec = stlt_b200.SOMETHING_ELSE
+    cfg = configs.StltModelConfig(num_classes=spec["num_classes"], unique_categories=spec["unique_categories"],
+                                  num_spatial_layers=2, num_temporal_layers=2)
+    torch.manual_seed(0)
+    ref = models.Stlt(cfg)              # the unmodified reference module
+    ref.train(False)
+    sd = random_state_dict(ref.state_dict(), seed=weight_seed)
+    ref.load_state_dict(sd, strict=True)
+    batch = make_batch(batch_size, layout="something", ragged=True, seed=batch_seed, num_frames=frames, max_objects=2)
+    with torch.no_grad():
+        logits = ref({k: v.clone() for k, v in batch.items()})["stlt"]
+    out = {"frames": np.int64(frames), "batch_size": np.int64(batch_size), "weight_seed": np.int64(weight_seed),
+           "batch_seed": np.int64(batch_seed), "weights_checksum": np.float64(weights_checksum(sd)),
+           "logits": logits.numpy()}
+    for k, v in batch.items():
+        out["in_" + k] = v.numpy()
+    np.savez_compressed(GOLDEN / f"stlt_long_{frames}.npz", **out)
+    print(f"stlt_long_{frames}.npz logits", tuple(logits.shape), "max|logit|", float(logits.abs().max()))
+
+
 def golden_training(configs, models, train_utils, layout: str, batch_size: int, weight_seed: int, batch_seed: int,
                     steps: int = 3):
     """Reference training loop body (src/train.py:117-135) with dropout p = 0 on a fixed batch:
@@ -337,6 +362,8 @@ def main():
     golden_dataset(configs, datasets, "action_genome", seed=22)
     golden_model(configs, models, "something", batch_size=3, weight_seed=1, batch_seed=3)
     golden_model(configs, models, "action_genome", batch_size=2, weight_seed=2, batch_seed=4)
+    golden_model_long(configs, models, frames=99, batch_size=2, weight_seed=14, batch_seed=15)
+    golden_model_long(configs, models, frames=255, batch_size=2, weight_seed=16, batch_seed=17)
     golden_cacnf(configs, models, batch_size=3, weight_seed=8, batch_seed=9)
     golden_charades_map()
     golden_caf_lcf(configs, models, batch_size=3, weight_seed=12, batch_seed=13)
