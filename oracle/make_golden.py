@@ -167,7 +167,8 @@ def golden_model(configs, models, layout: str, batch_size: int, weight_seed: int
     print(f"stlt_{layout}.npz logits", tuple(logits.shape), "max|logit|", float(logits.abs().max()))
 
 
-def golden_model_long(configs, models, frames: int, batch_size: int, weight_seed: int, batch_seed: int):
+def golden_model_long(configs, models, frames: int, batch_size: int, weight_seed: int, batch_seed: int,
+                      max_objects: int = 2, name: str = ""):
     """Long-sequence case: more sampled frames than the CLIs' default 16 (the position table allows 256,
     models.py:88-96); 2 spatial + 2 temporal layers keep the fixture and the CPU test small. Logits only."""
     import stlt_b200
@@ -180,7 +181,8 @@ def golden_model_long(configs, models, frames: int, batch_size: int, weight_seed
     ref.train(False)
     sd = random_state_dict(ref.state_dict(), seed=weight_seed)
     ref.load_state_dict(sd, strict=True)
-    batch = make_batch(batch_size, layout="something", ragged=True, seed=batch_seed, num_frames=frames, max_objects=2)
+    batch = make_batch(batch_size, layout="something", ragged=True, seed=batch_seed, num_frames=frames,
+                       max_objects=max_objects)
     with torch.no_grad():
         logits = ref({k: v.clone() for k, v in batch.items()})["stlt"]
     out = {"frames": np.int64(frames), "batch_size": np.int64(batch_size), "weight_seed": np.int64(weight_seed),
@@ -188,8 +190,9 @@ def golden_model_long(configs, models, frames: int, batch_size: int, weight_seed
            "logits": logits.numpy()}
     for k, v in batch.items():
         out["in_" + k] = v.numpy()
-    np.savez_compressed(GOLDEN / f"stlt_long_{frames}.npz", **out)
-    print(f"stlt_long_{frames}.npz logits", tuple(logits.shape), "max|logit|", float(logits.abs().max()))
+    name = name or f"stlt_long_{frames}"
+    np.savez_compressed(GOLDEN / f"{name}.npz", **out)
+    print(f"{name}.npz logits", tuple(logits.shape), "max|logit|", float(logits.abs().max()))
 
 
 def golden_training(configs, models, train_utils, layout: str, batch_size: int, weight_seed: int, batch_seed: int,
@@ -364,6 +367,9 @@ def main():
     golden_model(configs, models, "action_genome", batch_size=2, weight_seed=2, batch_seed=4)
     golden_model_long(configs, models, frames=99, batch_size=2, weight_seed=14, batch_seed=15)
     golden_model_long(configs, models, frames=255, batch_size=2, weight_seed=16, batch_seed=17)
+    # wide frames: 41 slots per frame (the 33..64-token attention tiles on the GPU side)
+    golden_model_long(configs, models, frames=16, batch_size=2, weight_seed=18, batch_seed=19, max_objects=40,
+                      name="stlt_wide_40")
     golden_cacnf(configs, models, batch_size=3, weight_seed=8, batch_seed=9)
     golden_charades_map()
     golden_caf_lcf(configs, models, batch_size=3, weight_seed=12, batch_seed=13)

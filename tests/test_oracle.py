@@ -75,20 +75,21 @@ def test_forward_matches_reference_golden(layout):
     assert nerr(taps["spatial"][0][valid], torch.from_numpy(g["spatial_b0"])[valid]) < 2e-5
 
 
-@pytest.mark.parametrize("frames", [99, 255])
-def test_forward_matches_reference_golden_on_long_sequences(frames):
+@pytest.mark.parametrize("name,frames,slots", [("stlt_long_99", 100, 3), ("stlt_long_255", 256, 3), ("stlt_wide_40", 17, 41)])
+def test_forward_matches_reference_golden_on_long_sequences(name, frames, slots):
     """The oracle is also pinned where the GPU path switches attention kernels: 100 and 256 frame tokens per video
-    (the reference's position table ends at 256, models.py:88-96), logits of the unmodified reference module."""
+    (the reference's position table ends at 256, models.py:88-96) and 41 slots per frame; logits of the unmodified
+    reference module."""
     import stlt_b200
     from stlt_b200.synthetic import random_state_dict
     from tests.util import weights_checksum
-    g = load_golden(f"stlt_long_{frames}.npz")
+    g = load_golden(f"{name}.npz")
     cfg = stlt_b200.StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=2, num_temporal_layers=2)
     torch.manual_seed(0)
     sd = random_state_dict(stlt_b200.Stlt(cfg).state_dict(), seed=int(g["weight_seed"]))
     assert abs(weights_checksum(sd) - float(g["weights_checksum"])) < 1e-6 * float(g["weights_checksum"])
     batch = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("in_")}
-    assert batch["categories"].shape[1] == frames + 1
+    assert tuple(batch["categories"].shape[1:]) == (frames, slots)
     with torch.no_grad():
         got = O.stlt_forward(sd, batch, num_spatial_layers=2, num_temporal_layers=2)
     assert nerr(got, torch.from_numpy(g["logits"])) < 2e-5
