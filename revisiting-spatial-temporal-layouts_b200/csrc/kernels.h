@@ -239,7 +239,9 @@ cudaError_t launch_gelu_ln(const float* h1, const float* g, const float* b, floa
 cudaError_t launch_gelu_ln_bwd(const float* d_h2, const float* h1, const float* gamma, float eps,
                                long long rows, float* d_h1, float* d_gamma, float* d_beta,
                                cudaStream_t stream);
-// out[i, j] (+)= sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj], fp32 CUDA cores (classifier-head gradients).
+// out[i, j] (+)= sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj], fp32 CUDA cores (classifier-head gradients; gemm_simt.cu).
+// B must be row-major (sbj == 1) and A contiguous along i or k; accumulate = true adds into `out` with atomics and
+// splits the reduction over the grid (weight gradients: few output tiles, the batch is the reduction).
 cudaError_t launch_gemm_strided(const float* a, long long sai, long long sak, const float* b,
                                 long long sbk, long long sbj, float* out, int m, int n, int k,
                                 bool accumulate, cudaStream_t stream);
