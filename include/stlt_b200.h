@@ -208,6 +208,13 @@ int stlt_set_pruning(void* handle, int32_t enable);
  * up to bf16 rounding; used by the tests as a cross-check). Has no effect in fp32 mode or with taps set. */
 int stlt_set_fused_ln(void* handle, int32_t enable);
 
+/* bf16 mode with fused LayerNorms also folds the attention into the epilogue of the in-projection GEMM (default
+ * on; sequences of at most 32 tokens): F.linear(x, in_proj_weight, in_proj_bias) and the scaled-dot-product
+ * attention of nn.MultiheadAttention (models.py:46-55,118-128) run as ONE kernel whose work unit is a
+ * (row block, head) and whose weights are packed head-major, so the packed Q | K | V activations never reach
+ * HBM. 0 restores the separate in-projection GEMM + attention kernel (cross-check for the tests). */
+int stlt_set_fused_attention(void* handle, int32_t enable);
+
 /* Test taps (NULL disables). The struct is copied. */
 int stlt_set_taps(void* handle, const StltTaps* taps);
 
@@ -324,6 +331,33 @@ int stlt_op_attention_bwd(void* handle, void* stream, const void* qkv, const voi
 int stlt_op_attention_cross(void* handle, void* stream, const void* q_qkv, const void* kv_qkv,
                             const int64_t* mask_src_or_null, int64_t num_seqs, int32_t q_len, int32_t kv_len,
                             int32_t causal, void* out_bf16);
+/* The LayerNorm-fused projection GEMMs of the bf16 inference path (what stlt_forward runs by default):
+ *   epilogue 1 (NORM_A): out bf16 [m_rows][n] = act(LN(z) W^T + b) computed from a = bf16(z) [m_rows][k],
+ *     w = gamma-folded bf16 weights [n][k] and vec_a / vec_b = s / c of stlt_op_pack_folded, stats_in = per-row
+ *     (sum, sum of squares) of z in 6 partial slots f32 [m_rows][6][2]; gelu 0 or 2.
+ *   epilogue 2 (RESID, n must be 768): z f32 [m_rows][768] is updated IN PLACE to
+ *     (prev_norm ? LN(z; vec_a = gamma, vec_b = beta, stats_in) : z) + a W^T + bias, out_bf16 receives its bf16
+ *     copy and stats_out f32 [m_rows][6][2] the partial row statistics of the new z. */
+int stlt_op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void* a, int32_t m_rows, const void* w,
+                       int32_t n, int32_t k, const float* bias_or_null, void* out, void* out_bf16_or_null,
+                       int32_t gelu, const float* stats_in_or_null, const float* vec_a, const float* vec_b,
+                       float* stats_out_or_null, float eps, int32_t prev_norm);
+/* gamma-folded bf16 copy of a projection matrix w f32 [n][k] for the NORM_A epilogue: w_folded[n][k] =
+ * bf16(w * gamma), s_out[n] = sum_k w_folded[n][k], c_out[n] = (w beta)[n] + bias[n]; gamma = beta = NULL
+ * folds the identity. head_major != 0 (n = 2304 only) writes the rows of a packed in-projection in the order
+ * h*192 + t*64 + j <- t*768 + h*64 + j (t = Q, K, V), the layout stlt_op_qkv_attention reads. */
+int stlt_op_pack_folded(void* handle, void* stream, const float* w, const float* gamma_or_null,
+                        const float* beta_or_null, const float* bias, int32_t n, int32_t k, void* w_folded,
+                        float* s_out, float* c_out, int32_t head_major);
+/* In-projection + masked self-attention in one kernel (see stlt_set_fused_attention): a bf16 [m_rows][768],
+ * w_head_major / vec_s / vec_c from stlt_op_pack_folded(head_major = 1), stats_or_null f32 [m_rows][6][2]
+ * (non-NULL: the rows of `a` are an un-normalised residual stream whose LayerNorm is folded into the weights),
+ * mask_src i64 [valid_rows] (key masked when 0), num_seqs sequences of seq_len <= 32 consecutive rows.
+ * ctx bf16 [m_rows][768]. */
+int stlt_op_qkv_attention(void* handle, void* stream, const void* a, int64_t m_rows, int64_t valid_rows,
+                          const void* w_head_major, const float* vec_s, const float* vec_c,
+                          const float* stats_or_null, float eps, const int64_t* mask_src, int64_t num_seqs,
+                          int32_t seq_len, int32_t causal, void* ctx);
 int stlt_op_gemm_simt(void* handle, void* stream, const float* a, const float* w,
                       const float* bias, float* out, int32_t m, int32_t n, int32_t k, int32_t gelu);
 int stlt_op_attention(void* handle, void* stream, const void* qkv, int32_t qkv_is_bf16,

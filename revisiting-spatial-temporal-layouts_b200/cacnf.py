@@ -188,7 +188,7 @@ class Cacnf(nn.Module):
         _lib.check(self._handle, lib.stlt_cacnf_packed_weights_bytes(self._handle, prec, ctypes.byref(n2)))
         a = (n1.value + 1023) // 1024 * 1024
         if self._packed is None or self._packed.numel() < a + n2.value or self._packed.device != device:
-            self._packed = torch.empty(a + n2.value, dtype=torch.uint8, device=device)
+            self._packed = _lib.aligned_empty(a + n2.value, device)
         _lib.check(self._handle, lib.stlt_pack_weights(self._handle, stream, prec, self._packed.data_ptr(), n1.value))
         _lib.check(self._handle, lib.stlt_cacnf_pack_weights(self._handle, stream, prec, self._packed.data_ptr() + a,
                                                              n2.value))
@@ -225,7 +225,7 @@ class Cacnf(nn.Module):
             prec = _lib.PRECISIONS[self.precision]
             _lib.check(self._handle, lib.stlt_cacnf_workspace_bytes(self._handle, B, L, S, prec, ctypes.byref(nbytes)))
             if self._workspace is None or self._workspace.numel() < nbytes.value or self._workspace.device != device:
-                self._workspace = torch.empty(max(nbytes.value, 1024), dtype=torch.uint8, device=device)
+                self._workspace = _lib.aligned_empty(max(nbytes.value, 1024), device)
             out = [torch.empty((B, c.num_classes), dtype=torch.float32, device=device) for _ in range(4)]
             _lib.check(self._handle, lib.stlt_cacnf_forward(
                 self._handle, stream, prec, cats.data_ptr(), boxes.data_ptr(),

@@ -1,54 +1,54 @@
-"""Model configuration of the STLT path; mirrors the reference's kwargs-popping config objects
-(reference src/modelling/configs.py:92-126: GeneralModelConfig + StltModelConfig) so callers can
-pass either this class or the reference's own instance (attributes are read duck-typed)."""
+"""Model configuration of the STLT path.
+
+Schema = the fields of the reference's GeneralModelConfig + StltModelConfig
+(reference src/modelling/configs.py:92-111) that the forward path reads, with the same names and defaults, so
+callers can pass either this class or the reference's own instance (attributes are read duck-typed). The
+classes are table-driven: keyword arguments not in the table are ignored, as the reference's kwargs.pop
+objects do; the two required fields raise when missing."""
 from __future__ import annotations
 
+_REQUIRED = object()
 
-class StltModelConfig:
+
+class _TableConfig:
+    """Keyword-constructed config whose fields and defaults come from the class attribute ``FIELDS``."""
+    FIELDS: dict = {}
+
     def __init__(self, **kwargs):
-        # GeneralModelConfig (configs.py:92-99)
-        self.num_classes = kwargs.pop("num_classes", None)
-        assert self.num_classes, "num_classes must not be None!"
-        self.hidden_size = kwargs.pop("hidden_size", 768)
-        self.hidden_dropout_prob = kwargs.pop("hidden_dropout_prob", 0.1)
-        self.layer_norm_eps = kwargs.pop("layer_norm_eps", 1e-12)
-        self.num_attention_heads = kwargs.pop("num_attention_heads", 12)
-        # StltModelConfig (configs.py:102-111)
-        self.unique_categories = kwargs.pop("unique_categories", None)
-        assert self.unique_categories, "unique_categories must not be None!"
-        self.num_spatial_layers = kwargs.pop("num_spatial_layers", 4)
-        self.num_temporal_layers = kwargs.pop("num_temporal_layers", 8)
-        self.layout_num_frames = kwargs.pop("layout_num_frames", 256)
-        self.load_backbone_path = kwargs.pop("load_backbone_path", None)
-        self.freeze_backbone = kwargs.pop("freeze_backbone", False)
+        for name, default in self.FIELDS.items():
+            value = kwargs.get(name, None if default is _REQUIRED else default)
+            if default is _REQUIRED and not value:
+                raise AssertionError(f"{name} must not be None!")
+            setattr(self, name, value)
 
-    def __repr__(self):
-        return (
-            f"- Unique categories: {self.unique_categories}\n"
-            f"- Number of classes: {self.num_classes}\n"
-            f"- Hidden size: {self.hidden_size}\n"
-            f"- Hidden dropout probability: {self.hidden_dropout_prob}\n"
-            f"- Layer normalization epsilon: {self.layer_norm_eps}\n"
-            f"- Number of attention heads: {self.num_attention_heads}\n"
-            f"- Number of spatial layers: {self.num_spatial_layers}\n"
-            f"- Number of temporal layers: {self.num_temporal_layers}\n"
-            f"- Max number of layout frames: {self.layout_num_frames}\n"
-            f"- The backbone path is: {self.load_backbone_path}\n"
-            f"- Freezing the backbone: {self.freeze_backbone}"
-        )
+    def to_dict(self) -> dict:
+        return {name: getattr(self, name) for name in self.FIELDS}
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}({', '.join(f'{k}={v!r}' for k, v in self.to_dict().items())})"
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, _TableConfig) and self.to_dict() == other.to_dict()
+
+
+class StltModelConfig(_TableConfig):
+    FIELDS = {
+        "num_classes": _REQUIRED, "unique_categories": _REQUIRED,
+        "hidden_size": 768, "num_attention_heads": 12, "hidden_dropout_prob": 0.1, "layer_norm_eps": 1e-12,
+        "num_spatial_layers": 4, "num_temporal_layers": 8,
+        "layout_num_frames": 256,  # rows of the position table; the data side samples 16
+        "load_backbone_path": None, "freeze_backbone": False,
+    }
 
 
 class CacnfModelConfig(StltModelConfig):
-    """Mirrors the reference MultimodalModelConfig (configs.py:150-175) + AppearanceModelConfig
-    (:128-147) for the CACNF path on precomputed features; no ``resnet_model_path`` is needed because
-    the 3D-ResNet trunk is outside this library."""
+    """Fields of the reference MultimodalModelConfig (configs.py:150-175) + AppearanceModelConfig (:128-147) that
+    the CACNF path on precomputed features reads; ``resnet_model_path`` is accepted and ignored because the
+    3D-ResNet trunk is outside this library."""
+    FIELDS = {**StltModelConfig.FIELDS, "appearance_num_frames": 32, "num_appearance_layers": 4,
+              "num_fusion_layers": 4, "feature_channels": 2048}
 
     def __init__(self, **kwargs):
-        self.appearance_num_frames = kwargs.pop("appearance_num_frames", 32)
-        self.num_appearance_layers = kwargs.pop("num_appearance_layers", 4)
-        self.num_fusion_layers = kwargs.pop("num_fusion_layers", 4)
-        self.feature_channels = kwargs.pop("feature_channels", 2048)
-        kwargs.pop("resnet_model_path", None)
         super().__init__(**kwargs)
         self.stlt_config = self
         self.appearance_config = self

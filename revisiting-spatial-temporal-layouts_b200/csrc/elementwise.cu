@@ -562,16 +562,18 @@ __global__ void pack_bf16_kernel(const float4* __restrict__ src, uint2* __restri
 __global__ void __launch_bounds__(256)
 pack_folded_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ bias, int k, __nv_bfloat16* __restrict__ wf, float* __restrict__ s_out,
-                   float* __restrict__ c_out) {
-  const int n = blockIdx.x;
-  const float* row = w + static_cast<long long>(n) * k;
+                   float* __restrict__ c_out, int head_major) {
+  const int n = blockIdx.x;  // output row
+  // head-major order of the packed in-projection: output row h*192 + t*64 + j <- source row t*768 + h*64 + j
+  const int src = head_major ? ((n % 192) / 64) * kHidden + (n / 192) * kHeadDim + (n % 64) : n;
+  const float* row = w + static_cast<long long>(src) * k;
   float s = 0.f, c = 0.f;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const float v = row[i];
-    const __nv_bfloat16 f = __float2bfloat16_rn(v * gamma[i]);
+    const __nv_bfloat16 f = __float2bfloat16_rn(gamma != nullptr ? v * gamma[i] : v);
     wf[static_cast<long long>(n) * k + i] = f;
     s += __bfloat162float(f);
-    c = fmaf(v, beta[i], c);
+    if (beta != nullptr) c = fmaf(v, beta[i], c);
   }
   s = warp_sum(s);
   c = warp_sum(c);
@@ -588,7 +590,7 @@ pack_folded_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
       tc += pc[i];
     }
     s_out[n] = ts;
-    c_out[n] = tc + bias[n];
+    c_out[n] = tc + bias[src];
   }
 }
 
@@ -731,8 +733,10 @@ cudaError_t launch_topk_count(const float* logits, const long long* labels, int 
 }
 
 cudaError_t launch_pack_folded(const float* w, const float* gamma, const float* beta, const float* bias, int n,
-                               int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream) {
-  pack_folded_kernel<<<n, 256, 0, stream>>>(w, gamma, beta, bias, k, wf, s_out, c_out);
+                               int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream,
+                               bool head_major) {
+  if (head_major && n != kQkv) return cudaErrorInvalidValue;
+  pack_folded_kernel<<<n, 256, 0, stream>>>(w, gamma, beta, bias, k, wf, s_out, c_out, head_major ? 1 : 0);
   return cudaGetLastError();
 }
 

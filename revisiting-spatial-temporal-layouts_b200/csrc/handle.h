@@ -33,6 +33,10 @@ struct LayerWeights {
   // the first layer of a stack), linear1 folded with this layer's norm1; s / c epilogue vectors
   const __nv_bfloat16 *in_f = nullptr, *l1_f = nullptr;
   const float *in_s = nullptr, *in_c = nullptr, *l1_s = nullptr, *l1_c = nullptr;
+  // in-projection + attention in one kernel (gemm_qkv_attn.cu): the same folded in-projection in HEAD-MAJOR row
+  // order (every layer; identity fold for the first layer of a stack) and its s / c vectors in that order
+  const __nv_bfloat16* in_h = nullptr;
+  const float *in_hs = nullptr, *in_hc = nullptr;
 };
 
 struct Weights {
@@ -93,6 +97,7 @@ struct Handle {
   __nv_bfloat16* cap_tm_xb = nullptr;
   // optional per-category timing (CUDA events on the launching stream)
   bool fused_ln = true;     // bf16 mode: LayerNorm folded into the GEMM epilogues (stlt_set_fused_ln)
+  bool fused_attn = true;   // ... and the attention into the in-projection's epilogue (stlt_set_fused_attention)
   bool bf16_branch = true;  // bf16 mode: out-projection / linear2 outputs travel as bf16 (see run_tail_part)
   bool pruning = true;  // run the row-wise tail of the last layer of each stack on the rows that are read
   bool profiling = false;
@@ -259,6 +264,41 @@ inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const vo
   g.epi = epi;
   ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
+  h->launches++;
+  return STLT_OK;
+}
+
+// ctx bf16 [m_rows, 768] = attention(act_in W_in^T + b_in) in one kernel (gemm_qkv_attn.cu). `a` = bf16 [m_rows, 768]
+// (un-normalised residual stream when stats != null: its LayerNorm is folded into w_h / vec_s / vec_c).
+inline int run_qkv_attention(Handle* h, cudaStream_t stream, const void* a, long long m_rows, long long valid_rows,
+                             const __nv_bfloat16* w_h, const float* vec_s, const float* vec_c, const float2* stats,
+                             float eps, const long long* mask_src, long long num_seqs, int T, bool causal, void* ctx) {
+  const int R = qkv_attention_rows_per_block(T);
+  if (R == 0) return fail(h, STLT_ERR_INVALID, "fused attention: sequence length %d outside [1, 32]", T);
+  const long long per_block = R / T;
+  CUtensorMap tm_a, tm_b, tm_out;
+  int rc = make_tm(h, &tm_a, a, 1, m_rows, kHidden, 64, 128);
+  if (rc) return rc;
+  rc = make_tm(h, &tm_b, w_h, 1, kQkv, kHidden, 64, 96);
+  if (rc) return rc;
+  rc = make_tm(h, &tm_out, ctx, 1, m_rows, kHidden, 64, R);
+  if (rc) return rc;
+  QkvAttnArgs p{};
+  p.vec_s = vec_s;
+  p.vec_c = vec_c;
+  p.stats_in = stats;
+  p.mask_src = mask_src;
+  p.m_rows = m_rows;
+  p.valid_rows = valid_rows;
+  p.eps = eps;
+  p.prev_norm = stats != nullptr ? 1 : 0;
+  p.seq_len = T;
+  p.rows_per_block = R;
+  p.row_blocks = static_cast<int>((num_seqs + per_block - 1) / per_block);
+  p.causal = causal ? 1 : 0;
+  // the executed MMAs cover 128-row blocks of which R rows are kept
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(p.row_blocks) * 128 * kQkv * kHidden);
+  STLT_CUDA(h, launch_qkv_attention(tm_a, tm_b, tm_out, p, stream, h->num_sms));
   h->launches++;
   return STLT_OK;
 }

@@ -84,6 +84,28 @@ struct GemmArgs {
 int gemm_smem_bytes();
 cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_sms);
 
+// In-projection + masked self-attention in one kernel (gemm_qkv_attn.cu; bf16 inference path, sequences of at
+// most 32 tokens). The weights are the HEAD-MAJOR gamma-folded pack of launch_pack_folded(head_major = true).
+struct QkvAttnArgs {
+  const float* vec_s;         // [2304] head-major: row sums of the folded weights (read when prev_norm)
+  const float* vec_c;         // [2304] head-major: (W beta)[n] + bias[n]
+  const float2* stats_in;     // [m_rows][kStatSlots] partial (sum, sum of squares) of the input rows (prev_norm)
+  const long long* mask_src;  // [valid_rows]: key j is masked when mask_src[j] == 0
+  long long m_rows;           // allocated rows of the activation / statistics / context tensors
+  long long valid_rows;       // real tokens
+  float eps;
+  int prev_norm;       // 1: the input rows still need LayerNorm (applied algebraically in the epilogue)
+  int seq_len;         // T <= 32
+  int rows_per_block;  // floor(128 / T) * T (qkv_attention_rows_per_block)
+  int row_blocks;      // ceil(sequences / floor(128 / T))
+  int causal;
+};
+int qkv_attention_rows_per_block(int seq_len);
+// tm_a: bf16 [m_rows, 768] box {64, 128}; tm_b: bf16 [2304, 768] box {64, 96}; tm_out: bf16 [m_rows, 768] box
+// {64, rows_per_block}; all SWIZZLE_128B.
+cudaError_t launch_qkv_attention(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_out,
+                                 const QkvAttnArgs& p, cudaStream_t stream, int num_sms);
+
 // fp32 SIMT GEMM: out[M, N] = act(A[M, K] * W[N, K]^T + bias). Used by the classifier head
 // (src/modelling/models.py:155-163) and as an independent cross-check of the tcgen05 path in tests.
 cudaError_t launch_gemm_simt(const float* a, const float* w, const float* bias, float* out, int m,
@@ -200,8 +222,11 @@ cudaError_t launch_attention_long(const __nv_bfloat16* qkv, int planes, long lon
                                   __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream);
 
 // gamma-folded bf16 weights + the two epilogue vectors of GEMM_EPI_NORM_A (see GemmEpilogue).
+// gamma / beta may be null (identity LayerNorm: plain bf16 weights, s = row sums, c = bias). head_major (n must be
+// 2304): output row h*192 + t*64 + j holds row t*768 + h*64 + j of the packed in-projection (t = Q, K, V).
 cudaError_t launch_pack_folded(const float* w, const float* gamma, const float* beta, const float* bias, int n,
-                               int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream);
+                               int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream,
+                               bool head_major = false);
 
 // fp32 -> bf16 plane(s) for weights.
 cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,

@@ -242,6 +242,10 @@ struct PendingNorm {
 int fused_attention_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, const Phase& ph,
                          const PendingNorm& in, const long long* mask_src, long long num_seqs, int T, bool causal) {
   int rc;
+  if (h->fused_attn && T <= 32 && lw.in_h != nullptr)  // one kernel: the packed QKV activations never reach HBM
+    return run_qkv_attention(h, stream, ph.xb, ph.m_pad, ph.m_valid, lw.in_h, lw.in_hs, lw.in_hc,
+                             in.gamma != nullptr ? in.stats : nullptr, h->dims.encoder_norm_eps, mask_src, num_seqs, T,
+                             causal, ph.att);
   if (in.gamma == nullptr) {
     rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv, 1, GEMM_OUT_BF16, 0);
   } else {
@@ -390,8 +394,8 @@ int stlt_packed_weights_bytes(void* handle, int32_t precision, size_t* bytes) {
   const size_t per_layer = static_cast<size_t>(kHidden) * (kQkv + kHidden + 2 * kFfn);
   const size_t layers = h->dims.num_spatial_layers + h->dims.num_temporal_layers;
   *bytes = layers * per_layer * planes * 2;
-  if (precision == STLT_PRECISION_BF16)  // fused-LayerNorm copies: folded in-proj / linear1 + their s, c vectors
-    *bytes += layers * (static_cast<size_t>(kHidden) * (kQkv + kFfn) * 2 + static_cast<size_t>(kQkv + kFfn) * 2 * 4);
+  if (precision == STLT_PRECISION_BF16)  // fused-LayerNorm copies: folded in-proj (row-major and head-major) / linear1 + their s, c vectors
+    *bytes += layers * (static_cast<size_t>(kHidden) * (2 * kQkv + kFfn) * 2 + static_cast<size_t>(2 * kQkv + kFfn) * 2 * 4);
   return STLT_OK;
 }
 
@@ -425,17 +429,29 @@ int stlt_pack_weights(void* handle, void* stream_, int32_t precision, void* pack
   for (auto& lw : h->w.spatial) STLT_CUDA(h, pack_layer(lw));
   for (auto& lw : h->w.temporal) STLT_CUDA(h, pack_layer(lw));
   if (precision == STLT_PRECISION_BF16) {
-    // fused-LayerNorm section (see GemmEpilogue): per layer [in_f | l1_f] bf16, then [in_s in_c l1_s l1_c] f32
+    // fused-LayerNorm section (see GemmEpilogue): per layer [in_f | l1_f | in_h] bf16, then
+    // [in_s in_c l1_s l1_c in_hs in_hc] f32
     auto fold_stack = [&](std::vector<LayerWeights>& stack) -> cudaError_t {
       for (size_t i = 0; i < stack.size(); ++i) {
         LayerWeights& lw = stack[i];
         __nv_bfloat16* in_f = cur;
         __nv_bfloat16* l1_f = in_f + static_cast<size_t>(kQkv) * kHidden;
-        float* vec = reinterpret_cast<float*>(l1_f + static_cast<size_t>(kFfn) * kHidden);
-        cur = reinterpret_cast<__nv_bfloat16*>(vec + 2 * (kQkv + kFfn));
+        __nv_bfloat16* in_h = l1_f + static_cast<size_t>(kFfn) * kHidden;
+        float* vec = reinterpret_cast<float*>(in_h + static_cast<size_t>(kQkv) * kHidden);
+        cur = reinterpret_cast<__nv_bfloat16*>(vec + 2 * (2 * kQkv + kFfn));
         lw.in_f = nullptr;
         lw.in_s = lw.in_c = nullptr;
         cudaError_t e;
+        {  // head-major copy for the attention-fused in-projection; the first layer of a stack reads a normalised input
+          const float* g2 = i > 0 ? stack[i - 1].n2_g : nullptr;
+          const float* b2 = i > 0 ? stack[i - 1].n2_b : nullptr;
+          float* vh = vec + 2 * (kQkv + kFfn);
+          e = launch_pack_folded(lw.in_w, g2, b2, lw.in_b, kQkv, kHidden, in_h, vh, vh + kQkv, stream, true);
+          if (e != cudaSuccess) return e;
+          lw.in_h = in_h;
+          lw.in_hs = vh;
+          lw.in_hc = vh + kQkv;
+        }
         if (i > 0) {  // the in-projection reads LN2 of the previous layer
           const LayerWeights& prev = stack[i - 1];
           e = launch_pack_folded(lw.in_w, prev.n2_g, prev.n2_b, lw.in_b, kQkv, kHidden, in_f, vec, vec + kQkv, stream);
@@ -775,6 +791,13 @@ int stlt_set_fused_ln(void* handle, int32_t enable) {
   return STLT_OK;
 }
 
+int stlt_set_fused_attention(void* handle, int32_t enable) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  h->fused_attn = enable != 0;
+  return STLT_OK;
+}
+
 int stlt_set_pruning(void* handle, int32_t enable) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
@@ -848,6 +871,63 @@ int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w
   if (m_rows % 128 || n % 256 || k % 64) return fail(h, STLT_ERR_INVALID, "shape not tile aligned");
   return run_gemm(h, static_cast<cudaStream_t>(stream), a_planes, m_rows, m_rows, w_planes, n, k, bias,
                   out, terms, out_kind, gelu);
+}
+
+int stlt_op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void* a, int32_t m_rows, const void* w,
+                       int32_t n, int32_t k, const float* bias, void* out, void* out_bf16, int32_t gelu,
+                       const float* stats_in, const float* vec_a, const float* vec_b, float* stats_out, float eps,
+                       int32_t prev_norm) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !a || !w || !out) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (m_rows % 128 || n % 256 || k % 64 || m_rows < 128) return fail(h, STLT_ERR_INVALID, "shape not tile aligned");
+  EpiArgs e{};
+  e.stats_in = reinterpret_cast<const float2*>(stats_in);
+  e.vec_a = vec_a;
+  e.vec_b = vec_b;
+  e.eps = eps;
+  if (epilogue == GEMM_EPI_NORM_A) {
+    if (!stats_in || !vec_a || !vec_b || (gelu != 0 && gelu != 2))
+      return fail(h, STLT_ERR_INVALID, "NORM_A: stats_in, vec_a (s), vec_b (c) required; gelu 0 or 2");
+    e.prev_norm = 1;
+    return run_gemm_fused(h, static_cast<cudaStream_t>(stream), GEMM_EPI_NORM_A, a, m_rows, w, n, k, nullptr, out,
+                          nullptr, gelu, e);
+  }
+  if (epilogue == GEMM_EPI_RESID) {
+    if (n != kHidden || !bias || !out_bf16 || !stats_out || gelu != 0 || (prev_norm && (!stats_in || !vec_a || !vec_b)))
+      return fail(h, STLT_ERR_INVALID, "RESID: n = 768, bias, out_bf16, stats_out (and LayerNorm inputs when prev_norm)");
+    e.z_prev = static_cast<const float*>(out);
+    e.stats_out = reinterpret_cast<float2*>(stats_out);
+    e.zb_out = static_cast<__nv_bfloat16*>(out_bf16);
+    e.prev_norm = prev_norm != 0 ? 1 : 0;
+    return run_gemm_fused(h, static_cast<cudaStream_t>(stream), GEMM_EPI_RESID, a, m_rows, w, n, k, bias, out, out_bf16,
+                          0, e);
+  }
+  return fail(h, STLT_ERR_INVALID, "epilogue must be 1 (NORM_A) or 2 (RESID)");
+}
+
+int stlt_op_pack_folded(void* handle, void* stream, const float* w, const float* gamma, const float* beta,
+                        const float* bias, int32_t n, int32_t k, void* w_folded, float* s_out, float* c_out,
+                        int32_t head_major) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !w || !bias || !w_folded || !s_out || !c_out) return fail(h, STLT_ERR_INVALID, "null argument");
+  if ((gamma == nullptr) != (beta == nullptr)) return fail(h, STLT_ERR_INVALID, "gamma and beta go together");
+  STLT_CUDA(h, launch_pack_folded(w, gamma, beta, bias, n, k, static_cast<__nv_bfloat16*>(w_folded), s_out, c_out,
+                                  static_cast<cudaStream_t>(stream), head_major != 0));
+  return STLT_OK;
+}
+
+int stlt_op_qkv_attention(void* handle, void* stream, const void* a, int64_t m_rows, int64_t valid_rows,
+                          const void* w_head_major, const float* vec_s, const float* vec_c, const float* stats,
+                          float eps, const int64_t* mask_src, int64_t num_seqs, int32_t seq_len, int32_t causal,
+                          void* ctx) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !a || !w_head_major || !vec_s || !vec_c || !mask_src || !ctx) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (m_rows % 128 || m_rows < 128 || valid_rows > m_rows || num_seqs * seq_len > valid_rows)
+    return fail(h, STLT_ERR_INVALID, "shape: m_rows must be a positive multiple of 128 covering the sequences");
+  return run_qkv_attention(h, static_cast<cudaStream_t>(stream), a, m_rows, valid_rows,
+                           static_cast<const __nv_bfloat16*>(w_head_major), vec_s, vec_c,
+                           reinterpret_cast<const float2*>(stats), eps, reinterpret_cast<const long long*>(mask_src),
+                           num_seqs, seq_len, causal != 0, ctx);
 }
 
 int stlt_op_gemm_grad(void* handle, void* stream, int32_t layout, const void* a, const void* b, void* out,

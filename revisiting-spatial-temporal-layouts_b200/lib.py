@@ -31,6 +31,7 @@ GEMM_OUT_BF16 = 1
 GEMM_OUT_BF16_SPLIT = 2
 GEMM_OUT_BF16_DUAL = 3
 GEMM_NT, GEMM_NN, GEMM_TN_RED = 0, 1, 2
+GEMM_EPI_PLAIN, GEMM_EPI_NORM_A, GEMM_EPI_RESID = 0, 1, 2
 
 BWD_TEMPORAL, BWD_SPATIAL, BWD_ALL = 1, 2, 3
 LOSS_CROSS_ENTROPY, LOSS_BCE_LOGITS = 0, 1
@@ -124,6 +125,7 @@ SIGNATURES = {
     "stlt_set_taps": (c_int32, [c_void_p, POINTER(StltTaps)]),
     "stlt_set_pruning": (c_int32, [c_void_p, c_int32]),
     "stlt_set_fused_ln": (c_int32, [c_void_p, c_int32]),
+    "stlt_set_fused_attention": (c_int32, [c_void_p, c_int32]),
     "stlt_set_profiling": (c_int32, [c_void_p, c_int32]),
     "stlt_get_profile": (c_int32, [c_void_p, POINTER(StltProfile)]),
     "stlt_bind_grads": (c_int32, [c_void_p, POINTER(StltTensor), c_int32]),
@@ -151,6 +153,13 @@ SIGNATURES = {
                                c_int32, c_int32, c_int32, c_int32, c_int32]),
     "stlt_op_gemm_grad": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_int32, c_int64, c_int32]),
+    "stlt_op_gemm_fused": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
+                                     c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_float, c_int32]),
+    "stlt_op_pack_folded": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                      c_void_p, c_void_p, c_void_p, c_int32]),
+    "stlt_op_qkv_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_float, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "stlt_op_attention_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                         c_int32, c_void_p, c_int32, c_void_p]),
     "stlt_op_attention_cross": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
@@ -183,6 +192,16 @@ def load_library() -> ctypes.CDLL:
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def aligned_empty(nbytes: int, device, alignment: int = 1024):
+    """uint8 device buffer of ``nbytes`` whose data pointer is ``alignment``-byte aligned. The library requires 1 KiB
+    aligned workspaces (128-byte-swizzled TMA tiles); PyTorch's caching allocator only guarantees 512 B, so the
+    buffer is over-allocated and a view starting at the aligned offset is returned (the view keeps it alive)."""
+    import torch
+    raw = torch.empty(max(int(nbytes), 1) + alignment, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % alignment
+    return raw[off:off + max(int(nbytes), 1)]
 
 
 class StltError(RuntimeError):

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import copy
 import ctypes
+import os
 import math
 from typing import Dict, Optional
 
@@ -243,6 +244,7 @@ class Stlt(nn.Module):
         self._handle_device = device
         _lib.check(handle, lib.stlt_set_pruning(handle, int(self._pruning)))
         _lib.check(handle, lib.stlt_set_fused_ln(handle, int(getattr(self, "_fused_ln", True))))
+        _lib.check(handle, lib.stlt_set_fused_attention(handle, int(getattr(self, "_fused_attn", os.environ.get("STLT_FUSED_ATTENTION", "1") != "0"))))
         self._weights_key = None
         self._packed.clear()
         self._packed_key.clear()
@@ -276,7 +278,7 @@ class Stlt(nn.Module):
             _lib.check(self._handle, lib.stlt_packed_weights_bytes(self._handle, prec, ctypes.byref(nbytes)))
             buf = self._packed.get(prec)
             if buf is None or buf.numel() < nbytes.value or buf.device != device:
-                buf = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+                buf = _lib.aligned_empty(nbytes.value, device)
                 self._packed[prec] = buf
             _lib.check(self._handle, lib.stlt_pack_weights(self._handle, stream, prec, buf.data_ptr(), buf.numel()))
             self._packed_key[prec] = key
@@ -291,7 +293,7 @@ class Stlt(nn.Module):
         _lib.check(self._handle, lib.stlt_workspace_bytes(self._handle, B, L, S, prec, ctypes.byref(nbytes)))
         ws = self._workspace
         if ws is None or ws.numel() < nbytes.value or ws.device != device:
-            ws = torch.empty(max(nbytes.value, 1024), dtype=torch.uint8, device=device)
+            ws = _lib.aligned_empty(max(nbytes.value, 1024), device)
             self._workspace = ws
         return ws
 
@@ -416,7 +418,7 @@ class Stlt(nn.Module):
         lib = _lib.load_library()
         nbytes = ctypes.c_size_t()
         _lib.check(self._handle, lib.stlt_train_workspace_bytes(self._handle, B, L, S, ctypes.byref(nbytes)))
-        return torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+        return _lib.aligned_empty(nbytes.value, device)
 
     def _forward_train(self, inputs, ws: torch.Tensor, dropout_p: float, seed: int) -> torch.Tensor:
         cats, boxes, scores, ftypes, lengths = inputs
@@ -494,6 +496,13 @@ class Stlt(nn.Module):
         self._fused_ln = bool(enable)
         if self._handle is not None:
             _lib.check(self._handle, _lib.load_library().stlt_set_fused_ln(self._handle, int(self._fused_ln)))
+
+    def set_fused_attention(self, enable: bool) -> None:
+        """bf16 mode: attention folded into the epilogue of the in-projection GEMM (default on; needs the fused
+        LayerNorm path and sequences of at most 32 tokens). Off = separate in-projection GEMM + attention kernel."""
+        self._fused_attn = bool(enable)
+        if self._handle is not None:
+            _lib.check(self._handle, _lib.load_library().stlt_set_fused_attention(self._handle, int(self._fused_attn)))
 
     def set_profiling(self, enable: bool) -> None:
         """Per-category CUDA-event timing of the kernels launched by forward (bench / profiles)."""

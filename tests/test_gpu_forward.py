@@ -366,6 +366,9 @@ def test_fused_layer_norm_path_matches_unfused_and_oracle(layout):
     gb = to_cuda(batch)
     with torch.no_grad():
         model.set_fused_layer_norm(True)
+        full = model(gb)["stlt"].float().cpu()   # default: LayerNorms and attention in the GEMM epilogues
+        n_full = model.last_launch_count()
+        model.set_fused_attention(False)
         fused = model(gb)["stlt"].float().cpu()
         n_fused = model.last_launch_count()
         model.set_fused_layer_norm(False)
@@ -375,8 +378,11 @@ def test_fused_layer_norm_path_matches_unfused_and_oracle(layout):
     print(layout, "fused vs oracle", nerr(fused, want), "plain vs oracle", nerr(plain, want), "fused vs plain",
           nerr(fused, plain), "launches", n_fused, n_plain)
     assert n_fused == n_plain - 23  # 24 residual + LayerNorm launches gone, one LayerNorm of the pooled rows added
-    assert nerr(fused, want) < 2e-2 and nerr(plain, want) < 2e-2
-    assert torch.equal(fused.argmax(-1), want.argmax(-1))
+    assert n_full == n_fused - 12   # the 12 attention launches live in the in-projection epilogues
+    print(layout, "attention-fused vs oracle", nerr(full, want), "vs LayerNorm-fused", nerr(full, fused))
+    assert nerr(fused, want) < 2e-2 and nerr(plain, want) < 2e-2 and nerr(full, want) < 2e-2
+    assert torch.equal(fused.argmax(-1), want.argmax(-1)) and torch.equal(full.argmax(-1), want.argmax(-1))
+    assert nerr(full, torch.from_numpy(g["logits"])) < 2e-2
     assert nerr(fused, torch.from_numpy(g["logits"])) < 2e-2
 
 
