@@ -16,8 +16,9 @@
 // = row t*768 + h*64 + j of in_proj_weight, t = Q, K, V), so the 192 output columns of a unit are exactly
 // [Q_h | K_h | V_h] of its rows. CTA pairs (cluster of 2, tcgen05 cta_group::2) run ONE M=256 x N=192 x K=16
 // MMA stream per unit; each CTA stages its own 128 activation rows and 96 of the 192 weight rows by TMA
-// (28 KB per stage, 6 stages). The accumulators are double buffered in TMEM (2 x 192 columns), so the epilogue
-// of unit i overlaps the MMAs of unit i+1.
+// (28 KB per stage, 5 stages). The accumulators are double buffered in TMEM (2 x 192 columns), so the epilogue
+// of unit i overlaps the MMAs of unit i+1. A cluster sweeps the 12 heads of a pair of row blocks back to back
+// (the activation rows are re-read from L2, the per-row epilogue state is loaded once per pair).
 //
 // Rows: sequences must not straddle row blocks, so a CTA's block holds R = floor(128 / T) * T rows (whole
 // sequences; 125 of 128 at T = 5, 119 at T = 17) and starts at row block * R. The TMA box still loads 128
@@ -26,13 +27,14 @@
 // Epilogue (8 warps per CTA, 128 rows x 192 columns of this CTA's accumulator):
 //   1. tcgen05.ld -> bias (or the deferred LayerNorm of the input, GEMM_EPI_NORM_A algebra: the A operand is
 //      the un-normalised bf16 residual stream and W is pre-multiplied by gamma) -> bf16 -> three XOR-swizzled
-//      [128 x 64] shared-memory tiles Q, K, V. The TMEM buffer is released as soon as it is in registers.
+//      [128 x 64] shared-memory tiles Q, K, V (rows past the real tokens as zeros). The TMEM buffer is released
+//      as soon as it has been read.
 //   2. warp w owns the 16 query rows 16w .. 16w+15: S = Q K^T on mma.sync.m16n8k16 against a band of
 //      8 * kNT key rows that covers every sequence touching those rows, block-diagonal (same sequence),
 //      key-padding and causal predicates on the accumulator fragments, fp32 softmax with quad shuffles,
 //      O = P V with P from registers.
-//   3. the normalised context replaces the warp's own Q rows (no other warp reads them) and one thread issues
-//      the TMA store of the [R x 64] tile to ctx[:, 64 h : 64 h + 64].
+//   3. the normalised context goes to a fourth staging tile and one thread issues the TMA store of its first R
+//      rows to ctx[:, 64 h : 64 h + 64]; two CTA-wide named barriers per unit (tiles complete / tiles free).
 #include "kernels.h"
 #include "mma_tiles.cuh"
 
@@ -46,14 +48,14 @@ constexpr int BK = 64;
 constexpr int kABytes = BM * BK * 2;            // 16 KiB
 constexpr int kBHalfBytes = (BN / 2) * BK * 2;  // 12 KiB: this CTA's 96 weight rows
 constexpr int kStageBytes = kABytes + kBHalfBytes;
-constexpr int kStages = 6;
+constexpr int kStages = 5;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
 constexpr int kCluster = 2;
 constexpr uint16_t kClusterMask = (1u << kCluster) - 1;
-constexpr int kTileBytes = BM * 128;  // one of the Q / K / V tiles: 128 rows x 64 bf16
-constexpr int kSmemBytes = kStages * kStageBytes + 3 * kTileBytes + 256 /*barriers*/;
+constexpr int kTileBytes = BM * 128;  // one of the Q / K / V / context tiles: 128 rows x 64 bf16
+constexpr int kSmemBytes = kStages * kStageBytes + 4 * kTileBytes + 256 /*barriers*/;
 static_assert(kSmemBytes <= 232448, "smem budget");
 static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024 B alignment");
 
@@ -83,15 +85,17 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smem_ab = smem;
   uint8_t* smem_qkv = smem + kStages * kStageBytes;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_qkv + 3 * kTileBytes);
+  uint8_t* smem_ctx = smem_qkv + 3 * kTileBytes;  // staging tile of the context store
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_ctx + kTileBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta_rank = static_cast<int>(cluster_ctarank());
   const int cluster_id = blockIdx.x / kCluster;
   const int num_clusters = gridDim.x / kCluster;
+  // a cluster sweeps the 12 heads of one pair of row blocks before it moves on: the activation rows are re-read from
+  // L2 by the same SM, and the epilogue's per-row state (LayerNorm statistics, key-padding bits) is loaded once per pair
   const int pair_blocks = (p.row_blocks + kCluster - 1) / kCluster;
-  const int num_units = pair_blocks * kHeads;
   constexpr int k_blocks = kHidden / BK;
 
   if (warp == 0 && lane == 0) {
@@ -125,21 +129,21 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-        const int blk = (unit / kHeads) * kCluster + cta_rank;
-        const int head = unit % kHeads;
-        const int a_row = blk * p.rows_per_block;  // rows past the end of the tensor are zero-filled
-        const int b_row = head * BN + cta_rank * (BN / kCluster);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&bars->empty[stage], phase ^ 1u);
-          if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], kCluster * kStageBytes);
-          uint8_t* sa = smem_ab + stage * kStageBytes;
-          const uint32_t full_leader = mapa_u32(&bars->full[stage], 0);
-          tma_load_2d_pair(&tm_a, full_leader, sa, kb * BK, a_row);
-          tma_load_2d_pair(&tm_b, full_leader, sa + kABytes, kb * BK, b_row);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
+      for (int pb = cluster_id; pb < pair_blocks; pb += num_clusters) {
+        const int a_row = (pb * kCluster + cta_rank) * p.rows_per_block;  // rows past the end of the tensor are zero-filled
+        for (int head = 0; head < kHeads; ++head) {
+          const int b_row = head * BN + cta_rank * (BN / kCluster);
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&bars->empty[stage], phase ^ 1u);
+            if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], kCluster * kStageBytes);
+            uint8_t* sa = smem_ab + stage * kStageBytes;
+            const uint32_t full_leader = mapa_u32(&bars->full[stage], 0);
+            tma_load_2d_pair(&tm_a, full_leader, sa, kb * BK, a_row);
+            tma_load_2d_pair(&tm_b, full_leader, sa + kABytes, kb * BK, b_row);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
       }
@@ -151,28 +155,30 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&bars->full[stage], phase);
+      for (int pb = cluster_id; pb < pair_blocks; pb += num_clusters) {
+        for (int head = 0; head < kHeads; ++head, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
-          const uint64_t da = umma_desc_k_sw128(sa);
-          const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
+            const uint64_t da = umma_desc_k_sw128(sa);
+            const uint64_t db = umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb != 0 || k != 0) ? 1u : 0u);
-          umma_commit_pair(&bars->empty[stage], kClusterMask);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb != 0 || k != 0) ? 1u : 0u);
+            umma_commit_pair(&bars->empty[stage], kClusterMask);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
+          umma_commit_pair(&bars->tmem_full[acc], kClusterMask);
         }
-        umma_commit_pair(&bars->tmem_full[acc], kClusterMask);
       }
     }
   } else if (warp >= 4) {
@@ -186,6 +192,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const uint32_t q_base = smem_u32(smem_qkv);
     const uint32_t k_base = q_base + kTileBytes;
     const uint32_t v_base = k_base + kTileBytes;
+    const uint32_t c_base = smem_u32(smem_ctx);
     const int arow = quarter * 32 + lane;  // accumulator row (block-local) of this thread
     int band0 = 16 * ew - kBandOff;        // first key row of this warp's band
     band0 = band0 < 0 ? 0 : (band0 > BM - kBand ? BM - kBand : band0);
@@ -211,17 +218,16 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
 
     int it = 0;
-    for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
-      const int blk = (unit / kHeads) * kCluster + cta_rank;
-      const int head = unit % kHeads;
+    for (int pb = cluster_id; pb < pair_blocks; pb += num_clusters) {
+      const int blk = pb * kCluster + cta_rank;
       const bool live = blk < p.row_blocks;  // odd block counts: the last pair has a dummy half
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
       const long long row0 = static_cast<long long>(blk) * R;
+      // rows past the real tokens hold whatever the workspace held: they are written as zeros (0 * NaN would poison P V)
+      const bool real_row = row0 + arow < p.valid_rows;
 
-      // deferred LayerNorm of the input rows (GEMM_EPI_NORM_A): statistics of this thread's accumulator row
+      // ---- per row block: deferred LayerNorm statistics of this thread's row, key-padding bits of the band ----
       float mu = 0.f, rstd = 1.f;
-      if (live && p.prev_norm && row0 + arow < p.m_rows) {
+      if (live && p.prev_norm && real_row && !(p.debug & 4)) {
         const float4* st4 = reinterpret_cast<const float4*>(p.stats_in + (row0 + arow) * kStatSlots);
         float sx = 0.f, sy = 0.f;
 #pragma unroll
@@ -235,7 +241,6 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         mu = sx * (1.0f / kHidden);
         rstd = rsqrtf(fmaxf(sy * (1.0f / kHidden) - mu * mu, 0.f) + p.eps);
       }
-      // key-padding bits of this warp's band (lane = key row), fetched while the MMAs run
       uint32_t kw[kMaskWords];
 #pragma unroll
       for (int i = 0; i < kMaskWords; ++i) {
@@ -253,152 +258,159 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           const int idx = nt * 8 + 2 * t + e;
           kbits |= ((kw[idx >> 5] >> (idx & 31)) & 1u) << (nt * 2 + e);
         }
+      const uint32_t ok0 = allow[0] & kbits, ok1 = allow[1] & kbits;
 
-      // the previous unit's context store has finished reading the Q tile, every warp has left its attention phase
-      if (live) {
-        if (ew == 0 && lane == 0) tma_store_wait_read0();
-        named_bar_sync(1, kEpiWarps * 32);
-      }
-      mbar_wait(&bars->tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + half * 96 + (static_cast<uint32_t>(quarter * 32) << 16);
-      const float4* vs4 = reinterpret_cast<const float4*>(p.vec_s + head * BN + half * 96);
-      const float4* vc4 = reinterpret_cast<const float4*>(p.vec_c + head * BN + half * 96);
+      for (int head = 0; head < kHeads; ++head, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BN + half * 96 + (static_cast<uint32_t>(quarter * 32) << 16);
+        const float4* vs4 = reinterpret_cast<const float4*>(p.vec_s + head * BN + half * 96);
+        const float4* vc4 = reinterpret_cast<const float4*>(p.vec_c + head * BN + half * 96);
 
-      // ---- 1. accumulator -> bias / deferred LayerNorm -> bf16 -> Q / K / V tiles ----
-      uint32_t vbuf[2][32];
-      tmem_ld_32x32(taddr, vbuf[0]);
+        // ---- 1. accumulator -> bias / deferred LayerNorm -> bf16 -> Q / K / V tiles (every warp has left the
+        //         attention phase of the previous unit: barrier B below) ----
+        uint32_t vbuf[2][32];
+        tmem_ld_32x32(taddr, vbuf[0]);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint32_t(&v)[32] = vbuf[c & 1];
-        tmem_ld_wait_regs(v);
-        if (c + 1 < 3) tmem_ld_32x32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
-        const int col = half * 96 + c * 32;  // a 32-column chunk never straddles two of the 64-wide tiles
-        const uint32_t base = q_base + (col >> 6) * kTileBytes;
-        const int chunk0 = (col & 63) >> 3;
+        for (int c = 0; c < 3; ++c) {
+          uint32_t(&v)[32] = vbuf[c & 1];
+          tmem_ld_wait_regs(v);
+          if (c + 1 < 3) tmem_ld_32x32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
+          const int col = half * 96 + c * 32;  // a 32-column chunk never straddles two of the 64-wide tiles
+          const uint32_t base = q_base + (col >> 6) * kTileBytes;
+          const int chunk0 = (col & 63) >> 3;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {  // 8 columns = one 16-byte store
-          uint32_t pk[4];
+          for (int j = 0; j < 4; ++j) {  // 8 columns = one 16-byte store
+            uint32_t pk[4];
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int e = 8 * j + 4 * q;
-            const float4 c4 = __ldg(vc4 + c * 8 + 2 * j + q);
-            float f0, f1, f2, f3;
-            if (p.prev_norm) {
-              const float4 s4 = __ldg(vs4 + c * 8 + 2 * j + q);
-              f0 = fmaf(rstd, fmaf(-mu, s4.x, __uint_as_float(v[e + 0])), c4.x);
-              f1 = fmaf(rstd, fmaf(-mu, s4.y, __uint_as_float(v[e + 1])), c4.y);
-              f2 = fmaf(rstd, fmaf(-mu, s4.z, __uint_as_float(v[e + 2])), c4.z);
-              f3 = fmaf(rstd, fmaf(-mu, s4.w, __uint_as_float(v[e + 3])), c4.w);
-            } else {
-              f0 = __uint_as_float(v[e + 0]) + c4.x;
-              f1 = __uint_as_float(v[e + 1]) + c4.y;
-              f2 = __uint_as_float(v[e + 2]) + c4.z;
-              f3 = __uint_as_float(v[e + 3]) + c4.w;
+            for (int q = 0; q < 2; ++q) {
+              const int e = 8 * j + 4 * q;
+              const float4 c4 = __ldg(vc4 + c * 8 + 2 * j + q);
+              float f0, f1, f2, f3;
+              if (p.prev_norm) {
+                const float4 s4 = __ldg(vs4 + c * 8 + 2 * j + q);
+                f0 = fmaf(rstd, fmaf(-mu, s4.x, __uint_as_float(v[e + 0])), c4.x);
+                f1 = fmaf(rstd, fmaf(-mu, s4.y, __uint_as_float(v[e + 1])), c4.y);
+                f2 = fmaf(rstd, fmaf(-mu, s4.z, __uint_as_float(v[e + 2])), c4.z);
+                f3 = fmaf(rstd, fmaf(-mu, s4.w, __uint_as_float(v[e + 3])), c4.w);
+              } else {
+                f0 = __uint_as_float(v[e + 0]) + c4.x;
+                f1 = __uint_as_float(v[e + 1]) + c4.y;
+                f2 = __uint_as_float(v[e + 2]) + c4.z;
+                f3 = __uint_as_float(v[e + 3]) + c4.w;
+              }
+              pk[2 * q] = real_row ? pack_bf16x2(f0, f1) : 0u;
+              pk[2 * q + 1] = real_row ? pack_bf16x2(f2, f3) : 0u;
             }
-            pk[2 * q] = pack_bf16x2(f0, f1);
-            pk[2 * q + 1] = pack_bf16x2(f2, f3);
+            if (live && !(p.debug & 2))
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(base, arow, chunk0 + j)),
+                           "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                           : "memory");
           }
-          if (live)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(base, arow, chunk0 + j)),
-                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                         : "memory");
         }
-      }
-      // every TMEM read of this accumulator has completed -> the MMAs of the next unit may overwrite it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(&bars->tmem_empty[acc], 0));
-      if (!live) continue;  // CTA-uniform: the dummy half only takes part in the TMEM handshake
-      named_bar_sync(2, kEpiWarps * 32);
+        // every TMEM read of this accumulator has completed -> the MMAs of the unit after next may overwrite it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(&bars->tmem_empty[acc], 0));
+        if (!live) continue;  // CTA-uniform: the dummy half only takes part in the TMEM handshake
 
-      // ---- 3. S = Q K^T over the band ----
-      float s[kNT][4];
+        // the context store of the previous unit was issued a whole phase ago: it has long finished reading the
+        // staging tile, which every warp rewrites after barrier A
+        if (ew == 0 && lane == 0) tma_store_wait_read0();
+        named_bar_sync(1, kEpiWarps * 32);  // A: Q / K / V tiles complete
+
+        if (p.debug & 8) __nanosleep(2000);  // decomposition: a 2 us stall here does not change the kernel time
+        if (!(p.debug & 1)) {
+          // ---- 2. S = Q K^T over the band ----
+          float s[kNT][4];
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt)
+          for (int nt = 0; nt < kNT; ++nt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
+            for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
 #pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {
-        uint32_t a[4];
-        ldmatrix_x4(tile_addr(q_base, 16 * ew + (lane & 7) + ((lane >> 3) & 1) * 8, kt * 2 + (lane >> 4)), a);
+          for (int kt = 0; kt < 4; ++kt) {
+            uint32_t a[4];
+            ldmatrix_x4(tile_addr(q_base, 16 * ew + (lane & 7) + ((lane >> 3) & 1) * 8, kt * 2 + (lane >> 4)), a);
 #pragma unroll
-        for (int np = 0; np < kNT / 2; ++np) {
-          uint32_t b[4];
-          ldmatrix_x4(tile_addr(k_base, band0 + (np * 2 + (lane >> 4)) * 8 + (lane & 7), kt * 2 + ((lane >> 3) & 1)), b);
-          mma_bf16(s[np * 2 + 0], a, b[0], b[1]);
-          mma_bf16(s[np * 2 + 1], a, b[2], b[3]);
-        }
-      }
-      // ---- masked softmax on the accumulator fragments (fp32) ----
-      float inv_sum[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t ok = allow[h] & kbits;
-        float m = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < kNT; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            float v = s[nt][2 * h + e] * kScale;
-            v = ((ok >> (nt * 2 + e)) & 1u) ? v : -INFINITY;
-            s[nt][2 * h + e] = v;
-            m = fmaxf(m, v);
+            for (int np = 0; np < kNT / 2; ++np) {
+              uint32_t b[4];
+              ldmatrix_x4(tile_addr(k_base, band0 + (np * 2 + (lane >> 4)) * 8 + (lane & 7), kt * 2 + ((lane >> 3) & 1)), b);
+              mma_bf16(s[np * 2 + 0], a, b[0], b[1]);
+              mma_bf16(s[np * 2 + 1], a, b[2], b[3]);
+            }
           }
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        const float mm = (m == -INFINITY) ? 0.f : m;  // fully masked row -> all-zero probabilities
-        float sum = 0.f;
+          // ---- masked softmax on the accumulator fragments (fp32) ----
+          float inv_sum[2];
 #pragma unroll
-        for (int nt = 0; nt < kNT; ++nt)
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t ok = h == 0 ? ok0 : ok1;
+            float m = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float pv = exp2f(s[nt][2 * h + e] - mm);
-            s[nt][2 * h + e] = pv;
-            sum += pv;
+            for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                float v = s[nt][2 * h + e] * kScale;
+                v = ((ok >> (nt * 2 + e)) & 1u) ? v : -INFINITY;
+                s[nt][2 * h + e] = v;
+                m = fmaxf(m, v);
+              }
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            const float mm = (m == -INFINITY) ? 0.f : m;  // fully masked row -> all-zero probabilities
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float pv = exp2f(s[nt][2 * h + e] - mm);
+                s[nt][2 * h + e] = pv;
+                sum += pv;
+              }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            inv_sum[h] = sum > 0.f ? 1.0f / sum : 0.f;
           }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        inv_sum[h] = sum > 0.f ? 1.0f / sum : 0.f;
-      }
-      // ---- O = P V ----
-      float o[8][4];
+          // ---- O = P V ----
+          float o[8][4];
 #pragma unroll
-      for (int dt = 0; dt < 8; ++dt)
+          for (int dt = 0; dt < 8; ++dt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[dt][i] = 0.f;
+            for (int i = 0; i < 4; ++i) o[dt][i] = 0.f;
 #pragma unroll
-      for (int j = 0; j < kNT / 2; ++j) {
-        uint32_t pa[4];
-        pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-        pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-        pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-        pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+          for (int j = 0; j < kNT / 2; ++j) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+            pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+            pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+            pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
 #pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {
-          uint32_t b[4];
-          ldmatrix_x4_trans(tile_addr(v_base, band0 + j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), dp * 2 + (lane >> 4)), b);
-          mma_bf16(o[dp * 2 + 0], pa, b[0], b[1]);
-          mma_bf16(o[dp * 2 + 1], pa, b[2], b[3]);
+            for (int dp = 0; dp < 4; ++dp) {
+              uint32_t b[4];
+              ldmatrix_x4_trans(tile_addr(v_base, band0 + j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), dp * 2 + (lane >> 4)), b);
+              mma_bf16(o[dp * 2 + 0], pa, b[0], b[1]);
+              mma_bf16(o[dp * 2 + 1], pa, b[2], b[3]);
+            }
+          }
+          // ---- 3. normalised context -> this warp's 16 rows of the staging tile ----
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = 16 * ew + g + 8 * h;
+            const float is = inv_sum[h];
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) {
+              const uint32_t v = pack_bf16x2(o[dt][2 * h] * is, o[dt][2 * h + 1] * is);
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_addr(c_base, row, dt) + 4 * t), "r"(v) : "memory");
+            }
+          }
         }
-      }
-      // ---- 4. normalised context -> this warp's own Q rows -> TMA store ----
-      __syncwarp();  // every lane has read its Q fragments
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = 16 * ew + g + 8 * h;
-        const float is = inv_sum[h];
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt) {
-          const uint32_t v = pack_bf16x2(o[dt][2 * h] * is, o[dt][2 * h + 1] * is);
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_addr(q_base, row, dt) + 4 * t), "r"(v) : "memory");
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiWarps * 32);  // B: context tile complete, Q / K / V tiles free
+        if (ew == 0 && lane == 0) {
+          tma_store_2d(&tm_out, smem_ctx, head * kHeadDim, static_cast<int>(row0));
+          tma_store_commit();
         }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(3, kEpiWarps * 32);
-      if (ew == 0 && lane == 0) {
-        tma_store_2d(&tm_out, smem_qkv, head * kHeadDim, static_cast<int>(row0));
-        tma_store_commit();
       }
     }
     if (ew == 0 && lane == 0) tma_store_wait_all();
@@ -421,9 +433,8 @@ cudaError_t launch_nt(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CU
   cudaError_t e = ensure_dynamic_smem(kern, kSmemBytes, &smem_done);
   if (e != cudaSuccess) return e;
   const int pair_blocks = (p.row_blocks + kCluster - 1) / kCluster;
-  const int units = pair_blocks * kHeads;
   const int max_clusters = num_sms / kCluster;
-  const int clusters = units < max_clusters ? units : max_clusters;
+  const int clusters = pair_blocks < max_clusters ? pair_blocks : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * kCluster);
   cfg.blockDim = dim3(kThreads);

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -97,6 +98,8 @@ struct Handle {
   __nv_bfloat16* cap_tm_xb = nullptr;
   // optional per-category timing (CUDA events on the launching stream)
   bool fused_ln = true;     // bf16 mode: LayerNorm folded into the GEMM epilogues (stlt_set_fused_ln)
+  int fused_attn_max_t = 32;  // longest sequence that takes the fused kernel (STLT_FUSED_ATTENTION_MAX_T, experiments)
+  int qkv_attn_debug = 0;   // QkvAttnArgs::debug (STLT_QKV_ATTN_DEBUG environment variable, read at stlt_create)
   bool fused_attn = true;   // ... and the attention into the in-projection's epilogue (stlt_set_fused_attention)
   bool bf16_branch = true;  // bf16 mode: out-projection / linear2 outputs travel as bf16 (see run_tail_part)
   bool pruning = true;  // run the row-wise tail of the last layer of each stack on the rows that are read
@@ -296,6 +299,7 @@ inline int run_qkv_attention(Handle* h, cudaStream_t stream, const void* a, long
   p.rows_per_block = R;
   p.row_blocks = static_cast<int>((num_seqs + per_block - 1) / per_block);
   p.causal = causal ? 1 : 0;
+  p.debug = h->qkv_attn_debug;
   // the executed MMAs cover 128-row blocks of which R rows are kept
   ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(p.row_blocks) * 128 * kQkv * kHidden);
   STLT_CUDA(h, launch_qkv_attention(tm_a, tm_b, tm_out, p, stream, h->num_sms));

@@ -99,6 +99,9 @@ struct QkvAttnArgs {
   int rows_per_block;  // floor(128 / T) * T (qkv_attention_rows_per_block)
   int row_blocks;      // ceil(sequences / floor(128 / T))
   int causal;
+  int debug;           // timing decomposition only (tools/bench_qkv_attention.py): 1 skip the attention math, 2 skip the
+                       // Q/K/V tile stores, 4 skip the statistics loads, 8 sleep 2 us per unit in the epilogue; results are
+                       // garbage when bits 1 / 2 / 4 are set
 };
 int qkv_attention_rows_per_block(int seq_len);
 // tm_a: bf16 [m_rows, 768] box {64, 128}; tm_b: bf16 [2304, 768] box {64, 96}; tm_out: bf16 [m_rows, 768] box

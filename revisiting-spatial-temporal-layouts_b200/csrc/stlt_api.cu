@@ -242,7 +242,7 @@ struct PendingNorm {
 int fused_attention_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, const Phase& ph,
                          const PendingNorm& in, const long long* mask_src, long long num_seqs, int T, bool causal) {
   int rc;
-  if (h->fused_attn && T <= 32 && lw.in_h != nullptr)  // one kernel: the packed QKV activations never reach HBM
+  if (h->fused_attn && T <= h->fused_attn_max_t && lw.in_h != nullptr)  // one kernel: the packed QKV activations never reach HBM
     return run_qkv_attention(h, stream, ph.xb, ph.m_pad, ph.m_valid, lw.in_h, lw.in_hs, lw.in_hc,
                              in.gamma != nullptr ? in.stats : nullptr, h->dims.encoder_norm_eps, mask_src, num_seqs, T,
                              causal, ph.att);
@@ -356,6 +356,11 @@ int stlt_create(const StltDims* dims, void** handle) {
     return STLT_ERR_CUDA;
   }
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* dbg = getenv("STLT_QKV_ATTN_DEBUG")) h->qkv_attn_debug = atoi(dbg);
+  if (const char* mt = getenv("STLT_FUSED_ATTENTION_MAX_T")) {
+    const int v = atoi(mt);
+    h->fused_attn_max_t = v < 0 ? 0 : (v > 32 ? 32 : v);
+  }
   *handle = h;
   return STLT_OK;
 }

@@ -153,6 +153,7 @@ class StltBackbone(nn.Module):
             runner.logit_names = ("stlt",)
             runner._handle = runner._handle_device = runner._weights_key = runner._workspace = runner._keepalive = None
             runner._packed, runner._packed_key, runner._pruning = {}, {}, True
+            runner._param_cache = runner._graphs = None
             runner.train(False)
             object.__setattr__(self, "_runner", runner)
         with torch.no_grad():
@@ -178,7 +179,14 @@ class Stlt(nn.Module):
     reference) or "bf16" (bf16 GEMM operands, fp32 accumulate / residual / LayerNorm / softmax).
     """
 
-    def __init__(self, config, precision: str = "fp32"):
+    # class-level defaults: StltBackbone builds its runner without calling __init__
+    _param_cache = None     # [(name, parameter)] of the last walk over the module tree
+    _graphs = None          # CUDA-graph cache of the inference forward (enable_cuda_graphs)
+    _cuda_graphs = False
+    _fused_ln = True
+    _fused_attn = os.environ.get("STLT_FUSED_ATTENTION", "1") != "0"
+
+    def __init__(self, config, precision: str = "fp32", cuda_graphs: bool = False):
         super().__init__()
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
@@ -204,6 +212,7 @@ class Stlt(nn.Module):
         self._workspace = None
         self._keepalive = None
         self._pruning = True
+        self._cuda_graphs = bool(cuda_graphs)
 
     # -- nn.Module protocol ------------------------------------------------------------------
     def train(self, mode: bool = True):  # reference models.py:180-183
@@ -211,6 +220,24 @@ class Stlt(nn.Module):
         if getattr(self.config, "load_backbone_path", None) and self.config.freeze_backbone:
             self.backbone.train(False)
         return self
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): parameters may be replaced
+        self._param_cache = None
+        self._graphs = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._param_cache = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def mark_weights_dirty(self) -> None:
+        """Call after changing parameters in a way PyTorch's version counters do not see — writes through
+        ``param.data`` (``p.data.mul_()``, EMA swaps), raw-pointer optimizers, replacing a parameter object. The
+        next forward re-binds the pointers and re-packs the bf16 copies; captured CUDA graphs are dropped."""
+        self._param_cache = None
+        self._weights_key = None
+        self._packed_key = {}
+        self._graphs = None
 
     def __del__(self):
         try:
@@ -243,16 +270,19 @@ class Stlt(nn.Module):
         self._handle = handle
         self._handle_device = device
         _lib.check(handle, lib.stlt_set_pruning(handle, int(self._pruning)))
-        _lib.check(handle, lib.stlt_set_fused_ln(handle, int(getattr(self, "_fused_ln", True))))
-        _lib.check(handle, lib.stlt_set_fused_attention(handle, int(getattr(self, "_fused_attn", os.environ.get("STLT_FUSED_ATTENTION", "1") != "0"))))
+        _lib.check(handle, lib.stlt_set_fused_ln(handle, int(self._fused_ln)))
+        _lib.check(handle, lib.stlt_set_fused_attention(handle, int(self._fused_attn)))
         self._weights_key = None
+        self._graphs = None
         self._packed.clear()
         self._packed_key.clear()
 
     def _sync_weights(self, device: torch.device, stream: int, precision: Optional[str] = None):
         lib = _lib.load_library()
-        named = [(n, p) for n, p in self.named_parameters()]
-        key = tuple((p.data_ptr(), p._version) for _, p in named)
+        named = self._param_cache
+        if named is None:  # the walk over the module tree is cached (invalidated by _apply / load_state_dict)
+            named = self._param_cache = [(n, p) for n, p in self.named_parameters()]
+        key = tuple([(p.data_ptr(), p._version) for _, p in named])
         if key != self._weights_key:
             arr = (_lib.StltTensor * len(named))()
             keep = []
@@ -352,6 +382,9 @@ class Stlt(nn.Module):
                                               *params)
             return {k: v for k, v in zip(self.logit_names, (logits,))}
 
+        if self._cuda_graphs and not want_taps and B > 0 and not torch.cuda.is_current_stream_capturing():
+            logits = self._run_graphed(cats, boxes, scores, ftypes, lengths)
+            return {k: v for k, v in zip(self.logit_names, (logits,))}
         lib = _lib.load_library()
         with torch.cuda.device(device):
             self._ensure_handle(device)
@@ -395,6 +428,58 @@ class Stlt(nn.Module):
         if want_taps:
             return out
         return {k: v for k, v in zip(self.logit_names, (logits,))}
+
+    # -- CUDA-graph replay of the steady-state inference forward -------------------------------------
+    def enable_cuda_graphs(self, enable: bool = True) -> None:
+        """Inference forwards of a shape seen before replay as ONE CUDA graph launch instead of ~60 kernel launches
+        through ctypes (the library enqueues on the caller's stream and never synchronises, so a forward is
+        capturable as is). The first forward of a (shape, precision) runs eagerly, the second is captured; inputs
+        are copied into the graph's static buffers and a fresh logits tensor is returned, so semantics are
+        unchanged. Parameter updates seen by PyTorch's version counters re-pack eagerly before the replay; moved
+        parameters or ``mark_weights_dirty()`` drop the graphs."""
+        self._cuda_graphs = bool(enable)
+        if not enable:
+            self._graphs = None
+
+    def _run_graphed(self, cats, boxes, scores, ftypes, lengths):
+        device = cats.device
+        B, L, S = cats.shape
+        inputs = {"categories": cats, "boxes": boxes, "frame_types": ftypes, "lengths": lengths}
+        if scores is not None:
+            inputs["scores"] = scores
+        with torch.cuda.device(device):
+            self._ensure_handle(device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            self._sync_weights(device, stream)  # eager: re-binds / re-packs when a parameter changed
+            ptrs = tuple([k[0] for k in self._weights_key])
+            shape_key = (device, B, L, S, scores is not None, self.precision, self._pruning, self._fused_ln,
+                         self._fused_attn)
+            if self._graphs is None:
+                self._graphs = {}
+            entry = self._graphs.get(shape_key)
+            if entry is not None and entry["ptrs"] != ptrs:  # parameters moved: the captured pointers are stale
+                entry = None
+            if entry is None or entry["graph"] is None:
+                if entry is None:  # first sight of this shape: plain eager forward (sizes the workspace, sets attributes)
+                    self._graphs[shape_key] = {"graph": None, "ptrs": ptrs}
+                    return self._eager(inputs)
+                static = {k: v.clone() for k, v in inputs.items()}
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self._eager(static)
+                entry = self._graphs[shape_key] = {"graph": graph, "ptrs": ptrs, "static": static, "out": out}
+            for k, v in inputs.items():
+                entry["static"][k].copy_(v, non_blocking=True)
+            entry["graph"].replay()
+            return entry["out"].clone()
+
+    def _eager(self, inputs):
+        graphs, self._cuda_graphs = self._cuda_graphs, False
+        try:
+            with torch.no_grad():
+                return self._run(inputs, want_taps=False)["stlt"]
+        finally:
+            self._cuda_graphs = graphs
 
     # -- training plumbing (used by _StltTrainFunction and training.FusedTrainStep) ----------------
     def _bind_grads(self, grads: Dict[str, torch.Tensor]) -> None:
@@ -466,8 +551,9 @@ class Stlt(nn.Module):
         weights_key = self._weights_key
 
         def run(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+            named = self._param_cache or [(n, p) for n, p in self.named_parameters()]
             if self._weights_key != weights_key or \
-                    tuple((p.data_ptr(), p._version) for p in self.parameters()) != weights_key:
+                    tuple([(p.data_ptr(), p._version) for _, p in named]) != weights_key:
                 raise RuntimeError("parameters changed since capture: call make_graphed again")
             for k in keys:
                 static[k].copy_(batch[k], non_blocking=True)

@@ -125,3 +125,46 @@ def make_appearance_features(batch_size: int, seed: int = 0, channels: int = 204
     activations [B, 2048, T', H', W'] of a 32-frame 112x112 clip (2 x 4 x 4 positions)."""
     g = torch.Generator().manual_seed(seed)
     return torch.relu(torch.randn((batch_size, channels, t, hw, hw), generator=g)).to(torch.float32)
+
+
+def make_layout_dataset(dataset: str = "something", n_videos: int = 64, seed: int = 0, dense: bool = True,
+                        num_frames: int = 16, max_objects: int | None = None):
+    """Synthetic RAW layout dataset in the JSON schema the reference reads (written by its
+    src/create_something_datasets.py:18-34 / create_action_genome_datasets.py): a list of
+    ``{"id", "frames": [{"frame_objects": [{"category", "x1", "y1", "x2", "y2", "score"}]}]}`` plus
+    ``videoid2size`` ``{id: [width, height]}`` — the input of ``LayoutStore`` here and of ``StltDataset`` there.
+    Pixel boxes include out-of-frame, swapped and degenerate ones so that fix_box has work to do.
+    ``dense``: every video has ``num_frames`` frames carrying ``max_objects`` confident detections (the throughput
+    workload); otherwise frame / object counts and scores vary. Returns (videos, videoid2size)."""
+    import random
+    rng = random.Random(seed)
+    spec = LAYOUTS[dataset]
+    max_objects = DEFAULT_MAX_OBJECTS[dataset] if max_objects is None else max_objects
+    names = {"something": ["hand", "object"],
+             "action_genome": None}[dataset]
+    if names is None:
+        from .data import _AG_NAMES
+        names = _AG_NAMES[2:]
+    videos, sizes = [], {}
+    for v in range(n_videos):
+        vid = f"{dataset}_{seed}_{v}"
+        w, h = VIDEO_SIZES[rng.randrange(len(VIDEO_SIZES))]
+        sizes[vid] = [w, h]
+        frames = []
+        for _ in range(num_frames if dense else rng.randint(1, 2 * num_frames)):
+            objs = []
+            for _ in range(max_objects if dense else rng.randint(0, max_objects)):
+                x1, x2 = rng.uniform(-0.1, 1.1) * w, rng.uniform(-0.1, 1.1) * w
+                y1, y2 = rng.uniform(-0.1, 1.1) * h, rng.uniform(-0.1, 1.1) * h
+                kind = rng.randrange(10)
+                if kind == 0:
+                    x2 = x1
+                elif kind == 1:
+                    y2 = y1
+                elif kind == 2:
+                    x1, y1, x2, y2 = round(x1), round(y1), round(x2), round(y2)
+                objs.append({"category": names[rng.randrange(len(names))], "x1": x1, "y1": y1, "x2": x2, "y2": y2,
+                             "score": rng.uniform(0.5, 1.0) if dense else rng.uniform(0.2, 1.0)})
+            frames.append({"frame_objects": objs})
+        videos.append({"id": vid, "frames": frames})
+    return videos, sizes

@@ -111,8 +111,11 @@ class FusedTrainStep:
         self.dropout_p = float(model.config.hidden_dropout_prob) if dropout_p is None else float(dropout_p)
         self.seed = seed
         self.step_count = 0
+        self.score_step_count = 0  # AdamW bias correction of the score embedding counts only the steps that updated it
+        self._checked_batch = None
         self._ws = None
         self._ws_key = None
+        self.num_buckets = 2  # all-reduce buckets per step (see all_reduce_buckets)
 
         device = next(model.parameters()).device
         if device.type != "cuda":
@@ -182,9 +185,20 @@ class FusedTrainStep:
             if self._ws_key != (B, L, S):
                 self._ws = model._train_workspace(B, L, S, device)
                 self._ws_key = (B, L, S)
+            if world > 1 and self._checked_batch != B:
+                # the 1/world scaling below is the global mean only when every rank holds the same number of videos
+                sizes = torch.tensor([B, -B], device=device)
+                dist.all_reduce(sizes, op=dist.ReduceOp.MAX, group=self.group)
+                if int(sizes[0]) != B or int(-sizes[1]) != B:
+                    raise RuntimeError("FusedTrainStep: every data-parallel rank must hold the same local batch size")
+                self._checked_batch = B
             self.flat_grads.zero_()  # optimizer.zero_grad()
             self.step_count += 1
-            drop = (self.dropout_p if model.training else 0.0, self.seed + self.step_count)
+            if has_scores:
+                self.score_step_count += 1
+            # independent dropout masks per rank and step (a DDP run draws from per-rank generators)
+            rank = dist.get_rank(self.group) if world > 1 else 0
+            drop = (self.dropout_p if model.training else 0.0, self.seed + self.step_count * world + rank)
             logits = model._forward_train(inputs, self._ws, *drop)
             d_logits = torch.empty_like(logits)
             # mean over the GLOBAL batch: local mean gradient scaled by 1/world, summed by the all-reduce
@@ -213,7 +227,8 @@ class FusedTrainStep:
                 _lib.check(model._handle, lib.stlt_adamw_step(
                     model._handle, stream, self.flat_params.data_ptr() + a * es, self.flat_grads.data_ptr() + a * es,
                     self.exp_avg.data_ptr() + a * es, self.exp_avg_sq.data_ptr() + a * es, b - a, lr,
-                    self.betas[0], self.betas[1], self.eps, wd, self.step_count, sumsq_ptr,
+                    self.betas[0], self.betas[1], self.eps, wd,
+                    self.score_step_count if key.startswith("sc") else self.step_count, sumsq_ptr,
                     float(self.clip_val or 0.0)))
             # the fp32 master weights changed in place behind PyTorch's back: re-pack the bf16 operands
             self._repack(stream)

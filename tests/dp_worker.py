@@ -59,8 +59,8 @@ if rank == 0:
     rel = float((a - b).norm() / b.norm())
     cos = float((a * b).sum() / (a.norm() * b.norm()))
     print(f"DP_VS_SINGLE update rel={rel:.3e} cos={cos:.6f}")
-    # not bit-equal: the per-tile bf16 gradient sums are split differently (2 x 32 videos vs 64)
-    assert rel < 3e-2 and cos > 0.999, (rel, cos)
+    # not bit-equal: the per-tile bf16 gradient sums are split differently (2 x 32 videos vs 64); measured 3.1e-4
+    assert rel < 1e-3 and cos > 0.9999, (rel, cos)
     print("DP_OK")
 dist.barrier()
 dist.destroy_process_group()

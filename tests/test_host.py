@@ -259,12 +259,16 @@ def test_embedding_layernorm_statistics_identity():
 
 def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     """`bench.py --impl reference` launched like the B200 arm (torchrun, N = 2): rank 0 alone runs the CPU arm and
-    prints ONE JSON line carrying the B200 arm's metric / unit / config; the other rank exits 0 without work."""
+    prints ONE JSON line carrying the B200 arm's metric / unit / workload; the other rank exits 0 without work. The
+    line says what ran: the unmodified reference from oracle/_ref when it has been built (kind "reference"), and the
+    number of videos every timed step really forwarded."""
     import json
+    from oracle import build_ref, ref_loader
+    build_ref.build()
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="4")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29523", str(ROOT / "bench.py"),
-           "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"]
+           "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--ref-batch", "16", "--no-extras"]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
@@ -273,5 +277,33 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     assert d["impl"] == "reference" and d["metric"] == "stlt_inference_videos_per_sec" and d["unit"] == "videos/s"
     assert d["n_gpus"] == 2 and d["higher_is_better"] is True and d["value"] > 0
     assert d["config"]["workload"].startswith("STLT inference, something shape (L=17 frames x S=5 slots, 174 classes), batch 4096")
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["executed_batch_per_step"] == 16 and "16 videos" in d["config"]["reference_sample"]
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert {(r["batch"], r["threads"]) for r in d["cpu_baseline"]["rows"]} >= {(8, 1), (16, d["cpu_baseline"]["cores"])}
     assert d["e2e"] == {"value": d["value"], "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_oracle_ref_is_the_unmodified_reference_and_agrees_with_the_port():
+    """oracle/_ref (byte-compiled from /root/reference by oracle/build_ref.py) imports as the reference's own
+    modelling.models and its Stlt forward equals the oracle restatement on re-drawn weights and a ragged batch."""
+    import torch
+    import stlt_b200
+    from oracle import build_ref, ref_loader, stlt_oracle
+    from stlt_b200.synthetic import make_batch, random_state_dict
+    if not build_ref.build():
+        import pytest
+        pytest.skip("no /root/reference and no earlier oracle/_ref build on this machine")
+    models, configs = ref_loader.load()
+    assert "_ref" in models.__file__ and models.__file__.endswith(".pyc")
+    cfg = stlt_b200.StltModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(0)
+    sd = random_state_dict(stlt_b200.Stlt(cfg).state_dict(), seed=11)
+    ref = models.Stlt(configs.StltModelConfig(num_classes=174, unique_categories=4))
+    ref.load_state_dict(sd)  # strict: same 174 keys
+    ref.train(False)
+    batch = make_batch(6, "something", ragged=True, seed=12)
+    with torch.no_grad():
+        want = ref(batch)["stlt"]
+        got = stlt_oracle.stlt_forward(sd, batch)
+    assert float((got - want).abs().max() / want.abs().max()) < 2e-5
