@@ -543,19 +543,47 @@ def run_inference(args, rank, local_rank, world, torch, dist, layout=None, batch
         res["whole_step_frac_of_peak"] = (prof["gemm"]["flops"] / steps) / (ms / steps * 1e-3) / 1e12 / \
             float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
         if precision == "bf16" and want_unfused:
-            # A/B of the two epilogue fusions on the same GPU, eager profiled passes of the same K steps
-            ab = {}
-            for name, (ln, at) in (("attention_unfused", (True, False)), ("layernorm_and_attention_unfused", (False, False))):
-                model.set_fused_layer_norm(ln)
-                model.set_fused_attention(at)
-                u_ms, _, u_prof = timed(fwd, steps, 2, world, torch, dist, before=lambda: model.set_profiling(True),
-                                        after=lambda: (model.get_profile(), model.set_profiling(False))[0])
-                ab[name] = {"value": videos / (u_ms * 1e-3), "unit": "videos/s", "ms_per_step": u_ms / steps,
-                            "breakdown_ms_per_step": {k: v["ms"] / steps for k, v in u_prof.items()}}
+            # A/B of the epilogue fusions and of the pad-skipping layout on the same GPU: graph-replayed passes of the
+            # same K steps, the variants interleaved twice (the parts drift by several percent over a run under their
+            # power cap, so back-to-back blocks of one variant are not comparable); best of the two rounds
+            variants = (("default", (True, True, True)), ("padded_grid", (True, True, False)),
+                        ("attention_unfused", (True, False, False)), ("layernorm_and_attention_unfused", (False, False, False)))
+            best = {}
+            model.enable_cuda_graphs(use_graphs)
+            for _ in range(2):
+                for name, (ln, at, cp) in variants:
+                    model.set_fused_layer_norm(ln)
+                    model.set_fused_attention(at)
+                    model.set_compaction(cp)
+                    u_ms, _, _ = timed(fwd, steps, 2, world, torch, dist)
+                    best[name] = min(best.get(name, u_ms), u_ms)
             model.set_fused_layer_norm(True)
             model.set_fused_attention(True)
-            ab["note"] = "eager passes with per-launch CUDA events; compare with profiled_pass_ms_per_step"
+            model.set_compaction(True)
+            ab = {name: {"value": videos / (u_ms * 1e-3), "unit": "videos/s", "ms_per_step": u_ms / steps}
+                  for name, u_ms in best.items()}
+            ab["note"] = ("graph-replayed, variants interleaved, best of 2 rounds. padded_grid = pad-skipping row layout off; "
+                          "the other two additionally un-fuse the attention / the LayerNorms from the GEMM epilogues")
             res["fusion_ab"] = ab
+            # the same model on a RAGGED batch of the same size (lengths ~ U{2..17}, 0..4 boxes per frame: the parity
+            # batch of SURVEY.md 8(d)): what the pad-skipping layout buys on data that is not dense
+            rag = make_batch(batch, layout, ragged=True, seed=300 + rank)
+            rag_dev = {k: rag[k].cuda() for k in keys}
+
+            def fwd_rag():
+                with torch.no_grad():
+                    model(rag_dev)
+
+            model.enable_cuda_graphs(use_graphs)
+            r_ms, _, _ = timed(fwd_rag, steps, 3, world, torch, dist)
+            model.set_compaction(False)
+            p_ms, _, _ = timed(fwd_rag, steps, 3, world, torch, dist)
+            model.set_compaction(True)
+            model.enable_cuda_graphs(False)
+            res["ragged_batch"] = {"value": videos / (r_ms * 1e-3), "unit": "videos/s", "ms_per_step": r_ms / steps,
+                                   "padded_grid_value": videos / (p_ms * 1e-3), "padded_grid_ms_per_step": p_ms / steps,
+                                   "note": "same batch size, lengths ~ U{2..L}, 0..max objects per frame; device-resident"}
+            del rag_dev
         return res, clocks
 
     main_res, clocks = measure(args.dtype, with_clocks=True, want_unfused=full)
@@ -593,7 +621,7 @@ def run_inference(args, rank, local_rank, world, torch, dist, layout=None, batch
         "breakdown_ms_per_step": main_res["breakdown_ms_per_step"],
         "profiled_pass_ms_per_step": main_res["profiled_pass_ms_per_step"],
         "per_rank": main_res["per_rank"], "cuda_graph": main_res["cuda_graph"],
-        "fusion_ab": main_res.get("fusion_ab"), "secondary": secondary,
+        "fusion_ab": main_res.get("fusion_ab"), "ragged_batch": main_res.get("ragged_batch"), "secondary": secondary,
     }
     del model, batch_dev
     gc.collect()

@@ -215,6 +215,13 @@ int stlt_set_fused_ln(void* handle, int32_t enable);
  * HBM. 0 restores the separate in-projection GEMM + attention kernel (cross-check for the tests). */
 int stlt_set_fused_attention(void* handle, int32_t enable);
 
+/* ... and runs the spatial stack on a pad-skipping row layout (default on): frames at or after lengths[b] and
+ * the padded slots of frames whose slots 1.. are all padding (the "extract" frame, datasets.py:97-113) can never
+ * reach the logits (key-padding / causal masks, models.py:66-71,79,142-150,192) and are not computed. Which rows
+ * exist is decided on the device from `lengths` / `categories`; allocation sizes do not change. 0 computes the
+ * whole padded [B, L, S] grid as the reference does (cross-check for the tests). */
+int stlt_set_compaction(void* handle, int32_t enable);
+
 /* Test taps (NULL disables). The struct is copied. */
 int stlt_set_taps(void* handle, const StltTaps* taps);
 

@@ -17,7 +17,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libstlt_b200.so"
 BUILD_DIR = PKG_DIR / "build"
-SOURCES = ["gemm_tcgen05.cu", "gemm_qkv_attn.cu", "gemm_simt.cu", "elementwise.cu", "attention.cu", "attention_mma.cu",
+SOURCES = ["gemm_tcgen05.cu", "gemm_qkv_attn.cu", "compact.cu", "gemm_simt.cu", "elementwise.cu", "attention.cu", "attention_mma.cu",
            "attention_bwd.cu", "attention_bwd_mma.cu", "train_kernels.cu", "stlt_api.cu", "stlt_train.cu",
            "attention_cross.cu", "attention_long.cu", "cacnf_kernels.cu", "stlt_cacnf.cu", "eval_kernels.cu"]
 NVCC_FLAGS = [

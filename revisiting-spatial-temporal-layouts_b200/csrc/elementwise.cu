@@ -284,7 +284,8 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
              const float* __restrict__ box_b, const float* __restrict__ score_w,
              const float* __restrict__ score_b, const float* __restrict__ ln_g,
              const float* __restrict__ ln_b, float eps, long long tokens, ActOut out,
-             int* __restrict__ err_flag, DropCfg drop, const double* __restrict__ stats) {
+             int* __restrict__ err_flag, DropCfg drop, const double* __restrict__ stats,
+             const int* __restrict__ frame_row, int S, long long* __restrict__ mask_out) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int c = 4 * tid;
   // resident, centred parameters of this thread's four columns
@@ -346,7 +347,16 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
     for (int i = 0; i < kEmbedTok; ++i) {
       const long long t = t0 + i;
       if (t >= tokens) break;
+      long long dst = t;  // output row
+      if (frame_row != nullptr) {  // pad-skipping layout: scatter to the compact row, skip dead tokens (block-uniform)
+        const long long f = t / S;
+        const int slot = static_cast<int>(t - f * S);
+        const int fr = __ldg(frame_row + f);
+        if (fr < 0 || ((fr & kSingleFrameFlag) && slot != 0)) continue;
+        dst = (fr & ~kSingleFrameFlag) + slot;
+      }
       const int cat = __shfl_sync(0xffffffffu, cat_i, i);
+      if (mask_out != nullptr && tid == 0) mask_out[dst] = cat;
       const float mean = __shfl_sync(0xffffffffu, mean_l, i);
       const float rstd = __shfl_sync(0xffffffffu, rstd_l, i);
       const float4 box = __ldg(boxes + t);
@@ -371,17 +381,17 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
         y.z *= drop_mul(b1, 0, drop);
         y.w *= drop_mul(b1, 1, drop);
       }
-      if (out.x != nullptr) *reinterpret_cast<float4*>(out.x + t * kHidden + c) = y;
+      if (out.x != nullptr) *reinterpret_cast<float4*>(out.x + dst * kHidden + c) = y;
       if (out.xb != nullptr) {
         uint2 h;
         h.x = pack_bf16x2(y.x, y.y);
         h.y = pack_bf16x2(y.z, y.w);
-        *reinterpret_cast<uint2*>(out.xb + t * kHidden + c) = h;
+        *reinterpret_cast<uint2*>(out.xb + dst * kHidden + c) = h;
         if (out.planes == 2) {
           uint2 l;
           l.x = pack_bf16x2(bf16_residual(y.x), bf16_residual(y.y));
           l.y = pack_bf16x2(bf16_residual(y.z), bf16_residual(y.w));
-          *reinterpret_cast<uint2*>(out.xb + (out.plane_rows + t) * kHidden + c) = l;
+          *reinterpret_cast<uint2*>(out.xb + (out.plane_rows + dst) * kHidden + c) = l;
         }
       }
     }
@@ -643,7 +653,7 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
                          const float* box_b, const float* score_w, const float* score_b,
                          const float* ln_g, const float* ln_b, float eps, long long tokens,
                          ActOut out, int* err_flag, cudaStream_t stream, float* scratch,
-                         size_t scratch_bytes, DropCfg drop) {
+                         size_t scratch_bytes, DropCfg drop, const int* frame_row, int S, long long* mask_out) {
   if (tokens == 0) return cudaSuccess;
   if (scratch == nullptr || scratch_bytes < embed_scratch_bytes(unique_categories) || unique_categories < 1)
     return cudaErrorInvalidValue;
@@ -655,7 +665,7 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
   embed_kernel<<<static_cast<unsigned>(blocks), kEmbedThreads, 0, stream>>>(
       categories, reinterpret_cast<const float4*>(boxes), scores, cat_table, unique_categories,
       box_w, box_b, score_w, score_b, ln_g, ln_b, eps, tokens, out, err_flag, drop,
-      reinterpret_cast<const double*>(scratch));
+      reinterpret_cast<const double*>(scratch), frame_row, S, mask_out);
   return cudaGetLastError();
 }
 

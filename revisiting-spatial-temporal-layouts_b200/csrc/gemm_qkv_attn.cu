@@ -75,7 +75,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 template <int kNT>
 __global__ void __launch_bounds__(kThreads, 1)
 qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                     const __grid_constant__ CUtensorMap tm_out, QkvAttnArgs p) {
+                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out1,
+                     QkvAttnArgs p) {
   static_assert(kNT == 4 || kNT == 6 || kNT == 10, "key band of 32, 48 or 80 rows");
   constexpr int kBand = 8 * kNT;
   constexpr int kBandOff = kNT == 4 ? 8 : (kNT == 6 ? 16 : 32);
@@ -95,13 +96,27 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   const int num_clusters = gridDim.x / kCluster;
   // a cluster sweeps the 12 heads of one pair of row blocks before it moves on: the activation rows are re-read from
   // L2 by the same SM, and the epilogue's per-row state (LayerNorm statistics, key-padding bits) is loaded once per pair
-  const int pair_blocks = (p.row_blocks + kCluster - 1) / kCluster;
+  // Row blocks: [0, nb_full) hold whole sequences of T tokens (R rows each, from row 0); with the pad-skipping layout
+  // (p.dyn, compact.cu) the counts come from the device and blocks [nb_full, nb_full + nb_single) hold one-token
+  // sequences, 128 per block, from row single_row0.
+  int nb_full = p.row_blocks, nb_single = 0;
+  long long n_full_seq = p.valid_rows / p.seq_len, n_single = 0, single_row0 = 0;
+  if (p.dyn != nullptr) {
+    n_full_seq = __ldg(p.dyn + kDynFull);
+    n_single = __ldg(p.dyn + kDynSingle);
+    nb_full = __ldg(p.dyn + kDynFullBlocks);
+    single_row0 = __ldg(p.dyn + kDynSingleRow0);
+    nb_single = __ldg(p.dyn + kDynSingleBlocks);
+  }
+  const int total_blocks = nb_full + nb_single;
+  const int pair_blocks = (total_blocks + kCluster - 1) / kCluster;
   constexpr int k_blocks = kHidden / BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_out);
+    tma_prefetch_desc(&tm_out1);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -130,7 +145,8 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int pb = cluster_id; pb < pair_blocks; pb += num_clusters) {
-        const int a_row = (pb * kCluster + cta_rank) * p.rows_per_block;  // rows past the end of the tensor are zero-filled
+        const int pblk = pb * kCluster + cta_rank;  // rows past the end of the tensor are zero-filled
+        const int a_row = pblk < nb_full ? pblk * p.rows_per_block : static_cast<int>(single_row0) + (pblk - nb_full) * BM;
         for (int head = 0; head < kHeads; ++head) {
           const int b_row = head * BN + cta_rank * (BN / kCluster);
           for (int kb = 0; kb < k_blocks; ++kb) {
@@ -215,19 +231,33 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
       allow[h] = bits;
     }
+    // one-token sequences: a query attends to its own row only
+    uint32_t allow1[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int d = 16 * ew + g + 8 * h - band0 - 2 * t;  // key index of the query row within this thread's columns
+      allow1[h] = (d >= 0 && d < kBand && (d & 7) < 2) ? 1u << ((d >> 3) * 2 + (d & 7)) : 0u;
+    }
+    const int seqs_per_block = R / T;
     const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
 
     int it = 0;
     for (int pb = cluster_id; pb < pair_blocks; pb += num_clusters) {
       const int blk = pb * kCluster + cta_rank;
-      const bool live = blk < p.row_blocks;  // odd block counts: the last pair has a dummy half
-      const long long row0 = static_cast<long long>(blk) * R;
-      // rows past the real tokens hold whatever the workspace held: they are written as zeros (0 * NaN would poison P V)
-      const bool real_row = row0 + arow < p.valid_rows;
+      const bool live = blk < total_blocks;  // odd block counts: the last pair has a dummy half
+      const bool single = blk >= nb_full;
+      const long long row0 = single ? single_row0 + static_cast<long long>(blk - nb_full) * BM : static_cast<long long>(blk) * R;
+      // is block-local row `r` a real token? (the rest of the 128-row box belongs to the next block or is padding)
+      auto row_live = [&](int r) -> bool {
+        if (single) return static_cast<long long>(blk - nb_full) * BM + r < n_single;
+        return r < R && static_cast<long long>(blk) * seqs_per_block + r / T < n_full_seq;
+      };
+      // rows that are no real token hold whatever the workspace held: written as zeros (0 * NaN would poison P V)
+      const bool real_row = live && row_live(arow);
 
       // ---- per row block: deferred LayerNorm statistics of this thread's row, key-padding bits of the band ----
       float mu = 0.f, rstd = 1.f;
-      if (live && p.prev_norm && real_row && !(p.debug & 4)) {
+      if (p.prev_norm && real_row && !(p.debug & 4)) {
         const float4* st4 = reinterpret_cast<const float4*>(p.stats_in + (row0 + arow) * kStatSlots);
         float sx = 0.f, sy = 0.f;
 #pragma unroll
@@ -245,9 +275,8 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 #pragma unroll
       for (int i = 0; i < kMaskWords; ++i) {
         const int key = band0 + i * 32 + lane;
-        const long long grow = row0 + key;
-        const bool in = live && i * 32 + lane < kBand && key < R && grow < p.valid_rows;
-        const bool ok = in && __ldg(p.mask_src + (in ? grow : 0)) != 0;
+        const bool in = live && i * 32 + lane < kBand && row_live(key);
+        const bool ok = in && __ldg(p.mask_src + (in ? row0 + key : 0)) != 0;
         kw[i] = __ballot_sync(0xffffffffu, ok);
       }
       uint32_t kbits = 0;  // this thread's 2 * kNT key columns
@@ -258,7 +287,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           const int idx = nt * 8 + 2 * t + e;
           kbits |= ((kw[idx >> 5] >> (idx & 31)) & 1u) << (nt * 2 + e);
         }
-      const uint32_t ok0 = allow[0] & kbits, ok1 = allow[1] & kbits;
+      const uint32_t ok0 = (single ? allow1[0] : allow[0]) & kbits, ok1 = (single ? allow1[1] : allow[1]) & kbits;
 
       for (int head = 0; head < kHeads; ++head, ++it) {
         const int acc = it & 1;
@@ -408,7 +437,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         fence_proxy_async_smem();
         named_bar_sync(2, kEpiWarps * 32);  // B: context tile complete, Q / K / V tiles free
         if (ew == 0 && lane == 0) {
-          tma_store_2d(&tm_out, smem_ctx, head * kHeadDim, static_cast<int>(row0));
+          tma_store_2d(single ? &tm_out1 : &tm_out, smem_ctx, head * kHeadDim, static_cast<int>(row0));
           tma_store_commit();
         }
       }
@@ -427,7 +456,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
 template <int kNT>
 cudaError_t launch_nt(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_out,
-                      const QkvAttnArgs& p, cudaStream_t stream, int num_sms) {
+                      const CUtensorMap& tm_out1, const QkvAttnArgs& p, cudaStream_t stream, int num_sms) {
   auto kern = qkv_attention_kernel<kNT>;
   static unsigned long long smem_done = 0;
   cudaError_t e = ensure_dynamic_smem(kern, kSmemBytes, &smem_done);
@@ -447,7 +476,7 @@ cudaError_t launch_nt(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CU
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, tm_out, p);
+  return cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, tm_out, tm_out1, p);
 }
 
 }  // namespace
@@ -458,13 +487,13 @@ int qkv_attention_rows_per_block(int seq_len) {
 }
 
 cudaError_t launch_qkv_attention(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_out,
-                                 const QkvAttnArgs& p, cudaStream_t stream, int num_sms) {
+                                 const CUtensorMap& tm_out1, const QkvAttnArgs& p, cudaStream_t stream, int num_sms) {
   if (p.seq_len < 1 || p.seq_len > 32 || p.rows_per_block != qkv_attention_rows_per_block(p.seq_len) ||
       p.row_blocks < 1 || p.vec_c == nullptr || p.mask_src == nullptr || (p.prev_norm && (!p.vec_s || !p.stats_in)))
     return cudaErrorInvalidValue;
-  if (p.seq_len <= 9) return launch_nt<4>(tm_a, tm_b, tm_out, p, stream, num_sms);
-  if (p.seq_len <= 17) return launch_nt<6>(tm_a, tm_b, tm_out, p, stream, num_sms);
-  return launch_nt<10>(tm_a, tm_b, tm_out, p, stream, num_sms);
+  if (p.seq_len <= 9) return launch_nt<4>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
+  if (p.seq_len <= 17) return launch_nt<6>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
+  return launch_nt<10>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
 }
 
 }  // namespace stlt

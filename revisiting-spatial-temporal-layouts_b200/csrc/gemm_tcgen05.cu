@@ -140,8 +140,10 @@ template <int kTerms, int kOut, int kGelu, int kLayout, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2,
-                    const float* __restrict__ bias, int m_tiles, int n_tiles, int k_blocks, int a_plane_rows,
+                    const float* __restrict__ bias, int m_tiles_arg, int n_tiles, int k_blocks, int a_plane_rows,
                     int b_plane_rows, int out_plane_rows, DropCfg drop, EpiArgs ep) {
+  // pad-skipping row layout (compact.cu): the number of live 128-row tiles is decided on the device
+  const int m_tiles = ep.m_tiles_dyn != nullptr ? min(m_tiles_arg, __ldg(ep.m_tiles_dyn)) : m_tiles_arg;
   static_assert(kEpi == GEMM_EPI_PLAIN || kEpi == GEMM_EPI_ACT_BWD || (kLayout == GEMM_NT && kTerms == 1),
                 "fused-LN epilogues: bf16 forward only");
   static_assert(kEpi != GEMM_EPI_ACT_BWD || (kLayout == GEMM_NN && kOut == GEMM_OUT_BF16 && kGelu == 0),

@@ -100,13 +100,16 @@ struct Handle {
   bool fused_ln = true;     // bf16 mode: LayerNorm folded into the GEMM epilogues (stlt_set_fused_ln)
   int fused_attn_max_t = 32;  // longest sequence that takes the fused kernel (STLT_FUSED_ATTENTION_MAX_T, experiments)
   int qkv_attn_debug = 0;   // QkvAttnArgs::debug (STLT_QKV_ATTN_DEBUG environment variable, read at stlt_create)
+  bool compaction = true;   // ... on the pad-skipping row layout of the spatial phase (stlt_set_compaction)
   bool fused_attn = true;   // ... and the attention into the in-projection's epilogue (stlt_set_fused_attention)
   bool bf16_branch = true;  // bf16 mode: out-projection / linear2 outputs travel as bf16 (see run_tail_part)
   bool pruning = true;  // run the row-wise tail of the last layer of each stack on the rows that are read
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
-  struct Span { int cat; cudaEvent_t a, b; double flops; };
+  // dyn != null: the launch covered *dyn units of dyn_flops each (pad-skipping layout: counts live on the device and
+  // are read back by stlt_get_profile, which synchronises anyway)
+  struct Span { int cat; cudaEvent_t a, b; double flops; const int* dyn; double dyn_flops; };
   std::vector<Span> spans;
   std::map<std::tuple<const void*, int, long long, long long, int, int>, CUtensorMap> tm_cache;
   char err[512] = {0};
@@ -139,8 +142,11 @@ struct ProfileScope {
   cudaEvent_t a = nullptr, b = nullptr;
   int cat;
   double flops;
-  ProfileScope(Handle* h_, cudaStream_t s_, int cat_, double flops_ = 0.0)
-      : h(h_), s(s_), cat(cat_), flops(flops_) {
+  const int* dyn = nullptr;
+  double dyn_flops = 0.0;
+  ProfileScope(Handle* h_, cudaStream_t s_, int cat_, double flops_ = 0.0, const int* dyn_ = nullptr,
+               double dyn_flops_ = 0.0)
+      : h(h_), s(s_), cat(cat_), flops(flops_), dyn(dyn_), dyn_flops(dyn_flops_) {
     if (!h->profiling) return;
     a = next_event(h);
     b = next_event(h);
@@ -149,7 +155,7 @@ struct ProfileScope {
   ~ProfileScope() {
     if (!h->profiling || !a || !b) return;
     cudaEventRecord(b, s);
-    h->spans.push_back({cat, a, b, flops});
+    h->spans.push_back({cat, a, b, flops, dyn, dyn_flops});
   }
 };
 
@@ -233,7 +239,7 @@ inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_r
 //   GEMM_EPI_RESID : z_out fp32 [m_rows, 768] (+ bf16 copy zb_out) = (prev_norm ? LN(z_prev) : z_prev) + A W^T + bias
 inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const void* a, long long m_rows,
                           const void* w, int n, int k, const float* bias, void* out, void* out_bf16, int gelu,
-                          const EpiArgs& epi) {
+                          const EpiArgs& epi, const int* m_tiles_dyn = nullptr) {
   GemmArgs g{};
   int rc = make_tm(h, &g.tm_a, a, 1, m_rows, k, 64, 128);
   if (rc) return rc;
@@ -265,7 +271,9 @@ inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const vo
   g.drop = DropCfg{0, 0, 1.f};
   g.epilogue = epilogue;
   g.epi = epi;
-  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
+  g.epi.m_tiles_dyn = m_tiles_dyn;
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, m_tiles_dyn ? 0.0 : 2.0 * static_cast<double>(m_rows) * n * k,
+                    m_tiles_dyn, 2.0 * 128 * n * k);
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
   return STLT_OK;
@@ -273,19 +281,27 @@ inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const vo
 
 // ctx bf16 [m_rows, 768] = attention(act_in W_in^T + b_in) in one kernel (gemm_qkv_attn.cu). `a` = bf16 [m_rows, 768]
 // (un-normalised residual stream when stats != null: its LayerNorm is folded into w_h / vec_s / vec_c).
+// dyn != null: pad-skipping layout (compact.cu) — rows and block counts are read from the device header, num_seqs is
+// the static upper bound (all frames) used to size the grid, the last counter of `dyn` is the executed block count.
 inline int run_qkv_attention(Handle* h, cudaStream_t stream, const void* a, long long m_rows, long long valid_rows,
                              const __nv_bfloat16* w_h, const float* vec_s, const float* vec_c, const float2* stats,
-                             float eps, const long long* mask_src, long long num_seqs, int T, bool causal, void* ctx) {
+                             float eps, const long long* mask_src, long long num_seqs, int T, bool causal, void* ctx,
+                             const int* dyn = nullptr) {
   const int R = qkv_attention_rows_per_block(T);
   if (R == 0) return fail(h, STLT_ERR_INVALID, "fused attention: sequence length %d outside [1, 32]", T);
   const long long per_block = R / T;
-  CUtensorMap tm_a, tm_b, tm_out;
+  CUtensorMap tm_a, tm_b, tm_out, tm_out1;
   int rc = make_tm(h, &tm_a, a, 1, m_rows, kHidden, 64, 128);
   if (rc) return rc;
   rc = make_tm(h, &tm_b, w_h, 1, kQkv, kHidden, 64, 96);
   if (rc) return rc;
   rc = make_tm(h, &tm_out, ctx, 1, m_rows, kHidden, 64, R);
   if (rc) return rc;
+  tm_out1 = tm_out;
+  if (dyn != nullptr) {
+    rc = make_tm(h, &tm_out1, ctx, 1, m_rows, kHidden, 64, 128);
+    if (rc) return rc;
+  }
   QkvAttnArgs p{};
   p.vec_s = vec_s;
   p.vec_c = vec_c;
@@ -298,11 +314,14 @@ inline int run_qkv_attention(Handle* h, cudaStream_t stream, const void* a, long
   p.seq_len = T;
   p.rows_per_block = R;
   p.row_blocks = static_cast<int>((num_seqs + per_block - 1) / per_block);
+  if (dyn != nullptr) p.row_blocks += static_cast<int>((num_seqs + 127) / 128);  // + blocks of single-token sequences
   p.causal = causal ? 1 : 0;
   p.debug = h->qkv_attn_debug;
+  p.dyn = dyn;
   // the executed MMAs cover 128-row blocks of which R rows are kept
-  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(p.row_blocks) * 128 * kQkv * kHidden);
-  STLT_CUDA(h, launch_qkv_attention(tm_a, tm_b, tm_out, p, stream, h->num_sms));
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, dyn ? 0.0 : 2.0 * static_cast<double>(p.row_blocks) * 128 * kQkv * kHidden,
+                    dyn ? dyn + kDynAttnBlocks : nullptr, 2.0 * 128 * kQkv * kHidden);
+  STLT_CUDA(h, launch_qkv_attention(tm_a, tm_b, tm_out, tm_out1, p, stream, h->num_sms));
   h->launches++;
   return STLT_OK;
 }

@@ -52,6 +52,7 @@ struct EpiArgs {
   const __nv_bfloat16* act_in;  // ACT_BWD: gelu'(u) * dropout mask, bf16 [M, N]
   float* colsum_out;            // ACT_BWD: [N] fp32, accumulated with atomics (may be null)
   int valid_rows;               // ACT_BWD: rows >= valid_rows are tile padding and stay out of the column sums
+  const int* m_tiles_dyn;       // device int (may be null): live 128-row tiles of A / out when the row count is dynamic
 };
 
 enum GemmLayout : int {
@@ -86,6 +87,27 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
 
 // In-projection + masked self-attention in one kernel (gemm_qkv_attn.cu; bf16 inference path, sequences of at
 // most 32 tokens). The weights are the HEAD-MAJOR gamma-folded pack of launch_pack_folded(head_major = true).
+// ---- pad-skipping row layout of the spatial phase (compact.cu) ----
+// header of dynamic counts written by launch_compact_plan (device int[8])
+enum CompactHeader : int {
+  kDynFull = 0,          // frames with at least one non-padding object slot (sequences of S tokens)
+  kDynSingle = 1,        // live frames whose slots 1.. are all padding (one-token sequences)
+  kDynFullBlocks = 2,    // row blocks of the full frames (floor(128 / S) frames each)
+  kDynSingleRow0 = 3,    // first row of the single-token frames = kDynFullBlocks * rows_per_block
+  kDynRows = 4,          // kDynSingleRow0 + kDynSingle
+  kDynTiles = 5,         // ceil(kDynRows / 128): live tiles of the row-wise GEMMs
+  kDynSingleBlocks = 6,  // ceil(kDynSingle / 128)
+  kDynAttnBlocks = 7,    // kDynFullBlocks + kDynSingleBlocks: row blocks the attention-fused in-projection executes
+};
+constexpr int kSingleFrameFlag = 0x40000000;  // frame_row[f]: row of slot 0 | flag when the frame is a single token; -1 dead
+size_t compact_plan_scratch_bytes(long long frames);
+long long compact_rows_bound(long long frames, int S);  // static upper bound of kDynRows (allocation)
+cudaError_t launch_compact_plan(const long long* categories, const long long* lengths, int B, int L, int S,
+                                int* frame_row, int* hdr, void* scratch, int* err_flag, cudaStream_t stream);
+cudaError_t launch_gather_frames(const float* src_x, const __nv_bfloat16* src_att, const int* frame_row,
+                                 long long frames, float* dst_x, __nv_bfloat16* dst_att, const float2* src_stats,
+                                 float2* dst_stats, cudaStream_t stream);
+
 struct QkvAttnArgs {
   const float* vec_s;         // [2304] head-major: row sums of the folded weights (read when prev_norm)
   const float* vec_c;         // [2304] head-major: (W beta)[n] + bias[n]
@@ -97,17 +119,20 @@ struct QkvAttnArgs {
   int prev_norm;       // 1: the input rows still need LayerNorm (applied algebraically in the epilogue)
   int seq_len;         // T <= 32
   int rows_per_block;  // floor(128 / T) * T (qkv_attention_rows_per_block)
-  int row_blocks;      // ceil(sequences / floor(128 / T))
+  int row_blocks;      // ceil(sequences / floor(128 / T)); with `dyn`: static upper bound of full + single blocks
   int causal;
+  const int* dyn;      // CompactHeader (device) or null: rows [0, dyn[kDynFull] * T) hold sequences of T tokens in blocks
+                       // of rows_per_block, rows from dyn[kDynSingleRow0] hold dyn[kDynSingle] one-token sequences
   int debug;           // timing decomposition only (tools/bench_qkv_attention.py): 1 skip the attention math, 2 skip the
                        // Q/K/V tile stores, 4 skip the statistics loads, 8 sleep 2 us per unit in the epilogue; results are
                        // garbage when bits 1 / 2 / 4 are set
 };
 int qkv_attention_rows_per_block(int seq_len);
 // tm_a: bf16 [m_rows, 768] box {64, 128}; tm_b: bf16 [2304, 768] box {64, 96}; tm_out: bf16 [m_rows, 768] box
-// {64, rows_per_block}; all SWIZZLE_128B.
+// {64, rows_per_block}; tm_out1: same tensor, box {64, 128} (blocks of single-token sequences; = tm_out without
+// `dyn`); all SWIZZLE_128B.
 cudaError_t launch_qkv_attention(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_out,
-                                 const QkvAttnArgs& p, cudaStream_t stream, int num_sms);
+                                 const CUtensorMap& tm_out1, const QkvAttnArgs& p, cudaStream_t stream, int num_sms);
 
 // fp32 SIMT GEMM: out[M, N] = act(A[M, K] * W[N, K]^T + bias). Used by the classifier head
 // (src/modelling/models.py:155-163) and as an independent cross-check of the tcgen05 path in tests.
@@ -166,7 +191,10 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
                          const float* box_b, const float* score_w, const float* score_b,
                          const float* ln_g, const float* ln_b, float eps, long long tokens,
                          ActOut out, int* err_flag, cudaStream_t stream, float* scratch, size_t scratch_bytes,
-                         DropCfg drop = DropCfg{0, 0, 1.f});
+                         DropCfg drop = DropCfg{0, 0, 1.f}, const int* frame_row = nullptr, int S = 1,
+                         long long* mask_out = nullptr);
+// frame_row != null (pad-skipping layout): token (f, s) of the padded grid goes to row frame_row[f] + s (full frame), to
+// row frame_row[f] & ~kSingleFrameFlag if s == 0 (single-token frame) or nowhere; mask_out[row] receives its category.
 // `scratch` (>= embed_scratch_bytes, any buffer that is dead until the kernel after the embedding) receives the
 // per-category LayerNorm statistics tables that embed_stats_kernel derives from the live parameters on every call.
 size_t embed_scratch_bytes(int unique_categories);

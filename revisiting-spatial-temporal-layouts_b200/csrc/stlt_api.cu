@@ -100,6 +100,8 @@ struct BufSet {
 };
 
 struct WorkspacePlan {
+  size_t off_plan = 0;  // pad-skipping layout: header int[8] | frame_row int[B*L] | mask i64[rows] | plan scratch
+  size_t off_frame_row = 0, off_mask = 0, off_plan_scratch = 0;
   BufSet sp;  // spatial phase : B*L*S object tokens
   BufSet tm;  // temporal phase: B*L frame tokens (also the CLS-only tail of the last spatial layer)
   BufSet hd;  // B extract-frame tokens (tail of the last temporal layer)
@@ -127,7 +129,11 @@ WorkspacePlan plan_workspace(int B, int L, int S, int precision, int ns = 0, int
   size_t off = 0;
   p.off_err = off;
   off += 1024;
-  off = plan_bufset(&p.sp, off, static_cast<long long>(B) * L * S, precision, true);
+  // bf16: the spatial phase may run on the pad-skipping layout, whose static row bound is a little larger
+  long long sp_rows = static_cast<long long>(B) * L * S;
+  const long long compact_rows = precision == STLT_PRECISION_BF16 ? compact_rows_bound(static_cast<long long>(B) * L, S) : 0;
+  if (compact_rows > sp_rows) sp_rows = compact_rows;
+  off = plan_bufset(&p.sp, off, sp_rows, precision, true);
   off = plan_bufset(&p.tm, off, static_cast<long long>(B) * L, precision, true);
   off = plan_bufset(&p.hd, off, B, precision, false);
   p.off_head = off;
@@ -140,6 +146,17 @@ WorkspacePlan plan_workspace(int B, int L, int S, int precision, int ns = 0, int
     p.stats_bytes = (static_cast<size_t>(2 * ns) * p.sp.m_pad + static_cast<size_t>(2 * nt + 6) * p.tm.m_pad) *
                     kStatSlots * sizeof(float2);
   off += align1k(p.stats_bytes);
+  if (compact_rows > 0) {
+    const long long frames = static_cast<long long>(B) * L;
+    p.off_plan = off;
+    off += 1024;
+    p.off_frame_row = off;
+    off += align1k(static_cast<size_t>(frames) * sizeof(int));
+    p.off_mask = off;
+    off += align1k(static_cast<size_t>(p.sp.m_pad) * sizeof(long long));
+    p.off_plan_scratch = off;
+    off += align1k(compact_plan_scratch_bytes(frames));
+  }
   p.total = off;
   return p;
 }
@@ -240,12 +257,13 @@ struct PendingNorm {
 
 // in-projection (+ deferred LayerNorm of its input) and attention over the full phase
 int fused_attention_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, const Phase& ph,
-                         const PendingNorm& in, const long long* mask_src, long long num_seqs, int T, bool causal) {
+                         const PendingNorm& in, const long long* mask_src, long long num_seqs, int T, bool causal,
+                         const int* dyn = nullptr) {
   int rc;
-  if (h->fused_attn && T <= h->fused_attn_max_t && lw.in_h != nullptr)  // one kernel: the packed QKV activations never reach HBM
+  if (dyn != nullptr || (h->fused_attn && T <= h->fused_attn_max_t && lw.in_h != nullptr))  // one kernel: the packed QKV activations never reach HBM
     return run_qkv_attention(h, stream, ph.xb, ph.m_pad, ph.m_valid, lw.in_h, lw.in_hs, lw.in_hc,
                              in.gamma != nullptr ? in.stats : nullptr, h->dims.encoder_norm_eps, mask_src, num_seqs, T,
-                             causal, ph.att);
+                             causal, ph.att, dyn);
   if (in.gamma == nullptr) {
     rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv, 1, GEMM_OUT_BF16, 0);
   } else {
@@ -264,35 +282,39 @@ int fused_attention_part(Handle* h, cudaStream_t stream, const LayerWeights& lw,
 
 // out-projection + residual, linear1 (+ LN1, GELU), linear2 + residual; LN2 stays pending (stats in s2)
 int fused_tail_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, const Phase& ph, const PendingNorm& in,
-                    float2* s1, float2* s2) {
+                    float2* s1, float2* s2, const int* tiles_dyn = nullptr) {
   const float eps = h->dims.encoder_norm_eps;
   EpiArgs e1{in.stats, in.gamma, in.beta, ph.x, s1, ph.xb, eps, in.gamma != nullptr ? 1 : 0};
-  int rc = run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.att, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.x, ph.xb, 0, e1);
+  int rc = run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.att, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.x, ph.xb, 0, e1,
+                          tiles_dyn);
   if (rc) return rc;
   EpiArgs e2{s1, lw.l1_s, lw.l1_c, nullptr, nullptr, nullptr, eps, 1};
-  rc = run_gemm_fused(h, stream, GEMM_EPI_NORM_A, ph.xb, ph.m_pad, lw.l1_f, kFfn, kHidden, nullptr, ph.hid, nullptr, 2, e2);
+  rc = run_gemm_fused(h, stream, GEMM_EPI_NORM_A, ph.xb, ph.m_pad, lw.l1_f, kFfn, kHidden, nullptr, ph.hid, nullptr, 2, e2,
+                      tiles_dyn);
   if (rc) return rc;
   EpiArgs e3{s1, lw.n1_g, lw.n1_b, ph.x, s2, ph.xb, eps, 1};
-  return run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.hid, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.x, ph.xb, 0, e3);
+  return run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.hid, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.x, ph.xb, 0, e3,
+                        tiles_dyn);
 }
 
 // One stack of post-norm encoder layers; the last layer's row-wise tail runs on the compacted rows of `tail`
 // (gathered with `stride` / `lengths`). On return tail.x holds the PRE-norm output of the stack on those rows
 // and *out the LayerNorm still to be applied to it.
+// dyn / frame_row != null: `full` is on the pad-skipping layout (compact.cu) and the tail rows are the frames in padded order.
 int fused_stack(Handle* h, cudaStream_t stream, const std::vector<LayerWeights>& layers, const Phase& full,
                 const Phase& tail, const long long* mask_src, long long num_seqs, int T, bool causal, int stride,
                 const long long* lengths, int L, float2* stats_full, float2* stats_tail, int* err_flag,
-                PendingNorm* out) {
+                PendingNorm* out, const int* dyn = nullptr, const int* frame_row = nullptr) {
   const int n = static_cast<int>(layers.size());
   PendingNorm pending;  // layer 0 reads the (already normalised) embedding output
   for (int i = 0; i < n; ++i) {
     const LayerWeights& lw = layers[i];
-    int rc = fused_attention_part(h, stream, lw, full, pending, mask_src, num_seqs, T, causal);
+    int rc = fused_attention_part(h, stream, lw, full, pending, mask_src, num_seqs, T, causal, dyn);
     if (rc) return rc;
     if (i < n - 1) {
       float2* s1 = stats_full + static_cast<size_t>(2 * i) * full.m_pad * kStatSlots;
       float2* s2 = s1 + full.m_pad * kStatSlots;
-      rc = fused_tail_part(h, stream, lw, full, pending, s1, s2);
+      rc = fused_tail_part(h, stream, lw, full, pending, s1, s2, dyn != nullptr ? dyn + kDynTiles : nullptr);
       if (rc) return rc;
       pending = PendingNorm{s2, lw.n2_g, lw.n2_b};
     } else {
@@ -301,8 +323,12 @@ int fused_stack(Handle* h, cudaStream_t stream, const std::vector<LayerWeights>&
       float2* sc2 = sc1 + tail.m_pad * kStatSlots;
       {
         ProfileScope prof(h, stream, STLT_PROF_OTHER);
-        STLT_CUDA(h, launch_gather_rows(full.x, full.att, 1, full.m_pad, stride, lengths, L, tail.m_valid, tail.x,
-                                        tail.att, tail.m_pad, err_flag, stream, pending.stats, sc_in));
+        if (frame_row != nullptr)
+          STLT_CUDA(h, launch_gather_frames(full.x, full.att, frame_row, tail.m_valid, tail.x, tail.att, pending.stats,
+                                            sc_in, stream));
+        else
+          STLT_CUDA(h, launch_gather_rows(full.x, full.att, 1, full.m_pad, stride, lengths, L, tail.m_valid, tail.x,
+                                          tail.att, tail.m_pad, err_flag, stream, pending.stats, sc_in));
       }
       h->launches++;
       PendingNorm tail_in{pending.gamma ? sc_in : nullptr, pending.gamma, pending.beta};
@@ -648,16 +674,37 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     float2* st_c_sp = st_tm + static_cast<size_t>(2 * d.num_temporal_layers) * p.tm.m_pad * kStatSlots;  // 3 compaction sites
     float2* st_c_tm = st_c_sp + 3 * p.tm.m_pad * kStatSlots;                                               // 3 more (B rows)
     ActOut emb{sp.x, sp.xb, 1, sp.m_pad};
+    // Pad-skipping layout of the spatial phase (compact.cu): padding frames and the padded slots of one-token frames
+    // are not computed. Needs the attention-fused in-projection (it understands the two row regions).
+    const bool compact = h->compaction && h->fused_attn && S <= h->fused_attn_max_t && p.off_plan != 0 &&
+                         h->w.spatial[0].in_h != nullptr;
+    const int* dyn = nullptr;
+    const int* frame_row = nullptr;
+    const long long* sp_mask = categories;
+    if (compact) {
+      int* hdr = reinterpret_cast<int*>(ws + p.off_plan);
+      int* fr = reinterpret_cast<int*>(ws + p.off_frame_row);
+      long long* mask_c = reinterpret_cast<long long*>(ws + p.off_mask);
+      {
+        ProfileScope prof(h, stream, STLT_PROF_OTHER);
+        STLT_CUDA(h, launch_compact_plan(categories, lengths, B, L, S, fr, hdr, ws + p.off_plan_scratch, err_flag, stream));
+      }
+      h->launches += 3;
+      dyn = hdr;
+      frame_row = fr;
+      sp_mask = mask_c;
+    }
     {
       ProfileScope prof(h, stream, STLT_PROF_OTHER);
       STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories, h->w.box_w, h->w.box_b,
                                 h->w.score_w, h->w.score_b, h->w.emb_g, h->w.emb_b, d.layer_norm_eps, n_sp, emb,
-                                err_flag, stream, reinterpret_cast<float*>(sp.hid), embed_scratch(sp)));
+                                err_flag, stream, reinterpret_cast<float*>(sp.hid), embed_scratch(sp), DropCfg{0, 0, 1.f},
+                                frame_row, S, compact ? reinterpret_cast<long long*>(ws + p.off_mask) : nullptr));
     }
     h->launches += 2;  // embed_stats_kernel + embed_kernel
     PendingNorm sp_out;
-    int rc = fused_stack(h, stream, h->w.spatial, sp, tm, categories, n_tm, S, false, S, nullptr, 0, st_sp, st_c_sp,
-                         err_flag, &sp_out);
+    int rc = fused_stack(h, stream, h->w.spatial, sp, tm, sp_mask, n_tm, S, false, S, nullptr, 0, st_sp, st_c_sp,
+                         err_flag, &sp_out, dyn, frame_row);
     if (rc) return rc;
     {
       ProfileScope prof(h, stream, STLT_PROF_OTHER);
@@ -796,6 +843,13 @@ int stlt_set_fused_ln(void* handle, int32_t enable) {
   return STLT_OK;
 }
 
+int stlt_set_compaction(void* handle, int32_t enable) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  h->compaction = enable != 0;
+  return STLT_OK;
+}
+
 int stlt_set_fused_attention(void* handle, int32_t enable) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
@@ -858,7 +912,13 @@ int stlt_get_profile(void* handle, StltProfile* out) {
     if (sp.cat < 0 || sp.cat >= STLT_PROF_CATEGORIES) continue;
     out->ms[sp.cat] += ms;
     out->launches[sp.cat] += 1;
-    out->flops[sp.cat] += sp.flops;
+    double flops = sp.flops;
+    if (sp.dyn != nullptr) {  // pad-skipping layout: units executed by this launch, from the device header
+      int units = 0;
+      STLT_CUDA(h, cudaMemcpy(&units, sp.dyn, sizeof(int), cudaMemcpyDeviceToHost));
+      flops += sp.dyn_flops * units;
+    }
+    out->flops[sp.cat] += flops;
   }
   h->spans.clear();
   h->ev_used = 0;

@@ -126,6 +126,7 @@ SIGNATURES = {
     "stlt_set_pruning": (c_int32, [c_void_p, c_int32]),
     "stlt_set_fused_ln": (c_int32, [c_void_p, c_int32]),
     "stlt_set_fused_attention": (c_int32, [c_void_p, c_int32]),
+    "stlt_set_compaction": (c_int32, [c_void_p, c_int32]),
     "stlt_set_profiling": (c_int32, [c_void_p, c_int32]),
     "stlt_get_profile": (c_int32, [c_void_p, POINTER(StltProfile)]),
     "stlt_bind_grads": (c_int32, [c_void_p, POINTER(StltTensor), c_int32]),

@@ -185,6 +185,7 @@ class Stlt(nn.Module):
     _cuda_graphs = False
     _fused_ln = True
     _fused_attn = os.environ.get("STLT_FUSED_ATTENTION", "1") != "0"
+    _compaction = os.environ.get("STLT_COMPACTION", "1") != "0"
 
     def __init__(self, config, precision: str = "fp32", cuda_graphs: bool = False):
         super().__init__()
@@ -272,6 +273,7 @@ class Stlt(nn.Module):
         _lib.check(handle, lib.stlt_set_pruning(handle, int(self._pruning)))
         _lib.check(handle, lib.stlt_set_fused_ln(handle, int(self._fused_ln)))
         _lib.check(handle, lib.stlt_set_fused_attention(handle, int(self._fused_attn)))
+        _lib.check(handle, lib.stlt_set_compaction(handle, int(self._compaction)))
         self._weights_key = None
         self._graphs = None
         self._packed.clear()
@@ -453,7 +455,7 @@ class Stlt(nn.Module):
             self._sync_weights(device, stream)  # eager: re-binds / re-packs when a parameter changed
             ptrs = tuple([k[0] for k in self._weights_key])
             shape_key = (device, B, L, S, scores is not None, self.precision, self._pruning, self._fused_ln,
-                         self._fused_attn)
+                         self._fused_attn, self._compaction)
             if self._graphs is None:
                 self._graphs = {}
             entry = self._graphs.get(shape_key)
@@ -589,6 +591,13 @@ class Stlt(nn.Module):
         self._fused_attn = bool(enable)
         if self._handle is not None:
             _lib.check(self._handle, _lib.load_library().stlt_set_fused_attention(self._handle, int(self._fused_attn)))
+
+    def set_compaction(self, enable: bool) -> None:
+        """bf16 mode: pad-skipping row layout of the spatial stack (default on): padding frames and the padded slots of
+        one-token frames are not computed. Off = the whole padded [B, L, S] grid, as the reference computes it."""
+        self._compaction = bool(enable)
+        if self._handle is not None:
+            _lib.check(self._handle, _lib.load_library().stlt_set_compaction(self._handle, int(self._compaction)))
 
     def set_profiling(self, enable: bool) -> None:
         """Per-category CUDA-event timing of the kernels launched by forward (bench / profiles)."""

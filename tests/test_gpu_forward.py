@@ -366,7 +366,10 @@ def test_fused_layer_norm_path_matches_unfused_and_oracle(layout):
     gb = to_cuda(batch)
     with torch.no_grad():
         model.set_fused_layer_norm(True)
-        full = model(gb)["stlt"].float().cpu()   # default: LayerNorms and attention in the GEMM epilogues
+        comp = model(gb)["stlt"].float().cpu()   # default: LayerNorms + attention in the GEMM epilogues, pad rows skipped
+        n_comp = model.last_launch_count()
+        model.set_compaction(False)
+        full = model(gb)["stlt"].float().cpu()   # the same on the whole padded [B, L, S] grid
         n_full = model.last_launch_count()
         model.set_fused_attention(False)
         fused = model(gb)["stlt"].float().cpu()
@@ -379,6 +382,9 @@ def test_fused_layer_norm_path_matches_unfused_and_oracle(layout):
           nerr(fused, plain), "launches", n_fused, n_plain)
     assert n_fused == n_plain - 23  # 24 residual + LayerNorm launches gone, one LayerNorm of the pooled rows added
     assert n_full == n_fused - 12   # the 12 attention launches live in the in-projection epilogues
+    assert n_comp == n_full + 3     # three tiny planning kernels of the pad-skipping layout
+    print(layout, "pad-skipping vs oracle", nerr(comp, want), "vs padded grid", nerr(comp, full))
+    assert nerr(comp, want) < 2e-2 and nerr(comp, full) < 5e-3 and torch.equal(comp.argmax(-1), want.argmax(-1))
     print(layout, "attention-fused vs oracle", nerr(full, want), "vs LayerNorm-fused", nerr(full, fused))
     assert nerr(fused, want) < 2e-2 and nerr(plain, want) < 2e-2 and nerr(full, want) < 2e-2
     assert torch.equal(fused.argmax(-1), want.argmax(-1)) and torch.equal(full.argmax(-1), want.argmax(-1))
@@ -480,3 +486,39 @@ def test_backbone_forward_returns_every_frame_seq_first():
         n = int(batch["lengths"][b])
         assert nerr(out[:n, b], torch.from_numpy(g["temporal"][b, :n])) < FP32_TOL
     assert len(m.state_dict()) == 174 and len(m.backbone.state_dict()) == 168  # the runner adds nothing
+
+
+@pytest.mark.parametrize("layout", ["something", "action_genome"])
+def test_pad_skipping_layout_on_ragged_and_degenerate_batches(layout):
+    """The pad-skipping row layout (csrc/compact.cu) decides on the device which rows exist. Ragged batches, batches
+    whose frames are all single-token (no objects anywhere), all-full batches and out-of-pattern inputs (an extract
+    frame that carries objects, objects in padding frames) must give the logits of the padded grid / the oracle."""
+    spec = stlt_b200.SOMETHING_ELSE if layout == "something" else stlt_b200.ACTION_GENOME
+    cfg = StltModelConfig(num_classes=spec["num_classes"], unique_categories=spec["unique_categories"],
+                          num_spatial_layers=2, num_temporal_layers=2)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=61)
+    m = _model(cfg, sd, "bf16")
+    cases = {
+        "ragged": make_batch(300, layout, ragged=True, seed=62),
+        "dense": make_batch(130, layout, ragged=False, seed=63),
+        "no_objects": make_batch(40, layout, ragged=True, seed=64, max_objects=0),
+        "single_frame": make_batch(9, layout, ragged=True, seed=65, num_frames=1),
+    }
+    odd = make_batch(50, layout, ragged=True, seed=66)
+    odd["categories"][:, :, 1] = spec["object_ids"][0]   # every frame (extract and padding frames too) carries an object
+    odd["boxes"][:, :, 1] = 0.25
+    if "scores" in odd:
+        odd["scores"][:, :, 1] = 0.9
+    cases["objects_everywhere"] = odd
+    for name, batch in cases.items():
+        gb = to_cuda(batch)
+        with torch.no_grad():
+            m.set_compaction(True)
+            got = m(gb)["stlt"].float().cpu()
+            m.set_compaction(False)
+            padded = m(gb)["stlt"].float().cpu()
+            want = O.stlt_forward(sd, batch, num_spatial_layers=2, num_temporal_layers=2)
+        m.check_inputs()
+        assert torch.isfinite(got).all(), name
+        assert nerr(got, want) < BF16_TOL and nerr(got, padded) < 5e-3, (name, nerr(got, want), nerr(got, padded))

@@ -295,7 +295,7 @@ def test_oracle_ref_is_the_unmodified_reference_and_agrees_with_the_port():
         import pytest
         pytest.skip("no /root/reference and no earlier oracle/_ref build on this machine")
     models, configs = ref_loader.load()
-    assert "_ref" in models.__file__ and models.__file__.endswith(".pyc")
+    assert "oracle/_ref/stlt_reference.bin" in models.__file__
     cfg = stlt_b200.StltModelConfig(num_classes=174, unique_categories=4)
     torch.manual_seed(0)
     sd = random_state_dict(stlt_b200.Stlt(cfg).state_dict(), seed=11)
