@@ -38,8 +38,11 @@ local = {k: v[lo:hi].cuda() for k, v in full.items()}
 model = fresh()
 stepper = FusedTrainStep(model, lr=1e-3, clip_val=5.0)
 start = stepper.flat_params.clone()
-for _ in range(3):
+grads_step1 = None
+for it in range(3):
     loss = stepper.step(local)
+    if it == 0:
+        grads_step1 = stepper.flat_grads.clone()  # all-reduced: the mean gradient over the global batch
 torch.cuda.synchronize()
 flat = stepper.flat_params.clone()
 # every rank holds the same parameters after the all-reduce
@@ -52,15 +55,25 @@ if rank == 0:
 dist.barrier()
 if rank == 0:
     whole = {k: v.cuda() for k, v in full.items()}
-    for _ in range(3):
+    ref_grads = None
+    for it in range(3):
         ref.step(whole)
+        if it == 0:
+            ref_grads = ref.flat_grads.clone()
     torch.cuda.synchronize()
+    # (1) the quantity the all-reduce produces: the gradient of step 1 (identical parameters on both sides)
+    ga, gb = grads_step1.double(), ref_grads.double()
+    grel = float((ga - gb).norm() / gb.norm())
+    print(f"DP_VS_SINGLE gradient rel={grel:.3e}")
+    assert grel < 1e-3, grel  # measured 5.2e-4 on 2 x B200 (profiles/r2_dp_two_gpu.log)
     a, b = (flat - start).double(), (ref.flat_params - start).double()   # the accumulated updates
     rel = float((a - b).norm() / b.norm())
     cos = float((a * b).sum() / (a.norm() * b.norm()))
     print(f"DP_VS_SINGLE update rel={rel:.3e} cos={cos:.6f}")
-    # not bit-equal: the per-tile bf16 gradient sums are split differently (2 x 32 videos vs 64); measured 3.1e-4
-    assert rel < 1e-3 and cos > 0.9999, (rel, cos)
+    # (2) the parameters after 3 clipped AdamW steps. Not bit-equal: the per-tile bf16 gradient sums are split
+    # differently (2 x 32 videos vs 64), and AdamW's first steps are sign-like (update ~ lr * g / |g|), which turns
+    # rounding noise on near-zero gradient entries into full-size update differences: rel = sqrt(2 (1 - cos)).
+    assert rel < 3e-2 and cos > 0.9998, (rel, cos)
     print("DP_OK")
 dist.barrier()
 dist.destroy_process_group()
