@@ -277,7 +277,7 @@ frame_embed_bwd_kernel(const float* __restrict__ d_a, const float* __restrict__ 
     const int r = i / kHidden, c = i - r * kHidden;
     if (r < L) {
       if (d_pos != nullptr) atomicAdd(d_pos + static_cast<long long>(r) * kHidden + c, v);
-    } else if (d_ft != nullptr) {
+    } else if (d_ft != nullptr && r != L) {  // row 0 is nn.Embedding's padding_idx (models.py:91): its gradient stays zero
       atomicAdd(d_ft + static_cast<long long>(r - L) * kHidden + c, v);
     }
   }
@@ -407,7 +407,7 @@ embed_param_grad_kernel(const float* __restrict__ d_pre, const long long* __rest
   }
   const int c = 4 * t;
   if (d_cat != nullptr)
-    for (int u = 0; u < unique_categories; ++u) {
+    for (int u = 1; u < unique_categories; ++u) {  // row 0 is nn.Embedding's padding_idx (models.py:19-23): no gradient
       const float4 v = *reinterpret_cast<const float4*>(cat_acc + u * kHidden + c);
       if (v.x != 0.f) atomicAdd(d_cat + u * kHidden + c + 0, v.x);
       if (v.y != 0.f) atomicAdd(d_cat + u * kHidden + c + 1, v.y);

@@ -45,7 +45,9 @@ class _Norm(nn.Module):
 
 
 class _Table(nn.Module):
-    """Embedding table; ``padding_idx`` only affects initialisation (row zeroed), as in nn.Embedding."""
+    """Embedding table. ``padding_idx`` zeroes that row at initialisation and, as in nn.Embedding, the row never
+    receives a gradient (the backward kernels skip row 0 of the category and frame-type tables); a loaded
+    checkpoint may hold anything there and the forward does a plain gather."""
 
     def __init__(self, rows: int, size: int, padding_idx: Optional[int] = None):
         super().__init__()
@@ -177,6 +179,17 @@ class Stlt(nn.Module):
 
     ``precision``: "fp32" (default; 3-term bf16 split on tcgen05, logits within 1e-4 of the fp32
     reference) or "bf16" (bf16 GEMM operands, fp32 accumulate / residual / LayerNorm / softmax).
+
+    Deviations from the reference module a caller should know (everything else is drop-in):
+      * ``precision`` applies to inference. A training step (train mode with grad enabled) ALWAYS runs in bf16 mixed
+        precision (bf16 GEMM operands, fp32 master weights / gradients), whatever ``precision`` says.
+      * In eval mode the logits carry no ``grad_fn`` even with grad enabled (the reference is differentiable in eval
+        mode); a warning is issued once. Call ``model.train(True)`` (with ``hidden_dropout_prob=0`` for deterministic
+        behaviour) to differentiate through the model.
+      * ``batch["src_key_padding_mask_boxes"]`` / ``["src_key_padding_mask_frames"]`` are not read: the masks are
+        re-derived as ``categories == 0`` / ``frame_types == 0``, which is what the reference collater produces
+        (datasets.py:274-286). ``verify_masks(batch)`` raises if a caller-supplied mask differs.
+      * Parameter writes that bypass PyTorch's version counters need ``mark_weights_dirty()``.
     """
 
     # class-level defaults: StltBackbone builds its runner without calling __init__
@@ -374,6 +387,13 @@ class Stlt(nn.Module):
         # The autograd / mixed-precision training path is taken in train mode only. In eval mode the logits come
         # from the inference path in the configured precision and carry no grad_fn, with or without torch.no_grad().
         needs_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not self.training and torch.is_grad_enabled() and not Stlt._warned_eval_grad and \
+                any(p.requires_grad for p in self.parameters()):
+            Stlt._warned_eval_grad = True
+            import warnings
+            warnings.warn("stlt_b200.Stlt in eval mode returns logits without a grad_fn even though grad is enabled "
+                          "(the reference is differentiable in eval mode): wrap inference in torch.no_grad(), or call "
+                          "model.train(True) to take the differentiable training path", stacklevel=3)
         if needs_grad or dropout_p > 0.0:
             # training step (src/train.py:125-127): logits carry a grad_fn whose backward is
             # stlt_backward; the reference's own criterion / clip_grad_norm_ / AdamW then work as is
@@ -564,6 +584,17 @@ class Stlt(nn.Module):
 
         run.graph, run.static_inputs = graph, static
         return run
+
+    _warned_eval_grad = False
+
+    @staticmethod
+    def verify_masks(batch: Dict[str, torch.Tensor]) -> None:
+        """Raises if the batch carries padding masks that differ from the ones this module derives
+        (``categories == 0``, ``frame_types == 0`` — the reference collater's, datasets.py:274-286). Synchronises."""
+        for key, src in (("src_key_padding_mask_boxes", "categories"), ("src_key_padding_mask_frames", "frame_types")):
+            if key in batch and not torch.equal(batch[key].to(torch.bool), batch[src] == 0):
+                raise ValueError(f"batch['{key}'] differs from batch['{src}'] == 0: custom padding masks are not "
+                                 f"supported by stlt_b200.Stlt (it derives the masks itself)")
 
     def check_inputs(self) -> None:
         """Synchronises and raises if the last forward saw an out-of-range index (debug aid)."""

@@ -522,3 +522,26 @@ def test_pad_skipping_layout_on_ragged_and_degenerate_batches(layout):
         m.check_inputs()
         assert torch.isfinite(got).all(), name
         assert nerr(got, want) < BF16_TOL and nerr(got, padded) < 5e-3, (name, nerr(got, want), nerr(got, padded))
+
+
+def test_bench_batch_parity_256_videos_both_precisions_identical_top1():
+    """The batch bench.py times (BASELINE configs[1]: dense Something-Else layouts, batch 4096, weights seed 0, data seed
+    100): logits of its first 256 videos, taken from forwards of the WHOLE batch on the default path (LayerNorms and
+    attention in the GEMM epilogues, pad-skipping layout), against the reference's CPU forward (oracle/_ref when built,
+    else the oracle port). fp32 <= 1e-4, bf16 <= 2e-2, identical arg-max on all 256 in both precisions."""
+    import bench
+    cfg = StltModelConfig(num_classes=174, unique_categories=4)
+    torch.manual_seed(0)
+    model = Stlt(cfg, precision="bf16")
+    sd = random_state_dict(model.state_dict(), seed=0)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    model.train(False)
+    data = make_batch(4096, "something", ragged=False, seed=100)
+    host = {k: data[k] for k in ("categories", "boxes", "frame_types", "lengths")}
+    dev = to_cuda(host)
+    stamp = bench.parity_stamp(model, host, dev, bench.CpuReference("something", sd), torch)
+    print(stamp)
+    assert stamp["videos"] == 256 and stamp["ok"]
+    assert stamp["fp32"] < FP32_TOL and stamp["bf16"] < BF16_TOL
+    assert stamp["fp32_top1_agree"] == 256 and stamp["bf16_top1_agree"] == 256

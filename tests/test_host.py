@@ -307,3 +307,32 @@ def test_oracle_ref_is_the_unmodified_reference_and_agrees_with_the_port():
         want = ref(batch)["stlt"]
         got = stlt_oracle.stlt_forward(sd, batch)
     assert float((got - want).abs().max() / want.abs().max()) < 2e-5
+
+
+def test_verify_masks_accepts_collater_masks_and_rejects_custom_ones():
+    import pytest
+    import torch
+    import stlt_b200
+    from stlt_b200.synthetic import make_batch
+    batch = make_batch(5, "something", ragged=True, seed=3)
+    stlt_b200.Stlt.verify_masks(batch)  # the collater's masks: categories == 0, frame_types == 0
+    bad = dict(batch)
+    bad["src_key_padding_mask_boxes"] = batch["src_key_padding_mask_boxes"].clone()
+    bad["src_key_padding_mask_boxes"][0, 0, 0] = True
+    with pytest.raises(ValueError, match="custom padding masks"):
+        stlt_b200.Stlt.verify_masks(bad)
+
+
+def test_config_table_matches_reference_defaults():
+    """The table-driven StltModelConfig carries the reference's field names and defaults (configs.py:92-111)."""
+    import pytest
+    import stlt_b200
+    from oracle import build_ref, ref_loader
+    cfg = stlt_b200.StltModelConfig(num_classes=174, unique_categories=4, some_future_kwarg=1)
+    with pytest.raises(AssertionError):
+        stlt_b200.StltModelConfig(unique_categories=4)
+    if build_ref.build():
+        _, configs = ref_loader.load()
+        ref = configs.StltModelConfig(num_classes=174, unique_categories=4)
+        for name in cfg.FIELDS:
+            assert getattr(ref, name) == getattr(cfg, name), name
