@@ -546,24 +546,29 @@ def run_inference(args, rank, local_rank, world, torch, dist, layout=None, batch
             # A/B of the epilogue fusions and of the pad-skipping layout on the same GPU: graph-replayed passes of the
             # same K steps, the variants interleaved twice (the parts drift by several percent over a run under their
             # power cap, so back-to-back blocks of one variant are not comparable); best of the two rounds
-            variants = (("default", (True, True, True)), ("padded_grid", (True, True, False)),
-                        ("attention_unfused", (True, False, False)), ("layernorm_and_attention_unfused", (False, False, False)))
+            variants = (("default", (True, True, True, False)), ("two_bf16_plane_residual_stream", (True, True, True, True)),
+                        ("padded_grid", (True, True, False, False)), ("attention_unfused", (True, False, False, False)),
+                        ("layernorm_and_attention_unfused", (False, False, False, False)))
             best = {}
             model.enable_cuda_graphs(use_graphs)
             for _ in range(2):
-                for name, (ln, at, cp) in variants:
+                for name, (ln, at, cp, hl) in variants:
                     model.set_fused_layer_norm(ln)
                     model.set_fused_attention(at)
                     model.set_compaction(cp)
+                    model.set_hilo_residual(hl)
                     u_ms, _, _ = timed(fwd, steps, 2, world, torch, dist)
                     best[name] = min(best.get(name, u_ms), u_ms)
             model.set_fused_layer_norm(True)
             model.set_fused_attention(True)
             model.set_compaction(True)
+            model.set_hilo_residual(False)
             ab = {name: {"value": videos / (u_ms * 1e-3), "unit": "videos/s", "ms_per_step": u_ms / steps}
                   for name, u_ms in best.items()}
-            ab["note"] = ("graph-replayed, variants interleaved, best of 2 rounds. padded_grid = pad-skipping row layout off; "
-                          "the other two additionally un-fuse the attention / the LayerNorms from the GEMM epilogues")
+            ab["note"] = ("graph-replayed, variants interleaved, best of 2 rounds. two_bf16_plane_residual_stream: an optional "
+                          "switch that is off by default. From padded_grid on, each variant switches one more default-on thing "
+                          "off: the pad-skipping row layout, the attention in the in-projection epilogue, the LayerNorms in the "
+                          "GEMM epilogues (= the round-1 kernels without LayerNorm fusion)")
             res["fusion_ab"] = ab
             # the same model on a RAGGED batch of the same size (lengths ~ U{2..17}, 0..4 boxes per frame: the parity
             # batch of SURVEY.md 8(d)): what the pad-skipping layout buys on data that is not dense

@@ -215,6 +215,13 @@ int stlt_set_fused_ln(void* handle, int32_t enable);
  * HBM. 0 restores the separate in-projection GEMM + attention kernel (cross-check for the tests). */
 int stlt_set_fused_attention(void* handle, int32_t enable);
 
+/* Optional (default OFF): keep the (pre-norm) residual stream of the two encoder stacks as two bf16 planes,
+ * z = hi + lo with hi = bf16(z) — which is also the A operand of the next projection — and lo = bf16(z - hi)
+ * (~2^-18 relative, far below the bf16 operand rounding): the residual epilogues then move 8 instead of 10 bytes
+ * per element, but straight from registers in 16-byte pieces, which measured 9 % slower per step than the
+ * TMA-staged fp32 stream + bf16 copy of the default path. Kept as a tested switch for that comparison. */
+int stlt_set_hilo_residual(void* handle, int32_t enable);
+
 /* ... and runs the spatial stack on a pad-skipping row layout (default on): frames at or after lengths[b] and
  * the padded slots of frames whose slots 1.. are all padding (the "extract" frame, datasets.py:97-113) can never
  * reach the logits (key-padding / causal masks, models.py:66-71,79,142-150,192) and are not computed. Which rows
@@ -349,6 +356,12 @@ int stlt_op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void*
                        int32_t n, int32_t k, const float* bias_or_null, void* out, void* out_bf16_or_null,
                        int32_t gelu, const float* stats_in_or_null, const float* vec_a, const float* vec_b,
                        float* stats_out_or_null, float eps, int32_t prev_norm);
+/* The same RESID epilogue on a residual stream stored as two bf16 planes (stlt_set_hilo_residual): z = z_hi + z_lo
+ * (bf16 [m_rows][768] each) is updated in place to (prev_norm ? LN(z) : z) + a W^T + bias, re-split into the planes. */
+int stlt_op_gemm_resid_hilo(void* handle, void* stream, const void* a, int32_t m_rows, const void* w, int32_t k,
+                            const float* bias, void* z_hi, void* z_lo, const float* stats_in_or_null,
+                            const float* gamma_or_null, const float* beta_or_null, float* stats_out, float eps,
+                            int32_t prev_norm);
 /* gamma-folded bf16 copy of a projection matrix w f32 [n][k] for the NORM_A epilogue: w_folded[n][k] =
  * bf16(w * gamma), s_out[n] = sum_k w_folded[n][k], c_out[n] = (w beta)[n] + bias[n]; gamma = beta = NULL
  * folds the identity. head_major != 0 (n = 2304 only) writes the rows of a packed in-projection in the order

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(256)
 gather_frames_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __restrict__ src_att,
                      const int* __restrict__ frame_row, long long frames, float* __restrict__ dst_x,
                      __nv_bfloat16* __restrict__ dst_att, const float2* __restrict__ src_stats,
-                     float2* __restrict__ dst_stats) {
+                     float2* __restrict__ dst_stats, const __nv_bfloat16* __restrict__ src_hi,
+                     const __nv_bfloat16* __restrict__ src_lo) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -170,7 +171,7 @@ gather_frames_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __res
     }
     const long long src = fr & ~kSingleFrameFlag;
     if (src_stats != nullptr && lane < kStatSlots) dst_stats[r * kStatSlots + lane] = src_stats[src * kStatSlots + lane];
-    const RowRegs x = load_row(src_x, src, lane);
+    const RowRegs x = src_hi != nullptr ? load_row_hilo(src_hi, src_lo, src, lane) : load_row(src_x, src, lane);
 #pragma unroll
     for (int k = 0; k < kVec; ++k) px[lane + 32 * k] = x.v[k];
     const uint4* sa = reinterpret_cast<const uint4*>(src_att + src * kHidden);
@@ -210,10 +211,11 @@ cudaError_t launch_compact_plan(const long long* categories, const long long* le
 
 cudaError_t launch_gather_frames(const float* src_x, const __nv_bfloat16* src_att, const int* frame_row,
                                  long long frames, float* dst_x, __nv_bfloat16* dst_att, const float2* src_stats,
-                                 float2* dst_stats, cudaStream_t stream) {
+                                 float2* dst_stats, cudaStream_t stream, const __nv_bfloat16* src_hi,
+                                 const __nv_bfloat16* src_lo) {
   if (frames == 0) return cudaSuccess;
   gather_frames_kernel<<<row_grid(frames, 8), 256, 0, stream>>>(src_x, src_att, frame_row, frames, dst_x, dst_att,
-                                                                src_stats, dst_stats);
+                                                                src_stats, dst_stats, src_hi, src_lo);
   return cudaGetLastError();
 }
 

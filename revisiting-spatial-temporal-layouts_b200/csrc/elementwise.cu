@@ -516,7 +516,8 @@ gather_rows_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __restr
                    const long long* __restrict__ lengths, int L, long long rows,
                    float* __restrict__ dst_x, __nv_bfloat16* __restrict__ dst_att,
                    long long dst_plane_rows, int* __restrict__ err_flag,
-                   const float2* __restrict__ src_stats, float2* __restrict__ dst_stats) {
+                   const float2* __restrict__ src_stats, float2* __restrict__ dst_stats,
+                   const __nv_bfloat16* __restrict__ src_hi, const __nv_bfloat16* __restrict__ src_lo) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -534,7 +535,7 @@ gather_rows_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __restr
     }
     if (src_stats != nullptr && lane < kStatSlots)  // fused-LN path: the row's partial statistics travel along
       dst_stats[r * kStatSlots + lane] = src_stats[src * kStatSlots + lane];
-    const RowRegs x = load_row(src_x, src, lane);
+    const RowRegs x = src_hi != nullptr ? load_row_hilo(src_hi, src_lo, src, lane) : load_row(src_x, src, lane);
     float4* px = reinterpret_cast<float4*>(dst_x + r * kHidden);
 #pragma unroll
     for (int k = 0; k < kVec; ++k) px[lane + 32 * k] = x.v[k];
@@ -710,11 +711,13 @@ cudaError_t launch_gather_rows(const float* src_x, const __nv_bfloat16* src_att,
                                long long src_plane_rows, int stride, const long long* lengths, int L,
                                long long rows, float* dst_x, __nv_bfloat16* dst_att,
                                long long dst_plane_rows, int* err_flag, cudaStream_t stream,
-                               const float2* src_stats, float2* dst_stats) {
+                               const float2* src_stats, float2* dst_stats, const __nv_bfloat16* src_hi,
+                               const __nv_bfloat16* src_lo) {
   if (rows == 0) return cudaSuccess;
   gather_rows_kernel<<<row_grid(rows, 8), 256, 0, stream>>>(src_x, src_att, planes, src_plane_rows,
                                                             stride, lengths, L, rows, dst_x, dst_att,
-                                                            dst_plane_rows, err_flag, src_stats, dst_stats);
+                                                            dst_plane_rows, err_flag, src_stats, dst_stats, src_hi,
+                                                            src_lo);
   return cudaGetLastError();
 }
 

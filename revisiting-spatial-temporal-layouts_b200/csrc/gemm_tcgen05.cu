@@ -67,7 +67,7 @@ struct Cfg {
       kOut == GEMM_OUT_BF16_SPLIT || kOut == GEMM_OUT_BF16_DUAL || kOut == GEMM_OUT_F32_BF16_DIRECT;
   // fused-LN residual epilogue: outgoing fp32 tile, incoming z tile (+ outgoing bf16 tile unless DIRECT)
   static constexpr int kStages = kOut == GEMM_OUT_F32_BF16 ? 4 : (kTwoPlanes ? 5 : 6);
-  static constexpr int kBufsPerWarp = kOut == GEMM_OUT_F32_BF16 ? 3 : (kTwoPlanes ? 2 : 1);
+  static constexpr int kBufsPerWarp = kOut == GEMM_OUT_F32_BF16 ? 3 : (kTwoPlanes ? 2 : (kOut == GEMM_OUT_HILO ? 0 : 1));
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kEpiWarps * kBufsPerWarp * kEpiBufBytes + 320 /*barriers*/;
 };
@@ -76,6 +76,7 @@ static_assert(Cfg<GEMM_OUT_BF16_SPLIT>::kSmemBytes <= 232448, "smem budget");
 static_assert(Cfg<GEMM_OUT_BF16_DUAL>::kSmemBytes <= 232448, "smem budget");
 static_assert(Cfg<GEMM_OUT_F32_BF16>::kSmemBytes <= 232448, "smem budget");
 static_assert(Cfg<GEMM_OUT_F32_BF16_DIRECT>::kSmemBytes <= 232448, "smem budget");
+static_assert(Cfg<GEMM_OUT_HILO>::kSmemBytes <= 232448, "smem budget");
 
 constexpr int kMnChunkBytes = 64 * BK * 2;  // one MN-major TMA box: 64 reduction rows x 128 B
 
@@ -148,7 +149,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 "fused-LN epilogues: bf16 forward only");
   static_assert(kEpi != GEMM_EPI_ACT_BWD || (kLayout == GEMM_NN && kOut == GEMM_OUT_BF16 && kGelu == 0),
                 "ACT_BWD: bf16 data gradient");
-  constexpr bool kResidOut = kOut == GEMM_OUT_F32_BF16 || kOut == GEMM_OUT_F32_BF16_DIRECT;
+  constexpr bool kResidOut = kOut == GEMM_OUT_F32_BF16 || kOut == GEMM_OUT_F32_BF16_DIRECT || kOut == GEMM_OUT_HILO;
+  constexpr bool kHiLo = kOut == GEMM_OUT_HILO;
   static_assert((kEpi == GEMM_EPI_RESID) == kResidOut, "RESID epilogue <-> fp32 + bf16 output");
   constexpr int kStages = Cfg<kOut>::kStages;
   constexpr int kBufsPerWarp = Cfg<kOut>::kBufsPerWarp;
@@ -333,13 +335,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       }
       const float4* va4 = reinterpret_cast<const float4*>(ep.vec_a + col0);
       const float4* vb4 = reinterpret_cast<const float4*>(ep.vec_b + col0);
-      if constexpr (kEpi == GEMM_EPI_RESID) {
+      if constexpr (kEpi == GEMM_EPI_RESID && !kHiLo) {
         // the residual input tile (32 rows x 32 fp32 columns) arrives by TMA, one chunk ahead of its use;
         // z is updated in place, so the output tensor map also describes the input
         if (store_ok && lane == 0) {
           mbar_expect_tx(&bars->zin[ew], kEpiBufBytes);
           tma_load_2d(&tm_out, &bars->zin[ew], zbuf, col0, row0);
         }
+      }
+      // HILO: this thread's 32 residual values of a chunk = 64 B of its row in each of the two bf16 planes
+      uint4 zh[kHiLo ? 4 : 1], zl[kHiLo ? 4 : 1];
+      __nv_bfloat16* hi_row = nullptr;
+      __nv_bfloat16* lo_row = nullptr;
+      if constexpr (kHiLo) {
+        const size_t off = static_cast<size_t>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0;
+        hi_row = ep.zb_out + off;
+        lo_row = ep.z_lo + off;
       }
       // ACT_BWD: this thread's 32 activation-gradient factors of a chunk (64 B of its row), fetched one chunk ahead
       uint4 ubuf[kEpi == GEMM_EPI_ACT_BWD ? 2 : 1][4];
@@ -363,6 +374,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t(&v)[32] = vbuf[c & 1];
+        if constexpr (kHiLo) {  // issued before the TMEM wait: in flight while the bias is added
+          if (store_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              zh[j] = *reinterpret_cast<const uint4*>(hi_row + c * 32 + 8 * j);
+              zl[j] = *reinterpret_cast<const uint4*>(lo_row + c * 32 + 8 * j);
+            }
+          }
+        }
         tmem_ld_wait_regs(v);
         if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
         if constexpr (kEpi == GEMM_EPI_ACT_BWD) {
@@ -400,9 +420,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           // z_new = x + branch, x = LN(z_prev) (or z_prev itself for the first layer of a stack); the row's
           // partial (sum, sum of squares) over these 32 columns feeds the next LayerNorm
           if (store_ok) {
+            float4 zrow[8];
+            if constexpr (kHiLo) {
+              const uint32_t* hw = reinterpret_cast<const uint32_t*>(zh);
+              const uint32_t* lw = reinterpret_cast<const uint32_t*>(zl);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[2 * j]));
+                const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[2 * j + 1]));
+                const float2 l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[2 * j]));
+                const float2 l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[2 * j + 1]));
+                zrow[j] = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+              }
+            } else {
             mbar_wait(&bars->zin[ew], zphase);
             zphase ^= 1u;
-            float4 zrow[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t addr = smem_u32(zbuf) + lane * 128 + ((static_cast<uint32_t>(j) ^ sw) << 4);
@@ -415,6 +447,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             if (c + 1 < 4 && lane == 0) {
               mbar_expect_tx(&bars->zin[ew], kEpiBufBytes);
               tma_load_2d(&tm_out, &bars->zin[ew], zbuf, col0 + (c + 1) * 32, row0);
+            }
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -491,7 +524,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
 
-        if (kOut == GEMM_OUT_F32 || kResidOut) {
+        if constexpr (kHiLo) {
+          // the new residual value as two bf16 planes, 64 contiguous bytes per thread and plane, from registers
+          if (store_ok) {
+            uint4* dh = reinterpret_cast<uint4*>(hi_row + c * 32);
+            uint4* dl = reinterpret_cast<uint4*>(lo_row + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dh[j] = make_uint4(pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                 pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              dl[j] = make_uint4(pack_bf16x2(bf16_residual(f[8 * j + 0]), bf16_residual(f[8 * j + 1])),
+                                 pack_bf16x2(bf16_residual(f[8 * j + 2]), bf16_residual(f[8 * j + 3])),
+                                 pack_bf16x2(bf16_residual(f[8 * j + 4]), bf16_residual(f[8 * j + 5])),
+                                 pack_bf16x2(bf16_residual(f[8 * j + 6]), bf16_residual(f[8 * j + 7])));
+            }
+          }
+        } else if (kOut == GEMM_OUT_F32 || kResidOut) {
           // 32 fp32 columns = 128 B per row -> one TMA store per chunk
           if (lane == 0) tma_store_wait_read0();  // previous store has finished reading ebuf
           __syncwarp();
@@ -744,6 +792,8 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
       return launch_one<1, GEMM_OUT_F32_BF16, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
     if (g.terms == 1 && g.out_kind == GEMM_OUT_F32_BF16_DIRECT && g.gelu == 0 && g.n == kHidden)
       return launch_one<1, GEMM_OUT_F32_BF16_DIRECT, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
+    if (g.terms == 1 && g.out_kind == GEMM_OUT_HILO && g.gelu == 0 && g.n == kHidden && g.epi.zb_out && g.epi.z_lo)
+      return launch_one<1, GEMM_OUT_HILO, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
     return cudaErrorInvalidValue;
   }
   if (g.epilogue != GEMM_EPI_PLAIN) return cudaErrorInvalidValue;

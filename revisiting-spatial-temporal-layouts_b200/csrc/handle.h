@@ -100,6 +100,10 @@ struct Handle {
   bool fused_ln = true;     // bf16 mode: LayerNorm folded into the GEMM epilogues (stlt_set_fused_ln)
   int fused_attn_max_t = 32;  // longest sequence that takes the fused kernel (STLT_FUSED_ATTENTION_MAX_T, experiments)
   int qkv_attn_debug = 0;   // QkvAttnArgs::debug (STLT_QKV_ATTN_DEBUG environment variable, read at stlt_create)
+  // ... with the residual stream of the full phases as two bf16 planes (stlt_set_hilo_residual). Off by default: the
+  // register-direct epilogue that reads / writes the planes moves 20 % fewer bytes but in 16-byte pieces per thread and
+  // row, and measured 9 % SLOWER per step than the TMA-staged fp32 tiles (DESIGN.md "Measured and rejected")
+  bool hilo = false;
   bool compaction = true;   // ... on the pad-skipping row layout of the spatial phase (stlt_set_compaction)
   bool fused_attn = true;   // ... and the attention into the in-projection's epilogue (stlt_set_fused_attention)
   bool bf16_branch = true;  // bf16 mode: out-projection / linear2 outputs travel as bf16 (see run_tail_part)
@@ -245,7 +249,11 @@ inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const vo
   if (rc) return rc;
   rc = make_tm(h, &g.tm_b, w, 1, n, k, 64, 128);
   if (rc) return rc;
-  if (epilogue == GEMM_EPI_RESID) {
+  if (epilogue == GEMM_EPI_RESID && epi.z_lo != nullptr) {
+    g.tm_out = g.tm_a;  // unused: the residual stream is read and written as two bf16 planes from registers
+    g.tm_out2 = g.tm_a;
+    g.out_kind = GEMM_OUT_HILO;
+  } else if (epilogue == GEMM_EPI_RESID) {
     rc = make_tm(h, &g.tm_out, out, 0, m_rows, n, 32, 32);
     if (rc) return rc;
     rc = make_tm(h, &g.tm_out2, out_bf16, 1, m_rows, n, 64, 32);

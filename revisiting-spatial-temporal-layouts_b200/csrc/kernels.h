@@ -19,6 +19,10 @@ enum GemmOutKind : int {
   // same outputs, the bf16 copy written straight from registers (ep.zb_out): one staging tile less per warp buys
   // a fifth pipeline stage, which pays for long reductions (linear2, K = 3072)
   GEMM_OUT_F32_BF16_DIRECT = 5,
+  // fused-LayerNorm residual epilogue on a residual stream stored ONCE as two bf16 planes, z = hi + lo (hi = bf16(z) is
+  // also the next GEMM's A operand, lo = bf16(z - hi); ~2^-18 relative): the epilogue reads and writes 2 x 2 bytes per
+  // element instead of 4 + 4 + 2 (fp32 in, fp32 out, bf16 copy), straight from / to registers (no staging tiles)
+  GEMM_OUT_HILO = 6,
 };
 
 // LayerNorm fused into the projection GEMMs (bf16 inference path, see DESIGN.md "fused LayerNorm"): the
@@ -53,6 +57,7 @@ struct EpiArgs {
   float* colsum_out;            // ACT_BWD: [N] fp32, accumulated with atomics (may be null)
   int valid_rows;               // ACT_BWD: rows >= valid_rows are tile padding and stay out of the column sums
   const int* m_tiles_dyn;       // device int (may be null): live 128-row tiles of A / out when the row count is dynamic
+  __nv_bfloat16* z_lo;          // GEMM_OUT_HILO: lo plane of the residual stream [M, 768], updated in place (hi = zb_out)
 };
 
 enum GemmLayout : int {
@@ -106,7 +111,8 @@ cudaError_t launch_compact_plan(const long long* categories, const long long* le
                                 int* frame_row, int* hdr, void* scratch, int* err_flag, cudaStream_t stream);
 cudaError_t launch_gather_frames(const float* src_x, const __nv_bfloat16* src_att, const int* frame_row,
                                  long long frames, float* dst_x, __nv_bfloat16* dst_att, const float2* src_stats,
-                                 float2* dst_stats, cudaStream_t stream);
+                                 float2* dst_stats, cudaStream_t stream, const __nv_bfloat16* src_hi = nullptr,
+                                 const __nv_bfloat16* src_lo = nullptr);  // src_hi / src_lo: the source stream as bf16 planes
 
 struct QkvAttnArgs {
   const float* vec_s;         // [2304] head-major: row sums of the folded weights (read when prev_norm)
@@ -228,7 +234,8 @@ cudaError_t launch_gather_rows(const float* src_x, const __nv_bfloat16* src_att,
                                long long src_plane_rows, int stride, const long long* lengths, int L,
                                long long rows, float* dst_x, __nv_bfloat16* dst_att,
                                long long dst_plane_rows, int* err_flag, cudaStream_t stream,
-                               const float2* src_stats = nullptr, float2* dst_stats = nullptr);
+                               const float2* src_stats = nullptr, float2* dst_stats = nullptr,
+                               const __nv_bfloat16* src_hi = nullptr, const __nv_bfloat16* src_lo = nullptr);
 
 // K3: masked multi-head attention over short sequences held in shared memory.
 //   qkv: [tokens, 2304] fp32 (fp32-parity mode; bf16 input is handled by launch_attention_mma); key j of a sequence is masked when mask_src[token_j] == 0,

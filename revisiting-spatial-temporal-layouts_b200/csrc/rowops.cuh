@@ -25,6 +25,23 @@ __device__ __forceinline__ RowRegs load_row(const float* base, long long row, in
   return r;
 }
 
+// Row of a residual stream stored as two bf16 planes (z = hi + lo, see GEMM_OUT_HILO).
+__device__ __forceinline__ RowRegs load_row_hilo(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long row, int lane) {
+  RowRegs r;
+  const uint2* ph = reinterpret_cast<const uint2*>(hi + row * kHidden);
+  const uint2* pl = reinterpret_cast<const uint2*>(lo + row * kHidden);
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    const uint2 h = __ldg(ph + lane + 32 * k), l = __ldg(pl + lane + 32 * k);
+    const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x));
+    const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
+    const float2 l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.x));
+    const float2 l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.y));
+    r.v[k] = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+  }
+  return r;
+}
+
 // LayerNorm over the 768 features held by one warp (biased variance, two-pass in registers).
 __device__ __forceinline__ void layer_norm_row(RowRegs& r, const float* __restrict__ gamma,
                                                const float* __restrict__ beta, float eps, int lane) {

@@ -116,7 +116,7 @@ size_t plan_bufset(BufSet* b, size_t off, long long rows, int precision, bool wi
   b->m_pad = static_cast<long long>(m);
   b->x = off;    off += align1k(m * kHidden * 4);
   b->y = off;    off += align1k(m * kHidden * 4);
-  b->xb = off;   off += align1k(m * kHidden * 2 * planes);
+  b->xb = off;   off += align1k(m * kHidden * 2 * 2);  // bf16 mode: second plane = lo plane of the hi/lo residual stream
   b->att = off;  off += align1k(m * kHidden * 2 * planes);
   b->qkv = off;
   if (with_qkv) off += align1k(m * kQkv * (precision == STLT_PRECISION_FP32 ? 4 : 2));
@@ -165,6 +165,7 @@ struct Phase {
   float* x;              // fp32 residual stream [m, 768]
   float* y;              // fp32 GEMM output [m, 768]
   __nv_bfloat16* xb;     // bf16 plane(s) of x
+  __nv_bfloat16* xlo = nullptr;  // hi/lo residual stream (GEMM_OUT_HILO): lo plane, xb is the hi plane; null = fp32 x
   __nv_bfloat16* att;    // bf16 plane(s) of the attention context
   void* qkv;             // bf16 [P, m, 2304]
   __nv_bfloat16* hid;    // bf16 plane(s) of the FFN hidden [m, 3072]
@@ -285,6 +286,7 @@ int fused_tail_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, cons
                     float2* s1, float2* s2, const int* tiles_dyn = nullptr) {
   const float eps = h->dims.encoder_norm_eps;
   EpiArgs e1{in.stats, in.gamma, in.beta, ph.x, s1, ph.xb, eps, in.gamma != nullptr ? 1 : 0};
+  e1.z_lo = ph.xlo;
   int rc = run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.att, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.x, ph.xb, 0, e1,
                           tiles_dyn);
   if (rc) return rc;
@@ -293,6 +295,7 @@ int fused_tail_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, cons
                       tiles_dyn);
   if (rc) return rc;
   EpiArgs e3{s1, lw.n1_g, lw.n1_b, ph.x, s2, ph.xb, eps, 1};
+  e3.z_lo = ph.xlo;
   return run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.hid, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.x, ph.xb, 0, e3,
                         tiles_dyn);
 }
@@ -323,12 +326,13 @@ int fused_stack(Handle* h, cudaStream_t stream, const std::vector<LayerWeights>&
       float2* sc2 = sc1 + tail.m_pad * kStatSlots;
       {
         ProfileScope prof(h, stream, STLT_PROF_OTHER);
+        const __nv_bfloat16* hi = full.xlo != nullptr ? full.xb : nullptr;
         if (frame_row != nullptr)
           STLT_CUDA(h, launch_gather_frames(full.x, full.att, frame_row, tail.m_valid, tail.x, tail.att, pending.stats,
-                                            sc_in, stream));
+                                            sc_in, stream, hi, full.xlo));
         else
           STLT_CUDA(h, launch_gather_rows(full.x, full.att, 1, full.m_pad, stride, lengths, L, tail.m_valid, tail.x,
-                                          tail.att, tail.m_pad, err_flag, stream, pending.stats, sc_in));
+                                          tail.att, tail.m_pad, err_flag, stream, pending.stats, sc_in, hi, full.xlo));
       }
       h->launches++;
       PendingNorm tail_in{pending.gamma ? sc_in : nullptr, pending.gamma, pending.beta};
@@ -673,7 +677,13 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     float2* st_tm = st_sp + static_cast<size_t>(2 * d.num_spatial_layers) * p.sp.m_pad * kStatSlots;
     float2* st_c_sp = st_tm + static_cast<size_t>(2 * d.num_temporal_layers) * p.tm.m_pad * kStatSlots;  // 3 compaction sites
     float2* st_c_tm = st_c_sp + 3 * p.tm.m_pad * kStatSlots;                                               // 3 more (B rows)
-    ActOut emb{sp.x, sp.xb, 1, sp.m_pad};
+    // the residual stream of the two full phases lives as two bf16 planes (hi = GEMM operand, lo = remainder)
+    Phase sp_f = sp, tm_f = tm;
+    if (h->hilo) {
+      sp_f.xlo = sp.xb + static_cast<size_t>(sp.m_pad) * kHidden;
+      tm_f.xlo = tm.xb + static_cast<size_t>(tm.m_pad) * kHidden;
+    }
+    ActOut emb{h->hilo ? nullptr : sp.x, sp.xb, h->hilo ? 2 : 1, sp.m_pad};
     // Pad-skipping layout of the spatial phase (compact.cu): padding frames and the padded slots of one-token frames
     // are not computed. Needs the attention-fused in-projection (it understands the two row regions).
     const bool compact = h->compaction && h->fused_attn && S <= h->fused_attn_max_t && p.off_plan != 0 &&
@@ -703,12 +713,12 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     }
     h->launches += 2;  // embed_stats_kernel + embed_kernel
     PendingNorm sp_out;
-    int rc = fused_stack(h, stream, h->w.spatial, sp, tm, sp_mask, n_tm, S, false, S, nullptr, 0, st_sp, st_c_sp,
+    int rc = fused_stack(h, stream, h->w.spatial, sp_f, tm, sp_mask, n_tm, S, false, S, nullptr, 0, st_sp, st_c_sp,
                          err_flag, &sp_out, dyn, frame_row);
     if (rc) return rc;
     {
       ProfileScope prof(h, stream, STLT_PROF_OTHER);
-      ActOut fr{tm.x, tm.xb, 1, tm.m_pad};
+      ActOut fr{h->hilo ? nullptr : tm.x, tm.xb, h->hilo ? 2 : 1, tm.m_pad};
       // the spatial stack's LayerNorm-2 is applied on the fly (row statistics recomputed in registers)
       STLT_CUDA(h, launch_frame_embed(tm.x, 1, frame_types, h->w.pos_table, h->w.ft_table, d.num_frame_types,
                                       h->w.fr_g, h->w.fr_b, d.layer_norm_eps, B, L, fr, err_flag, stream,
@@ -716,7 +726,7 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     }
     h->launches++;
     PendingNorm tm_out;
-    rc = fused_stack(h, stream, h->w.temporal, tm, hd, frame_types, B, L, true, 0, lengths, L, st_tm, st_c_tm, err_flag,
+    rc = fused_stack(h, stream, h->w.temporal, tm_f, hd, frame_types, B, L, true, 0, lengths, L, st_tm, st_c_tm, err_flag,
                      &tm_out);
     if (rc) return rc;
     float* h1f = reinterpret_cast<float*>(ws + p.off_head);
@@ -840,6 +850,13 @@ int stlt_set_fused_ln(void* handle, int32_t enable) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
   h->fused_ln = enable != 0;
+  return STLT_OK;
+}
+
+int stlt_set_hilo_residual(void* handle, int32_t enable) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  h->hilo = enable != 0;
   return STLT_OK;
 }
 
@@ -968,6 +985,26 @@ int stlt_op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void*
                           0, e);
   }
   return fail(h, STLT_ERR_INVALID, "epilogue must be 1 (NORM_A) or 2 (RESID)");
+}
+
+int stlt_op_gemm_resid_hilo(void* handle, void* stream, const void* a, int32_t m_rows, const void* w, int32_t k,
+                            const float* bias, void* z_hi, void* z_lo, const float* stats_in, const float* gamma,
+                            const float* beta, float* stats_out, float eps, int32_t prev_norm) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !a || !w || !bias || !z_hi || !z_lo || !stats_out) return fail(h, STLT_ERR_INVALID, "null argument");
+  if (m_rows % 128 || k % 64 || m_rows < 128) return fail(h, STLT_ERR_INVALID, "shape not tile aligned");
+  if (prev_norm && (!stats_in || !gamma || !beta)) return fail(h, STLT_ERR_INVALID, "prev_norm needs stats_in, gamma, beta");
+  EpiArgs e{};
+  e.stats_in = reinterpret_cast<const float2*>(stats_in);
+  e.vec_a = gamma;
+  e.vec_b = beta;
+  e.stats_out = reinterpret_cast<float2*>(stats_out);
+  e.zb_out = static_cast<__nv_bfloat16*>(z_hi);
+  e.z_lo = static_cast<__nv_bfloat16*>(z_lo);
+  e.eps = eps;
+  e.prev_norm = prev_norm != 0 ? 1 : 0;
+  return run_gemm_fused(h, static_cast<cudaStream_t>(stream), GEMM_EPI_RESID, a, m_rows, w, kHidden, k, bias, nullptr,
+                        z_hi, 0, e);
 }
 
 int stlt_op_pack_folded(void* handle, void* stream, const float* w, const float* gamma, const float* beta,

@@ -30,6 +30,7 @@ GEMM_OUT_F32 = 0
 GEMM_OUT_BF16 = 1
 GEMM_OUT_BF16_SPLIT = 2
 GEMM_OUT_BF16_DUAL = 3
+GEMM_OUT_HILO = 6
 GEMM_NT, GEMM_NN, GEMM_TN_RED = 0, 1, 2
 GEMM_EPI_PLAIN, GEMM_EPI_NORM_A, GEMM_EPI_RESID = 0, 1, 2
 
@@ -127,6 +128,7 @@ SIGNATURES = {
     "stlt_set_fused_ln": (c_int32, [c_void_p, c_int32]),
     "stlt_set_fused_attention": (c_int32, [c_void_p, c_int32]),
     "stlt_set_compaction": (c_int32, [c_void_p, c_int32]),
+    "stlt_set_hilo_residual": (c_int32, [c_void_p, c_int32]),
     "stlt_set_profiling": (c_int32, [c_void_p, c_int32]),
     "stlt_get_profile": (c_int32, [c_void_p, POINTER(StltProfile)]),
     "stlt_bind_grads": (c_int32, [c_void_p, POINTER(StltTensor), c_int32]),
@@ -157,6 +159,8 @@ SIGNATURES = {
     "stlt_op_gemm_fused": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_float, c_int32]),
+    "stlt_op_gemm_resid_hilo": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32]),
     "stlt_op_pack_folded": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                       c_void_p, c_void_p, c_void_p, c_int32]),
     "stlt_op_qkv_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,

@@ -199,6 +199,7 @@ class Stlt(nn.Module):
     _fused_ln = True
     _fused_attn = os.environ.get("STLT_FUSED_ATTENTION", "1") != "0"
     _compaction = os.environ.get("STLT_COMPACTION", "1") != "0"
+    _hilo = os.environ.get("STLT_HILO_RESIDUAL", "0") != "0"
 
     def __init__(self, config, precision: str = "fp32", cuda_graphs: bool = False):
         super().__init__()
@@ -287,6 +288,7 @@ class Stlt(nn.Module):
         _lib.check(handle, lib.stlt_set_fused_ln(handle, int(self._fused_ln)))
         _lib.check(handle, lib.stlt_set_fused_attention(handle, int(self._fused_attn)))
         _lib.check(handle, lib.stlt_set_compaction(handle, int(self._compaction)))
+        _lib.check(handle, lib.stlt_set_hilo_residual(handle, int(self._hilo)))
         self._weights_key = None
         self._graphs = None
         self._packed.clear()
@@ -475,7 +477,7 @@ class Stlt(nn.Module):
             self._sync_weights(device, stream)  # eager: re-binds / re-packs when a parameter changed
             ptrs = tuple([k[0] for k in self._weights_key])
             shape_key = (device, B, L, S, scores is not None, self.precision, self._pruning, self._fused_ln,
-                         self._fused_attn, self._compaction)
+                         self._fused_attn, self._compaction, self._hilo)
             if self._graphs is None:
                 self._graphs = {}
             entry = self._graphs.get(shape_key)
@@ -629,6 +631,13 @@ class Stlt(nn.Module):
         self._compaction = bool(enable)
         if self._handle is not None:
             _lib.check(self._handle, _lib.load_library().stlt_set_compaction(self._handle, int(self._compaction)))
+
+    def set_hilo_residual(self, enable: bool) -> None:
+        """bf16 mode: residual stream of the encoder stacks stored as two bf16 planes instead of fp32 + a bf16 copy.
+        Off by default (fewer bytes, but measured slower: see DESIGN.md "Measured and rejected")."""
+        self._hilo = bool(enable)
+        if self._handle is not None:
+            _lib.check(self._handle, _lib.load_library().stlt_set_hilo_residual(self._handle, int(self._hilo)))
 
     def set_profiling(self, enable: bool) -> None:
         """Per-category CUDA-event timing of the kernels launched by forward (bench / profiles)."""

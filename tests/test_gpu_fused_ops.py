@@ -144,6 +144,44 @@ def test_gemm_resid_epilogue(handle, m, k, prev_norm):
     assert nerr(so[:, 1], (ref * ref).sum(-1)) < 1e-5
 
 
+@pytest.mark.parametrize("m,k,prev_norm", [(128, 768, 0), (384, 768, 1), (148 * 128 + 128, 768, 1), (256, 3072, 1)])
+def test_gemm_resid_epilogue_hilo_planes(handle, m, k, prev_norm):
+    """The same residual update on a stream stored as two bf16 planes (z = hi + lo), in place."""
+    lib = L.load_library()
+    g = torch.Generator(device="cuda").manual_seed(7 * m + k + prev_norm)
+    z = torch.randn(m, H, device="cuda", generator=g) * 1.3 - 0.2
+    hi = z.to(torch.bfloat16)
+    lo = (z - hi.float()).to(torch.bfloat16)
+    z_in = hi.double() + lo.double()          # what the kernel reads
+    a = torch.randn(m, k, device="cuda", generator=g).to(torch.bfloat16).contiguous()
+    w = (torch.randn(H, k, device="cuda", generator=g) / math.sqrt(k)).to(torch.bfloat16).contiguous()
+    bias = 0.1 * torch.randn(H, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(H, device="cuda", generator=g)
+    eps = 1e-5
+    stats_in = _row_stats(z_in.float())
+    hi_io, lo_io = hi.clone().contiguous(), lo.clone().contiguous()
+    stats_out = torch.full((m, 6, 2), float("nan"), device="cuda")
+    L.check(handle, lib.stlt_op_gemm_resid_hilo(handle, _stream(), a.data_ptr(), m, w.data_ptr(), k, bias.data_ptr(),
+                                                hi_io.data_ptr(), lo_io.data_ptr(), stats_in.data_ptr(), gamma.data_ptr(),
+                                                beta.data_ptr(), stats_out.data_ptr(), eps, prev_norm))
+    torch.cuda.synchronize()
+    if prev_norm:
+        st = stats_in.double().sum(1)
+        mu = (st[:, 0] / H).unsqueeze(1)
+        var = (st[:, 1] / H).unsqueeze(1) - mu * mu
+        x = (z_in - mu) / torch.sqrt(var + eps) * gamma.double() + beta.double()
+    else:
+        x = z_in
+    ref = x + a.double() @ w.double().T + bias.double()
+    got = hi_io.double() + lo_io.double()
+    assert nerr(got, ref) < 2e-5                      # two bf16 planes carry ~2^-17 relative
+    assert torch.equal(hi_io, got.float().to(torch.bfloat16)) or nerr(hi_io.float(), ref) < 4e-3
+    assert (lo_io.float().abs() <= hi_io.float().abs() * 2.0 ** -8 + 1e-30).all()
+    so = stats_out.double().sum(1)
+    assert nerr(so[:, 0], ref.sum(-1)) < 1e-5 and nerr(so[:, 1], (ref * ref).sum(-1)) < 1e-5
+
+
 def _attention_ref(qkv: torch.Tensor, valid: torch.Tensor, T: int, causal: bool) -> torch.Tensor:
     """qkv fp64 [N*T, 2304] (reference row order Q | K | V), valid bool [N*T] -> ctx fp64 [N*T, 768]."""
     n = qkv.shape[0] // T
