@@ -370,8 +370,7 @@ def test_fused_layer_norm_path_matches_unfused_and_oracle(layout):
         n_comp = model.last_launch_count()
         model.set_hilo_residual(True)
         hilo = model(gb)["stlt"].float().cpu()   # optional: residual stream as two bf16 planes instead of fp32 + bf16 copy
-        # bf16 rounding of the GEMM operands flips on 2^-18 perturbations of the stream: equal at the bf16-noise level only
-        assert model.last_launch_count() == n_comp and nerr(hilo, want) < 2e-2 and nerr(comp, hilo) < 1.5e-2
+        n_hilo = model.last_launch_count()
         model.set_hilo_residual(False)
         model.set_compaction(False)
         full = model(gb)["stlt"].float().cpu()   # the same on the whole padded [B, L, S] grid
@@ -388,6 +387,8 @@ def test_fused_layer_norm_path_matches_unfused_and_oracle(layout):
     assert n_fused == n_plain - 23  # 24 residual + LayerNorm launches gone, one LayerNorm of the pooled rows added
     assert n_full == n_fused - 12   # the 12 attention launches live in the in-projection epilogues
     assert n_comp == n_full + 3     # three tiny planning kernels of the pad-skipping layout
+    # bf16 rounding of the GEMM operands flips on 2^-18 perturbations of the stream: equal at the bf16-noise level only
+    assert n_hilo == n_comp and nerr(hilo, want) < 2e-2 and nerr(comp, hilo) < 1.5e-2
     print(layout, "pad-skipping vs oracle", nerr(comp, want), "vs padded grid", nerr(comp, full))
     assert nerr(comp, want) < 2e-2 and nerr(comp, full) < 5e-3 and torch.equal(comp.argmax(-1), want.argmax(-1))
     print(layout, "attention-fused vs oracle", nerr(full, want), "vs LayerNorm-fused", nerr(full, fused))
