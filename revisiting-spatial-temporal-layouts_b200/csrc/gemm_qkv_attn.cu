@@ -29,10 +29,10 @@
 //      the un-normalised bf16 residual stream and W is pre-multiplied by gamma) -> bf16 -> three XOR-swizzled
 //      [128 x 64] shared-memory tiles Q, K, V (rows past the real tokens as zeros). The TMEM buffer is released
 //      as soon as it has been read.
-//   2. warp w owns the 16 query rows 16w .. 16w+15: S = Q K^T on mma.sync.m16n8k16 against a band of
-//      8 * kNT key rows that covers every sequence touching those rows, block-diagonal (same sequence),
-//      key-padding and causal predicates on the accumulator fragments, fp32 softmax with quad shuffles,
-//      O = P V with P from registers.
+//   2. attention in 16-query tiles on mma.sync.m16n8k16 (attend_tile): for T <= 16 a tile holds whole sequences, so its
+//      keys are its own 16 rows; for longer sequences warp w owns rows 16w .. 16w+15 and attends a band of 8 * kNT key
+//      rows that covers every sequence touching them. Same-sequence, key-padding and causal predicates on the
+//      accumulator fragments, fp32 softmax with quad shuffles, O = P V with P from registers.
 //   3. the normalised context goes to a fourth staging tile and one thread issues the TMA store of its first R
 //      rows to ctx[:, 64 h : 64 h + 64]; two CTA-wide named barriers per unit (tiles complete / tiles free).
 #include "kernels.h"
@@ -72,14 +72,115 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Masked attention of one tile of 16 query rows [q_row0, q_row0 + 16) of the Q / K / V tiles against the 8 * kNT key rows
+// from band0: S = Q K^T on mma.sync.m16n8k16, predicates ok[h] (bit nt*2+e = key band0 + nt*8 + 2t + e may be attended by
+// query row q_row0 + g + 8h) on the accumulator fragments, fp32 softmax with quad shuffles, O = P V with P from registers;
+// the normalised context rows below row_limit (tile-local) go to the staging tile. Row indices are clamped to the 128-row
+// tiles (keys past the end are masked by the caller).
 template <int kNT>
+__device__ __forceinline__ void attend_tile(uint32_t q_base, uint32_t k_base, uint32_t v_base, uint32_t c_base, int q_row0,
+                                            int band0, uint32_t ok0, uint32_t ok1, int row_limit, int lane) {
+  static_assert(kNT % 2 == 0, "P V consumes the keys 16 at a time");
+  const int g = lane >> 2, t = lane & 3;
+  const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  auto clampr = [](int r) { return r > BM - 1 ? BM - 1 : r; };
+  float s[kNT][4];
+#pragma unroll
+  for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t a[4];
+    ldmatrix_x4(tile_addr(q_base, clampr(q_row0 + (lane & 7) + ((lane >> 3) & 1) * 8), kt * 2 + (lane >> 4)), a);
+#pragma unroll
+    for (int np = 0; np < kNT / 2; ++np) {
+      uint32_t b[4];
+      ldmatrix_x4(tile_addr(k_base, clampr(band0 + (np * 2 + (lane >> 4)) * 8 + (lane & 7)), kt * 2 + ((lane >> 3) & 1)), b);
+      mma_bf16(s[np * 2 + 0], a, b[0], b[1]);
+      mma_bf16(s[np * 2 + 1], a, b[2], b[3]);
+    }
+  }
+  // ---- masked softmax on the accumulator fragments (fp32) ----
+  float inv_sum[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t ok = h == 0 ? ok0 : ok1;
+    float m = -INFINITY;  // maximum of the raw scores (the scale 1/8 * log2 e > 0 is folded into the exponent below)
+#pragma unroll
+    for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float v = ((ok >> (nt * 2 + e)) & 1u) ? s[nt][2 * h + e] : -INFINITY;
+        s[nt][2 * h + e] = v;
+        m = fmaxf(m, v);
+      }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    const float mm = (m == -INFINITY) ? 0.f : m * kScale;  // fully masked row -> all-zero probabilities
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float pv;  // 2^(-inf) = 0 for masked keys
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv) : "f"(fmaf(s[nt][2 * h + e], kScale, -mm)));
+        s[nt][2 * h + e] = pv;
+        sum += pv;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    inv_sum[h] = sum > 0.f ? __frcp_rn(sum) : 0.f;
+  }
+  // ---- O = P V ----
+  float o[8][4];
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[dt][i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kNT / 2; ++j) {
+    uint32_t pa[4];
+    pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+    pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+    pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+    pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(tile_addr(v_base, clampr(band0 + j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)), dp * 2 + (lane >> 4)), b);
+      mma_bf16(o[dp * 2 + 0], pa, b[0], b[1]);
+      mma_bf16(o[dp * 2 + 1], pa, b[2], b[3]);
+    }
+  }
+  // ---- normalised context -> the tile's rows of the staging tile ----
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int lr = g + 8 * h;
+    const int row = q_row0 + lr;
+    if (lr < row_limit && row < BM) {
+      const float is = inv_sum[h];
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const uint32_t v = pack_bf16x2(o[dt][2 * h] * is, o[dt][2 * h + 1] * is);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_addr(c_base, row, dt) + 4 * t), "r"(v) : "memory");
+      }
+    }
+  }
+}
+
+template <int kNT, int kBandOff, bool kAligned>
 __global__ void __launch_bounds__(kThreads, 1)
 qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out1,
                      QkvAttnArgs p) {
-  static_assert(kNT == 4 || kNT == 6 || kNT == 10, "key band of 32, 48 or 80 rows");
+  // Two ways to cut the 128 rows of a block into 16-query tiles:
+  //  kAligned (T <= 16): a tile holds floor(16 / T) WHOLE sequences (15 rows at T = 5, 11 at T = 11), so its keys are its own
+  //    rows (kNT = 2); a block has ceil(sequences / floor(16 / T)) tiles, dealt round-robin to the 8 warps (at most 2 each);
+  //  band (17 <= T <= 32): warp w owns query rows 16w .. 16w+15 and attends a band of 8 * kNT key rows from 16w - kBandOff
+  //    that covers every sequence touching them (causal launches need no keys after the tile: narrower band).
+  static_assert(kAligned ? (kNT == 2 && kBandOff == 0) : (kNT == 4 || kNT == 6 || kNT == 10), "tiling");
   constexpr int kBand = 8 * kNT;
-  constexpr int kBandOff = kNT == 4 ? 8 : (kNT == 6 ? 16 : 32);
   constexpr int kMaskWords = (kBand + 31) / 32;
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -210,36 +311,34 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const uint32_t v_base = k_base + kTileBytes;
     const uint32_t c_base = smem_u32(smem_ctx);
     const int arow = quarter * 32 + lane;  // accumulator row (block-local) of this thread
-    int band0 = 16 * ew - kBandOff;        // first key row of this warp's band
+    int band0 = 16 * ew - kBandOff;        // band scheme: first key row of this warp's band
     band0 = band0 < 0 ? 0 : (band0 > BM - kBand ? BM - kBand : band0);
+    // aligned scheme: whole sequences per 16-row tile
+    const int seqs_per_tile = kAligned ? 16 / T : 0;
+    const int tile_rows = kAligned ? seqs_per_tile * T : 16;
 
-    // static part of the mask (block origins are multiples of T): bit nt*2+e of allow[h] = key band0 + nt*8 + 2t + e
-    // belongs to the sequence of query row 16 ew + g + 8 h (and is not in its future when causal)
-    uint32_t allow[2];
+    // static part of the mask (block and tile origins are multiples of T): bit nt*2+e of allow[h] = the key in this thread's
+    // column nt*8 + 2t + e belongs to the sequence of the query in fragment row g + 8h (and is not in its future when causal)
+    uint32_t allow[2], allow1[2];  // sequences of T tokens / one-token sequences (a query attends to its own row only)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int q = 16 * ew + g + 8 * h;
-      const int qs = q / T;
+      const int q = (kAligned ? 0 : 16 * ew) + g + 8 * h;  // tile-local (aligned) or block-local (band) row
+      const int lim = kAligned ? tile_rows : R;
       uint32_t bits = 0;
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int key = band0 + nt * 8 + 2 * t + e;
-          const bool ok = q < R && key < R && key / T == qs && (!p.causal || key <= q);
+          const int key = (kAligned ? 0 : band0) + nt * 8 + 2 * t + e;
+          const bool ok = q < lim && key < lim && key / T == q / T && (!p.causal || key <= q);
           bits |= (ok ? 1u : 0u) << (nt * 2 + e);
         }
       allow[h] = bits;
-    }
-    // one-token sequences: a query attends to its own row only
-    uint32_t allow1[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int d = 16 * ew + g + 8 * h - band0 - 2 * t;  // key index of the query row within this thread's columns
+      const int d = q - (kAligned ? 0 : band0) - 2 * t;  // column index of the query's own row
       allow1[h] = (d >= 0 && d < kBand && (d & 7) < 2) ? 1u << ((d >> 3) * 2 + (d & 7)) : 0u;
     }
     const int seqs_per_block = R / T;
-    const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const int tiles_full = kAligned ? (seqs_per_block + seqs_per_tile - 1) / seqs_per_tile : kEpiWarps;
 
     int it = 0;
     for (int pb = cluster_id; pb < pair_blocks; pb += num_clusters) {
@@ -271,23 +370,32 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         mu = sx * (1.0f / kHidden);
         rstd = rsqrtf(fmaxf(sy * (1.0f / kHidden) - mu * mu, 0.f) + p.eps);
       }
-      uint32_t kw[kMaskWords];
+      // key-padding bits of this warp's tiles (aligned: tiles ew and ew + 8; band: the band of rows 16 ew ..), lane = key row
+      const int tile_rows_b = kAligned ? (single ? 16 : tile_rows) : 16;
+      const int tiles_b = kAligned ? (single ? kEpiWarps : tiles_full) : kEpiWarps;
+      uint32_t okm[kAligned ? 2 : 1][2];
 #pragma unroll
-      for (int i = 0; i < kMaskWords; ++i) {
-        const int key = band0 + i * 32 + lane;
-        const bool in = live && i * 32 + lane < kBand && row_live(key);
-        const bool ok = in && __ldg(p.mask_src + (in ? row0 + key : 0)) != 0;
-        kw[i] = __ballot_sync(0xffffffffu, ok);
-      }
-      uint32_t kbits = 0;  // this thread's 2 * kNT key columns
+      for (int ti = 0; ti < (kAligned ? 2 : 1); ++ti) {
+        const int key0 = kAligned ? (ew + ti * kEpiWarps) * tile_rows_b : band0;
+        uint32_t kw[kMaskWords];
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int idx = nt * 8 + 2 * t + e;
-          kbits |= ((kw[idx >> 5] >> (idx & 31)) & 1u) << (nt * 2 + e);
+        for (int i = 0; i < kMaskWords; ++i) {
+          const int key = key0 + i * 32 + lane;
+          const bool in = live && i * 32 + lane < kBand && key < BM && row_live(key);
+          const bool ok = in && __ldg(p.mask_src + (in ? row0 + key : 0)) != 0;
+          kw[i] = __ballot_sync(0xffffffffu, ok);
         }
-      const uint32_t ok0 = (single ? allow1[0] : allow[0]) & kbits, ok1 = (single ? allow1[1] : allow[1]) & kbits;
+        uint32_t kbits = 0;  // this thread's 2 * kNT key columns
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int idx = nt * 8 + 2 * t + e;
+            kbits |= ((kw[idx >> 5] >> (idx & 31)) & 1u) << (nt * 2 + e);
+          }
+        okm[ti][0] = (single ? allow1[0] : allow[0]) & kbits;
+        okm[ti][1] = (single ? allow1[1] : allow[1]) & kbits;
+      }
 
       for (int head = 0; head < kHeads; ++head, ++it) {
         const int acc = it & 1;
@@ -316,20 +424,13 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const int e = 8 * j + 4 * q;
+              // one code path: without a pending LayerNorm mu = 0, rstd = 1 (exact: acc * 1 - 0 * s + c)
               const float4 c4 = __ldg(vc4 + c * 8 + 2 * j + q);
-              float f0, f1, f2, f3;
-              if (p.prev_norm) {
-                const float4 s4 = __ldg(vs4 + c * 8 + 2 * j + q);
-                f0 = fmaf(rstd, fmaf(-mu, s4.x, __uint_as_float(v[e + 0])), c4.x);
-                f1 = fmaf(rstd, fmaf(-mu, s4.y, __uint_as_float(v[e + 1])), c4.y);
-                f2 = fmaf(rstd, fmaf(-mu, s4.z, __uint_as_float(v[e + 2])), c4.z);
-                f3 = fmaf(rstd, fmaf(-mu, s4.w, __uint_as_float(v[e + 3])), c4.w);
-              } else {
-                f0 = __uint_as_float(v[e + 0]) + c4.x;
-                f1 = __uint_as_float(v[e + 1]) + c4.y;
-                f2 = __uint_as_float(v[e + 2]) + c4.z;
-                f3 = __uint_as_float(v[e + 3]) + c4.w;
-              }
+              const float4 s4 = __ldg(vs4 + c * 8 + 2 * j + q);
+              const float f0 = fmaf(rstd, fmaf(-mu, s4.x, __uint_as_float(v[e + 0])), c4.x);
+              const float f1 = fmaf(rstd, fmaf(-mu, s4.y, __uint_as_float(v[e + 1])), c4.y);
+              const float f2 = fmaf(rstd, fmaf(-mu, s4.z, __uint_as_float(v[e + 2])), c4.z);
+              const float f3 = fmaf(rstd, fmaf(-mu, s4.w, __uint_as_float(v[e + 3])), c4.w);
               pk[2 * q] = real_row ? pack_bf16x2(f0, f1) : 0u;
               pk[2 * q + 1] = real_row ? pack_bf16x2(f2, f3) : 0u;
             }
@@ -352,86 +453,17 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
         if (p.debug & 8) __nanosleep(2000);  // decomposition: a 2 us stall here does not change the kernel time
         if (!(p.debug & 1)) {
-          // ---- 2. S = Q K^T over the band ----
-          float s[kNT][4];
+          // ---- 2. / 3. attention of this warp's tile(s); the normalised context goes to the staging tile ----
+          if constexpr (kAligned) {
 #pragma unroll
-          for (int nt = 0; nt < kNT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
-#pragma unroll
-          for (int kt = 0; kt < 4; ++kt) {
-            uint32_t a[4];
-            ldmatrix_x4(tile_addr(q_base, 16 * ew + (lane & 7) + ((lane >> 3) & 1) * 8, kt * 2 + (lane >> 4)), a);
-#pragma unroll
-            for (int np = 0; np < kNT / 2; ++np) {
-              uint32_t b[4];
-              ldmatrix_x4(tile_addr(k_base, band0 + (np * 2 + (lane >> 4)) * 8 + (lane & 7), kt * 2 + ((lane >> 3) & 1)), b);
-              mma_bf16(s[np * 2 + 0], a, b[0], b[1]);
-              mma_bf16(s[np * 2 + 1], a, b[2], b[3]);
+            for (int ti = 0; ti < 2; ++ti) {
+              const int tile = ew + ti * kEpiWarps;
+              if (tile < tiles_b)
+                attend_tile<kNT>(q_base, k_base, v_base, c_base, tile * tile_rows_b, tile * tile_rows_b, okm[ti][0],
+                                 okm[ti][1], tile_rows_b, lane);
             }
-          }
-          // ---- masked softmax on the accumulator fragments (fp32) ----
-          float inv_sum[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t ok = h == 0 ? ok0 : ok1;
-            float m = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < kNT; ++nt)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                float v = s[nt][2 * h + e] * kScale;
-                v = ((ok >> (nt * 2 + e)) & 1u) ? v : -INFINITY;
-                s[nt][2 * h + e] = v;
-                m = fmaxf(m, v);
-              }
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-            const float mm = (m == -INFINITY) ? 0.f : m;  // fully masked row -> all-zero probabilities
-            float sum = 0.f;
-#pragma unroll
-            for (int nt = 0; nt < kNT; ++nt)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float pv = exp2f(s[nt][2 * h + e] - mm);
-                s[nt][2 * h + e] = pv;
-                sum += pv;
-              }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            inv_sum[h] = sum > 0.f ? 1.0f / sum : 0.f;
-          }
-          // ---- O = P V ----
-          float o[8][4];
-#pragma unroll
-          for (int dt = 0; dt < 8; ++dt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[dt][i] = 0.f;
-#pragma unroll
-          for (int j = 0; j < kNT / 2; ++j) {
-            uint32_t pa[4];
-            pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-            pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-            pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-            pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
-#pragma unroll
-            for (int dp = 0; dp < 4; ++dp) {
-              uint32_t b[4];
-              ldmatrix_x4_trans(tile_addr(v_base, band0 + j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), dp * 2 + (lane >> 4)), b);
-              mma_bf16(o[dp * 2 + 0], pa, b[0], b[1]);
-              mma_bf16(o[dp * 2 + 1], pa, b[2], b[3]);
-            }
-          }
-          // ---- 3. normalised context -> this warp's 16 rows of the staging tile ----
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int row = 16 * ew + g + 8 * h;
-            const float is = inv_sum[h];
-#pragma unroll
-            for (int dt = 0; dt < 8; ++dt) {
-              const uint32_t v = pack_bf16x2(o[dt][2 * h] * is, o[dt][2 * h + 1] * is);
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_addr(c_base, row, dt) + 4 * t), "r"(v) : "memory");
-            }
+          } else {
+            attend_tile<kNT>(q_base, k_base, v_base, c_base, 16 * ew, band0, okm[0][0], okm[0][1], 16, lane);
           }
         }
         fence_proxy_async_smem();
@@ -454,10 +486,10 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   }
 }
 
-template <int kNT>
+template <int kNT, int kBandOff, bool kAligned>
 cudaError_t launch_nt(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_out,
                       const CUtensorMap& tm_out1, const QkvAttnArgs& p, cudaStream_t stream, int num_sms) {
-  auto kern = qkv_attention_kernel<kNT>;
+  auto kern = qkv_attention_kernel<kNT, kBandOff, kAligned>;
   static unsigned long long smem_done = 0;
   cudaError_t e = ensure_dynamic_smem(kern, kSmemBytes, &smem_done);
   if (e != cudaSuccess) return e;
@@ -483,17 +515,28 @@ cudaError_t launch_nt(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CU
 
 int qkv_attention_rows_per_block(int seq_len) {
   if (seq_len < 1 || seq_len > 32) return 0;
-  return (BM / seq_len) * seq_len;
+  const int full = BM / seq_len;  // whole sequences that fit a 128-row block
+  if (seq_len <= 16) {
+    // sequence-aligned 16-row tiles: 8 tiles (one per epilogue warp, one round) hold 8 * floor(16 / T) sequences. Taken when
+    // that gives up at most 7 % of the block (T = 5: 120 of 125 rows); otherwise some warps attend a second tile per unit.
+    const int one_round = kEpiWarps * (16 / seq_len);
+    if (one_round * 100 >= full * 93) return (one_round < full ? one_round : full) * seq_len;
+  }
+  return full * seq_len;
 }
 
 cudaError_t launch_qkv_attention(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_out,
                                  const CUtensorMap& tm_out1, const QkvAttnArgs& p, cudaStream_t stream, int num_sms) {
   if (p.seq_len < 1 || p.seq_len > 32 || p.rows_per_block != qkv_attention_rows_per_block(p.seq_len) ||
-      p.row_blocks < 1 || p.vec_c == nullptr || p.mask_src == nullptr || (p.prev_norm && (!p.vec_s || !p.stats_in)))
+      p.row_blocks < 1 || p.vec_c == nullptr || p.vec_s == nullptr || p.mask_src == nullptr || (p.prev_norm && !p.stats_in))
     return cudaErrorInvalidValue;
-  if (p.seq_len <= 9) return launch_nt<4>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
-  if (p.seq_len <= 17) return launch_nt<6>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
-  return launch_nt<10>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
+  if (p.seq_len <= 16) return launch_nt<2, 0, true>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
+  if (p.causal) {  // no keys after the query tile
+    if (p.seq_len <= 17) return launch_nt<4, 16, false>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
+    return launch_nt<6, 32, false>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
+  }
+  if (p.seq_len <= 17) return launch_nt<6, 16, false>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
+  return launch_nt<10, 32, false>(tm_a, tm_b, tm_out, tm_out1, p, stream, num_sms);
 }
 
 }  // namespace stlt

@@ -307,19 +307,20 @@ int fused_tail_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, cons
 int fused_stack(Handle* h, cudaStream_t stream, const std::vector<LayerWeights>& layers, const Phase& full,
                 const Phase& tail, const long long* mask_src, long long num_seqs, int T, bool causal, int stride,
                 const long long* lengths, int L, float2* stats_full, float2* stats_tail, int* err_flag,
-                PendingNorm* out, const int* dyn = nullptr, const int* frame_row = nullptr) {
+                PendingNorm* out, const int* dyn = nullptr, const int* frame_row = nullptr, bool prune_last = true) {
   const int n = static_cast<int>(layers.size());
   PendingNorm pending;  // layer 0 reads the (already normalised) embedding output
   for (int i = 0; i < n; ++i) {
     const LayerWeights& lw = layers[i];
     int rc = fused_attention_part(h, stream, lw, full, pending, mask_src, num_seqs, T, causal, dyn);
     if (rc) return rc;
-    if (i < n - 1) {
+    if (i < n - 1 || !prune_last) {  // !prune_last (CACNF: every frame token is consumed): full.x keeps the PRE-norm output
       float2* s1 = stats_full + static_cast<size_t>(2 * i) * full.m_pad * kStatSlots;
       float2* s2 = s1 + full.m_pad * kStatSlots;
       rc = fused_tail_part(h, stream, lw, full, pending, s1, s2, dyn != nullptr ? dyn + kDynTiles : nullptr);
       if (rc) return rc;
       pending = PendingNorm{s2, lw.n2_g, lw.n2_b};
+      if (i == n - 1) *out = pending;
     } else {
       float2* sc_in = stats_tail;
       float2* sc1 = stats_tail + tail.m_pad * kStatSlots;
@@ -668,8 +669,7 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
 
   const bool fused = !fp32 && h->fused_ln && h->pruning && d.num_spatial_layers > 0 && d.num_temporal_layers > 0 &&
                      h->taps.embed == nullptr && h->taps.spatial == nullptr && h->taps.frames == nullptr &&
-                     h->taps.temporal == nullptr && h->taps.pooled == nullptr && h->cap_tm_x == nullptr &&
-                     h->w.spatial[0].l1_f != nullptr;
+                     h->taps.temporal == nullptr && h->taps.pooled == nullptr && h->w.spatial[0].l1_f != nullptr;
   if (fused) {
     // ---- bf16 path with LayerNorm folded into the GEMM epilogues (no add_ln launches) ----
     float2* stats = reinterpret_cast<float2*>(ws + p.off_stats);
@@ -726,8 +726,10 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     }
     h->launches++;
     PendingNorm tm_out;
+    const bool capture = h->cap_tm_x != nullptr;  // CACNF: the fusion layers consume every frame token of the stack
+    if (capture && h->hilo) return fail(h, STLT_ERR_STATE, "the two-plane residual stream is not available under CACNF");
     rc = fused_stack(h, stream, h->w.temporal, tm_f, hd, frame_types, B, L, true, 0, lengths, L, st_tm, st_c_tm, err_flag,
-                     &tm_out);
+                     &tm_out, nullptr, nullptr, !capture);
     if (rc) return rc;
     float* h1f = reinterpret_cast<float*>(ws + p.off_head);
     float* h2f = h1f + static_cast<size_t>(B) * kHidden;
@@ -735,6 +737,13 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     {
       ProfileScope prof(h, stream, STLT_PROF_OTHER);
       ActOut po{pooledf, nullptr, 1, 0};
+      if (capture) {
+        // the stack's last LayerNorm over all frames, straight into the caller's buffers (fp32 stream + bf16 operand)
+        ActOut cap{h->cap_tm_x, h->cap_tm_xb, 1, tm.m_pad};
+        STLT_CUDA(h, launch_add_ln(tm.x, nullptr, tm_out.gamma, tm_out.beta, d.encoder_norm_eps, n_tm, cap, stream));
+        STLT_CUDA(h, launch_gather_last(h->cap_tm_x, lengths, B, L, pooledf, err_flag, stream));
+        h->launches++;
+      } else
       STLT_CUDA(h, launch_add_ln(hd.x, nullptr, tm_out.gamma, tm_out.beta, d.encoder_norm_eps, B, po, stream));
       STLT_CUDA(h, launch_gemm_simt(pooledf, h->w.fc1_w, h->w.fc1_b, h1f, B, kHidden, kHidden, true, stream));
       ActOut ho{h2f, nullptr, 1, 0};
