@@ -55,7 +55,8 @@ constexpr int kTmemCols = 512;
 constexpr int kCluster = 2;
 constexpr uint16_t kClusterMask = (1u << kCluster) - 1;
 constexpr int kTileBytes = BM * 128;  // one of the Q / K / V / context tiles: 128 rows x 64 bf16
-constexpr int kSmemBytes = kStages * kStageBytes + 4 * kTileBytes + 256 /*barriers*/;
+constexpr int kVecBytes = 2 * kQkv * 4;  // the epilogue vectors s[2304], c[2304] (head-major), staged once per CTA
+constexpr int kSmemBytes = kStages * kStageBytes + 4 * kTileBytes + kVecBytes + 256 /*barriers*/;
 static_assert(kSmemBytes <= 232448, "smem budget");
 static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024 B alignment");
 
@@ -188,7 +189,8 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   uint8_t* smem_ab = smem;
   uint8_t* smem_qkv = smem + kStages * kStageBytes;
   uint8_t* smem_ctx = smem_qkv + 3 * kTileBytes;  // staging tile of the context store
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_ctx + kTileBytes);
+  float* smem_vec = reinterpret_cast<float*>(smem_ctx + kTileBytes);  // s[2304] then c[2304]
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_ctx + kTileBytes + kVecBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -233,6 +235,15 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   if (warp == 2) {
     tmem_alloc_pair(&bars->tmem_base, kTmemCols);
     tmem_relinquish_pair();
+  }
+  if (warp >= 4) {  // every lane of an epilogue warp reads the same s / c entries: from shared memory, not through L1
+    const float4* gs = reinterpret_cast<const float4*>(p.vec_s);
+    const float4* gc = reinterpret_cast<const float4*>(p.vec_c);
+    float4* ds = reinterpret_cast<float4*>(smem_vec);
+    for (int i = threadIdx.x - 128; i < kQkv / 4; i += kEpiWarps * 32) {
+      ds[i] = __ldg(gs + i);
+      ds[kQkv / 4 + i] = __ldg(gc + i);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -403,8 +414,8 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + half * 96 + (static_cast<uint32_t>(quarter * 32) << 16);
-        const float4* vs4 = reinterpret_cast<const float4*>(p.vec_s + head * BN + half * 96);
-        const float4* vc4 = reinterpret_cast<const float4*>(p.vec_c + head * BN + half * 96);
+        const float4* vs4 = reinterpret_cast<const float4*>(smem_vec + head * BN + half * 96);
+        const float4* vc4 = reinterpret_cast<const float4*>(smem_vec + kQkv + head * BN + half * 96);
 
         // ---- 1. accumulator -> bias / deferred LayerNorm -> bf16 -> Q / K / V tiles (every warp has left the
         //         attention phase of the previous unit: barrier B below) ----
@@ -425,8 +436,8 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             for (int q = 0; q < 2; ++q) {
               const int e = 8 * j + 4 * q;
               // one code path: without a pending LayerNorm mu = 0, rstd = 1 (exact: acc * 1 - 0 * s + c)
-              const float4 c4 = __ldg(vc4 + c * 8 + 2 * j + q);
-              const float4 s4 = __ldg(vs4 + c * 8 + 2 * j + q);
+              const float4 c4 = vc4[c * 8 + 2 * j + q];
+              const float4 s4 = vs4[c * 8 + 2 * j + q];
               const float f0 = fmaf(rstd, fmaf(-mu, s4.x, __uint_as_float(v[e + 0])), c4.x);
               const float f1 = fmaf(rstd, fmaf(-mu, s4.y, __uint_as_float(v[e + 1])), c4.y);
               const float f2 = fmaf(rstd, fmaf(-mu, s4.z, __uint_as_float(v[e + 2])), c4.z);
