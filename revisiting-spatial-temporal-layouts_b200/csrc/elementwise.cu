@@ -343,14 +343,24 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
       rstd_l = 1.0f / sqrtf(fmaxf(static_cast<float>(var), 0.f) + eps);
     }
     const int cat_i = static_cast<int>(cat_l);
+    // pad-skipping layout: (frame, slot) of the group's first token, advanced per token (one 32-bit division per group; the
+    // token count is below 2^31, checked by the caller)
+    int fcur = 0, scur = 0;
+    if (frame_row != nullptr) {
+      fcur = static_cast<int>(static_cast<unsigned>(t0) / static_cast<unsigned>(S));
+      scur = static_cast<int>(t0) - fcur * S;
+    }
 #pragma unroll
     for (int i = 0; i < kEmbedTok; ++i) {
       const long long t = t0 + i;
       if (t >= tokens) break;
       long long dst = t;  // output row
-      if (frame_row != nullptr) {  // pad-skipping layout: scatter to the compact row, skip dead tokens (block-uniform)
-        const long long f = t / S;
-        const int slot = static_cast<int>(t - f * S);
+      if (frame_row != nullptr) {  // scatter to the compact row, skip dead tokens (block-uniform)
+        const int f = fcur, slot = scur;
+        if (++scur == S) {
+          scur = 0;
+          ++fcur;
+        }
         const int fr = __ldg(frame_row + f);
         if (fr < 0 || ((fr & kSingleFrameFlag) && slot != 0)) continue;
         dst = (fr & ~kSingleFrameFlag) + slot;
