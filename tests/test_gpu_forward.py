@@ -551,3 +551,49 @@ def test_bench_batch_parity_256_videos_both_precisions_identical_top1():
     assert stamp["videos"] == 256 and stamp["ok"]
     assert stamp["fp32"] < FP32_TOL and stamp["bf16"] < BF16_TOL
     assert stamp["fp32_top1_agree"] == 256 and stamp["bf16_top1_agree"] == 256
+
+
+def test_forward_cuda_graph_mode_matches_eager_and_follows_weight_updates():
+    """Stlt.enable_cuda_graphs (what bench.py times): the first forward of a shape is eager, the second is captured, later
+    ones replay. Replays must equal the eager logits bit for bit, for new data of the same shape, for a second shape, through
+    HostPipeline, after in-place parameter updates PyTorch's version counters see (re-pack before the replay) and after
+    raw `.data` writes announced with mark_weights_dirty()."""
+    from stlt_b200.pipeline import HostPipeline
+    cfg = StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=2, num_temporal_layers=2)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=71)
+    m = _model(cfg, sd, "bf16")
+    b1 = to_cuda(make_batch(37, "something", ragged=True, seed=72))
+    b2 = to_cuda(make_batch(37, "something", ragged=True, seed=73))
+    b3 = to_cuda(make_batch(5, "something", ragged=False, seed=74))
+    keys = ("categories", "boxes", "frame_types", "lengths")
+    with torch.no_grad():
+        e1, e2, e3 = (m(b)["stlt"].clone() for b in (b1, b2, b3))
+        m.enable_cuda_graphs(True)
+        first = m(b1)["stlt"]           # eager
+        second = m(b1)["stlt"]          # captured + replayed
+        assert torch.equal(first, e1) and torch.equal(second, e1)
+        assert torch.equal(m(b2)["stlt"], e2)                      # replay, new data
+        assert torch.equal(m(b3)["stlt"], e3) and torch.equal(m(b3)["stlt"], e3)   # second shape: its own graph
+        assert torch.equal(m(b1)["stlt"], e1)
+        assert second.data_ptr() != m(b1)["stlt"].data_ptr()       # every call returns a fresh tensor
+        host = [{k: b[k].cpu().pin_memory() for k in keys} for b in (b1, b2, b1)]
+        got = [h.clone() for h in HostPipeline(m, "stlt").run(host)]
+        assert torch.equal(got[0].cuda(), e1) and torch.equal(got[1].cuda(), e2) and torch.equal(got[2].cuda(), e1)
+        # (a) an update PyTorch sees: version counter bumps -> bf16 copies re-packed eagerly, same graph replayed
+        m.backbone.transformer.layers[0].linear1.weight.mul_(0.5)
+        m.prediction_head.fc2.bias.add_(1.0)
+        g = m(b2)["stlt"].clone()
+        m.enable_cuda_graphs(False)
+        want = m(b2)["stlt"].clone()
+        assert torch.equal(g, want) and not torch.equal(g, e2)
+        # (b) a write behind PyTorch's back: needs mark_weights_dirty()
+        m.enable_cuda_graphs(True)
+        m(b2), m(b2)
+        m.backbone.frames_embeddings.layout_embedding.transformer.layers[1].self_attn.in_proj_weight.data.mul_(1.5)
+        m.mark_weights_dirty()
+        g = m(b2)["stlt"].clone()   # eager again (graphs were dropped)
+        g2 = m(b2)["stlt"].clone()  # re-captured
+        m.enable_cuda_graphs(False)
+        want2 = m(b2)["stlt"].clone()
+        assert torch.equal(g, want2) and torch.equal(g2, want2) and not torch.equal(want2, want)
