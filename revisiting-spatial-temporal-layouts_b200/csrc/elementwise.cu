@@ -343,12 +343,14 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
       rstd_l = 1.0f / sqrtf(fmaxf(static_cast<float>(var), 0.f) + eps);
     }
     const int cat_i = static_cast<int>(cat_l);
-    // pad-skipping layout: (frame, slot) of the group's first token, advanced per token (one 32-bit division per group; the
-    // token count is below 2^31, checked by the caller)
-    int fcur = 0, scur = 0;
+    // pad-skipping layout: the compact row of token t0 + (lane & 7) (-1: dead), looked up next to its statistics so that the
+    // stores below do not wait for a dependent load (32-bit division: the token count is below 2^31, checked by the caller)
+    int dst_l = static_cast<int>(tl);
     if (frame_row != nullptr) {
-      fcur = static_cast<int>(static_cast<unsigned>(t0) / static_cast<unsigned>(S));
-      scur = static_cast<int>(t0) - fcur * S;
+      const unsigned f = static_cast<unsigned>(tl) / static_cast<unsigned>(S);
+      const int slot = static_cast<int>(static_cast<unsigned>(tl) - f * static_cast<unsigned>(S));
+      const int fr = __ldg(frame_row + f);
+      dst_l = (fr < 0 || ((fr & kSingleFrameFlag) && slot != 0)) ? -1 : (fr & ~kSingleFrameFlag) + slot;
     }
 #pragma unroll
     for (int i = 0; i < kEmbedTok; ++i) {
@@ -356,14 +358,9 @@ embed_kernel(const long long* __restrict__ categories, const float4* __restrict_
       if (t >= tokens) break;
       long long dst = t;  // output row
       if (frame_row != nullptr) {  // scatter to the compact row, skip dead tokens (block-uniform)
-        const int f = fcur, slot = scur;
-        if (++scur == S) {
-          scur = 0;
-          ++fcur;
-        }
-        const int fr = __ldg(frame_row + f);
-        if (fr < 0 || ((fr & kSingleFrameFlag) && slot != 0)) continue;
-        dst = (fr & ~kSingleFrameFlag) + slot;
+        const int d = __shfl_sync(0xffffffffu, dst_l, i);
+        if (d < 0) continue;
+        dst = d;
       }
       const int cat = __shfl_sync(0xffffffffu, cat_i, i);
       if (mask_out != nullptr && tid == 0) mask_out[dst] = cat;
