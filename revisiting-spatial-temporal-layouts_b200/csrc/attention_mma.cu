@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kSplit ? 128 : 256, 2)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_plane_elems,
                      const long long* __restrict__ mask_src, long long num_seqs, int T, int G,
                      int causal, __nv_bfloat16* __restrict__ out, long long out_plane_elems,
-                     long long num_items, DropCfg drop) {
+                     long long num_items, DropCfg drop, const int* __restrict__ dyn, int dyn_region) {
   constexpr int kWarps = kSplit ? 4 : 8;
   constexpr int kTiles = kSplit ? 6 : 3;  // Q, K, V (+ their lo planes)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -70,6 +70,13 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_plane_
       allow[mt][h] = bits;
     }
 
+  // pad-skipping layout (compact.cu): the number of sequences and the first row of the region come from the device header
+  long long row_base = 0;
+  if (dyn != nullptr) {
+    num_seqs = __ldg(dyn + (dyn_region == 0 ? kDynFull : kDynSingle));
+    row_base = dyn_region == 0 ? 0 : __ldg(dyn + kDynSingleRow0);
+    num_items = ((num_seqs + G - 1) / G) * kHeads;
+  }
   const long long total_tokens = num_seqs * T;
   const long long gwarp = blockIdx.x * static_cast<long long>(kWarps) + warp;
   const long long nwarps = gridDim.x * static_cast<long long>(kWarps);
@@ -78,8 +85,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_plane_
   for (long long item = gwarp; item < num_items; item += nwarps) {
     const long long grp = item / kHeads;
     const int head = static_cast<int>(item - grp * kHeads);
-    const long long base = grp * R;
-    const long long remaining = total_tokens - base;
+    const long long remaining = total_tokens - grp * R;
+    const long long base = row_base + grp * R;
     const int nrows = remaining < R ? static_cast<int>(remaining) : R;
 
     // ---- stage Q, K, V (coalesced: 8 lanes x 16 B per row, 4 rows per instruction) ----
@@ -310,7 +317,7 @@ template <bool kSplit>
 static cudaError_t launch_mma(const __nv_bfloat16* qkv, long long qkv_plane_rows,
                               const long long* mask_src, long long num_seqs, int T, bool causal,
                               __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream,
-                              DropCfg drop) {
+                              DropCfg drop, const int* dyn, int dyn_region) {
   constexpr int kWarps = kSplit ? 4 : 8;
   constexpr int kTiles = kSplit ? 6 : 3;
   const int G = 32 / T;
@@ -327,7 +334,7 @@ static cudaError_t launch_mma(const __nv_bfloat16* qkv, long long qkv_plane_rows
   if (blocks > cap) blocks = cap;
   attention_mma_kernel<kSplit><<<static_cast<unsigned>(blocks), kWarps * 32, smem, stream>>>(
       qkv, qkv_plane_rows * kQkv, mask_src, num_seqs, T, G, causal ? 1 : 0, out,
-      out_plane_rows * kHidden, items, drop);
+      out_plane_rows * kHidden, items, drop, dyn, dyn_region);
   return cudaGetLastError();
 }
 
@@ -336,14 +343,15 @@ static cudaError_t launch_mma(const __nv_bfloat16* qkv, long long qkv_plane_rows
 cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long qkv_plane_rows,
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
                                  __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream,
-                                 DropCfg drop) {
+                                 DropCfg drop, const int* dyn, int dyn_region) {
   if (T < 1 || T > 32) return cudaErrorInvalidValue;
   if (num_seqs == 0) return cudaSuccess;
   if (planes == 2) {
     if (drop.thr16 != 0) return cudaErrorInvalidValue;  // training runs the single-plane flavour
-    return launch_mma<true>(qkv, qkv_plane_rows, mask_src, num_seqs, T, causal, out, out_plane_rows, stream, drop);
+    return launch_mma<true>(qkv, qkv_plane_rows, mask_src, num_seqs, T, causal, out, out_plane_rows, stream, drop, dyn,
+                            dyn_region);
   }
-  return launch_mma<false>(qkv, 0, mask_src, num_seqs, T, causal, out, 0, stream, drop);
+  return launch_mma<false>(qkv, 0, mask_src, num_seqs, T, causal, out, 0, stream, drop, dyn, dyn_region);
 }
 
 }  // namespace stlt

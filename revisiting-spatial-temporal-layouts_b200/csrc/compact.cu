@@ -153,20 +153,23 @@ gather_frames_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __res
                      const int* __restrict__ frame_row, long long frames, float* __restrict__ dst_x,
                      __nv_bfloat16* __restrict__ dst_att, const float2* __restrict__ src_stats,
                      float2* __restrict__ dst_stats, const __nv_bfloat16* __restrict__ src_hi,
-                     const __nv_bfloat16* __restrict__ src_lo) {
+                     const __nv_bfloat16* __restrict__ src_lo, int att_planes, long long src_plane_rows,
+                     long long dst_plane_rows) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
   for (long long r = warp0; r < frames; r += nwarps) {
     const int fr = frame_row[r];
     float4* px = reinterpret_cast<float4*>(dst_x + r * kHidden);
-    uint4* da = reinterpret_cast<uint4*>(dst_att + r * kHidden);
     if (fr < 0) {
       if (src_stats != nullptr && lane < kStatSlots) dst_stats[r * kStatSlots + lane] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < kVec; ++k) px[lane + 32 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pl = 0; pl < att_planes; ++pl) {
+        uint4* da = reinterpret_cast<uint4*>(dst_att + (pl * dst_plane_rows + r) * kHidden);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) da[lane + 32 * k] = make_uint4(0u, 0u, 0u, 0u);
+        for (int k = 0; k < 3; ++k) da[lane + 32 * k] = make_uint4(0u, 0u, 0u, 0u);
+      }
       continue;
     }
     const long long src = fr & ~kSingleFrameFlag;
@@ -174,9 +177,12 @@ gather_frames_kernel(const float* __restrict__ src_x, const __nv_bfloat16* __res
     const RowRegs x = src_hi != nullptr ? load_row_hilo(src_hi, src_lo, src, lane) : load_row(src_x, src, lane);
 #pragma unroll
     for (int k = 0; k < kVec; ++k) px[lane + 32 * k] = x.v[k];
-    const uint4* sa = reinterpret_cast<const uint4*>(src_att + src * kHidden);
+    for (int pl = 0; pl < att_planes; ++pl) {  // 1 plane (bf16 mode) or hi / lo planes (fp32-parity mode)
+      const uint4* sa = reinterpret_cast<const uint4*>(src_att + (pl * src_plane_rows + src) * kHidden);
+      uint4* da = reinterpret_cast<uint4*>(dst_att + (pl * dst_plane_rows + r) * kHidden);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) da[lane + 32 * k] = __ldg(sa + lane + 32 * k);  // 96 x 16 B
+      for (int k = 0; k < 3; ++k) da[lane + 32 * k] = __ldg(sa + lane + 32 * k);  // 96 x 16 B
+    }
   }
 }
 
@@ -212,10 +218,12 @@ cudaError_t launch_compact_plan(const long long* categories, const long long* le
 cudaError_t launch_gather_frames(const float* src_x, const __nv_bfloat16* src_att, const int* frame_row,
                                  long long frames, float* dst_x, __nv_bfloat16* dst_att, const float2* src_stats,
                                  float2* dst_stats, cudaStream_t stream, const __nv_bfloat16* src_hi,
-                                 const __nv_bfloat16* src_lo) {
+                                 const __nv_bfloat16* src_lo, int att_planes, long long src_plane_rows,
+                                 long long dst_plane_rows) {
   if (frames == 0) return cudaSuccess;
   gather_frames_kernel<<<row_grid(frames, 8), 256, 0, stream>>>(src_x, src_att, frame_row, frames, dst_x, dst_att,
-                                                                src_stats, dst_stats, src_hi, src_lo);
+                                                                src_stats, dst_stats, src_hi, src_lo, att_planes,
+                                                                src_plane_rows, dst_plane_rows);
   return cudaGetLastError();
 }
 

@@ -426,7 +426,11 @@ template <typename TY>
 __global__ void __launch_bounds__(256)
 add_ln_kernel(const float* __restrict__ x_in, const TY* __restrict__ y,
               const float* __restrict__ g, const float* __restrict__ b, float eps, long long rows,
-              ActOut out, float* __restrict__ z_out, DropCfg drop) {
+              ActOut out, float* __restrict__ z_out, DropCfg drop, const int* __restrict__ rows_dyn) {
+  if (rows_dyn != nullptr) {  // pad-skipping layout: the live row count is decided on the device
+    const long long r = __ldg(rows_dyn);
+    rows = r < rows ? r : rows;
+  }
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -679,17 +683,17 @@ cudaError_t launch_embed(const long long* categories, const float* boxes, const 
 
 cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, const float* b,
                           float eps, long long rows, ActOut out, cudaStream_t stream, float* z_out,
-                          DropCfg drop) {
+                          DropCfg drop, const int* rows_dyn) {
   if (rows == 0) return cudaSuccess;
-  add_ln_kernel<float><<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out, drop);
+  add_ln_kernel<float><<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out, drop, rows_dyn);
   return cudaGetLastError();
 }
 
 cudaError_t launch_add_ln_bf16y(const float* x_in, const __nv_bfloat16* y, const float* g, const float* b,
                                 float eps, long long rows, ActOut out, cudaStream_t stream, float* z_out,
-                                DropCfg drop) {
+                                DropCfg drop, const int* rows_dyn) {
   if (rows == 0) return cudaSuccess;
-  add_ln_kernel<__nv_bfloat16><<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out, drop);
+  add_ln_kernel<__nv_bfloat16><<<row_grid(rows, 8), 256, 0, stream>>>(x_in, y, g, b, eps, rows, out, z_out, drop, rows_dyn);
   return cudaGetLastError();
 }
 

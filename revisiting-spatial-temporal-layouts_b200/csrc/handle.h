@@ -203,7 +203,7 @@ inline int make_tm(Handle* h, CUtensorMap* tm, const void* ptr, int dtype, long 
 // out = epilogue(A W^T + bias) on tcgen05. a/w point at plane 0; planes are a_plane_rows / n rows apart.
 inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_rows, long long a_plane_rows,
              const void* w, int n, int k, const float* bias, void* out, int terms, int out_kind,
-             int gelu, DropCfg drop = DropCfg{0, 0, 1.f}) {
+             int gelu, DropCfg drop = DropCfg{0, 0, 1.f}, const int* m_tiles_dyn = nullptr) {
   GemmArgs g{};
   const int planes = terms == 3 ? 2 : 1;
   int rc = make_tm(h, &g.tm_a, a, 1, a_plane_rows * (planes - 1) + m_rows, k, 64, 128);
@@ -231,8 +231,10 @@ inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_r
   g.drop = drop;
   g.epilogue = GEMM_EPI_PLAIN;
   g.epi = EpiArgs{};
+  g.epi.m_tiles_dyn = m_tiles_dyn;  // pad-skipping layout: live 128-row tiles decided on the device
   g.tm_out2 = g.tm_out;
-  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * k);
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, m_tiles_dyn ? 0.0 : 2.0 * static_cast<double>(m_rows) * n * k, m_tiles_dyn,
+                    2.0 * 128 * n * k);
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
   return STLT_OK;

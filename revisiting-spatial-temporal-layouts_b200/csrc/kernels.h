@@ -112,7 +112,8 @@ cudaError_t launch_compact_plan(const long long* categories, const long long* le
 cudaError_t launch_gather_frames(const float* src_x, const __nv_bfloat16* src_att, const int* frame_row,
                                  long long frames, float* dst_x, __nv_bfloat16* dst_att, const float2* src_stats,
                                  float2* dst_stats, cudaStream_t stream, const __nv_bfloat16* src_hi = nullptr,
-                                 const __nv_bfloat16* src_lo = nullptr);  // src_hi / src_lo: the source stream as bf16 planes
+                                 const __nv_bfloat16* src_lo = nullptr,  // src_hi / src_lo: the source stream as bf16 planes
+                                 int att_planes = 1, long long src_plane_rows = 0, long long dst_plane_rows = 0);
 
 struct QkvAttnArgs {
   const float* vec_s;         // [2304] head-major: row sums of the folded weights (read when prev_norm)
@@ -209,13 +210,14 @@ size_t embed_scratch_bytes(int unique_categories);
 // z_out (optional, training): receives the pre-LayerNorm sum x + y.
 cudaError_t launch_add_ln(const float* x_in, const float* y, const float* g, const float* b,
                           float eps, long long rows, ActOut out, cudaStream_t stream,
-                          float* z_out = nullptr, DropCfg drop = DropCfg{0, 0, 1.f});
+                          float* z_out = nullptr, DropCfg drop = DropCfg{0, 0, 1.f}, const int* rows_dyn = nullptr);
+// rows_dyn (device int, may be null): live row count when it is decided on the device (rows is then the static bound)
 
 // Same with the branch output y in bf16 (bf16 inference mode: the out-projection / linear2 GEMMs store
 // bf16, which halves their HBM write and this kernel's y read).
 cudaError_t launch_add_ln_bf16y(const float* x_in, const __nv_bfloat16* y, const float* g, const float* b,
                                 float eps, long long rows, ActOut out, cudaStream_t stream,
-                                float* z_out = nullptr, DropCfg drop = DropCfg{0, 0, 1.f});
+                                float* z_out = nullptr, DropCfg drop = DropCfg{0, 0, 1.f}, const int* rows_dyn = nullptr);
 
 // K7: frame tokens = LN(spatial CLS slot + position + frame type) (src/modelling/models.py:98-111).
 cudaError_t launch_frame_embed(const float* spatial_x, int S, const long long* frame_types,
@@ -251,7 +253,9 @@ cudaError_t launch_attention(const void* qkv, bool qkv_is_bf16, const long long*
 cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int planes, long long qkv_plane_rows,
                                  const long long* mask_src, long long num_seqs, int T, bool causal,
                                  __nv_bfloat16* out, long long out_plane_rows, cudaStream_t stream,
-                                 DropCfg drop = DropCfg{0, 0, 1.f});
+                                 DropCfg drop = DropCfg{0, 0, 1.f}, const int* dyn = nullptr, int dyn_region = 0);
+// dyn (CompactHeader, pad-skipping layout): region 0 = dyn[kDynFull] sequences of T tokens from row 0 (num_seqs is then only the
+// static bound that sizes the grid), region 1 = dyn[kDynSingle] sequences from row dyn[kDynSingleRow0] (call with T = 1).
 
 // K3 for 65..256-token sequences (attention_long.cu): one CTA per (sequence, head), Q / K / V staged once in shared
 // memory, online softmax over 64-key blocks. planes as in launch_attention_mma; inference only.

@@ -129,9 +129,9 @@ WorkspacePlan plan_workspace(int B, int L, int S, int precision, int ns = 0, int
   size_t off = 0;
   p.off_err = off;
   off += 1024;
-  // bf16: the spatial phase may run on the pad-skipping layout, whose static row bound is a little larger
+  // the spatial phase may run on the pad-skipping layout, whose static row bound is a little larger
   long long sp_rows = static_cast<long long>(B) * L * S;
-  const long long compact_rows = precision == STLT_PRECISION_BF16 ? compact_rows_bound(static_cast<long long>(B) * L, S) : 0;
+  const long long compact_rows = compact_rows_bound(static_cast<long long>(B) * L, S);  // 0 when S > 32
   if (compact_rows > sp_rows) sp_rows = compact_rows;
   off = plan_bufset(&p.sp, off, sp_rows, precision, true);
   off = plan_bufset(&p.tm, off, static_cast<long long>(B) * L, precision, true);
@@ -191,18 +191,30 @@ size_t embed_scratch(const Phase& ph) { return static_cast<size_t>(ph.m_pad) * k
 
 // First half of a post-norm nn.TransformerEncoderLayer (eval mode): in-projection + attention.
 // Needs every token of the sequences (keys / values), so it always runs on the full phase.
+// dyn != null: the phase is on the pad-skipping layout (compact.cu): row / sequence counts come from the device header,
+// `num_seqs` is the static bound; the one-token sequences of the second row region get their own attention launch.
 int run_attention_part(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw,
                        const Phase& ph, const long long* mask_src, long long num_seqs, int T,
-                       bool causal) {
+                       bool causal, const int* dyn = nullptr) {
   const bool fp32 = precision == STLT_PRECISION_FP32;
   int rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv,
-                    fp32 ? 3 : 1, fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, 0);
+                    fp32 ? 3 : 1, fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, 0, DropCfg{0, 0, 1.f},
+                    dyn != nullptr ? dyn + kDynTiles : nullptr);
   if (rc) return rc;
   // fp32 mode: q/k/v and the context travel as bf16 hi/lo planes; products are 3-term splits
   ActOut att{nullptr, ph.att, fp32 ? 2 : 1, ph.m_pad};
   {
     ProfileScope prof(h, stream, STLT_PROF_ATTENTION);
-    STLT_CUDA(h, launch_attention(ph.qkv, true, mask_src, num_seqs, T, causal, att, stream));
+    if (dyn != nullptr) {
+      const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(ph.qkv);
+      STLT_CUDA(h, launch_attention_mma(q, att.planes, ph.m_pad, mask_src, num_seqs, T, causal, ph.att, ph.m_pad, stream,
+                                        DropCfg{0, 0, 1.f}, dyn, 0));
+      STLT_CUDA(h, launch_attention_mma(q, att.planes, ph.m_pad, mask_src, num_seqs, 1, false, ph.att, ph.m_pad, stream,
+                                        DropCfg{0, 0, 1.f}, dyn, 1));
+      h->launches++;
+    } else {
+      STLT_CUDA(h, launch_attention(ph.qkv, true, mask_src, num_seqs, T, causal, att, stream));
+    }
   }
   h->launches++;
   return STLT_OK;
@@ -211,7 +223,10 @@ int run_attention_part(Handle* h, cudaStream_t stream, int precision, const Laye
 // Second half: out-projection -> +residual -> LN -> FFN -> +residual -> LN. Row-wise, so it may
 // run on a compacted subset of the rows (the pruned last layer of each stack).
 int run_tail_part(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw,
-                  const Phase& ph) {
+                  const Phase& ph, const int* dyn = nullptr) {
+  const int* tiles_dyn = dyn != nullptr ? dyn + kDynTiles : nullptr;
+  const int* rows_dyn = dyn != nullptr ? dyn + kDynRows : nullptr;
+  const DropCfg nodrop{0, 0, 1.f};
   const bool fp32 = precision == STLT_PRECISION_FP32;
   const int terms = fp32 ? 3 : 1;
   const int planes = fp32 ? 2 : 1;
@@ -221,25 +236,27 @@ int run_tail_part(Handle* h, cudaStream_t stream, int precision, const LayerWeig
   const bool y16 = !fp32 && h->bf16_branch;
   __nv_bfloat16* y_b = reinterpret_cast<__nv_bfloat16*>(ph.y);
   int rc = run_gemm(h, stream, ph.att, ph.m_pad, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.y,
-                    terms, y16 ? GEMM_OUT_BF16 : GEMM_OUT_F32, 0);
+                    terms, y16 ? GEMM_OUT_BF16 : GEMM_OUT_F32, 0, nodrop, tiles_dyn);
   if (rc) return rc;
   ActOut xo{ph.x, ph.xb, planes, ph.m_pad};
+  // on the pad-skipping layout the row bound is the allocation and the live count comes from the device
+  const long long ln_rows = dyn != nullptr ? ph.m_pad : ph.m_valid;
   {
     ProfileScope prof(h, stream, STLT_PROF_ADD_LN);
-    if (y16) STLT_CUDA(h, launch_add_ln_bf16y(ph.x, y_b, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
-    else STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n1_g, lw.n1_b, eps, ph.m_valid, xo, stream));
+    if (y16) STLT_CUDA(h, launch_add_ln_bf16y(ph.x, y_b, lw.n1_g, lw.n1_b, eps, ln_rows, xo, stream, nullptr, nodrop, rows_dyn));
+    else STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n1_g, lw.n1_b, eps, ln_rows, xo, stream, nullptr, nodrop, rows_dyn));
   }
   h->launches++;
   rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.l1_p, kFfn, kHidden, lw.l1_b, ph.hid, terms,
-                fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, fp32 ? 1 : 2);
+                fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, fp32 ? 1 : 2, nodrop, tiles_dyn);
   if (rc) return rc;
   rc = run_gemm(h, stream, ph.hid, ph.m_pad, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.y, terms,
-                y16 ? GEMM_OUT_BF16 : GEMM_OUT_F32, 0);
+                y16 ? GEMM_OUT_BF16 : GEMM_OUT_F32, 0, nodrop, tiles_dyn);
   if (rc) return rc;
   {
     ProfileScope prof(h, stream, STLT_PROF_ADD_LN);
-    if (y16) STLT_CUDA(h, launch_add_ln_bf16y(ph.x, y_b, lw.n2_g, lw.n2_b, eps, ph.m_valid, xo, stream));
-    else STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n2_g, lw.n2_b, eps, ph.m_valid, xo, stream));
+    if (y16) STLT_CUDA(h, launch_add_ln_bf16y(ph.x, y_b, lw.n2_g, lw.n2_b, eps, ln_rows, xo, stream, nullptr, nodrop, rows_dyn));
+    else STLT_CUDA(h, launch_add_ln(ph.x, ph.y, lw.n2_g, lw.n2_b, eps, ln_rows, xo, stream, nullptr, nodrop, rows_dyn));
   }
   h->launches++;
   return STLT_OK;
@@ -755,12 +772,32 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   }
 
   ActOut emb{sp.x, sp.xb, planes, sp.m_pad};
+  // the pad-skipping layout of the spatial phase (compact.cu) on the separate kernels: fp32-parity mode, or bf16 with the
+  // epilogue fusions switched off. Needs the pruned last layer (its tail is what maps back to the padded [B, L] grid).
+  const bool compact_u = h->compaction && prune_sp && p.off_plan != 0 && S <= 32 && h->taps.embed == nullptr &&
+                         h->taps.frames == nullptr;
+  const int* dyn_u = nullptr;
+  const int* frame_row_u = nullptr;
+  const long long* sp_mask_u = categories;
+  if (compact_u) {
+    int* hdr = reinterpret_cast<int*>(ws + p.off_plan);
+    int* fr = reinterpret_cast<int*>(ws + p.off_frame_row);
+    {
+      ProfileScope prof(h, stream, STLT_PROF_OTHER);
+      STLT_CUDA(h, launch_compact_plan(categories, lengths, B, L, S, fr, hdr, ws + p.off_plan_scratch, err_flag, stream));
+    }
+    h->launches += 3;
+    dyn_u = hdr;
+    frame_row_u = fr;
+    sp_mask_u = reinterpret_cast<long long*>(ws + p.off_mask);
+  }
   {
     ProfileScope prof(h, stream, STLT_PROF_OTHER);
     STLT_CUDA(h, launch_embed(categories, boxes, scores, h->w.cat_table, d.unique_categories,
                               h->w.box_w, h->w.box_b, h->w.score_w, h->w.score_b, h->w.emb_g,
                               h->w.emb_b, d.layer_norm_eps, n_sp, emb, err_flag, stream,
-                              reinterpret_cast<float*>(sp.hid), embed_scratch(sp)));
+                              reinterpret_cast<float*>(sp.hid), embed_scratch(sp), DropCfg{0, 0, 1.f}, frame_row_u, S,
+                              compact_u ? reinterpret_cast<long long*>(ws + p.off_mask) : nullptr));
   }
   h->launches += 2;  // embed_stats_kernel + embed_kernel
   if (h->taps.embed)
@@ -769,19 +806,23 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   bool cls_compact = false;  // spatial CLS rows already compacted into tm.x
   for (int i = 0; i < d.num_spatial_layers; ++i) {
     const LayerWeights& lw = h->w.spatial[i];
-    int rc = run_attention_part(h, stream, precision, lw, sp, categories, n_tm, S, false);
+    int rc = run_attention_part(h, stream, precision, lw, sp, sp_mask_u, n_tm, S, false, dyn_u);
     if (rc) return rc;
     if (prune_sp && i == d.num_spatial_layers - 1) {
       {
         ProfileScope prof(h, stream, STLT_PROF_OTHER);
-        STLT_CUDA(h, launch_gather_rows(sp.x, sp.att, planes, sp.m_pad, S, nullptr, 0, n_tm, tm.x, tm.att,
-                                        tm.m_pad, err_flag, stream));
+        if (compact_u)
+          STLT_CUDA(h, launch_gather_frames(sp.x, sp.att, frame_row_u, n_tm, tm.x, tm.att, nullptr, nullptr, stream, nullptr,
+                                            nullptr, planes, sp.m_pad, tm.m_pad));
+        else
+          STLT_CUDA(h, launch_gather_rows(sp.x, sp.att, planes, sp.m_pad, S, nullptr, 0, n_tm, tm.x, tm.att,
+                                          tm.m_pad, err_flag, stream));
       }
       h->launches++;
       rc = run_tail_part(h, stream, precision, lw, tm);
       cls_compact = true;
     } else {
-      rc = run_tail_part(h, stream, precision, lw, sp);
+      rc = run_tail_part(h, stream, precision, lw, sp, dyn_u);
     }
     if (rc) return rc;
   }

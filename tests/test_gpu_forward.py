@@ -184,6 +184,7 @@ def test_last_layer_pruning_is_bit_identical(precision):
     m = _model(cfg, sd, precision)
     batch = to_cuda(make_batch(37, "action_genome", ragged=True, seed=62))
     m.set_fused_layer_norm(False)  # the LayerNorm-fused bf16 path only exists in its pruned form
+    m.set_compaction(False)        # the pad-skipping layout moves rows to other tile positions: round-off, not bits (below)
     with torch.no_grad():
         pruned = m(batch)["stlt"].clone()
         n_pruned = m.last_launch_count()
@@ -191,8 +192,16 @@ def test_last_layer_pruning_is_bit_identical(precision):
         full = m(batch)["stlt"].clone()
         n_full = m.last_launch_count()
         m.set_pruning(True)
+        m.set_compaction(True)
+        compact = m(batch)["stlt"].clone()
+        n_compact = m.last_launch_count()
     assert torch.equal(pruned, full)
     assert n_pruned == n_full + 1  # two gathers replace the final gather_last
+    # the same separate kernels on the pad-skipping layout: 3 planning kernels + one more attention launch per spatial layer
+    print(precision, "pad-skipping vs padded grid", nerr(compact, pruned), "launches", n_compact, n_pruned)
+    assert n_compact == n_pruned + 3 + cfg.num_spatial_layers
+    # bf16: operand rounding flips with the tile position of a row, so the two layouts agree at the bf16-noise level only
+    assert nerr(compact, pruned) < (2e-5 if precision == "fp32" else 1.5e-2)
 
 
 def test_weight_update_is_picked_up():
@@ -258,7 +267,10 @@ def test_full_size_batch_properties():
     batch = make_batch(4096, "something", ragged=True, seed=52)
     gb = to_cuda(batch)
     with torch.no_grad():
+        compact_full = m(gb)["stlt"].clone()   # default: pad-skipping layout (rows of a video depend on the videos before it)
+        m.set_compaction(False)                 # the bit-exactness properties below are properties of the padded grid
         full = m(gb)["stlt"].clone()
+        assert nerr(compact_full, full) < 2e-5
         assert torch.isfinite(full).all()
         sub = {k: v[1000:1064].contiguous() for k, v in gb.items()}
         part = m(sub)["stlt"]
@@ -278,6 +290,10 @@ def test_full_size_batch_properties():
     with torch.no_grad():
         want = O.stlt_forward(sd, small)
     assert nerr(full[idx.cuda()].cpu(), want) < FP32_TOL
+    assert nerr(compact_full[idx.cuda()].cpu(), want) < FP32_TOL
+    with torch.no_grad():  # padded payload cannot leak on the pad-skipping layout either (bit-exact: same rows, same tiles)
+        m.set_compaction(True)
+        assert torch.equal(m(scr)["stlt"], compact_full)
     m.precision = "bf16"
     with torch.no_grad():
         b16 = m(gb)["stlt"]
