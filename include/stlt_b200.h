@@ -285,6 +285,16 @@ int stlt_op_dropout_mask(void* handle, float dropout_p, uint64_t seed, int32_t s
 int stlt_loss(void* handle, void* stream, int32_t kind, const float* logits, const void* labels,
               int32_t rows, int32_t classes, float grad_scale, float* loss_out, float* d_logits_out);
 
+/* Data-parallel training overlaps the gradient all-reduce with the rest of the backward pass (what DistributedDataParallel's
+ * bucketed hooks do around the loop of src/train.py:117-135). With stage events enabled, stlt_backward records one event on
+ * its stream as soon as the parameter gradients of a STAGE are final; stages in completion order:
+ *   0 classifier head | 1 .. nt temporal layers nt-1 .. 0 | nt+1 frame embedding (position / frame-type tables, LayerNorm)
+ *   | nt+2 .. nt+1+ns spatial layers ns-1 .. 0 | nt+ns+2 category / box / score embedding      (count = nt + ns + 3)
+ * stlt_stream_wait_backward_stage makes `stream` (the communication stream) wait for the event of `stage` of the most
+ * recent stlt_backward call, so that the all-reduce of that stage's gradient bucket starts while later stages still run. */
+int stlt_backward_stage_events(void* handle, int32_t enable, int32_t* num_stages_out);
+int stlt_stream_wait_backward_stage(void* handle, void* stream, int32_t stage);
+
 /* sumsq_out[0] = sum(grads^2) over a flat fp32 buffer (the squared total norm of clip_grad_norm_), reduced in
  * a fixed order so that data-parallel ranks derive bit-identical clip coefficients from their all-reduced
  * gradients. scratch: caller-owned device floats (up to 1184 are used). */

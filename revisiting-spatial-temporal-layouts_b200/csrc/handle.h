@@ -86,6 +86,7 @@ struct Handle {
   Weights g;  // fp32 gradient buffers bound by stlt_bind_grads (same names; null = not wanted)
   bool bound = false;
   bool grads_bound = false;
+  std::vector<cudaEvent_t> bwd_stage_events;  // stlt_backward_stage_events: recorded as each stage's gradients are final
   int packed_precision = -1;
   const void* packed_ptr = nullptr;
   int num_sms = 0;

@@ -416,7 +416,10 @@ int stlt_create(const StltDims* dims, void** handle) {
 int stlt_destroy(void* handle) {
   Handle* h = static_cast<Handle*>(handle);
   if (h)
+  {
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->bwd_stage_events) cudaEventDestroy(e);
+  }
   delete h;
   return STLT_OK;
 }

@@ -405,6 +405,34 @@ int stlt_forward_train(void* handle, void* stream_, const int64_t* categories_, 
   return STLT_OK;
 }
 
+int stlt_backward_stage_events(void* handle, int32_t enable, int32_t* num_stages_out) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  const int n = h->dims.num_temporal_layers + h->dims.num_spatial_layers + 3;
+  if (num_stages_out) *num_stages_out = n;
+  if (enable && h->bwd_stage_events.empty()) {
+    for (int i = 0; i < n; ++i) {
+      cudaEvent_t e;
+      STLT_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->bwd_stage_events.push_back(e);
+    }
+  } else if (!enable) {
+    for (cudaEvent_t e : h->bwd_stage_events) cudaEventDestroy(e);
+    h->bwd_stage_events.clear();
+  }
+  return STLT_OK;
+}
+
+int stlt_stream_wait_backward_stage(void* handle, void* stream, int32_t stage) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  if (h->bwd_stage_events.empty()) return fail(h, STLT_ERR_STATE, "stlt_backward_stage_events has not been enabled");
+  if (stage < 0 || stage >= static_cast<int>(h->bwd_stage_events.size()))
+    return fail(h, STLT_ERR_INVALID, "stage %d out of range [0, %zu)", stage, h->bwd_stage_events.size());
+  STLT_CUDA(h, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->bwd_stage_events[stage], 0));
+  return STLT_OK;
+}
+
 int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const float* boxes,
                   const float* scores, const int64_t* frame_types_, const int64_t* lengths_, int32_t B,
                   int32_t L, int32_t S, void* workspace, size_t workspace_bytes, float dropout_p,
@@ -442,6 +470,10 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
   float* f3 = at<float>(ws, p.f[3]);
   // gradient w.r.t. the spatial stack's output (CLS rows); survives between the two phases
   float* d_cls = at<float>(ws, p.cls_x);  // cls_x itself is consumed by frame_embed_bwd before being overwritten
+  // the parameter gradients of `stage` are final: the communication stream may start their all-reduce (stlt_b200.h)
+  auto stage_done = [&](int stage) -> cudaError_t {
+    return h->bwd_stage_events.empty() ? cudaSuccess : cudaEventRecord(h->bwd_stage_events[stage], stream);
+  };
 
   if (phases & STLT_BWD_TEMPORAL) {
     // ---- head ----
@@ -466,6 +498,7 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
       STLT_CUDA(h, launch_gemm_strided(dh1, kHidden, 1, w.fc1_w, kHidden, 1, f0, B, kHidden, kHidden, false, stream));
       h->launches += 7;
     }
+    STLT_CUDA(h, stage_done(0));
     // ---- temporal stack, last layer first ----
     const float* d_a = f0;
     const float* d_b = nullptr;
@@ -479,6 +512,7 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
       if (rc) return rc;
       d_a = f0;
       d_b = fb_used ? f1 : nullptr;
+      STLT_CUDA(h, stage_done(nt - i));
     }
     // ---- frame embedding ----
     {
@@ -491,6 +525,7 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
                                    stream));
       h->launches++;
     }
+    STLT_CUDA(h, stage_done(nt + 1));
   }
 
   if (phases & STLT_BWD_SPATIAL) {
@@ -506,6 +541,7 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
       if (rc) return rc;
       d_a = f0;
       d_b = fb_used ? f1 : nullptr;
+      STLT_CUDA(h, stage_done(nt + 2 + (ns - 1 - i)));
     }
     {
       ProfileScope prof(h, stream, STLT_PROF_OTHER);
@@ -518,6 +554,7 @@ int stlt_backward(void* handle, void* stream_, const int64_t* categories_, const
                                     grad_ptr(g.emb_b), stream, site_cfg(dropout_p, seed, 0)));
       h->launches += 2;
     }
+    STLT_CUDA(h, stage_done(nt + ns + 2));
   }
   return STLT_OK;
 }

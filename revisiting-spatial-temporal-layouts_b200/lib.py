@@ -142,6 +142,8 @@ SIGNATURES = {
     "stlt_op_dropout_mask": (c_int32, [c_void_p, c_float, c_uint64, c_int32, c_int64, c_int64, c_void_p]),
     "stlt_loss": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_float,
                             c_void_p, c_void_p]),
+    "stlt_backward_stage_events": (c_int32, [c_void_p, c_int32, c_void_p]),
+    "stlt_stream_wait_backward_stage": (c_int32, [c_void_p, c_void_p, c_int32]),
     "stlt_grad_sumsq": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32]),
     "stlt_adamw_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_float, c_float, c_float, c_int32, c_void_p, c_float]),

@@ -5,8 +5,8 @@ with a grad_fn, see module._StltTrainFunction). This module is the B200-first ve
 body (reference src/train.py:117-135) with no host synchronisation and no per-tensor launches:
 
     zero grads -> forward (activations kept) -> criterion -> backward
-               -> gradient all-reduce over NCCL (data parallel; overlapped with the second half of
-                  the backward pass) -> global-norm clip + AdamW on flat fp32 buffers -> bf16 re-pack
+               -> gradient all-reduce over NCCL (data parallel; buckets leave on a communication stream as the
+                  backward stages that produce them finish) -> global-norm clip + AdamW on flat fp32 buffers -> bf16 re-pack
 
 Semantics follow the reference: ``Criterion`` (src/utils/train_inference_utils.py:64-76),
 ``add_weight_decay`` (:37-54; 1-D tensors and ``*.bias`` are not decayed),
@@ -18,6 +18,8 @@ has no ``scores``) are left untouched, exactly as AdamW skips ``grad is None``.
 from __future__ import annotations
 
 import ctypes
+import os
+import re
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -42,60 +44,131 @@ def _is_no_decay(name: str, p: torch.Tensor) -> bool:  # add_weight_decay, :46
     return p.dim() == 1 or name.endswith(".bias")
 
 
-def _phase_of(name: str) -> int:
-    """0: gradients produced by STLT_BWD_TEMPORAL (head, temporal stack, frame embedding);
-    1: by STLT_BWD_SPATIAL (spatial stack, category/box embedding)."""
-    return 1 if ".layout_embedding." in name else 0
+_LAYER = re.compile(r"transformer\.layers\.(\d+)\.")
 
 
-SEGMENT_ORDER = ("t_nd", "t_d", "s_nd", "s_d", "sc_nd", "sc_d")
+def backward_stage_of(name: str, num_spatial_layers: int, num_temporal_layers: int) -> int:
+    """The stage of stlt_backward (include/stlt_b200.h, stlt_backward_stage_events) after which the gradient of
+    parameter ``name`` is final: 0 head | 1..nt temporal layers nt-1..0 | nt+1 frame embedding |
+    nt+2..nt+1+ns spatial layers ns-1..0 | nt+ns+2 category / box / score embedding."""
+    ns, nt = num_spatial_layers, num_temporal_layers
+    m = _LAYER.search(name)
+    if name.startswith("prediction_head."):
+        return 0
+    if ".layout_embedding." in name:
+        return nt + 2 + (ns - 1 - int(m.group(1))) if m else nt + ns + 2
+    if m:
+        return 1 + (nt - 1 - int(m.group(1)))
+    return nt + 1
+
+
+SEGMENT_ORDER = ("d", "nd", "sc_nd", "sc_d")
+BUCKET_SCHEMES = ("one", "two", "per_layer")
 
 
 def plan_flat_layout(named_parameters):
     """Flat-buffer layout of the trainable parameters: [(name, param, offset)], {segment: (start, end)},
-    total. Segments: {temporal, spatial backward phase} x {no-decay, decay} and the score embedding
-    (which only gets a gradient when the batch carries ``scores``)."""
+    total, stage_ends.
+
+    Segments: ``d`` the weight-decayed tensors (add_weight_decay, train_inference_utils.py:37-54) ordered by the
+    backward stage that finishes their gradient, so that every all-reduce bucket is one contiguous slice that can
+    leave while the backward pass is still running; ``nd`` the 1-D tensors and biases (0.5 MB in all, they travel
+    with the last bucket); ``sc_*`` the score embedding, which only gets a gradient when the batch carries
+    ``scores``. ``stage_ends[k]`` = end offset (inside ``d``) of the tensors of stages <= k."""
+    named = [(n, p) for n, p in named_parameters if p.requires_grad and ".encoder_layer." not in n]
+    layers = {"s": 0, "t": 0}
+    for n, _ in named:
+        m = _LAYER.search(n)
+        if m:
+            key = "s" if ".layout_embedding." in n else "t"
+            layers[key] = max(layers[key], int(m.group(1)) + 1)
+    ns, nt = layers["s"], layers["t"]
+    num_stages = ns + nt + 3
     segs: Dict[str, List] = {k: [] for k in SEGMENT_ORDER}
-    for name, p in named_parameters:
-        if not p.requires_grad or ".encoder_layer." in name:
-            continue
+    for name, p in named:
         nd = _is_no_decay(name, p)
         if "score_embeddings" in name:
-            segs["sc_nd" if nd else "sc_d"].append((name, p))
+            segs["sc_nd" if nd else "sc_d"].append((num_stages - 1, name, p))
         else:
-            segs[("t" if _phase_of(name) == 0 else "s") + ("_nd" if nd else "_d")].append((name, p))
+            segs["nd" if nd else "d"].append((backward_stage_of(name, ns, nt), name, p))
+    segs["d"].sort(key=lambda t: t[0])  # stable: declaration order inside a stage
     segments, layout, off = {}, [], 0
+    stage_ends = [0] * num_stages
     for key in SEGMENT_ORDER:
         start = off
-        for name, p in segs[key]:
+        for stage, name, p in segs[key]:
             layout.append((name, p, off))
             off += (p.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned
+            if key == "d":
+                stage_ends[stage] = off
         segments[key] = (start, off)
-    return layout, segments, off
+    for k in range(1, num_stages):
+        stage_ends[k] = max(stage_ends[k], stage_ends[k - 1])
+    return layout, segments, off, stage_ends
 
 
-def all_reduce_buckets(flat_grads: torch.Tensor, segments, group=None, between=None):
-    """Sums the flat gradient over the data-parallel group in two contiguous buckets. ``between`` (the
-    second half of the backward pass) runs while the first bucket — the temporal-phase gradients, which
-    are final by then — is in flight."""
+def plan_buckets(scheme: str, stage_ends: List[int], total: int, num_temporal_stages: int,
+                 min_bucket_elems: int = 2 << 20):
+    """All-reduce buckets [(stage, start, end)] of the flat gradient buffer, in backward-completion order; bucket i may
+    leave once backward stage ``stage`` has finished. ``one``: the whole buffer after the backward pass. ``two``: the
+    temporal-phase gradients (stages < num_temporal_stages), then the rest. ``per_layer``: one bucket per stage, stages
+    smaller than ``min_bucket_elems`` merged into the next one. The last bucket always runs to ``total`` (it carries
+    the no-decay tensors and the score embedding)."""
+    last = len(stage_ends) - 1
+    if scheme == "one":
+        cuts = []
+    elif scheme == "two":
+        cuts = [num_temporal_stages - 1]
+    elif scheme == "per_layer":
+        cuts, start = [], 0
+        for k in range(last):
+            if stage_ends[k] - start >= min_bucket_elems:
+                cuts.append(k)
+                start = stage_ends[k]
+    else:
+        raise ValueError(f"bucket scheme must be one of {BUCKET_SCHEMES}")
+    buckets, start = [], 0
+    for k in cuts:
+        if stage_ends[k] > start:
+            buckets.append((k, start, stage_ends[k]))
+            start = stage_ends[k]
+    buckets.append((last, start, total))
+    return buckets
+
+
+def all_reduce_buckets(flat_grads: torch.Tensor, buckets, group=None, before_bucket=None, works=None):
+    """Issues the SUM all-reduce of every bucket asynchronously, in order; ``before_bucket(stage)`` runs first
+    (FusedTrainStep makes the communication stream wait for the backward stage's event there). Returns the list of
+    work handles (appended to ``works`` when given); the caller waits on them before it reads the gradients."""
     import torch.distributed as dist
-    t0, t1 = segments["t_nd"][0], segments["t_d"][1]
-    s0 = segments["s_nd"][0]
-    work = dist.all_reduce(flat_grads[t0:t1], op=dist.ReduceOp.SUM, group=group, async_op=True)
-    if between is not None:
-        between()
-    dist.all_reduce(flat_grads[s0:], op=dist.ReduceOp.SUM, group=group)
-    work.wait()
+    works = [] if works is None else works
+    for stage, a, b in buckets:
+        if before_bucket is not None:
+            before_bucket(stage)
+        works.append(dist.all_reduce(flat_grads[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return works
 
 
 class FusedTrainStep:
     """Owns flat fp32 parameter / gradient / AdamW-state buffers of an ``Stlt`` module.
 
     The module's parameters are re-pointed at views of one flat buffer (state_dict keys, shapes and
-    values are unchanged), laid out as [temporal-phase no-decay | temporal-phase decay |
-    spatial-phase no-decay | spatial-phase decay | score-embedding bias | score-embedding weight], so
-    the optimizer is four launches and each all-reduce bucket is one contiguous slice.
+    values are unchanged), laid out as [weight-decayed tensors in backward-completion order | 1-D tensors
+    and biases | score-embedding bias | score-embedding weight] (plan_flat_layout), so the optimizer is two
+    to four launches and each all-reduce bucket is one contiguous slice.
+
+    Data parallel (``bucket_scheme``): stlt_backward records an event per finished stage (head, each encoder
+    layer, the embeddings); a communication stream waits for the event of a bucket's last stage and the NCCL
+    all-reduce of that bucket runs underneath the rest of the backward pass. ``two`` (default): the temporal-phase
+    gradients (230 MB) travel under the spatial stack's backward pass, the spatial-phase gradients (114 MB, 0.3 ms on
+    8 B200s over NVSwitch) at the end. ``per_layer``: 13 buckets of one encoder layer each, only the last 0.5 MB
+    exposed - measured SLOWER on 8 GPUs (53.15 vs 52.56 ms per step, 51.4 without any all-reduce;
+    profiles/r2_v9_train_comm_probe.md): the whole 344 MB all-reduce takes 0.9 ms alone, so there is little to hide,
+    while every collective that runs beside the persistent 148-CTA GEMM grids takes SMs away from them. ``one``: a
+    single all-reduce after the backward pass (52.79 ms).
     """
+
+    BUCKET_SCHEMES = BUCKET_SCHEMES
 
     def __init__(self, model: Stlt, lr: float = 5e-5, weight_decay: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, clip_val: Optional[float] = 5.0, loss: str = "cross_entropy",
@@ -115,14 +188,16 @@ class FusedTrainStep:
         self._checked_batch = None
         self._ws = None
         self._ws_key = None
-        self.num_buckets = 2  # all-reduce buckets per step (see all_reduce_buckets)
+        self.bucket_scheme = os.environ.get("STLT_TRAIN_BUCKETS", "two")  # plan_buckets
+        self._comm_stream = None
 
         device = next(model.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("FusedTrainStep needs the module on a CUDA device (there is no CPU path)")
         self.device = device
-        layout, self.segments, off = plan_flat_layout(model.named_parameters())
+        layout, self.segments, off, self.stage_ends = plan_flat_layout(model.named_parameters())
         self.total = off
+        self.num_temporal_stages = int(model.config.num_temporal_layers) + 2  # head, temporal layers, frame embedding
         self.flat_params = torch.zeros(off, dtype=torch.float32, device=device)
         self.flat_grads = torch.zeros(off, dtype=torch.float32, device=device)
         self.exp_avg = torch.zeros(off, dtype=torch.float32, device=device)
@@ -145,6 +220,18 @@ class FusedTrainStep:
         if self.group is None and not (dist.is_available() and dist.is_initialized()):
             return 1
         return dist.get_world_size(self.group)
+
+    def buckets(self, scheme: Optional[str] = None):
+        """[(stage, start, end)] of the current (or given) bucket scheme."""
+        return plan_buckets(scheme or self.bucket_scheme, self.stage_ends, self.total, self.num_temporal_stages)
+
+    @property
+    def num_buckets(self) -> int:
+        return len(self.buckets())
+
+    def bucket_bounds(self) -> Dict[str, tuple]:
+        """{label: (start, end)} of the per-layer buckets (tools/train_comm_probe.py)."""
+        return {f"stage<={k}": (a, b) for k, a, b in self.buckets("per_layer")}
 
     def _bind(self, has_scores: bool) -> None:
         if self._bound_scores == has_scores:
@@ -205,12 +292,10 @@ class FusedTrainStep:
             _lib.check(model._handle, lib.stlt_loss(model._handle, stream, kind, logits.data_ptr(),
                                                     labels.data_ptr(), B, C, 1.0 / world,
                                                     self._loss.data_ptr(), d_logits.data_ptr()))
-            model._backward(inputs, self._ws, d_logits, _lib.BWD_TEMPORAL, *drop)
-            spatial = lambda: model._backward(inputs, self._ws, None, _lib.BWD_SPATIAL, *drop)  # noqa: E731
-            if world > 1:  # bucket 1 travels over NVLink while the spatial stack's backward runs
-                all_reduce_buckets(self.flat_grads, self.segments, self.group, between=spatial)
+            if world > 1:
+                self._backward_overlapped(inputs, d_logits, drop, device)
             else:
-                spatial()
+                model._backward(inputs, self._ws, d_logits, _lib.BWD_ALL, *drop)
             sumsq_ptr = None
             if self.clip_val is not None:
                 _lib.check(model._handle, lib.stlt_grad_sumsq(model._handle, stream, self.flat_grads.data_ptr(),
@@ -218,11 +303,11 @@ class FusedTrainStep:
                                                               self._sumsq_scratch.data_ptr(), self._sumsq_scratch.numel()))
                 sumsq_ptr = self._sumsq.data_ptr()
             lr = self.lr * self.lr_lambda(self.step_count - 1)
-            for key in ("t_nd", "t_d", "s_nd", "s_d", "sc_nd", "sc_d"):
+            for key in SEGMENT_ORDER:
                 a, b = self.segments[key]
                 if b == a or (key.startswith("sc") and not has_scores):
                     continue
-                wd = 0.0 if key.endswith("_nd") else self.weight_decay
+                wd = 0.0 if key.endswith("nd") else self.weight_decay
                 es = 4  # bytes per element
                 _lib.check(model._handle, lib.stlt_adamw_step(
                     model._handle, stream, self.flat_params.data_ptr() + a * es, self.flat_grads.data_ptr() + a * es,
@@ -235,6 +320,32 @@ class FusedTrainStep:
         self._keepalive = (inputs, labels, d_logits, logits)
         self.last_logits = logits
         return self._loss[0].clone()  # a fresh device scalar: the accumulator is reused by the next step
+
+    def _backward_overlapped(self, inputs, d_logits, drop, device) -> None:
+        """Backward pass with the gradient all-reduce underneath it: each bucket leaves on the communication stream as soon
+        as the event of its last backward stage has fired; the compute stream waits for all of them at the end. The
+        temporal-phase buckets are issued before the spatial half of the backward pass is enqueued, so a host that is not
+        far ahead of the GPU does not delay them."""
+        model, lib = self.model, _lib.load_library()
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=device)
+            _lib.check(model._handle, lib.stlt_backward_stage_events(model._handle, 1, None))
+        comm = self._comm_stream
+
+        def wait_stage(stage: int) -> None:
+            _lib.check(model._handle, lib.stlt_stream_wait_backward_stage(model._handle, comm.cuda_stream, stage))
+
+        buckets = self.buckets()
+        first = [b for b in buckets if b[0] < self.num_temporal_stages]
+        rest = [b for b in buckets if b[0] >= self.num_temporal_stages]
+        model._backward(inputs, self._ws, d_logits, _lib.BWD_TEMPORAL, *drop)
+        with torch.cuda.stream(comm):
+            works = all_reduce_buckets(self.flat_grads, first, self.group, before_bucket=wait_stage)
+        model._backward(inputs, self._ws, None, _lib.BWD_SPATIAL, *drop)
+        with torch.cuda.stream(comm):
+            all_reduce_buckets(self.flat_grads, rest, self.group, before_bucket=wait_stage, works=works)
+        for w in works:  # the compute stream waits for the NCCL stream; no host synchronisation
+            w.wait()
 
     def _repack(self, stream: int) -> None:
         model, lib = self.model, _lib.load_library()

@@ -74,6 +74,6 @@ if rank == 0:
     # differently (2 x 32 videos vs 64), and AdamW's first steps are sign-like (update ~ lr * g / |g|), which turns
     # rounding noise on near-zero gradient entries into full-size update differences: rel = sqrt(2 (1 - cos)).
     assert rel < 3e-2 and cos > 0.9998, (rel, cos)
-    print("DP_OK")
+    print(f"DP_OK scheme={stepper.bucket_scheme} buckets={stepper.num_buckets}")
 dist.barrier()
 dist.destroy_process_group()

@@ -332,9 +332,11 @@ def test_training_converges_on_a_learnable_synthetic_task():
     assert losses[-5:].mean() < 0.5 * losses[:5].mean()
 
 
-def test_two_gpu_data_parallel_step_equals_single_process(tmp_path):
-    """NCCL data parallelism (mean over the GLOBAL batch: 1/world folded into d loss, SUM all-reduce in two
-    buckets): after 3 steps two ranks on half batches hold the parameters of one process on the whole batch."""
+@pytest.mark.parametrize("scheme", ["two", "per_layer", "one"])
+def test_two_gpu_data_parallel_step_equals_single_process(tmp_path, scheme):
+    """NCCL data parallelism (mean over the GLOBAL batch: 1/world folded into d loss, SUM all-reduce in buckets that leave on
+    a communication stream as stlt_backward's stage events fire): after 3 steps two ranks on half batches hold the
+    parameters of one process on the whole batch, for every bucket scheme of FusedTrainStep."""
     import os
     import subprocess
     import sys
@@ -342,12 +344,12 @@ def test_two_gpu_data_parallel_step_equals_single_process(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     worker = Path(__file__).resolve().parent / "dp_worker.py"
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", STLT_TRAIN_BUCKETS=scheme)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", "29547", str(worker)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
-    assert "DP_OK" in res.stdout
+    assert "DP_OK" in res.stdout and f"scheme={scheme}" in res.stdout
 
 
 def test_gradients_match_oracle_at_multi_tile_scale():

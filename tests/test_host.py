@@ -100,26 +100,52 @@ def test_training_mode_has_no_cpu_path_either():
 
 
 def test_flat_training_layout_groups_parameters_like_the_reference_optimizer():
-    """plan_flat_layout: add_weight_decay's two groups (train_inference_utils.py:37-54), split by the
-    backward phase that produces the gradient; orphan tensors are not part of the optimizer."""
-    from stlt_b200.training import plan_flat_layout
+    """plan_flat_layout: add_weight_decay's two groups (train_inference_utils.py:37-54); the decayed tensors are ordered by
+    the backward stage that finishes their gradient; orphan tensors are not part of the optimizer."""
+    from stlt_b200.training import backward_stage_of, plan_buckets, plan_flat_layout
     m = Stlt(StltModelConfig(num_classes=174, unique_categories=4))
-    layout, segments, total = plan_flat_layout(m.named_parameters())
+    layout, segments, total, stage_ends = plan_flat_layout(m.named_parameters())
     names = [n for n, _, _ in layout]
     assert len(names) == len(set(names)) == 161  # 173 parameters - 12 orphan encoder_layer.* tensors
     assert not any(".encoder_layer." in n for n in names)
     offs = [o for _, _, o in layout]
     assert offs == sorted(offs) and all(o % 4 == 0 for o in offs)
     params = dict(m.named_parameters())
+    ns, nt = 4, 8
+    assert len(stage_ends) == ns + nt + 3 and stage_ends == sorted(stage_ends) and stage_ends[-1] == segments["d"][1]
     for n, p, o in layout:
         key = next(k for k, (a, b) in segments.items() if a <= o < b)
-        assert key.endswith("_nd") == (p.dim() == 1 or n.endswith(".bias")), n
-        if "score_embeddings" in n:
-            assert key.startswith("sc")
-        else:
-            assert key.startswith("s_") == (".layout_embedding." in n), n
-    assert segments["t_nd"][0] == 0 and segments["sc_d"][1] == total
+        assert key.endswith("nd") == (p.dim() == 1 or n.endswith(".bias")), n
+        assert key.startswith("sc") == ("score_embeddings" in n), n
+        if key == "d":  # inside the slice of its backward stage
+            k = backward_stage_of(n, ns, nt)
+            assert (stage_ends[k - 1] if k else 0) <= o and o + p.numel() <= stage_ends[k], n
+    assert segments["d"][0] == 0 and segments["sc_d"][1] == total
     assert total >= sum(params[n].numel() for n in names)
+    # stage order = order in which stlt_backward finishes the gradients
+    assert backward_stage_of("prediction_head.fc2.weight", ns, nt) == 0
+    assert backward_stage_of("backbone.transformer.layers.7.linear1.weight", ns, nt) == 1
+    assert backward_stage_of("backbone.transformer.layers.0.linear1.weight", ns, nt) == 8
+    assert backward_stage_of("backbone.frames_embeddings.position_embeddings.weight", ns, nt) == 9
+    assert backward_stage_of("backbone.frames_embeddings.layout_embedding.transformer.layers.3.linear2.weight", ns, nt) == 10
+    assert backward_stage_of("backbone.frames_embeddings.layout_embedding.transformer.layers.0.linear2.weight", ns, nt) == 13
+    assert backward_stage_of(
+        "backbone.frames_embeddings.layout_embedding.category_box_embeddings.box_embedding.weight", ns, nt) == 14
+    # every scheme tiles [0, total) with contiguous buckets in stage order; "two" cuts after the temporal phase
+    for scheme in ("one", "two", "per_layer"):
+        buckets = plan_buckets(scheme, stage_ends, total, nt + 2)
+        assert buckets[0][1] == 0 and buckets[-1][2] == total and buckets[-1][0] == ns + nt + 2
+        assert all(b0[2] == b1[1] and b0[0] < b1[0] for b0, b1 in zip(buckets, buckets[1:]))
+        assert all(e > s_ for _, s_, e in buckets)
+    assert len(plan_buckets("one", stage_ends, total, nt + 2)) == 1
+    two = plan_buckets("two", stage_ends, total, nt + 2)
+    assert len(two) == 2 and two[0] == (nt + 1, 0, stage_ends[nt + 1])
+    per_layer = plan_buckets("per_layer", stage_ends, total, nt + 2)
+    # one per encoder layer (the head and the frame embedding ride with the next layer) + the tail: category / box embedding,
+    # the no-decay block and the score embedding (0.5 MB), the only bucket that waits for the very end of the backward pass
+    assert len(per_layer) == 13 and per_layer[-1][2] - per_layer[-1][1] < 1 << 18
+    with pytest.raises(ValueError):
+        plan_buckets("three", stage_ends, total, nt + 2)
 
 
 @pytest.mark.parametrize("layout,S,has_scores", [("something", 5, False), ("action_genome", 11, True)])
@@ -189,24 +215,25 @@ _TRAIN_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["STLT_ROOT"])
 import stlt_b200
-from stlt_b200.training import all_reduce_buckets, plan_flat_layout
+from stlt_b200.training import all_reduce_buckets, plan_buckets, plan_flat_layout
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 model = stlt_b200.Stlt(stlt_b200.StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=1,
                                                  num_temporal_layers=1))
-layout, segments, total = plan_flat_layout(model.named_parameters())
+layout, segments, total, stage_ends = plan_flat_layout(model.named_parameters())
 # per-rank "gradients": the local-mean gradient already scaled by 1/world, as FusedTrainStep feeds the
 # all-reduce (stlt_loss grad_scale = 1/world), so the SUM over ranks is the global-batch mean
-g = torch.Generator().manual_seed(100 + rank)
-local = torch.randn(total, generator=g)
-flat = (local / world).clone()
-ran = []
-all_reduce_buckets(flat, segments, between=lambda: ran.append(True))
-assert ran == [True]
 want = sum(torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
-a, b = segments["t_nd"][0], segments["s_d"][1]
-assert torch.allclose(flat[a:b], want[a:b], atol=1e-6), rank
-# every trainable, non-orphan tensor lies inside one of the two buckets
+for scheme in ("one", "two", "per_layer"):
+    local = torch.randn(total, generator=torch.Generator().manual_seed(100 + rank))
+    flat = (local / world).clone()
+    buckets = plan_buckets(scheme, stage_ends, total, 1 + 2)
+    seen = []
+    for w in all_reduce_buckets(flat, buckets, before_bucket=seen.append):
+        w.wait()
+    assert seen == [b[0] for b in buckets] and seen == sorted(seen), (scheme, seen)
+    # every trainable, non-orphan tensor lies inside exactly one bucket and holds the global mean
+    assert torch.allclose(flat, want, atol=1e-6), (rank, scheme)
 for name, p, off in layout:
     assert 0 <= off and off + p.numel() <= total
 dist.barrier()
