@@ -415,7 +415,41 @@ def measured_traffic(precision: str):
         return None, f"unreadable traffic file: {e!r}"
 
 
-def roofline_from_profile(prof, steps, precision, peaks, peak_src):
+KERNEL_OF_ROLE = {
+    "in_proj": "gemm_tcgen05_kernel (in-projection, plain epilogue)",
+    "qkv_attention": "qkv_attention_kernel (in-projection + attention; FLOPs of the in-projection)",
+    "out_proj": "gemm_tcgen05_kernel (out-projection; bf16 mode: + residual add and LayerNorm statistics, RESID epilogue)",
+    "linear1": "gemm_tcgen05_kernel (linear1 + GELU; bf16 mode: + the pending LayerNorm, NORM_A epilogue)",
+    "linear2": "gemm_tcgen05_kernel (linear2; bf16 mode: + residual add and LayerNorm statistics, RESID epilogue)",
+    "gradient": "gemm_tcgen05_kernel (data- and weight-gradient GEMMs)",
+    "other_gemm": "gemm_tcgen05_kernel (other shapes)",
+}
+
+
+def roofline_by_kernel(roles, steps, precision, peaks):
+    """Per-role split of the GEMM-class time (stlt_get_profile_by_role): ms and algorithmic TFLOP/s per step against
+    the sustained bf16 peak; for the out-projection, whose fused epilogue makes it HBM-bound in bf16 mode, also the
+    algorithmic bytes (context in, residual stream in / out, bf16 operand copy out) against the HBM peak."""
+    peak = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
+    hbm = float(peaks.get("hbm_gbs") or 0.0)
+    rows = []
+    for role, v in roles.items():
+        ms = v["ms"] / max(steps, 1)
+        flops = v["flops"] / max(steps, 1)
+        tf = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        row = {"role": role, "kernel": KERNEL_OF_ROLE.get(role, role), "launches_per_step": v["launches"] / max(steps, 1),
+               "ms_per_step": ms, "achieved_tflops": tf, "frac_of_tensor_peak": tf / peak}
+        if precision == "fp32":  # 3 bf16 MMAs per algorithmic MMA
+            row["mma_frac_of_tensor_peak"] = 3.0 * tf / peak
+        if role == "out_proj" and precision == "bf16" and hbm > 0 and ms > 0:
+            m_rows = flops / (2.0 * 768 * 768)
+            gbps = m_rows * 768 * (2 + 4 + 4 + 2) / (ms * 1e-3) / 1e9
+            row.update({"algorithmic_gbps": gbps, "frac_of_hbm_peak": gbps / hbm})
+        rows.append(row)
+    return rows
+
+
+def roofline_from_profile(prof, steps, precision, peaks, peak_src, roles=None):
     gemm = prof["gemm"]
     algorithmic = gemm["flops"] / max(steps, 1)                   # 2*M*N*K of the launches actually issued
     executed = algorithmic * (3.0 if precision == "fp32" else 1.0)  # fp32 mode: 3 bf16 MMAs per algorithmic MMA
@@ -437,6 +471,8 @@ def roofline_from_profile(prof, steps, precision, peaks, peak_src):
         out["note"] = ("kernel_ms_per_step includes the attention (it runs inside the in-projection kernel and adds time but no "
                        "counted FLOPs). Round 1 quoted 0.76 for its GEMM launches alone; with its 3.3 ms of separate attention "
                        "kernels counted the same way that figure was 23.95 TFLOP / (22.58 + 3.28 ms) = 0.664 of the same peak")
+    if roles:
+        out["by_kernel"] = roofline_by_kernel(roles, steps, precision, peaks)
     if precision == "fp32":
         out["mma_tflops_issued"] = executed / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         out["note"] = ("fp32-parity mode issues 3 bf16 MMAs (hi*hi + lo*hi + hi*lo) per algorithmic MMA; "
@@ -526,6 +562,7 @@ def run_inference(args, rank, local_rank, world, torch, dist, layout=None, batch
         model.enable_cuda_graphs(False)
         prof_ms, prof_local, prof = timed(fwd, steps, 1, world, torch, dist, before=lambda: model.set_profiling(True),
                                           after=lambda: (model.get_profile(), model.set_profiling(False))[0])
+        roles = model.get_profile_by_role()
         launches = model.last_launch_count() * steps
         kernel_ms = sum(v["ms"] for v in prof.values()) / steps
         per_rank = gather_ranks([local_ms / steps, prof_local / steps, kernel_ms], world, torch, dist)
@@ -534,7 +571,7 @@ def run_inference(args, rank, local_rank, world, torch, dist, layout=None, batch
             "value": videos / (ms * 1e-3), "ms_per_step": ms / steps,
             "e2e": {"value": videos / (e2e_ms * 1e-3), "unit": "videos/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps},
-            "roofline": roofline_from_profile(prof, steps, precision, peaks, peak_src),
+            "roofline": roofline_from_profile(prof, steps, precision, peaks, peak_src, roles),
             "gpu_launches": launches,
             "breakdown_ms_per_step": {k: v["ms"] / steps for k, v in prof.items()},
             "profiled_pass_ms_per_step": prof_ms / steps,

@@ -195,6 +195,24 @@ typedef struct StltProfile {
 int stlt_set_profiling(void* handle, int32_t enable);
 int stlt_get_profile(void* handle, StltProfile* out);
 
+/* The STLT_PROF_GEMM category of the most recent stlt_get_profile call, split by the role of the launch in the encoder layer
+ * (models.py:46-55,118-128): the measurement behind a per-kernel roofline. QKV_ATTENTION is the in-projection with the
+ * attention in its epilogue (bf16 path; its FLOPs are the in-projection's), GRADIENT the backward GEMMs of the training step. */
+#define STLT_PROF_ROLE_IN_PROJ 0
+#define STLT_PROF_ROLE_QKV_ATTENTION 1
+#define STLT_PROF_ROLE_OUT_PROJ 2
+#define STLT_PROF_ROLE_LINEAR1 3
+#define STLT_PROF_ROLE_LINEAR2 4
+#define STLT_PROF_ROLE_GRADIENT 5
+#define STLT_PROF_ROLE_OTHER_GEMM 6
+#define STLT_PROF_ROLES 7
+typedef struct StltRoleProfile {
+  double ms[STLT_PROF_ROLES];
+  double flops[STLT_PROF_ROLES];
+  int64_t launches[STLT_PROF_ROLES];
+} StltRoleProfile;
+int stlt_get_profile_by_role(void* handle, StltRoleProfile* out);
+
 /* Last-layer pruning (default on): only slot 0 of the spatial stack's output (models.py:79) and
  * only frame lengths-1 of the temporal stack's output (models.py:192) are read, so the row-wise
  * half of the last layer of each stack (out-proj, FFN, LayerNorms) runs on those rows only. The

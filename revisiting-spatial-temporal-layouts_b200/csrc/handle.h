@@ -114,8 +114,9 @@ struct Handle {
   size_t ev_used = 0;
   // dyn != null: the launch covered *dyn units of dyn_flops each (pad-skipping layout: counts live on the device and
   // are read back by stlt_get_profile, which synchronises anyway)
-  struct Span { int cat; cudaEvent_t a, b; double flops; const int* dyn; double dyn_flops; };
+  struct Span { int cat; cudaEvent_t a, b; double flops; const int* dyn; double dyn_flops; int role; };
   std::vector<Span> spans;
+  StltRoleProfile last_roles{};  // STLT_PROF_GEMM of the most recent stlt_get_profile, by role of the launch
   std::map<std::tuple<const void*, int, long long, long long, int, int>, CUtensorMap> tm_cache;
   char err[512] = {0};
 };
@@ -149,9 +150,10 @@ struct ProfileScope {
   double flops;
   const int* dyn = nullptr;
   double dyn_flops = 0.0;
+  int role = -1;  // STLT_PROF_ROLE_* of a STLT_PROF_GEMM span
   ProfileScope(Handle* h_, cudaStream_t s_, int cat_, double flops_ = 0.0, const int* dyn_ = nullptr,
-               double dyn_flops_ = 0.0)
-      : h(h_), s(s_), cat(cat_), flops(flops_), dyn(dyn_), dyn_flops(dyn_flops_) {
+               double dyn_flops_ = 0.0, int role_ = -1)
+      : h(h_), s(s_), cat(cat_), flops(flops_), dyn(dyn_), dyn_flops(dyn_flops_), role(role_) {
     if (!h->profiling) return;
     a = next_event(h);
     b = next_event(h);
@@ -160,7 +162,7 @@ struct ProfileScope {
   ~ProfileScope() {
     if (!h->profiling || !a || !b) return;
     cudaEventRecord(b, s);
-    h->spans.push_back({cat, a, b, flops, dyn, dyn_flops});
+    h->spans.push_back({cat, a, b, flops, dyn, dyn_flops, role});
   }
 };
 
@@ -173,6 +175,15 @@ struct ProfileScope {
   } while (0)
 
 inline long long pad128(long long v) { return (v + 127) / 128 * 128; }
+
+// Role of a forward projection GEMM, from its shape (stlt_get_profile_by_role).
+inline int gemm_role(int n, int k) {
+  if (n == kQkv && k == kHidden) return STLT_PROF_ROLE_IN_PROJ;
+  if (n == kHidden && k == kHidden) return STLT_PROF_ROLE_OUT_PROJ;
+  if (n == kFfn && k == kHidden) return STLT_PROF_ROLE_LINEAR1;
+  if (n == kHidden && k == kFfn) return STLT_PROF_ROLE_LINEAR2;
+  return STLT_PROF_ROLE_OTHER_GEMM;
+}
 inline size_t align1k(size_t v) { return (v + 1023) / 1024 * 1024; }
 
 // 2-D row-major tensor map with 128-byte swizzle. dtype: 0 = f32, 1 = bf16.
@@ -235,7 +246,7 @@ inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_r
   g.epi.m_tiles_dyn = m_tiles_dyn;  // pad-skipping layout: live 128-row tiles decided on the device
   g.tm_out2 = g.tm_out;
   ProfileScope prof(h, stream, STLT_PROF_GEMM, m_tiles_dyn ? 0.0 : 2.0 * static_cast<double>(m_rows) * n * k, m_tiles_dyn,
-                    2.0 * 128 * n * k);
+                    2.0 * 128 * n * k, gemm_role(n, k));
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
   return STLT_OK;
@@ -284,7 +295,7 @@ inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const vo
   g.epi = epi;
   g.epi.m_tiles_dyn = m_tiles_dyn;
   ProfileScope prof(h, stream, STLT_PROF_GEMM, m_tiles_dyn ? 0.0 : 2.0 * static_cast<double>(m_rows) * n * k,
-                    m_tiles_dyn, 2.0 * 128 * n * k);
+                    m_tiles_dyn, 2.0 * 128 * n * k, gemm_role(n, k));
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
   return STLT_OK;
@@ -331,7 +342,7 @@ inline int run_qkv_attention(Handle* h, cudaStream_t stream, const void* a, long
   p.dyn = dyn;
   // the executed MMAs cover 128-row blocks of which R rows are kept
   ProfileScope prof(h, stream, STLT_PROF_GEMM, dyn ? 0.0 : 2.0 * static_cast<double>(p.row_blocks) * 128 * kQkv * kHidden,
-                    dyn ? dyn + kDynAttnBlocks : nullptr, 2.0 * 128 * kQkv * kHidden);
+                    dyn ? dyn + kDynAttnBlocks : nullptr, 2.0 * 128 * kQkv * kHidden, STLT_PROF_ROLE_QKV_ATTENTION);
   STLT_CUDA(h, launch_qkv_attention(tm_a, tm_b, tm_out, tm_out1, p, stream, h->num_sms));
   h->launches++;
   return STLT_OK;
@@ -382,7 +393,8 @@ inline int run_gemm_grad(Handle* h, cudaStream_t stream, int layout, const void*
     g.epi.valid_rows = static_cast<int>(valid_rows);
   }
   g.tm_out2 = g.tm_out;
-  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * static_cast<double>(k));
+  ProfileScope prof(h, stream, STLT_PROF_GEMM, 2.0 * static_cast<double>(m_rows) * n * static_cast<double>(k), nullptr, 0.0,
+                    STLT_PROF_ROLE_GRADIENT);
   STLT_CUDA(h, launch_gemm_tcgen05(g, stream, h->num_sms));
   h->launches++;
   return STLT_OK;

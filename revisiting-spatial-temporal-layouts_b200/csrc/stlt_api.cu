@@ -975,6 +975,7 @@ int stlt_get_profile(void* handle, StltProfile* out) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h || !out) return fail(h, STLT_ERR_INVALID, "null argument");
   std::memset(out, 0, sizeof(*out));
+  h->last_roles = StltRoleProfile{};
   for (const auto& sp : h->spans) {
     STLT_CUDA(h, cudaEventSynchronize(sp.b));
     float ms = 0.f;
@@ -989,9 +990,22 @@ int stlt_get_profile(void* handle, StltProfile* out) {
       flops += sp.dyn_flops * units;
     }
     out->flops[sp.cat] += flops;
+    if (sp.cat == STLT_PROF_GEMM) {
+      const int r = sp.role >= 0 && sp.role < STLT_PROF_ROLES ? sp.role : STLT_PROF_ROLE_OTHER_GEMM;
+      h->last_roles.ms[r] += ms;
+      h->last_roles.flops[r] += flops;
+      h->last_roles.launches[r] += 1;
+    }
   }
   h->spans.clear();
   h->ev_used = 0;
+  return STLT_OK;
+}
+
+int stlt_get_profile_by_role(void* handle, StltRoleProfile* out) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h || !out) return fail(h, STLT_ERR_INVALID, "null argument");
+  *out = h->last_roles;
   return STLT_OK;
 }
 

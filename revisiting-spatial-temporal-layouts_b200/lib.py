@@ -90,6 +90,7 @@ class StltLayoutIds(Structure):
 
 
 PROF_CATEGORIES = ("gemm", "attention", "add_ln", "other")
+PROF_ROLES = ("in_proj", "qkv_attention", "out_proj", "linear1", "linear2", "gradient", "other_gemm")
 
 
 class StltProfile(Structure):
@@ -97,6 +98,14 @@ class StltProfile(Structure):
         ("ms", c_double * 4),
         ("flops", c_double * 4),
         ("launches", c_int64 * 4),
+    ]
+
+
+class StltRoleProfile(Structure):
+    _fields_ = [
+        ("ms", c_double * 7),
+        ("flops", c_double * 7),
+        ("launches", c_int64 * 7),
     ]
 
 
@@ -131,6 +140,7 @@ SIGNATURES = {
     "stlt_set_hilo_residual": (c_int32, [c_void_p, c_int32]),
     "stlt_set_profiling": (c_int32, [c_void_p, c_int32]),
     "stlt_get_profile": (c_int32, [c_void_p, POINTER(StltProfile)]),
+    "stlt_get_profile_by_role": (c_int32, [c_void_p, POINTER(StltRoleProfile)]),
     "stlt_bind_grads": (c_int32, [c_void_p, POINTER(StltTensor), c_int32]),
     "stlt_train_workspace_bytes": (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(c_size_t)]),
     "stlt_forward_train": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -651,6 +651,13 @@ class Stlt(nn.Module):
         return {name: {"ms": prof.ms[i], "flops": prof.flops[i], "launches": int(prof.launches[i])}
                 for i, name in enumerate(_lib.PROF_CATEGORIES)}
 
+    def get_profile_by_role(self) -> Dict[str, Dict[str, float]]:
+        """The "gemm" entry of the most recent get_profile(), split by the role of the launch in the encoder layer."""
+        prof = _lib.StltRoleProfile()
+        _lib.check(self._handle, _lib.load_library().stlt_get_profile_by_role(self._handle, ctypes.byref(prof)))
+        return {name: {"ms": prof.ms[i], "flops": prof.flops[i], "launches": int(prof.launches[i])}
+                for i, name in enumerate(_lib.PROF_ROLES) if prof.launches[i]}
+
     def last_launch_count(self) -> int:
         if self._handle is None:
             return 0

@@ -613,3 +613,33 @@ def test_forward_cuda_graph_mode_matches_eager_and_follows_weight_updates():
         m.enable_cuda_graphs(False)
         want2 = m(b2)["stlt"].clone()
         assert torch.equal(g, want2) and torch.equal(g2, want2) and not torch.equal(want2, want)
+
+
+def test_profile_by_role_splits_the_gemm_category_exactly():
+    """stlt_get_profile_by_role (bench.py's per-kernel roofline rows): the roles partition the "gemm" category — same
+    launches, FLOPs and (to rounding) time — and name what each precision mode runs: the bf16 path has the in-projection
+    inside qkv_attention_kernel, the fp32-parity mode a plain in-projection GEMM; the pruned last layers run 3 GEMMs on
+    the compacted rows, so every role counts one launch per layer."""
+    ns, nt = 2, 3
+    cfg = StltModelConfig(num_classes=174, unique_categories=4, num_spatial_layers=ns, num_temporal_layers=nt)
+    torch.manual_seed(0)
+    sd = random_state_dict(Stlt(cfg).state_dict(), seed=81)
+    batch = to_cuda(make_batch(19, "something", ragged=True, seed=82))
+    for precision, in_role in (("bf16", "qkv_attention"), ("fp32", "in_proj")):
+        m = _model(cfg, sd, precision)
+        with torch.no_grad():
+            m(batch)
+            m.set_profiling(True)
+            m(batch)
+            prof = m.get_profile()
+            roles = m.get_profile_by_role()
+            m.set_profiling(False)
+        assert set(roles) == {in_role, "out_proj", "linear1", "linear2"}, (precision, roles)
+        assert all(v["launches"] == ns + nt for v in roles.values()), (precision, roles)
+        assert sum(v["launches"] for v in roles.values()) == prof["gemm"]["launches"]
+        assert sum(v["flops"] for v in roles.values()) == pytest.approx(prof["gemm"]["flops"], rel=1e-12)
+        assert sum(v["ms"] for v in roles.values()) == pytest.approx(prof["gemm"]["ms"], rel=1e-6)
+        assert all(v["ms"] > 0 and v["flops"] > 0 for v in roles.values())
+        # a profile that was not refreshed is not re-reported: the next get_profile() without spans clears the roles
+        m.get_profile()
+        assert m.get_profile_by_role() == {}
