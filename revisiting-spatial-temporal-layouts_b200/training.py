@@ -66,7 +66,8 @@ SEGMENT_ORDER = ("d", "nd", "sc_nd", "sc_d")
 BUCKET_SCHEMES = ("one", "two", "per_layer")
 
 
-def plan_flat_layout(named_parameters):
+def plan_flat_layout(named_parameters, num_spatial_layers: Optional[int] = None,
+                     num_temporal_layers: Optional[int] = None):
     """Flat-buffer layout of the trainable parameters: [(name, param, offset)], {segment: (start, end)},
     total, stage_ends.
 
@@ -74,7 +75,9 @@ def plan_flat_layout(named_parameters):
     backward stage that finishes their gradient, so that every all-reduce bucket is one contiguous slice that can
     leave while the backward pass is still running; ``nd`` the 1-D tensors and biases (0.5 MB in all, they travel
     with the last bucket); ``sc_*`` the score embedding, which only gets a gradient when the batch carries
-    ``scores``. ``stage_ends[k]`` = end offset (inside ``d``) of the tensors of stages <= k."""
+    ``scores``. ``stage_ends[k]`` = end offset (inside ``d``) of the tensors of stages <= k. The layer counts fix the
+    stage numbering (it must be stlt_backward's); without them they are read off the parameter names, which is only
+    right when every layer has a trainable tensor."""
     named = [(n, p) for n, p in named_parameters if p.requires_grad and ".encoder_layer." not in n]
     layers = {"s": 0, "t": 0}
     for n, _ in named:
@@ -82,7 +85,8 @@ def plan_flat_layout(named_parameters):
         if m:
             key = "s" if ".layout_embedding." in n else "t"
             layers[key] = max(layers[key], int(m.group(1)) + 1)
-    ns, nt = layers["s"], layers["t"]
+    ns = layers["s"] if num_spatial_layers is None else int(num_spatial_layers)
+    nt = layers["t"] if num_temporal_layers is None else int(num_temporal_layers)
     num_stages = ns + nt + 3
     segs: Dict[str, List] = {k: [] for k in SEGMENT_ORDER}
     for name, p in named:
@@ -195,7 +199,8 @@ class FusedTrainStep:
         if device.type != "cuda":
             raise RuntimeError("FusedTrainStep needs the module on a CUDA device (there is no CPU path)")
         self.device = device
-        layout, self.segments, off, self.stage_ends = plan_flat_layout(model.named_parameters())
+        layout, self.segments, off, self.stage_ends = plan_flat_layout(
+            model.named_parameters(), model.config.num_spatial_layers, model.config.num_temporal_layers)
         self.total = off
         self.num_temporal_stages = int(model.config.num_temporal_layers) + 2  # head, temporal layers, frame embedding
         self.flat_params = torch.zeros(off, dtype=torch.float32, device=device)
