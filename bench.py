@@ -416,11 +416,11 @@ def measured_traffic(precision: str):
 
 
 KERNEL_OF_ROLE = {
-    "in_proj": "gemm_tcgen05_kernel (in-projection, plain epilogue)",
+    "in_proj": "gemm_tcgen05_kernel (pending LayerNorm + in-projection: NORM_A epilogue; plain for the first layer of a stack)",
     "qkv_attention": "qkv_attention_kernel (in-projection + attention; FLOPs of the in-projection)",
-    "out_proj": "gemm_tcgen05_kernel (out-projection; bf16 mode: + residual add and LayerNorm statistics, RESID epilogue)",
-    "linear1": "gemm_tcgen05_kernel (linear1 + GELU; bf16 mode: + the pending LayerNorm, NORM_A epilogue)",
-    "linear2": "gemm_tcgen05_kernel (linear2; bf16 mode: + residual add and LayerNorm statistics, RESID epilogue)",
+    "out_proj": "gemm_tcgen05_kernel (out-projection + residual add + LayerNorm statistics: RESID epilogue)",
+    "linear1": "gemm_tcgen05_kernel (pending LayerNorm + linear1 + GELU: NORM_A epilogue)",
+    "linear2": "gemm_tcgen05_kernel (linear2 + residual add + LayerNorm statistics: RESID epilogue)",
     "gradient": "gemm_tcgen05_kernel (data- and weight-gradient GEMMs)",
     "other_gemm": "gemm_tcgen05_kernel (other shapes)",
 }
@@ -441,9 +441,10 @@ def roofline_by_kernel(roles, steps, precision, peaks):
                "ms_per_step": ms, "achieved_tflops": tf, "frac_of_tensor_peak": tf / peak}
         if precision == "fp32":  # 3 bf16 MMAs per algorithmic MMA
             row["mma_frac_of_tensor_peak"] = 3.0 * tf / peak
-        if role == "out_proj" and precision == "bf16" and hbm > 0 and ms > 0:
+        if role == "out_proj" and hbm > 0 and ms > 0:
             m_rows = flops / (2.0 * 768 * 768)
-            gbps = m_rows * 768 * (2 + 4 + 4 + 2) / (ms * 1e-3) / 1e9
+            planes = 2 if precision == "fp32" else 1  # bf16 planes of the context read and of the operand copy written
+            gbps = m_rows * 768 * (2 * planes + 4 + 4 + 2 * planes) / (ms * 1e-3) / 1e9
             row.update({"algorithmic_gbps": gbps, "frac_of_hbm_peak": gbps / hbm})
         rows.append(row)
     return rows
@@ -638,7 +639,23 @@ def run_inference(args, rank, local_rank, world, torch, dist, layout=None, batch
         other = "fp32" if args.dtype == "bf16" else "bf16"
         sec, _ = measure(other, with_clocks=False, want_unfused=False)
         secondary = {"dtype": other, "value": sec["value"], "unit": "videos/s", "ms_per_step": sec["ms_per_step"],
-                     "e2e": sec["e2e"], "roofline": sec["roofline"], "model_tflops": sec["model_tflops"]}
+                     "e2e": sec["e2e"], "roofline": sec["roofline"], "model_tflops": sec["model_tflops"],
+                     "breakdown_ms_per_step": sec["breakdown_ms_per_step"]}
+        if other == "fp32" and not args.no_extras:
+            # the LayerNorm-fused epilogues of the fp32-parity mode against its separate add + LayerNorm kernels:
+            # graph-replayed, interleaved on this GPU, best of two rounds (as fusion_ab above)
+            model.precision = "fp32"
+            model.enable_cuda_graphs(use_graphs)
+            best = {}
+            for _ in range(2):
+                for name, flag in (("default", True), ("separate_layernorm_kernels", False)):
+                    model.set_fused_layer_norm(True, fp32=flag)
+                    u_ms, _, _ = timed(fwd, steps, 2, world, torch, dist)
+                    best[name] = min(best.get(name, u_ms), u_ms)
+            model.set_fused_layer_norm(True)
+            model.enable_cuda_graphs(False)
+            secondary["fusion_ab"] = {name: {"value": batch * world * steps / (u_ms * 1e-3), "unit": "videos/s",
+                                             "ms_per_step": u_ms / steps} for name, u_ms in best.items()}
         model.precision = args.dtype
 
     cpu = cpu_line = parity = None

@@ -223,8 +223,12 @@ int stlt_set_pruning(void* handle, int32_t enable);
  * residual stream is kept pre-norm with per-row statistics, the in-projection / linear1 GEMMs read it with
  * gamma-folded weights and normalise in their epilogue, the out-projection / linear2 GEMMs add the residual
  * and accumulate the next statistics. 0 restores the separate residual + LayerNorm kernels (same results
- * up to bf16 rounding; used by the tests as a cross-check). Has no effect in fp32 mode or with taps set. */
+ * up to bf16 rounding; used by the tests as a cross-check). Has no effect with taps set.
+ * stlt_set_fused_ln_fp32 is the same switch for the fp32-parity mode (default on): there the GEMMs run on hi / lo
+ * split operands (3 bf16 MMAs per product), the folded weights are split the same way, the residual epilogues write
+ * the split of the new stream as the next operand, and the attention stays a separate kernel. */
 int stlt_set_fused_ln(void* handle, int32_t enable);
+int stlt_set_fused_ln_fp32(void* handle, int32_t enable);
 
 /* bf16 mode with fused LayerNorms also folds the attention into the epilogue of the in-projection GEMM (default
  * on; sequences of at most 32 tokens): F.linear(x, in_proj_weight, in_proj_bias) and the scaled-dot-product
@@ -386,6 +390,14 @@ int stlt_op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void*
                        float* stats_out_or_null, float eps, int32_t prev_norm);
 /* The same RESID epilogue on a residual stream stored as two bf16 planes (stlt_set_hilo_residual): z = z_hi + z_lo
  * (bf16 [m_rows][768] each) is updated in place to (prev_norm ? LN(z) : z) + a W^T + bias, re-split into the planes. */
+/* The same two epilogues on the split operands of the fp32-parity mode (3 bf16 MMAs per product): a_planes bf16
+ * [2][m_rows][k] and w_planes bf16 [2][n][k] are hi / lo plane pairs (stlt_op_pack_folded with flag 2 writes the
+ * folded pair), NORM_A writes out bf16 [2][m_rows][n] (gelu 0 or 1 = exact erf), RESID updates z f32 in place and
+ * writes its split to out_bf16_planes bf16 [2][m_rows][768]. */
+int stlt_op_gemm_fused_split(void* handle, void* stream, int32_t epilogue, const void* a_planes, int32_t m_rows,
+                             const void* w_planes, int32_t n, int32_t k, const float* bias, void* out,
+                             void* out_bf16_planes, int32_t gelu, const float* stats_in, const float* vec_a,
+                             const float* vec_b, float* stats_out, float eps, int32_t prev_norm);
 int stlt_op_gemm_resid_hilo(void* handle, void* stream, const void* a, int32_t m_rows, const void* w, int32_t k,
                             const float* bias, void* z_hi, void* z_lo, const float* stats_in_or_null,
                             const float* gamma_or_null, const float* beta_or_null, float* stats_out, float eps,
@@ -393,7 +405,9 @@ int stlt_op_gemm_resid_hilo(void* handle, void* stream, const void* a, int32_t m
 /* gamma-folded bf16 copy of a projection matrix w f32 [n][k] for the NORM_A epilogue: w_folded[n][k] =
  * bf16(w * gamma), s_out[n] = sum_k w_folded[n][k], c_out[n] = (w beta)[n] + bias[n]; gamma = beta = NULL
  * folds the identity. head_major != 0 (n = 2304 only) writes the rows of a packed in-projection in the order
- * h*192 + t*64 + j <- t*768 + h*64 + j (t = Q, K, V), the layout stlt_op_qkv_attention reads. */
+ * h*192 + t*64 + j <- t*768 + h*64 + j (t = Q, K, V), the layout stlt_op_qkv_attention reads. Flag 2 in
+ * head_major (fp32-parity mode): w_folded holds two planes [2][n][k], hi = bf16(w gamma), lo = bf16(w gamma - hi),
+ * and s sums hi + lo. */
 int stlt_op_pack_folded(void* handle, void* stream, const float* w, const float* gamma_or_null,
                         const float* beta_or_null, const float* bias, int32_t n, int32_t k, void* w_folded,
                         float* s_out, float* c_out, int32_t head_major);

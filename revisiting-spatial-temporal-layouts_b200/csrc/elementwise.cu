@@ -584,7 +584,7 @@ __global__ void pack_bf16_kernel(const float4* __restrict__ src, uint2* __restri
 __global__ void __launch_bounds__(256)
 pack_folded_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ bias, int k, __nv_bfloat16* __restrict__ wf, float* __restrict__ s_out,
-                   float* __restrict__ c_out, int head_major) {
+                   float* __restrict__ c_out, int head_major, long long lo_offset) {
   const int n = blockIdx.x;  // output row
   // head-major order of the packed in-projection: output row h*192 + t*64 + j <- source row t*768 + h*64 + j
   const int src = head_major ? ((n % 192) / 64) * kHidden + (n / 192) * kHeadDim + (n % 64) : n;
@@ -592,9 +592,15 @@ pack_folded_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
   float s = 0.f, c = 0.f;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const float v = row[i];
-    const __nv_bfloat16 f = __float2bfloat16_rn(gamma != nullptr ? v * gamma[i] : v);
+    const float folded = gamma != nullptr ? v * gamma[i] : v;
+    const __nv_bfloat16 f = __float2bfloat16_rn(folded);
     wf[static_cast<long long>(n) * k + i] = f;
     s += __bfloat162float(f);
+    if (lo_offset != 0) {  // fp32-parity mode: the remainder plane; s sums what the 3-term product multiplies
+      const __nv_bfloat16 lo = __float2bfloat16_rn(folded - __bfloat162float(f));
+      wf[lo_offset + static_cast<long long>(n) * k + i] = lo;
+      s += __bfloat162float(lo);
+    }
     if (beta != nullptr) c = fmaf(v, beta[i], c);
   }
   s = warp_sum(s);
@@ -758,9 +764,10 @@ cudaError_t launch_topk_count(const float* logits, const long long* labels, int 
 
 cudaError_t launch_pack_folded(const float* w, const float* gamma, const float* beta, const float* bias, int n,
                                int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream,
-                               bool head_major) {
+                               bool head_major, bool split) {
   if (head_major && n != kQkv) return cudaErrorInvalidValue;
-  pack_folded_kernel<<<n, 256, 0, stream>>>(w, gamma, beta, bias, k, wf, s_out, c_out, head_major ? 1 : 0);
+  pack_folded_kernel<<<n, 256, 0, stream>>>(w, gamma, beta, bias, k, wf, s_out, c_out, head_major ? 1 : 0,
+                                            split ? static_cast<long long>(n) * k : 0);
   return cudaGetLastError();
 }
 

@@ -145,8 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     int b_plane_rows, int out_plane_rows, DropCfg drop, EpiArgs ep) {
   // pad-skipping row layout (compact.cu): the number of live 128-row tiles is decided on the device
   const int m_tiles = ep.m_tiles_dyn != nullptr ? min(m_tiles_arg, __ldg(ep.m_tiles_dyn)) : m_tiles_arg;
-  static_assert(kEpi == GEMM_EPI_PLAIN || kEpi == GEMM_EPI_ACT_BWD || (kLayout == GEMM_NT && kTerms == 1),
-                "fused-LN epilogues: bf16 forward only");
+  static_assert(kEpi == GEMM_EPI_PLAIN || kEpi == GEMM_EPI_ACT_BWD || kLayout == GEMM_NT, "fused-LN epilogues: forward only");
   static_assert(kEpi != GEMM_EPI_ACT_BWD || (kLayout == GEMM_NN && kOut == GEMM_OUT_BF16 && kGelu == 0),
                 "ACT_BWD: bf16 data gradient");
   constexpr bool kResidOut = kOut == GEMM_OUT_F32_BF16 || kOut == GEMM_OUT_F32_BF16_DIRECT || kOut == GEMM_OUT_HILO;
@@ -572,6 +571,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               for (int j = 0; j < 4; ++j)
                 dst[j] = make_uint4(pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              if constexpr (kTerms == 3) {  // fp32-parity mode: the remainder plane of the split
+                uint4* dlo = reinterpret_cast<uint4*>(
+                    ep.zb_lo_out + static_cast<size_t>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dlo[j] = make_uint4(pack_bf16x2(bf16_residual(f[8 * j + 0]), bf16_residual(f[8 * j + 1])),
+                                      pack_bf16x2(bf16_residual(f[8 * j + 2]), bf16_residual(f[8 * j + 3])),
+                                      pack_bf16x2(bf16_residual(f[8 * j + 4]), bf16_residual(f[8 * j + 5])),
+                                      pack_bf16x2(bf16_residual(f[8 * j + 6]), bf16_residual(f[8 * j + 7])));
+              }
             }
           }
           fence_proxy_async_smem();
@@ -785,6 +794,11 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
       return launch_one<1, GEMM_OUT_BF16, 0, GEMM_NT, GEMM_EPI_NORM_A>(g, stream, num_sms);
     if (g.terms == 1 && g.out_kind == GEMM_OUT_BF16 && g.gelu == 2)
       return launch_one<1, GEMM_OUT_BF16, 2, GEMM_NT, GEMM_EPI_NORM_A>(g, stream, num_sms);
+    // fp32-parity mode: split operands (the NORM_A algebra is linear in the accumulator), split output, exact erf GELU
+    if (g.terms == 3 && g.out_kind == GEMM_OUT_BF16_SPLIT && g.gelu == 0)
+      return launch_one<3, GEMM_OUT_BF16_SPLIT, 0, GEMM_NT, GEMM_EPI_NORM_A>(g, stream, num_sms);
+    if (g.terms == 3 && g.out_kind == GEMM_OUT_BF16_SPLIT && g.gelu == 1)
+      return launch_one<3, GEMM_OUT_BF16_SPLIT, 1, GEMM_NT, GEMM_EPI_NORM_A>(g, stream, num_sms);
     return cudaErrorInvalidValue;
   }
   if (g.epilogue == GEMM_EPI_RESID) {
@@ -792,6 +806,8 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
       return launch_one<1, GEMM_OUT_F32_BF16, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
     if (g.terms == 1 && g.out_kind == GEMM_OUT_F32_BF16_DIRECT && g.gelu == 0 && g.n == kHidden)
       return launch_one<1, GEMM_OUT_F32_BF16_DIRECT, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
+    if (g.terms == 3 && g.out_kind == GEMM_OUT_F32_BF16_DIRECT && g.gelu == 0 && g.n == kHidden && g.epi.zb_lo_out)
+      return launch_one<3, GEMM_OUT_F32_BF16_DIRECT, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
     if (g.terms == 1 && g.out_kind == GEMM_OUT_HILO && g.gelu == 0 && g.n == kHidden && g.epi.zb_out && g.epi.z_lo)
       return launch_one<1, GEMM_OUT_HILO, 0, GEMM_NT, GEMM_EPI_RESID>(g, stream, num_sms);
     return cudaErrorInvalidValue;

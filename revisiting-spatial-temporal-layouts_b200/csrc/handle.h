@@ -99,6 +99,7 @@ struct Handle {
   __nv_bfloat16* cap_tm_xb = nullptr;
   // optional per-category timing (CUDA events on the launching stream)
   bool fused_ln = true;     // bf16 mode: LayerNorm folded into the GEMM epilogues (stlt_set_fused_ln)
+  bool fused_ln_fp32 = true;  // fp32-parity mode: the same on split operands (stlt_set_fused_ln_fp32)
   int fused_attn_max_t = 32;  // longest sequence that takes the fused kernel (STLT_FUSED_ATTENTION_MAX_T, experiments)
   int qkv_attn_debug = 0;   // QkvAttnArgs::debug (STLT_QKV_ATTN_DEBUG environment variable, read at stlt_create)
   // ... with the residual stream of the full phases as two bf16 planes (stlt_set_hilo_residual). Off by default: the
@@ -255,15 +256,28 @@ inline int run_gemm(Handle* h, cudaStream_t stream, const void* a, long long m_r
 // Projection GEMM with a fused-LayerNorm epilogue (bf16 inference path):
 //   GEMM_EPI_NORM_A: out bf16 [m_rows, n] = act(LN(z) W^T + b) from A = bf16(z) and gamma-folded weights
 //   GEMM_EPI_RESID : z_out fp32 [m_rows, 768] (+ bf16 copy zb_out) = (prev_norm ? LN(z_prev) : z_prev) + A W^T + bias
+// terms == 3 (fp32-parity mode): A, W and the bf16 outputs are hi / lo plane pairs (planes m_rows resp. n rows apart);
+// the RESID epilogue then writes the split of the new z as the next GEMM's operand (out_bf16 = hi plane, lo plane behind it).
 inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const void* a, long long m_rows,
                           const void* w, int n, int k, const float* bias, void* out, void* out_bf16, int gelu,
-                          const EpiArgs& epi, const int* m_tiles_dyn = nullptr) {
+                          const EpiArgs& epi_in, const int* m_tiles_dyn = nullptr, int terms = 1) {
   GemmArgs g{};
-  int rc = make_tm(h, &g.tm_a, a, 1, m_rows, k, 64, 128);
+  EpiArgs epi = epi_in;
+  const int planes = terms == 3 ? 2 : 1;
+  int rc = make_tm(h, &g.tm_a, a, 1, m_rows * planes, k, 64, 128);
   if (rc) return rc;
-  rc = make_tm(h, &g.tm_b, w, 1, n, k, 64, 128);
+  rc = make_tm(h, &g.tm_b, w, 1, static_cast<long long>(n) * planes, k, 64, 128);
   if (rc) return rc;
-  if (epilogue == GEMM_EPI_RESID && epi.z_lo != nullptr) {
+  if (terms == 3 && epilogue == GEMM_EPI_RESID) {
+    rc = make_tm(h, &g.tm_out, out, 0, m_rows, n, 32, 32);
+    g.tm_out2 = g.tm_out;  // unused: both bf16 planes are written from registers
+    g.out_kind = GEMM_OUT_F32_BF16_DIRECT;
+    epi.zb_lo_out = static_cast<__nv_bfloat16*>(out_bf16) + static_cast<size_t>(m_rows) * n;
+  } else if (terms == 3) {
+    rc = make_tm(h, &g.tm_out, out, 1, m_rows * 2, n, 64, 32);
+    g.tm_out2 = g.tm_out;
+    g.out_kind = GEMM_OUT_BF16_SPLIT;
+  } else if (epilogue == GEMM_EPI_RESID && epi.z_lo != nullptr) {
     g.tm_out = g.tm_a;  // unused: the residual stream is read and written as two bf16 planes from registers
     g.tm_out2 = g.tm_a;
     g.out_kind = GEMM_OUT_HILO;
@@ -284,7 +298,7 @@ inline int run_gemm_fused(Handle* h, cudaStream_t stream, int epilogue, const vo
   g.m_rows = static_cast<int>(m_rows);
   g.n = n;
   g.k = k;
-  g.terms = 1;
+  g.terms = terms;
   g.gelu = gelu;
   g.a_plane_rows = static_cast<int>(m_rows);
   g.b_plane_rows = n;

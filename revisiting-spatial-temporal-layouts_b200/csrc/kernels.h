@@ -58,6 +58,8 @@ struct EpiArgs {
   int valid_rows;               // ACT_BWD: rows >= valid_rows are tile padding and stay out of the column sums
   const int* m_tiles_dyn;       // device int (may be null): live 128-row tiles of A / out when the row count is dynamic
   __nv_bfloat16* z_lo;          // GEMM_OUT_HILO: lo plane of the residual stream [M, 768], updated in place (hi = zb_out)
+  __nv_bfloat16* zb_lo_out;     // RESID, GEMM_OUT_F32_BF16_DIRECT: lo plane of the bf16 copy (fp32-parity mode: the next GEMM's
+                                // A operand is the hi / lo split of z); null = one plane
 };
 
 enum GemmLayout : int {
@@ -266,9 +268,10 @@ cudaError_t launch_attention_long(const __nv_bfloat16* qkv, int planes, long lon
 // gamma-folded bf16 weights + the two epilogue vectors of GEMM_EPI_NORM_A (see GemmEpilogue).
 // gamma / beta may be null (identity LayerNorm: plain bf16 weights, s = row sums, c = bias). head_major (n must be
 // 2304): output row h*192 + t*64 + j holds row t*768 + h*64 + j of the packed in-projection (t = Q, K, V).
+// split (fp32-parity mode): wf holds two planes n rows apart, hi = bf16(w'), lo = bf16(w' - hi); s sums hi + lo.
 cudaError_t launch_pack_folded(const float* w, const float* gamma, const float* beta, const float* bias, int n,
                                int k, __nv_bfloat16* wf, float* s_out, float* c_out, cudaStream_t stream,
-                               bool head_major = false);
+                               bool head_major = false, bool split = false);
 
 // fp32 -> bf16 plane(s) for weights.
 cudaError_t launch_pack_bf16(const float* src, __nv_bfloat16* dst, long long n, int planes,

@@ -142,9 +142,8 @@ WorkspacePlan plan_workspace(int B, int L, int S, int precision, int ns = 0, int
   // layer + 6 compaction sites over the frame tokens
   p.off_stats = off;
   p.stats_bytes = 0;
-  if (precision == STLT_PRECISION_BF16)
-    p.stats_bytes = (static_cast<size_t>(2 * ns) * p.sp.m_pad + static_cast<size_t>(2 * nt + 6) * p.tm.m_pad) *
-                    kStatSlots * sizeof(float2);
+  p.stats_bytes = (static_cast<size_t>(2 * ns) * p.sp.m_pad + static_cast<size_t>(2 * nt + 6) * p.tm.m_pad) *
+                  kStatSlots * sizeof(float2);
   off += align1k(p.stats_bytes);
   if (compact_rows > 0) {
     const long long frames = static_cast<long long>(B) * L;
@@ -193,14 +192,9 @@ size_t embed_scratch(const Phase& ph) { return static_cast<size_t>(ph.m_pad) * k
 // Needs every token of the sequences (keys / values), so it always runs on the full phase.
 // dyn != null: the phase is on the pad-skipping layout (compact.cu): row / sequence counts come from the device header,
 // `num_seqs` is the static bound; the one-token sequences of the second row region get their own attention launch.
-int run_attention_part(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw,
-                       const Phase& ph, const long long* mask_src, long long num_seqs, int T,
-                       bool causal, const int* dyn = nullptr) {
-  const bool fp32 = precision == STLT_PRECISION_FP32;
-  int rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv,
-                    fp32 ? 3 : 1, fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, 0, DropCfg{0, 0, 1.f},
-                    dyn != nullptr ? dyn + kDynTiles : nullptr);
-  if (rc) return rc;
+// The attention of the separate-kernel paths on the packed q | k | v of ph.qkv (context -> ph.att).
+int run_attention_only(Handle* h, cudaStream_t stream, bool fp32, const Phase& ph, const long long* mask_src,
+                       long long num_seqs, int T, bool causal, const int* dyn) {
   // fp32 mode: q/k/v and the context travel as bf16 hi/lo planes; products are 3-term splits
   ActOut att{nullptr, ph.att, fp32 ? 2 : 1, ph.m_pad};
   {
@@ -218,6 +212,17 @@ int run_attention_part(Handle* h, cudaStream_t stream, int precision, const Laye
   }
   h->launches++;
   return STLT_OK;
+}
+
+int run_attention_part(Handle* h, cudaStream_t stream, int precision, const LayerWeights& lw,
+                       const Phase& ph, const long long* mask_src, long long num_seqs, int T,
+                       bool causal, const int* dyn = nullptr) {
+  const bool fp32 = precision == STLT_PRECISION_FP32;
+  int rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv,
+                    fp32 ? 3 : 1, fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, 0, DropCfg{0, 0, 1.f},
+                    dyn != nullptr ? dyn + kDynTiles : nullptr);
+  if (rc) return rc;
+  return run_attention_only(h, stream, fp32, ph, mask_src, num_seqs, T, causal, dyn);
 }
 
 // Second half: out-projection -> +residual -> LN -> FFN -> +residual -> LN. Row-wise, so it may
@@ -276,19 +281,25 @@ struct PendingNorm {
 // in-projection (+ deferred LayerNorm of its input) and attention over the full phase
 int fused_attention_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, const Phase& ph,
                          const PendingNorm& in, const long long* mask_src, long long num_seqs, int T, bool causal,
-                         const int* dyn = nullptr) {
+                         const int* dyn = nullptr, bool fp32 = false) {
   int rc;
-  if (dyn != nullptr || (h->fused_attn && T <= h->fused_attn_max_t && lw.in_h != nullptr))  // one kernel: the packed QKV activations never reach HBM
+  if (!fp32 && (dyn != nullptr || (h->fused_attn && T <= h->fused_attn_max_t && lw.in_h != nullptr)))  // one kernel: the packed QKV activations never reach HBM
     return run_qkv_attention(h, stream, ph.xb, ph.m_pad, ph.m_valid, lw.in_h, lw.in_hs, lw.in_hc,
                              in.gamma != nullptr ? in.stats : nullptr, h->dims.encoder_norm_eps, mask_src, num_seqs, T,
                              causal, ph.att, dyn);
+  const int terms = fp32 ? 3 : 1;
+  const int* tiles_dyn = dyn != nullptr ? dyn + kDynTiles : nullptr;
   if (in.gamma == nullptr) {
-    rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv, 1, GEMM_OUT_BF16, 0);
+    rc = run_gemm(h, stream, ph.xb, ph.m_pad, ph.m_pad, lw.in_p, kQkv, kHidden, lw.in_b, ph.qkv, terms,
+                  fp32 ? GEMM_OUT_BF16_SPLIT : GEMM_OUT_BF16, 0, DropCfg{0, 0, 1.f}, tiles_dyn);
   } else {
     EpiArgs e{in.stats, lw.in_s, lw.in_c, nullptr, nullptr, nullptr, h->dims.encoder_norm_eps, 1};
-    rc = run_gemm_fused(h, stream, GEMM_EPI_NORM_A, ph.xb, ph.m_pad, lw.in_f, kQkv, kHidden, nullptr, ph.qkv, nullptr, 0, e);
+    rc = run_gemm_fused(h, stream, GEMM_EPI_NORM_A, ph.xb, ph.m_pad, lw.in_f, kQkv, kHidden, nullptr, ph.qkv, nullptr, 0, e,
+                        tiles_dyn, terms);
   }
   if (rc) return rc;
+  // fp32-parity mode: the attention stays the separate split-plane kernel (on the pad-skipping layout: one launch per row region)
+  if (fp32) return run_attention_only(h, stream, true, ph, mask_src, num_seqs, T, causal, dyn);
   ActOut att{nullptr, ph.att, 1, ph.m_pad};
   {
     ProfileScope prof(h, stream, STLT_PROF_ATTENTION);
@@ -300,21 +311,22 @@ int fused_attention_part(Handle* h, cudaStream_t stream, const LayerWeights& lw,
 
 // out-projection + residual, linear1 (+ LN1, GELU), linear2 + residual; LN2 stays pending (stats in s2)
 int fused_tail_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, const Phase& ph, const PendingNorm& in,
-                    float2* s1, float2* s2, const int* tiles_dyn = nullptr) {
+                    float2* s1, float2* s2, const int* tiles_dyn = nullptr, bool fp32 = false) {
   const float eps = h->dims.encoder_norm_eps;
+  const int terms = fp32 ? 3 : 1;  // fp32-parity mode: split operands, exact erf GELU, hi / lo copy of the new z
   EpiArgs e1{in.stats, in.gamma, in.beta, ph.x, s1, ph.xb, eps, in.gamma != nullptr ? 1 : 0};
   e1.z_lo = ph.xlo;
   int rc = run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.att, ph.m_pad, lw.out_p, kHidden, kHidden, lw.out_b, ph.x, ph.xb, 0, e1,
-                          tiles_dyn);
+                          tiles_dyn, terms);
   if (rc) return rc;
   EpiArgs e2{s1, lw.l1_s, lw.l1_c, nullptr, nullptr, nullptr, eps, 1};
-  rc = run_gemm_fused(h, stream, GEMM_EPI_NORM_A, ph.xb, ph.m_pad, lw.l1_f, kFfn, kHidden, nullptr, ph.hid, nullptr, 2, e2,
-                      tiles_dyn);
+  rc = run_gemm_fused(h, stream, GEMM_EPI_NORM_A, ph.xb, ph.m_pad, lw.l1_f, kFfn, kHidden, nullptr, ph.hid, nullptr,
+                      fp32 ? 1 : 2, e2, tiles_dyn, terms);
   if (rc) return rc;
   EpiArgs e3{s1, lw.n1_g, lw.n1_b, ph.x, s2, ph.xb, eps, 1};
   e3.z_lo = ph.xlo;
   return run_gemm_fused(h, stream, GEMM_EPI_RESID, ph.hid, ph.m_pad, lw.l2_p, kHidden, kFfn, lw.l2_b, ph.x, ph.xb, 0, e3,
-                        tiles_dyn);
+                        tiles_dyn, terms);
 }
 
 // One stack of post-norm encoder layers; the last layer's row-wise tail runs on the compacted rows of `tail`
@@ -324,17 +336,19 @@ int fused_tail_part(Handle* h, cudaStream_t stream, const LayerWeights& lw, cons
 int fused_stack(Handle* h, cudaStream_t stream, const std::vector<LayerWeights>& layers, const Phase& full,
                 const Phase& tail, const long long* mask_src, long long num_seqs, int T, bool causal, int stride,
                 const long long* lengths, int L, float2* stats_full, float2* stats_tail, int* err_flag,
-                PendingNorm* out, const int* dyn = nullptr, const int* frame_row = nullptr, bool prune_last = true) {
+                PendingNorm* out, const int* dyn = nullptr, const int* frame_row = nullptr, bool prune_last = true,
+                bool fp32 = false) {
   const int n = static_cast<int>(layers.size());
+  const int planes = fp32 ? 2 : 1;  // bf16 planes of the context rows the gather compacts
   PendingNorm pending;  // layer 0 reads the (already normalised) embedding output
   for (int i = 0; i < n; ++i) {
     const LayerWeights& lw = layers[i];
-    int rc = fused_attention_part(h, stream, lw, full, pending, mask_src, num_seqs, T, causal, dyn);
+    int rc = fused_attention_part(h, stream, lw, full, pending, mask_src, num_seqs, T, causal, dyn, fp32);
     if (rc) return rc;
     if (i < n - 1 || !prune_last) {  // !prune_last (CACNF: every frame token is consumed): full.x keeps the PRE-norm output
       float2* s1 = stats_full + static_cast<size_t>(2 * i) * full.m_pad * kStatSlots;
       float2* s2 = s1 + full.m_pad * kStatSlots;
-      rc = fused_tail_part(h, stream, lw, full, pending, s1, s2, dyn != nullptr ? dyn + kDynTiles : nullptr);
+      rc = fused_tail_part(h, stream, lw, full, pending, s1, s2, dyn != nullptr ? dyn + kDynTiles : nullptr, fp32);
       if (rc) return rc;
       pending = PendingNorm{s2, lw.n2_g, lw.n2_b};
       if (i == n - 1) *out = pending;
@@ -347,14 +361,14 @@ int fused_stack(Handle* h, cudaStream_t stream, const std::vector<LayerWeights>&
         const __nv_bfloat16* hi = full.xlo != nullptr ? full.xb : nullptr;
         if (frame_row != nullptr)
           STLT_CUDA(h, launch_gather_frames(full.x, full.att, frame_row, tail.m_valid, tail.x, tail.att, pending.stats,
-                                            sc_in, stream, hi, full.xlo));
+                                            sc_in, stream, hi, full.xlo, planes, full.m_pad, tail.m_pad));
         else
-          STLT_CUDA(h, launch_gather_rows(full.x, full.att, 1, full.m_pad, stride, lengths, L, tail.m_valid, tail.x,
+          STLT_CUDA(h, launch_gather_rows(full.x, full.att, planes, full.m_pad, stride, lengths, L, tail.m_valid, tail.x,
                                           tail.att, tail.m_pad, err_flag, stream, pending.stats, sc_in, hi, full.xlo));
       }
       h->launches++;
       PendingNorm tail_in{pending.gamma ? sc_in : nullptr, pending.gamma, pending.beta};
-      rc = fused_tail_part(h, stream, lw, tail, tail_in, sc1, sc2);
+      rc = fused_tail_part(h, stream, lw, tail, tail_in, sc1, sc2, nullptr, fp32);
       if (rc) return rc;
       *out = PendingNorm{sc2, lw.n2_g, lw.n2_b};
     }
@@ -452,6 +466,8 @@ int stlt_packed_weights_bytes(void* handle, int32_t precision, size_t* bytes) {
   *bytes = layers * per_layer * planes * 2;
   if (precision == STLT_PRECISION_BF16)  // fused-LayerNorm copies: folded in-proj (row-major and head-major) / linear1 + their s, c vectors
     *bytes += layers * (static_cast<size_t>(kHidden) * (2 * kQkv + kFfn) * 2 + static_cast<size_t>(2 * kQkv + kFfn) * 2 * 4);
+  else  // fp32-parity mode: folded in-proj / linear1 as hi / lo plane pairs + their s, c vectors
+    *bytes += layers * (static_cast<size_t>(kHidden) * (kQkv + kFfn) * 2 * 2 + static_cast<size_t>(kQkv + kFfn) * 2 * 4);
   return STLT_OK;
 }
 
@@ -518,6 +534,40 @@ int stlt_pack_weights(void* handle, void* stream_, int32_t precision, void* pack
         }
         float* v1 = vec + 2 * kQkv;
         e = launch_pack_folded(lw.l1_w, lw.n1_g, lw.n1_b, lw.l1_b, kFfn, kHidden, l1_f, v1, v1 + kFfn, stream);
+        if (e != cudaSuccess) return e;
+        lw.l1_f = l1_f;
+        lw.l1_s = v1;
+        lw.l1_c = v1 + kFfn;
+      }
+      return cudaSuccess;
+    };
+    STLT_CUDA(h, fold_stack(h->w.spatial));
+    STLT_CUDA(h, fold_stack(h->w.temporal));
+  }
+  if (precision == STLT_PRECISION_FP32) {
+    // fused-LayerNorm section of the fp32-parity mode: per layer [in_f hi | in_f lo | l1_f hi | l1_f lo] bf16, then
+    // [in_s in_c l1_s l1_c] f32 (no head-major copy: the attention stays a separate kernel in this mode)
+    auto fold_stack = [&](std::vector<LayerWeights>& stack) -> cudaError_t {
+      for (size_t i = 0; i < stack.size(); ++i) {
+        LayerWeights& lw = stack[i];
+        __nv_bfloat16* in_f = cur;
+        __nv_bfloat16* l1_f = in_f + static_cast<size_t>(kQkv) * kHidden * 2;
+        float* vec = reinterpret_cast<float*>(l1_f + static_cast<size_t>(kFfn) * kHidden * 2);
+        cur = reinterpret_cast<__nv_bfloat16*>(vec + 2 * (kQkv + kFfn));
+        lw.in_f = lw.in_h = nullptr;
+        lw.in_s = lw.in_c = lw.in_hs = lw.in_hc = nullptr;
+        cudaError_t e;
+        if (i > 0) {  // the in-projection reads LN2 of the previous layer
+          const LayerWeights& prev = stack[i - 1];
+          e = launch_pack_folded(lw.in_w, prev.n2_g, prev.n2_b, lw.in_b, kQkv, kHidden, in_f, vec, vec + kQkv, stream, false,
+                                 true);
+          if (e != cudaSuccess) return e;
+          lw.in_f = in_f;
+          lw.in_s = vec;
+          lw.in_c = vec + kQkv;
+        }
+        float* v1 = vec + 2 * kQkv;
+        e = launch_pack_folded(lw.l1_w, lw.n1_g, lw.n1_b, lw.l1_b, kFfn, kHidden, l1_f, v1, v1 + kFfn, stream, false, true);
         if (e != cudaSuccess) return e;
         lw.l1_f = l1_f;
         lw.l1_s = v1;
@@ -687,11 +737,14 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   const bool prune_tm = h->pruning && h->taps.temporal == nullptr && h->cap_tm_x == nullptr &&
                         d.num_temporal_layers > 0;
 
-  const bool fused = !fp32 && h->fused_ln && h->pruning && d.num_spatial_layers > 0 && d.num_temporal_layers > 0 &&
+  // fp32-parity mode: the same epilogue fusions on split operands (stlt_set_fused_ln_fp32); CACNF's capture of every frame
+  // token keeps the separate kernels there
+  const bool fused = (fp32 ? h->fused_ln_fp32 && h->cap_tm_x == nullptr : h->fused_ln) && h->pruning &&
+                     d.num_spatial_layers > 0 && d.num_temporal_layers > 0 &&
                      h->taps.embed == nullptr && h->taps.spatial == nullptr && h->taps.frames == nullptr &&
                      h->taps.temporal == nullptr && h->taps.pooled == nullptr && h->w.spatial[0].l1_f != nullptr;
   if (fused) {
-    // ---- bf16 path with LayerNorm folded into the GEMM epilogues (no add_ln launches) ----
+    // ---- LayerNorm folded into the GEMM epilogues (no add_ln launches) ----
     float2* stats = reinterpret_cast<float2*>(ws + p.off_stats);
     float2* st_sp = stats;
     float2* st_tm = st_sp + static_cast<size_t>(2 * d.num_spatial_layers) * p.sp.m_pad * kStatSlots;
@@ -699,15 +752,17 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     float2* st_c_tm = st_c_sp + 3 * p.tm.m_pad * kStatSlots;                                               // 3 more (B rows)
     // the residual stream of the two full phases lives as two bf16 planes (hi = GEMM operand, lo = remainder)
     Phase sp_f = sp, tm_f = tm;
-    if (h->hilo) {
+    const bool hilo = h->hilo && !fp32;
+    if (hilo) {
       sp_f.xlo = sp.xb + static_cast<size_t>(sp.m_pad) * kHidden;
       tm_f.xlo = tm.xb + static_cast<size_t>(tm.m_pad) * kHidden;
     }
-    ActOut emb{h->hilo ? nullptr : sp.x, sp.xb, h->hilo ? 2 : 1, sp.m_pad};
+    ActOut emb{hilo ? nullptr : sp.x, sp.xb, hilo || fp32 ? 2 : 1, sp.m_pad};
     // Pad-skipping layout of the spatial phase (compact.cu): padding frames and the padded slots of one-token frames
-    // are not computed. Needs the attention-fused in-projection (it understands the two row regions).
-    const bool compact = h->compaction && h->fused_attn && S <= h->fused_attn_max_t && p.off_plan != 0 &&
-                         h->w.spatial[0].in_h != nullptr;
+    // are not computed. bf16: needs the attention-fused in-projection (it understands the two row regions); fp32-parity
+    // mode: the separate attention kernel runs once per row region.
+    const bool compact = h->compaction && p.off_plan != 0 &&
+                         (fp32 ? S <= 32 : h->fused_attn && S <= h->fused_attn_max_t && h->w.spatial[0].in_h != nullptr);
     const int* dyn = nullptr;
     const int* frame_row = nullptr;
     const long long* sp_mask = categories;
@@ -734,11 +789,11 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     h->launches += 2;  // embed_stats_kernel + embed_kernel
     PendingNorm sp_out;
     int rc = fused_stack(h, stream, h->w.spatial, sp_f, tm, sp_mask, n_tm, S, false, S, nullptr, 0, st_sp, st_c_sp,
-                         err_flag, &sp_out, dyn, frame_row);
+                         err_flag, &sp_out, dyn, frame_row, true, fp32);
     if (rc) return rc;
     {
       ProfileScope prof(h, stream, STLT_PROF_OTHER);
-      ActOut fr{h->hilo ? nullptr : tm.x, tm.xb, h->hilo ? 2 : 1, tm.m_pad};
+      ActOut fr{hilo ? nullptr : tm.x, tm.xb, hilo || fp32 ? 2 : 1, tm.m_pad};
       // the spatial stack's LayerNorm-2 is applied on the fly (row statistics recomputed in registers)
       STLT_CUDA(h, launch_frame_embed(tm.x, 1, frame_types, h->w.pos_table, h->w.ft_table, d.num_frame_types,
                                       h->w.fr_g, h->w.fr_b, d.layer_norm_eps, B, L, fr, err_flag, stream,
@@ -747,9 +802,9 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
     h->launches++;
     PendingNorm tm_out;
     const bool capture = h->cap_tm_x != nullptr;  // CACNF: the fusion layers consume every frame token of the stack
-    if (capture && h->hilo) return fail(h, STLT_ERR_STATE, "the two-plane residual stream is not available under CACNF");
+    if (capture && hilo) return fail(h, STLT_ERR_STATE, "the two-plane residual stream is not available under CACNF");
     rc = fused_stack(h, stream, h->w.temporal, tm_f, hd, frame_types, B, L, true, 0, lengths, L, st_tm, st_c_tm, err_flag,
-                     &tm_out, nullptr, nullptr, !capture);
+                     &tm_out, nullptr, nullptr, !capture, fp32);
     if (rc) return rc;
     float* h1f = reinterpret_cast<float*>(ws + p.off_head);
     float* h2f = h1f + static_cast<size_t>(B) * kHidden;
@@ -899,6 +954,13 @@ int stlt_forward(void* handle, void* stream_, int32_t precision, const int64_t* 
   return STLT_OK;
 }
 
+int stlt_set_fused_ln_fp32(void* handle, int32_t enable) {
+  Handle* h = static_cast<Handle*>(handle);
+  if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
+  h->fused_ln_fp32 = enable != 0;
+  return STLT_OK;
+}
+
 int stlt_set_fused_ln(void* handle, int32_t enable) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h) return fail(h, STLT_ERR_INVALID, "null handle");
@@ -1022,10 +1084,34 @@ int stlt_op_gemm(void* handle, void* stream, const void* a_planes, const void* w
                   out, terms, out_kind, gelu);
 }
 
+namespace {
+int op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void* a, int32_t m_rows, const void* w,
+                  int32_t n, int32_t k, const float* bias, void* out, void* out_bf16, int32_t gelu,
+                  const float* stats_in, const float* vec_a, const float* vec_b, float* stats_out, float eps,
+                  int32_t prev_norm, int terms);
+}  // namespace
+
 int stlt_op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void* a, int32_t m_rows, const void* w,
                        int32_t n, int32_t k, const float* bias, void* out, void* out_bf16, int32_t gelu,
                        const float* stats_in, const float* vec_a, const float* vec_b, float* stats_out, float eps,
                        int32_t prev_norm) {
+  return op_gemm_fused(handle, stream, epilogue, a, m_rows, w, n, k, bias, out, out_bf16, gelu, stats_in, vec_a, vec_b,
+                       stats_out, eps, prev_norm, 1);
+}
+
+int stlt_op_gemm_fused_split(void* handle, void* stream, int32_t epilogue, const void* a_planes, int32_t m_rows,
+                             const void* w_planes, int32_t n, int32_t k, const float* bias, void* out,
+                             void* out_bf16_planes, int32_t gelu, const float* stats_in, const float* vec_a,
+                             const float* vec_b, float* stats_out, float eps, int32_t prev_norm) {
+  return op_gemm_fused(handle, stream, epilogue, a_planes, m_rows, w_planes, n, k, bias, out, out_bf16_planes, gelu, stats_in,
+                       vec_a, vec_b, stats_out, eps, prev_norm, 3);
+}
+
+namespace {
+int op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void* a, int32_t m_rows, const void* w,
+                  int32_t n, int32_t k, const float* bias, void* out, void* out_bf16, int32_t gelu,
+                  const float* stats_in, const float* vec_a, const float* vec_b, float* stats_out, float eps,
+                  int32_t prev_norm, int terms) {
   Handle* h = static_cast<Handle*>(handle);
   if (!h || !a || !w || !out) return fail(h, STLT_ERR_INVALID, "null argument");
   if (m_rows % 128 || n % 256 || k % 64 || m_rows < 128) return fail(h, STLT_ERR_INVALID, "shape not tile aligned");
@@ -1035,11 +1121,11 @@ int stlt_op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void*
   e.vec_b = vec_b;
   e.eps = eps;
   if (epilogue == GEMM_EPI_NORM_A) {
-    if (!stats_in || !vec_a || !vec_b || (gelu != 0 && gelu != 2))
-      return fail(h, STLT_ERR_INVALID, "NORM_A: stats_in, vec_a (s), vec_b (c) required; gelu 0 or 2");
+    if (!stats_in || !vec_a || !vec_b || (gelu != 0 && gelu != (terms == 3 ? 1 : 2)))
+      return fail(h, STLT_ERR_INVALID, "NORM_A: stats_in, vec_a (s), vec_b (c) required; gelu 0 or 2 (split operands: 0 or 1)");
     e.prev_norm = 1;
     return run_gemm_fused(h, static_cast<cudaStream_t>(stream), GEMM_EPI_NORM_A, a, m_rows, w, n, k, nullptr, out,
-                          nullptr, gelu, e);
+                          nullptr, gelu, e, nullptr, terms);
   }
   if (epilogue == GEMM_EPI_RESID) {
     if (n != kHidden || !bias || !out_bf16 || !stats_out || gelu != 0 || (prev_norm && (!stats_in || !vec_a || !vec_b)))
@@ -1049,10 +1135,11 @@ int stlt_op_gemm_fused(void* handle, void* stream, int32_t epilogue, const void*
     e.zb_out = static_cast<__nv_bfloat16*>(out_bf16);
     e.prev_norm = prev_norm != 0 ? 1 : 0;
     return run_gemm_fused(h, static_cast<cudaStream_t>(stream), GEMM_EPI_RESID, a, m_rows, w, n, k, bias, out, out_bf16,
-                          0, e);
+                          0, e, nullptr, terms);
   }
   return fail(h, STLT_ERR_INVALID, "epilogue must be 1 (NORM_A) or 2 (RESID)");
 }
+}  // namespace
 
 int stlt_op_gemm_resid_hilo(void* handle, void* stream, const void* a, int32_t m_rows, const void* w, int32_t k,
                             const float* bias, void* z_hi, void* z_lo, const float* stats_in, const float* gamma,
@@ -1080,8 +1167,9 @@ int stlt_op_pack_folded(void* handle, void* stream, const float* w, const float*
   Handle* h = static_cast<Handle*>(handle);
   if (!h || !w || !bias || !w_folded || !s_out || !c_out) return fail(h, STLT_ERR_INVALID, "null argument");
   if ((gamma == nullptr) != (beta == nullptr)) return fail(h, STLT_ERR_INVALID, "gamma and beta go together");
+  // head_major: bit 0 = head-major row order, bit 1 = hi / lo split planes (fp32-parity mode)
   STLT_CUDA(h, launch_pack_folded(w, gamma, beta, bias, n, k, static_cast<__nv_bfloat16*>(w_folded), s_out, c_out,
-                                  static_cast<cudaStream_t>(stream), head_major != 0));
+                                  static_cast<cudaStream_t>(stream), (head_major & 1) != 0, (head_major & 2) != 0));
   return STLT_OK;
 }
 

@@ -135,6 +135,7 @@ SIGNATURES = {
     "stlt_set_taps": (c_int32, [c_void_p, POINTER(StltTaps)]),
     "stlt_set_pruning": (c_int32, [c_void_p, c_int32]),
     "stlt_set_fused_ln": (c_int32, [c_void_p, c_int32]),
+    "stlt_set_fused_ln_fp32": (c_int32, [c_void_p, c_int32]),
     "stlt_set_fused_attention": (c_int32, [c_void_p, c_int32]),
     "stlt_set_compaction": (c_int32, [c_void_p, c_int32]),
     "stlt_set_hilo_residual": (c_int32, [c_void_p, c_int32]),
@@ -169,6 +170,9 @@ SIGNATURES = {
     "stlt_op_gemm_grad": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_int32, c_int64, c_int32]),
     "stlt_op_gemm_fused": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
+                                     c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_float, c_int32]),
+    "stlt_op_gemm_fused_split": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_float, c_int32]),
     "stlt_op_gemm_resid_hilo": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p,

@@ -197,6 +197,7 @@ class Stlt(nn.Module):
     _graphs = None          # CUDA-graph cache of the inference forward (enable_cuda_graphs)
     _cuda_graphs = False
     _fused_ln = True
+    _fused_ln_fp32 = os.environ.get("STLT_FUSED_LN_FP32", "1") != "0"
     _fused_attn = os.environ.get("STLT_FUSED_ATTENTION", "1") != "0"
     _compaction = os.environ.get("STLT_COMPACTION", "1") != "0"
     _hilo = os.environ.get("STLT_HILO_RESIDUAL", "0") != "0"
@@ -286,6 +287,7 @@ class Stlt(nn.Module):
         self._handle_device = device
         _lib.check(handle, lib.stlt_set_pruning(handle, int(self._pruning)))
         _lib.check(handle, lib.stlt_set_fused_ln(handle, int(self._fused_ln)))
+        _lib.check(handle, lib.stlt_set_fused_ln_fp32(handle, int(self._fused_ln_fp32)))
         _lib.check(handle, lib.stlt_set_fused_attention(handle, int(self._fused_attn)))
         _lib.check(handle, lib.stlt_set_compaction(handle, int(self._compaction)))
         _lib.check(handle, lib.stlt_set_hilo_residual(handle, int(self._hilo)))
@@ -477,7 +479,7 @@ class Stlt(nn.Module):
             self._sync_weights(device, stream)  # eager: re-binds / re-packs when a parameter changed
             ptrs = tuple([k[0] for k in self._weights_key])
             shape_key = (device, B, L, S, scores is not None, self.precision, self._pruning, self._fused_ln,
-                         self._fused_attn, self._compaction, self._hilo)
+                         self._fused_ln_fp32, self._fused_attn, self._compaction, self._hilo)
             if self._graphs is None:
                 self._graphs = {}
             entry = self._graphs.get(shape_key)
@@ -612,11 +614,15 @@ class Stlt(nn.Module):
         if self._handle is not None:
             _lib.check(self._handle, _lib.load_library().stlt_set_pruning(self._handle, int(self._pruning)))
 
-    def set_fused_layer_norm(self, enable: bool) -> None:
-        """bf16 mode: LayerNorm folded into the GEMM epilogues (default on). Off = separate add+LN kernels."""
+    def set_fused_layer_norm(self, enable: bool, fp32: Optional[bool] = None) -> None:
+        """LayerNorm folded into the GEMM epilogues (default on; bf16 mode, and the fp32-parity mode on split operands;
+        ``fp32`` sets the switch of the fp32-parity mode separately). Off = separate add+LN kernels."""
         self._fused_ln = bool(enable)
+        self._fused_ln_fp32 = bool(enable if fp32 is None else fp32)
         if self._handle is not None:
-            _lib.check(self._handle, _lib.load_library().stlt_set_fused_ln(self._handle, int(self._fused_ln)))
+            lib = _lib.load_library()
+            _lib.check(self._handle, lib.stlt_set_fused_ln(self._handle, int(self._fused_ln)))
+            _lib.check(self._handle, lib.stlt_set_fused_ln_fp32(self._handle, int(self._fused_ln_fp32)))
 
     def set_fused_attention(self, enable: bool) -> None:
         """bf16 mode: attention folded into the epilogue of the in-projection GEMM (default on; needs the fused

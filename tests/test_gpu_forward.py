@@ -643,3 +643,31 @@ def test_profile_by_role_splits_the_gemm_category_exactly():
         # a profile that was not refreshed is not re-reported: the next get_profile() without spans clears the roles
         m.get_profile()
         assert m.get_profile_by_role() == {}
+
+
+@pytest.mark.parametrize("layout", ["something", "action_genome"])
+def test_fp32_parity_mode_with_fused_layer_norm_matches_separate_kernels_and_oracle(layout):
+    """The fp32-parity mode folds its LayerNorms into the epilogues of the 3-term GEMMs (split operands, split folded
+    weights, hi / lo copy of the residual stream as a by-product). A/B against the separate add + LayerNorm kernels,
+    on the pad-skipping layout and on the padded grid, all inside the 1e-4 gate of the reference golden."""
+    from tests.util import golden_model_case
+    cfg, sd, batch, g = golden_model_case(layout)
+    model = _model(cfg, sd, "fp32")
+    gb = to_cuda(batch)
+    want = torch.from_numpy(g["logits"])
+    got, launches = {}, {}
+    with torch.no_grad():
+        for name, (ln, cp) in {"fused": (True, True), "fused_padded_grid": (True, False), "separate": (False, True),
+                               "separate_padded_grid": (False, False)}.items():
+            model.set_fused_layer_norm(ln)
+            model.set_compaction(cp)
+            got[name] = model(gb)["stlt"].float().cpu()
+            launches[name] = model.last_launch_count()
+    print(layout, {k: nerr(v, want) for k, v in got.items()}, launches)
+    for name, v in got.items():
+        assert nerr(v, want) < FP32_TOL, (name, nerr(v, want))
+        assert torch.equal(v.argmax(-1), want.argmax(-1))
+    assert nerr(got["fused"], got["separate"]) < 5e-5
+    # 24 residual + LayerNorm launches gone, one LayerNorm of the pooled rows added (as in bf16 mode)
+    assert launches["fused_padded_grid"] == launches["separate_padded_grid"] - 23
+    assert launches["fused"] == launches["separate"] - 23

@@ -259,3 +259,99 @@ def test_qkv_attention_kernel(handle, T, n_seq, causal, prev_norm):
                                           int(causal), ctx2.data_ptr(), 1, m))
     torch.cuda.synchronize()
     assert nerr(got, ctx2[:tokens].float()) < 1e-2
+
+
+# ---- the same epilogues on the split operands of the fp32-parity mode (3 bf16 MMAs per product) ----
+def _split(x: torch.Tensor) -> torch.Tensor:
+    """[2, ...] bf16 planes: hi = bf16(x), lo = bf16(x - hi)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def _joined(planes: torch.Tensor) -> torch.Tensor:
+    return planes[0].double() + planes[1].double()
+
+
+def test_pack_folded_split_planes(handle):
+    lib = L.load_library()
+    g = torch.Generator(device="cuda").manual_seed(15)
+    n = 3072
+    w = torch.randn(n, H, device="cuda", generator=g) / math.sqrt(H)
+    gamma = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(H, device="cuda", generator=g)
+    bias = torch.randn(n, device="cuda", generator=g)
+    wf = torch.empty(2, n, H, dtype=torch.bfloat16, device="cuda")
+    s = torch.empty(n, device="cuda")
+    c = torch.empty(n, device="cuda")
+    L.check(handle, lib.stlt_op_pack_folded(handle, _stream(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                            bias.data_ptr(), n, H, wf.data_ptr(), s.data_ptr(), c.data_ptr(), 2))
+    torch.cuda.synchronize()
+    assert torch.equal(wf, _split(w * gamma))
+    assert nerr(_joined(wf), (w * gamma).double()) < 2e-5   # 16 mantissa bits
+    assert nerr(s, _joined(wf).sum(-1)) < 1e-6
+    assert nerr(c, w.double() @ beta.double() + bias.double()) < 1e-6
+
+
+@pytest.mark.parametrize("m,n,gelu", [(128, 2304, 0), (384, 3072, 1), (148 * 128 + 128, 2304, 0), (640, 3072, 1)])
+def test_gemm_norm_a_epilogue_split_operands(handle, m, n, gelu):
+    """fp32-parity mode: act(LN(z) W^T + b) from the hi / lo split of the un-normalised stream and of the folded weights;
+    the error budget of the whole forward is 1e-4, so the op has to sit near 1e-5."""
+    lib = L.load_library()
+    g = torch.Generator(device="cuda").manual_seed(m + n + 1)
+    z = torch.randn(m, H, device="cuda", generator=g) * 1.7 + 0.3
+    w = torch.randn(n, H, device="cuda", generator=g) / math.sqrt(H)
+    gamma = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(H, device="cuda", generator=g)
+    bias = 0.1 * torch.randn(n, device="cuda", generator=g)
+    eps = 1e-5
+    wf = torch.empty(2, n, H, dtype=torch.bfloat16, device="cuda")
+    s = torch.empty(n, device="cuda")
+    c = torch.empty(n, device="cuda")
+    L.check(handle, lib.stlt_op_pack_folded(handle, _stream(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                            bias.data_ptr(), n, H, wf.data_ptr(), s.data_ptr(), c.data_ptr(), 2))
+    zp = _split(z)
+    stats = _row_stats(z)
+    out = torch.full((2, m, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.check(handle, lib.stlt_op_gemm_fused_split(handle, _stream(), L.GEMM_EPI_NORM_A, zp.data_ptr(), m, wf.data_ptr(), n, H,
+                                                 None, out.data_ptr(), None, gelu, stats.data_ptr(), s.data_ptr(),
+                                                 c.data_ptr(), None, eps, 1))
+    torch.cuda.synchronize()
+    exact = _layer_norm64(z, gamma, beta, eps) @ w.double().T + bias.double()
+    if gelu:
+        exact = torch.nn.functional.gelu(exact)
+    assert torch.isfinite(out.float()).all()
+    assert nerr(_joined(out), exact) < 3e-5
+    assert torch.equal(out[1], (_joined(out).float() - out[0].float()).to(torch.bfloat16))  # lo is the remainder of hi
+
+
+@pytest.mark.parametrize("m,k,prev_norm", [(128, 768, 0), (384, 768, 1), (148 * 128 + 128, 768, 1), (256, 3072, 1),
+                                           (640, 3072, 0)])
+def test_gemm_resid_epilogue_split_operands(handle, m, k, prev_norm):
+    """fp32-parity mode: z <- (LN(z) | z) + A W^T + b in place on split operands; the hi / lo split of the new z (the next
+    GEMM's operand) and the partial row statistics are by-products."""
+    lib = L.load_library()
+    g = torch.Generator(device="cuda").manual_seed(m + k + prev_norm + 7)
+    z = torch.randn(m, H, device="cuda", generator=g) * 1.3 - 0.2
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(H, k, device="cuda", generator=g) / math.sqrt(k)
+    bias = 0.1 * torch.randn(H, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(H, device="cuda", generator=g)
+    eps = 1e-5
+    ap, wp = _split(a), _split(w)
+    stats_in = _row_stats(z)
+    z_io = z.clone()
+    zb = torch.full((2, m, H), float("nan"), dtype=torch.bfloat16, device="cuda")
+    stats_out = torch.full((m, 6, 2), float("nan"), device="cuda")
+    L.check(handle, lib.stlt_op_gemm_fused_split(handle, _stream(), L.GEMM_EPI_RESID, ap.data_ptr(), m, wp.data_ptr(), H, k,
+                                                 bias.data_ptr(), z_io.data_ptr(), zb.data_ptr(), 0, stats_in.data_ptr(),
+                                                 gamma.data_ptr(), beta.data_ptr(), stats_out.data_ptr(), eps, prev_norm))
+    torch.cuda.synchronize()
+    x = _layer_norm64(z, gamma, beta, eps) if prev_norm else z.double()
+    ref = x + a.double() @ w.double().T + bias.double()
+    assert nerr(z_io, ref) < 2e-5
+    assert torch.equal(zb, _split(z_io))
+    so = stats_out.double().sum(1)
+    assert nerr(so[:, 0], ref.sum(-1)) < 2e-5
+    assert nerr(so[:, 1], (ref * ref).sum(-1)) < 2e-5
