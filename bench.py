@@ -817,6 +817,7 @@ def run_train(args, rank, local_rank, world, torch, dist, steps=None, full=True)
     prof_ms, prof_local, prof = timed(step_resident, steps, 1, world, torch, dist,
                                       before=lambda: model.set_profiling(True),
                                       after=lambda: (model.get_profile(), model.set_profiling(False))[0])
+    roles = model.get_profile_by_role()
     e2e_ms, _, _ = timed(step_e2e, steps, max(args.warmup, 1), world, torch, dist)
     videos = B * world * steps
     gemm = prof["gemm"]
@@ -851,7 +852,10 @@ def run_train(args, rank, local_rank, world, torch, dist, steps=None, full=True)
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "gemm_tcgen05_kernel (forward, data-gradient and weight-gradient GEMMs of a step)",
                      "launches_per_step": gemm["launches"] / steps, "kernel_ms_per_step": gemm_ms,
-                     "algorithmic_flops_per_step": gemm_flops, "peak_source": f"bf16 dense sustained, {peak_src}"},
+                     "algorithmic_flops_per_step": gemm_flops, "peak_source": f"bf16 dense sustained, {peak_src}",
+                     # forward GEMMs by role (linear1 = the dual-output epilogue: act and act' * mask), all backward GEMMs
+                     "by_kernel": [{k: v for k, v in row.items() if k not in ("algorithmic_gbps", "frac_of_hbm_peak")}
+                                   for row in roofline_by_kernel(roles, steps, "bf16", peaks)]},
         "cpu_baseline": cpu, "clocks": clocks,
         "model_tflops": 3 * FLOPS_PER_VIDEO[args.layout] * B / (ms / steps * 1e-3) / 1e12,
         "breakdown_ms_per_step": {k: v["ms"] / steps for k, v in prof.items()},

@@ -484,25 +484,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // before their two 16-byte staging stores (below), so that only one group of results is live at a time.
         const unsigned long long dual_e0 =
             static_cast<unsigned long long>(row0 + lane) * (static_cast<unsigned>(n_tiles) * BN) + col0 + c * 32;
-        // pair indices below 2^32 (every shape this model produces) take drop_bits' single hash round without its
-        // per-pair test of the high word; the choice is uniform over the launch
-        const bool dual_idx32 =
-            (static_cast<unsigned long long>(m_tiles) * BM * (static_cast<unsigned>(n_tiles) * BN) >> 33) == 0;
-        auto dual_group = [&](int g8, uint32_t (&ap)[4], uint32_t (&gp)[4], auto bits_of) {
+        // ONE code path (the epilogue is instruction-fetch sensitive: ncu showed 4 specialised copies of this block and
+        // `no_instruction` stalls): pair indices are 32-bit — launch_gemm_tcgen05 rejects DUAL outputs of 2^33 elements
+        // or more, where drop_bits would need its second hash round — and the mask is applied unconditionally
+        // (thr16 = 0 keeps everything, scale = 1)
+        const uint32_t dual_p0 = static_cast<uint32_t>(dual_e0 >> 1);
+        auto dual_group = [&](int g8, uint32_t (&ap)[4], uint32_t (&gp)[4]) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int j = 8 * g8 + 2 * q;
             __half2 act, grad;
             gelu_erf_and_grad_fast_h2(__floats2half2_rn(f[j], f[j + 1]), act, grad);
-            float2 a2 = __half22float2(act), g2 = __half22float2(grad);
-            if (drop.thr16 != 0) {
-              const uint32_t bits = bits_of(j);
-              const float m0 = drop_mul(bits, 0, drop), m1 = drop_mul(bits, 1, drop);
-              a2.x *= m0; a2.y *= m1;
-              g2.x *= m0; g2.y *= m1;
-            }
-            ap[q] = pack_bf16x2(a2.x, a2.y);
-            gp[q] = pack_bf16x2(g2.x, g2.y);
+            // drop_mul on both 16-bit fields at once: a per-halfword compare gives the keep mask, dropped halves are
+            // zeroed in the fp16 domain, the (exact, fp32) scale follows the widening
+            const uint32_t keep = __vcmpgeu2(lowbias32((dual_p0 + (j >> 1)) ^ drop.key), drop.thr16 * 0x00010001u);
+            *reinterpret_cast<uint32_t*>(&act) &= keep;
+            *reinterpret_cast<uint32_t*>(&grad) &= keep;
+            const float scale = drop.scale;
+            const float2 a2 = __half22float2(act), g2 = __half22float2(grad);
+            ap[q] = pack_bf16x2(a2.x * scale, a2.y * scale);
+            gp[q] = pack_bf16x2(g2.x * scale, g2.y * scale);
           }
         };
         if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
@@ -600,21 +601,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             if (lane == 0) tma_store_wait_read0();
             __syncwarp();
           }
+          if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
+            // two groups of eight columns are evaluated before their four staging stores: eight independent
+            // polynomial / MUFU chains in flight per thread (the stores are compiler barriers)
+#pragma unroll
+            for (int jj = 0; jj < 4; jj += 2) {
+              uint32_t ap[2][4], gp[2][4];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) dual_group(jj + u, ap[u], gp[u]);
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const uint32_t addr = row_smem + ((static_cast<uint32_t>(hc * 4 + jj + u) ^ sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ap[u][0]), "r"(ap[u][1]),
+                             "r"(ap[u][2]), "r"(ap[u][3])
+                             : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kEpiBufBytes), "r"(gp[u][0]),
+                             "r"(gp[u][1]), "r"(gp[u][2]), "r"(gp[u][3])
+                             : "memory");
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t addr = row_smem + ((static_cast<uint32_t>(hc * 4 + j) ^ sw) << 4);
             if constexpr (kOut == GEMM_OUT_BF16_DUAL) {
-              uint32_t ap[4], gp[4];
-              if (dual_idx32)
-                dual_group(j, ap, gp, [&](int e) { return lowbias32((static_cast<uint32_t>(dual_e0 >> 1) + (e >> 1)) ^ drop.key); });
-              else
-                dual_group(j, ap, gp, [&](int e) { return drop_bits(drop.key, (dual_e0 + e) >> 1); });
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ap[0]), "r"(ap[1]), "r"(ap[2]),
-                           "r"(ap[3])
-                           : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kEpiBufBytes), "r"(gp[0]), "r"(gp[1]),
-                           "r"(gp[2]), "r"(gp[3])
-                           : "memory");
             } else if constexpr (kNormInStore || (kOut == GEMM_OUT_BF16 && kGelu == 2)) {
               float gv[8];
               if constexpr (kNormInStore) {
@@ -822,6 +832,8 @@ cudaError_t launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t stream, int num_
   STLT_GEMM_CASE(3, GEMM_OUT_F32, 0)
   STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 1)
   STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 0)
+  // the dropout mask of the DUAL epilogue hashes 32-bit pair indices (drop_bits without its second round)
+  if (g.out_kind == GEMM_OUT_BF16_DUAL && (static_cast<unsigned long long>(g.m_rows) * g.n >> 33) != 0) return cudaErrorInvalidValue;
   STLT_GEMM_CASE(1, GEMM_OUT_BF16_DUAL, 2)
   STLT_GEMM_CASE(1, GEMM_OUT_BF16, 3)
   STLT_GEMM_CASE(3, GEMM_OUT_BF16_SPLIT, 3)
