@@ -363,3 +363,41 @@ def test_config_table_matches_reference_defaults():
         ref = configs.StltModelConfig(num_classes=174, unique_categories=4)
         for name in cfg.FIELDS:
             assert getattr(ref, name) == getattr(cfg, name), name
+
+
+def test_bench_per_kernel_roofline_rows_and_frozen_layer_buckets():
+    """Host logic without a GPU: (1) bench.roofline_by_kernel turns the per-role GEMM profile (stlt_get_profile_by_role)
+    into fractions of the measured peaks — tensor peak for every role, HBM peak for the out-projection whose fused
+    epilogue makes it bandwidth-bound; (2) the flat training layout keeps stlt_backward's stage numbering when whole
+    layers are frozen (the layer counts come from the config, not from the trainable names)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("stlt_bench", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    peaks = {"bf16_tflops_sustained": 1000.0, "bf16_tflops": 1200.0, "hbm_gbs": 6000.0}
+    rows_per_step = 1000 * 128
+    roles = {"linear1": {"ms": 20.0, "flops": 2 * 2.0 * rows_per_step * 3072 * 768, "launches": 24},
+             "out_proj": {"ms": 4.0, "flops": 2 * 2.0 * rows_per_step * 768 * 768, "launches": 24}}
+    out = {r["role"]: r for r in bench.roofline_by_kernel(roles, 2, "bf16", peaks)}
+    l1, op = out["linear1"], out["out_proj"]
+    assert l1["launches_per_step"] == 12 and l1["ms_per_step"] == 10.0
+    assert l1["achieved_tflops"] == pytest.approx(2.0 * rows_per_step * 3072 * 768 / 10e-3 / 1e12)
+    assert l1["frac_of_tensor_peak"] == pytest.approx(l1["achieved_tflops"] / 1000.0) and "frac_of_hbm_peak" not in l1
+    # out-projection, bf16: context in (2 B) + fp32 stream in and out (4 + 4) + bf16 operand copy out (2) per element
+    assert op["algorithmic_gbps"] == pytest.approx(rows_per_step * 768 * 12 / 2e-3 / 1e9)
+    assert op["frac_of_hbm_peak"] == pytest.approx(op["algorithmic_gbps"] / 6000.0)
+    op32 = bench.roofline_by_kernel({"out_proj": roles["out_proj"]}, 2, "fp32", peaks)[0]
+    assert op32["algorithmic_gbps"] == pytest.approx(rows_per_step * 768 * 16 / 2e-3 / 1e9)   # two planes each way
+    assert op32["mma_frac_of_tensor_peak"] == pytest.approx(3 * op32["frac_of_tensor_peak"])
+
+    from stlt_b200.training import plan_buckets, plan_flat_layout
+    m = Stlt(StltModelConfig(num_classes=174, unique_categories=4))
+    for n, p in m.named_parameters():
+        p.requires_grad_(n.startswith("prediction_head.") or ".layers.7." in n)   # head + the last temporal layer
+    layout, segments, total, stage_ends = plan_flat_layout(m.named_parameters(), 4, 8)
+    assert len(stage_ends) == 15 and stage_ends[0] > 0 and stage_ends[1] > stage_ends[0]
+    assert all(e == stage_ends[1] for e in stage_ends[1:])       # nothing trainable after stage 1
+    two = plan_buckets("two", stage_ends, total, 10)
+    assert two[0][0] == 9 and two[-1] == (14, stage_ends[9], total)   # the stage numbers the library's events use
+    guessed = plan_flat_layout(m.named_parameters())[3]
+    assert len(guessed) != 15   # read off the names alone the numbering would be wrong: hence the explicit counts
