@@ -632,8 +632,8 @@ class Stlt(nn.Module):
             _lib.check(self._handle, _lib.load_library().stlt_set_fused_attention(self._handle, int(self._fused_attn)))
 
     def set_compaction(self, enable: bool) -> None:
-        """bf16 mode: pad-skipping row layout of the spatial stack (default on): padding frames and the padded slots of
-        one-token frames are not computed. Off = the whole padded [B, L, S] grid, as the reference computes it."""
+        """Pad-skipping row layout of the spatial stack (default on, both precision modes): padding frames and the padded
+        slots of one-token frames are not computed. Off = the whole padded [B, L, S] grid, as the reference computes it."""
         self._compaction = bool(enable)
         if self._handle is not None:
             _lib.check(self._handle, _lib.load_library().stlt_set_compaction(self._handle, int(self._compaction)))
